@@ -1,0 +1,139 @@
+// Host-side model of the CI string spaces: GAS/ORMAS occupation patterns, string classes
+// (occupation pattern x irrep), string enumeration in the reference's address order, string
+// addressing, determinant blocks, and the sign-carrying replacement lists.
+//
+// Behavioural contract (bit-exact): forte2/ci/ci_occupation.cc:35-142,361-417,
+// forte2/ci/ci_strings.cc:34-184, forte2/ci/ci_strings_makers.cc:13-322,
+// forte2/ci/ci_string_class.cc:7-102, forte2/ci/ci_string_address.cc:6-23.
+// The data structures are not the reference's (no hash maps, no std::map of vectors): strings
+// live in flat per-class tables with a sorted index for look-ups, and every list is a flat
+// CSR/ELL array that is uploaded to the GPU as is.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace f2 {
+
+constexpr int kMaxGas = 6; // forte2/ci/ci_occupation.h:10
+using occ_t = std::array<int, kMaxGas>;
+
+enum Kind : int {
+    K_STR_N = 0,
+    K_STR_1H = 1,
+    K_STR_2H = 2,
+    K_STR_3H = 3,
+    K_STR_1H1P = 4,
+    K_VO = 10,
+    K_VO2 = 11,
+    K_1H = 12,
+    K_1H2 = 13,
+    K_2H = 14,
+    K_3H = 15,
+};
+
+inline int popcount_below(uint64_t w, int n) {
+    return __builtin_popcountll(w & ((n >= 64) ? ~0ull : ((1ull << n) - 1ull)));
+}
+/// (-1)^(number of occupied orbitals below n); forte2/determinant/bitarray.hpp:575-583
+inline int slater_sign(uint64_t w, int n) { return (popcount_below(w, n) & 1) ? -1 : 1; }
+
+/// One family of strings (N-electron, 1h, 2h, 3h or 1h1p) of one spin.
+struct StringSpace {
+    int nirrep = 1;
+    std::vector<occ_t> occs;                // occupation patterns, reference order
+    std::vector<std::vector<uint64_t>> cls; // class -> strings in address order
+    std::vector<uint32_t> cls_off;          // class -> first global index (size nclasses+1)
+    // sorted look-up table: string -> (address in class, class)
+    std::vector<uint64_t> key;
+    std::vector<uint32_t> key_add, key_cls;
+    bool built = false;
+
+    size_t nclasses() const { return cls.size(); }
+    size_t nstr() const { return cls_off.empty() ? 0 : cls_off.back(); }
+    size_t strpcls(size_t c) const { return cls[c].size(); }
+    bool find(uint64_t s, uint32_t& add, uint32_t& c) const;
+    void index();
+};
+
+struct DetBlock {
+    int cA, cB;
+    int64_t offset, nA, nB;
+};
+
+/// Packed device-format list entries (see DESIGN.md "data layout in HBM").
+/// alpha single replacement seen from the OUTPUT row Ia:  <Ia| E^a_kl |Ja> = sign
+///   bits  0..31 Ja (global alpha index), 32..47 k*norb+l, bit 48 sign (1 = negative)
+/// beta scatter entry seen from the SOURCE column Jb:   <Ib| E^b_ij |Jb> = sign
+///   bits  0..27 Ib address inside its class, 28..39 class of Ib, 40..55 row m of the integral
+///   matrix, bit 56 sign, all-ones = padding
+/// two-hole member: string I = K + {p,q}, a_p a_q |I> = sign |K>
+///   bits 0..31 I (global index), 32..47 pair index p(p-1)/2+q, bit 48 sign
+constexpr uint64_t kNullEntry = ~0ull;
+
+struct DeviceLists {
+    // alpha singles, CSR over global alpha string index
+    std::vector<uint32_t> as_ptr;
+    std::vector<uint64_t> as_ent;
+    int as_max = 0;
+    // beta scatter, ELL: entry t of string Jb at [t * nbs + Jb]
+    std::vector<uint64_t> bs_ent;
+    int bs_width = 0;
+    // two-hole members per spin, CSR over global 2h string index, plus a colouring of the 2h
+    // strings such that two strings of one colour never share a parent N-electron string
+    std::vector<uint32_t> h2_ptr[2];
+    std::vector<uint64_t> h2_ent[2];
+    std::vector<uint32_t> h2_color_ptr[2];  // colour -> range in h2_color_list
+    std::vector<uint32_t> h2_color_list[2]; // 2h string ids grouped by colour
+    int h2_max[2] = {0, 0};
+    // per global string: class and address in class
+    std::vector<uint32_t> a_cls, a_loc, b_cls, b_loc;
+};
+
+class CIStringsHost {
+  public:
+    CIStringsHost(int64_t na, int64_t nb, int symmetry,
+                  const std::vector<std::vector<int>>& orbital_symmetry,
+                  const std::vector<int>& gas_min, const std::vector<int>& gas_max);
+
+    int na, nb, symmetry, norb = 0, nirrep = 1, ngas = 0;
+    std::vector<int> gas_size, gas_start, mo_sym;
+    std::vector<occ_t> aocc, bocc;
+    std::vector<std::pair<size_t, size_t>> occ_pairs;
+    std::vector<DetBlock> blocks;
+    std::vector<int64_t> block_of; // [cA * nclsB + cB] -> block id or -1
+    int64_t ndet = 0, nas = 0, nbs = 0;
+
+    /// kind in {N,1H,2H,3H,1H1P}; built on first use except N, 1H, 2H
+    const StringSpace& space(int spin, int kind) const;
+    size_t nclsA() const { return space(0, K_STR_N).nclasses(); }
+    size_t nclsB() const { return space(1, K_STR_N).nclasses(); }
+
+    /// Reference-format flat export (same row layouts and row order as oracle/ref_cabi.cc).
+    std::vector<int64_t> export_kind(int kind, int spin) const;
+    /// (alpha word, beta word) of every determinant in CI-vector order
+    void determinants(uint64_t* out) const;
+    void determinant(int64_t address, uint64_t& a, uint64_t& b) const;
+    int64_t determinant_index(uint64_t a, uint64_t b) const;
+
+    /// Device-format lists; rowmap[i*norb+j] = row of the integral matrix used for E_ij.
+    const DeviceLists& device_lists() const;
+
+    int symmetry_of(uint64_t s) const;
+
+  private:
+    mutable StringSpace sp_[2][5];
+    mutable DeviceLists dl_;
+    mutable bool dl_built_ = false;
+    void build_space(int spin, int kind) const;
+    std::vector<occ_t> occs_of(int spin, int kind) const;
+    void build_device_lists() const;
+};
+
+std::vector<occ_t> one_hole_occupations(const std::vector<occ_t>& occ);
+std::vector<occ_t> one_hole_one_particle_occupations(const std::vector<occ_t>& occ);
+
+} // namespace f2

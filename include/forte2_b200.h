@@ -1,0 +1,118 @@
+/* forte2_b200 — C ABI of the B200-native determinant-CI sigma builder.
+ *
+ * This is the boundary a forte2 maintainer binds instead of the nanobind classes
+ *   forte2.lib.ci_helpers.CIStrings       (forte2/api/ci_helpers_api.cc:52-85)
+ *   forte2.lib.ci_helpers.CISigmaBuilder  (forte2/api/ci_helpers_api.cc:88-187, hot-path subset)
+ * Plain pointers and sizes only; no exceptions cross it.  Every function that can fail returns an
+ * int status (0 = ok) or a NULL handle / negative count, and leaves a message in f2_last_error().
+ * The Python mirror in forte2_b200/ maps the status codes to the exception types nanobind gives the
+ * reference: 1 -> ValueError (std::invalid_argument), 2 -> RuntimeError (std::runtime_error),
+ * 3 -> OverflowError (std::overflow_error), 4 -> IndexError (std::out_of_range), 5 -> RuntimeError
+ * carrying a CUDA error string.
+ */
+#ifndef FORTE2_B200_H
+#define FORTE2_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct f2_strings f2_strings;
+typedef struct f2_sigma f2_sigma;
+
+enum { F2_OK = 0, F2_EINVAL = 1, F2_ERUNTIME = 2, F2_EOVERFLOW = 3, F2_EINDEX = 4, F2_ECUDA = 5 };
+
+/* kinds understood by f2_strings_export (string tables and replacement lists) */
+enum {
+    F2_STR_N = 0, F2_STR_1H = 1, F2_STR_2H = 2, F2_STR_3H = 3, F2_STR_1H1P = 4,
+    F2_VO = 10, F2_VO2 = 11, F2_1H = 12, F2_1H2 = 13, F2_2H = 14, F2_3H = 15
+};
+
+const char* f2_last_error(void);
+int f2_abi_version(void);
+
+/* ---- CIStrings: forte2/ci/ci_strings.h:15, ctor forte2/ci/ci_strings.cc:26-184 ------------------
+ * orbital_symmetry is passed flattened: ngas spaces of gas_sizes[g] irrep labels each. */
+f2_strings* f2_strings_create(int64_t na, int64_t nb, int symmetry, int ngas, const int* gas_sizes,
+                              const int* orbsym_flat, int n_min, const int* gas_min, int n_max,
+                              const int* gas_max);
+void f2_strings_destroy(f2_strings* h);
+/* out[0..11] = na nb nas nbs ndet norb nirrep ngas_spaces nblocks symmetry nclasses_a nclasses_b
+ * (properties of forte2/api/ci_helpers_api.cc:71-81) */
+int f2_strings_info(const f2_strings* h, int64_t* out);
+/* determinant blocks, rows (class_Ia, class_Ib, offset, nIa, nIb); CI-vector layout of
+ * forte2/ci/ci_strings.cc:152-160,196-203 */
+int f2_strings_blocks(const f2_strings* h, int64_t* out);
+/* which: 0 alpha patterns (rows of 6), 1 beta patterns (rows of 6), 2 allowed pairs (rows of 2);
+ * returns the number of int64 (gas_alpha_occupations / gas_beta_occupations / gas_occupations) */
+int64_t f2_strings_occupations(const f2_strings* h, int which, int64_t* out, int64_t cap);
+/* Flatten a string table or replacement list to int64 in the reference's container order
+ * (forte2/ci/ci_strings_makers.cc:75-322).  Returns the int64 count (call with out = NULL to size),
+ * negative on error.
+ *   strings: [nclasses, strpcls[0..nclasses), then the occupation words class by class]
+ *   VO   rows: class_I class_J p q sign I J          J = sign a+_p a_q I
+ *   VO2  rows: class_K class_I K sign(+-1,+-2) pq J  K in the 1h1p space, pq = pair_geq(p,q)
+ *   1H   rows: class_K add_K class_I sign p I        a_p I = sign K
+ *   1H2  rows: class_K class_I K sign p I
+ *   2H   rows: class_K add_K class_I sign p q I      a_p a_q I = sign K, p > q
+ *   3H   rows: class_K add_K class_I sign p q r I */
+int64_t f2_strings_export(const f2_strings* h, int kind, int spin, int64_t* out, int64_t cap);
+/* CIStrings::make_determinants / determinant / determinant_index (ci_strings.cc:186-230):
+ * occupation words (alpha, beta) */
+int f2_strings_determinants(const f2_strings* h, uint64_t* out /* 2*ndet */);
+int f2_strings_determinant(const f2_strings* h, int64_t address, uint64_t* out2);
+int64_t f2_strings_determinant_index(const f2_strings* h, uint64_t a, uint64_t b);
+
+/* ---- CISigmaBuilder: forte2/ci/ci_sigma_builder.h:26, ctor ci_sigma_builder.cc:29-47 -------------
+ * H[norb*norb], V[norb^4] are HOST pointers, C-contiguous, V in physicist order <pq|rs>
+ * (integral hand-off of forte2/jkbuilder/mointegrals.py:40,84).  device = CUDA ordinal.
+ * The strings handle must outlive the builder (same rule as the reference, ci_sigma_builder.h:290). */
+f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const double* V,
+                          int log_level, int device);
+void f2_sigma_destroy(f2_sigma* h);
+/* CISigmaBuilder::set_Hamiltonian (ci_sigma_builder.cc:102-185): new integrals, lists are kept */
+int f2_sigma_set_hamiltonian(f2_sigma* h, double E, const double* H, const double* V);
+/* "hz" | "harrison-zarrabian" | "kh" | "knowles-handy" (ci_sigma_builder.cc:49-57) */
+int f2_sigma_set_algorithm(f2_sigma* h, const char* name);
+const char* f2_sigma_get_algorithm(const f2_sigma* h);
+/* scratch budget in MB (ci_sigma_builder.cc:70-78) */
+int f2_sigma_set_memory(f2_sigma* h, int64_t mb);
+int f2_sigma_set_log_level(f2_sigma* h, int level);
+/* CISigmaBuilder::Hamiltonian (ci_sigma_builder.cc:187-218) on DEVICE buffers of ndet doubles,
+ * sigma overwritten; stream = cudaStream_t (NULL = default stream). */
+int f2_sigma_apply(f2_sigma* h, const double* C_dev, double* sigma_dev, int64_t n, void* stream);
+/* same call on HOST buffers (what the reference's numpy-facing method receives): H2D copy, device
+ * build, D2H copy, synchronous. */
+int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, int64_t n);
+/* avg_build_time (ci_sigma_builder.h:93-102): seconds per build [total, aabb, aaaa, bbbb] */
+int f2_sigma_times(f2_sigma* h, double* out4);
+/* per-term device time of the LAST build in ms: [H0, same-spin alpha, same-spin beta (with
+ * transposes), opposite spin, total] */
+int f2_sigma_last_ms(f2_sigma* h, double* out5);
+/* determinant energies <I|H|I> (SlaterRules::energy, forte2/determinant/slater_rules.cc:86-121)
+ * for every determinant in CI-vector order, on the device: the determinant-basis Davidson
+ * preconditioner. */
+int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream);
+
+/* ---- alpha-row partition for multi-GPU (no reference counterpart) ----------
+ * Rank r of world owns, in every determinant block, the alpha rows [r*nIa/world, (r+1)*nIa/world).
+ * The local vector is the concatenation of the owned row slabs in block order. */
+int64_t f2_strings_local_size(const f2_strings* h, int rank, int world);
+/* rows (block, first_row, nrows, local_offset) for this rank; returns nblocks */
+int f2_strings_local_layout(const f2_strings* h, int rank, int world, int64_t* out);
+/* sigma_local (owned rows only) from the FULL trial vector (all-gathered by the caller over NCCL).
+ * The alpha same-spin term is computed for the columns rank owns of every row and written to
+ * exch_dev (full layout, only owned columns non-zero); the caller reduces it (reduce-scatter over
+ * rows) and adds it to sigma_local.  See forte2_b200/dist.py. */
+int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev,
+                        double* exch_dev, int rank, int world, void* stream);
+/* pack / unpack between the local slab layout and the full layout (device buffers) */
+int f2_sigma_scatter_local(f2_sigma* h, const double* full_dev, double* local_dev, int rank,
+                           int world, int accumulate, void* stream);
+int f2_sigma_gather_local(f2_sigma* h, const double* local_dev, double* full_dev, int rank,
+                          int world, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
