@@ -1,0 +1,135 @@
+"""CISigmaBuilder: the Python face of forte2.lib.ci_helpers.CISigmaBuilder
+(forte2/api/ci_helpers_api.cc:88-109,146-148; hot-path subset) running on one B200.
+
+`Hamiltonian(basis, sigma)` accepts
+  * torch CUDA float64 tensors (or any DLPack-exporting device array): zero-copy, asynchronous on the
+    current torch stream;
+  * numpy float64 vectors, as the reference does: staged through pinned memory inside the C ABI
+    (f2_sigma_apply_host), synchronous.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .ci_strings import CIStrings
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+class CISigmaBuilder:
+    def __init__(self, lists: CIStrings, E: float, H, V, log_level: int = 3, device: int | None = None):
+        if not isinstance(lists, CIStrings):
+            raise TypeError("lists must be a forte2_b200.CIStrings")
+        self.ci_strings = lists  # keep-alive (the reference leaves this to the caller, ci.py:172)
+        n = lists.norb
+        H = np.asarray(H, dtype=np.float64)
+        V = np.asarray(V, dtype=np.float64)
+        if H.ndim != 2:
+            raise RuntimeError("H must be a 2D matrix.")
+        if H.shape != (n, n):
+            raise RuntimeError("H shape does not match the number of orbitals.")
+        if V.ndim != 4:
+            raise RuntimeError("V must be a 4D tensor.")
+        if V.shape != (n, n, n, n):
+            raise RuntimeError("V shape does not match the number of orbitals.")
+        H = np.ascontiguousarray(H)
+        V = np.ascontiguousarray(V)
+        if device is None:
+            device = self._current_device()
+        self.device = int(device)
+        L = _lib.lib()
+        self._h = L.f2_sigma_create(lists._h, float(E), H.ctypes.data_as(_lib.f64p),
+                                    V.ctypes.data_as(_lib.f64p), int(log_level), self.device)
+        if not self._h:
+            raise RuntimeError(_lib.last_error())
+
+    @staticmethod
+    def _current_device():
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.cuda.current_device()
+        except ImportError:
+            pass
+        return 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib._lib is not None:
+            _lib._lib.f2_sigma_destroy(h)
+
+    def set_Hamiltonian(self, E, H, V):
+        n = self.ci_strings.norb
+        H = np.ascontiguousarray(H, dtype=np.float64)
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        if H.shape != (n, n):
+            raise RuntimeError("H shape does not match the number of orbitals.")
+        if V.shape != (n, n, n, n):
+            raise RuntimeError("V shape does not match the number of orbitals.")
+        _lib.check(_lib.lib().f2_sigma_set_hamiltonian(self._h, float(E), H.ctypes.data_as(_lib.f64p),
+                                                       V.ctypes.data_as(_lib.f64p)))
+
+    def set_algorithm(self, algorithm: str):
+        _lib.check(_lib.lib().f2_sigma_set_algorithm(self._h, str(algorithm).encode()))
+
+    def get_algorithm(self) -> str:
+        return _lib.lib().f2_sigma_get_algorithm(self._h).decode()
+
+    def set_memory(self, memory: int):
+        _lib.check(_lib.lib().f2_sigma_set_memory(self._h, int(memory)))
+
+    def set_log_level(self, level: int):
+        _lib.check(_lib.lib().f2_sigma_set_log_level(self._h, int(level)))
+
+    def Hamiltonian(self, basis, sigma) -> None:
+        L = _lib.lib()
+        if isinstance(basis, np.ndarray) and isinstance(sigma, np.ndarray):
+            if basis.dtype != np.float64 or sigma.dtype != np.float64:
+                raise TypeError("basis and sigma must be float64")
+            if basis.ndim != 1 or sigma.ndim != 1:
+                raise TypeError("basis and sigma must be one-dimensional")
+            if (basis.size > 1 and basis.strides[0] != 8) or (sigma.size > 1 and sigma.strides[0] != 8):
+                raise RuntimeError("np_vector must have stride 1 to convert to std::span.")
+            if basis.shape[0] != sigma.shape[0]:
+                raise ValueError("basis and sigma must have the same length")
+            _lib.check(L.f2_sigma_apply_host(self._h, basis.ctypes.data_as(_lib.f64p),
+                                             sigma.ctypes.data_as(_lib.f64p), basis.shape[0]))
+            return
+        import torch
+        if not _is_torch_tensor(basis):
+            basis = torch.from_dlpack(basis)
+        if not _is_torch_tensor(sigma):
+            sigma = torch.from_dlpack(sigma)
+        for name, t in (("basis", basis), ("sigma", sigma)):
+            if not t.is_cuda or t.dtype != torch.float64 or t.dim() != 1:
+                raise TypeError(f"{name} must be a one-dimensional float64 CUDA tensor")
+            if t.numel() > 1 and t.stride(0) != 1:
+                raise RuntimeError("np_vector must have stride 1 to convert to std::span.")
+            if t.device.index != self.device:
+                raise ValueError(f"{name} lives on cuda:{t.device.index}, the builder on cuda:{self.device}")
+        if basis.numel() != sigma.numel():
+            raise ValueError("basis and sigma must have the same length")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(L.f2_sigma_apply(self._h, basis.data_ptr(), sigma.data_ptr(), basis.numel(), stream))
+
+    def avg_build_time(self):
+        out = np.zeros(4)
+        _lib.check(_lib.lib().f2_sigma_times(self._h, out.ctypes.data_as(_lib.f64p)))
+        return [float(x) for x in out]
+
+    def last_build_ms(self):
+        """[H0, same-spin alpha, same-spin beta, opposite spin, total] of the last build (device ms)."""
+        out = np.zeros(5)
+        _lib.check(_lib.lib().f2_sigma_last_ms(self._h, out.ctypes.data_as(_lib.f64p)))
+        return [float(x) for x in out]
+
+    def form_Hdiag_det(self):
+        """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""
+        import torch
+        out = torch.empty(self.ci_strings.ndet, dtype=torch.float64, device=f"cuda:{self.device}")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_hdiag(self._h, out.data_ptr(), stream))
+        return out

@@ -1,0 +1,491 @@
+// Device kernels of the sigma build (sm_100a).  See DESIGN.md for the algebra and the data layout.
+//
+//   t3_kernel   opposite-spin term: per output alpha row Ia, G[ij, Jb] = sum_r A_Ia[ij, r] C[Ja_r, Jb]
+//               on the FP64 tensor pipe (DMMA), A = signed columns of the integral matrix held in
+//               registers, B = rows of C staged in shared memory with cp.async; then the beta
+//               replacement list scatters G into sigma[Ia, :].
+//               Reference counterpart: CISigmaBuilder::H2_hz_opposite_spin
+//               (forte2/ci/ci_sigma_builder_harrison_zarrabian.cc:197-308) and the alpha gather /
+//               beta scatter halves of H2_kh (forte2/ci/ci_sigma_builder_knowles_handy.cc:88-171).
+//   ss_kernel   same-spin term (one- and two-electron): per (N-2)-electron string K a dense
+//               m x m block of antisymmetrised integrals acts on the m parent strings of K.
+//               Reference counterpart: CISigmaBuilder::H2_hz_same_spin and H1_hz
+//               (ci_sigma_builder_harrison_zarrabian.cc:14-195).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace f2 {
+
+constexpr int NT = 64; // columns per tile
+constexpr int BS = 72; // shared-memory row stride in doubles (== 8 mod 16: conflict-free fragments)
+
+__device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1, double b0) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, "
+                 "{%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a0), "d"(a1), "d"(b0));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+struct T3Params {
+    const double* C;
+    double* sigma;
+    const uint32_t* items; // 2 per CTA: alpha string (global index), beta class | m-split << 16
+    const uint32_t *a_cls, *a_loc, *as_ptr;
+    const uint64_t* as_ent;
+    const uint64_t* bs_ent;
+    int bs_width;
+    int64_t nbs;
+    const int64_t* blk_off;  // [nclsA*nclsB] offset of block (cA,cB) in C, -1 if not allowed
+    const int64_t* sblk_off; // same for sigma (differs when sigma holds the owned rows only)
+    const uint32_t* srow0;   // [nclsA] first owned row of each alpha class
+    const uint32_t *nB_cls, *b_off;
+    int nclsA, nclsB, norb;
+    const double* Vx; // [M][norb*norb]  Vx[m(i,j)][k*norb+l] = <k i | l j>
+    int M;
+    const uint16_t* rowmap; // [norb*norb] (i,j) -> m
+};
+
+template <int KS, bool AL16>
+__global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3Params p) {
+    constexpr int KP = KS * 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int nwarps = nthr >> 5, g = lane >> 2, t = lane & 3;
+    double* Bs = reinterpret_cast<double*>(smem_raw);
+    double* Gs = Bs + 2 * KP * BS;
+    long long* ksrc = reinterpret_cast<long long*>(Gs + nwarps * 16 * BS);
+    long long* rowbase = ksrc + KP;
+    unsigned* kinfo = reinterpret_cast<unsigned*>(rowbase + p.nclsB);
+    unsigned short* rowmap_s = reinterpret_cast<unsigned short*>(kinfo + KP);
+    __shared__ int s_Kn;
+
+    const uint32_t Ia = p.items[2 * blockIdx.x];
+    const uint32_t packed = p.items[2 * blockIdx.x + 1];
+    const int cBp = packed & 0xffff, msp = packed >> 16;
+    const int cA = p.a_cls[Ia];
+    const uint32_t ia = p.a_loc[Ia];
+    const int nBp = p.nB_cls[cBp];
+
+    if (warp == 0) {
+        const int e0 = p.as_ptr[Ia], e1 = p.as_ptr[Ia + 1];
+        int cnt = 0;
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            bool ok = false;
+            long long src = -1;
+            unsigned info = 0;
+            if (e < e1) {
+                const uint64_t ent = p.as_ent[e];
+                const uint32_t Ja = static_cast<uint32_t>(ent);
+                const long long off = p.blk_off[p.a_cls[Ja] * p.nclsB + cBp];
+                if (off >= 0) {
+                    ok = true;
+                    src = off + static_cast<long long>(p.a_loc[Ja]) * nBp;
+                    info = static_cast<unsigned>((ent >> 32) & 0xffff) |
+                           (static_cast<unsigned>((ent >> 48) & 1) << 31);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+                ksrc[pos] = src;
+                kinfo[pos] = info;
+            }
+            cnt += __popc(mask);
+        }
+        for (int r = cnt + lane; r < KP; r += 32) {
+            ksrc[r] = -1;
+            kinfo[r] = 0;
+        }
+        if (lane == 0)
+            s_Kn = cnt;
+    }
+    for (int c = tid; c < p.nclsB; c += nthr) {
+        const long long off = p.sblk_off[cA * p.nclsB + c];
+        rowbase[c] = off >= 0 ? off + static_cast<long long>(ia - p.srow0[cA]) * p.nB_cls[c] : -1;
+    }
+    for (int i = tid; i < p.norb * p.norb; i += nthr)
+        rowmap_s[i] = p.rowmap[i];
+    for (int i = tid; i < 2 * KP * BS; i += nthr)
+        Bs[i] = 0.0;
+    __syncthreads();
+    const int Kn = s_Kn;
+    if (Kn == 0)
+        return;
+    const int nks = (Kn + 3) >> 2;
+
+    // A fragments: this warp owns rows [m0, m0+16) of the integral matrix for the whole row Ia
+    const int mbase = msp * nwarps * 16;
+    const int m0 = mbase + warp * 16;
+    const int ldv = p.norb * p.norb;
+    double a[KS][2];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        a[ks][0] = 0.0;
+        a[ks][1] = 0.0;
+        const int r = 4 * ks + t;
+        if (r < Kn) {
+            const unsigned info = kinfo[r];
+            const double sg = (info >> 31) ? -1.0 : 1.0;
+            const int kl = info & 0xffff;
+            if (m0 + g < p.M)
+                a[ks][0] = sg * p.Vx[static_cast<size_t>(m0 + g) * ldv + kl];
+            if (m0 + g + 8 < p.M)
+                a[ks][1] = sg * p.Vx[static_cast<size_t>(m0 + g + 8) * ldv + kl];
+        }
+    }
+
+    const int ntiles = (nBp + NT - 1) / NT;
+    auto load_tile = [&](int tile, int stage) {
+        const int j0 = tile * NT;
+        double* dst = Bs + stage * KP * BS;
+        if (AL16) {
+            for (int idx = tid; idx < Kn * (NT / 2); idx += nthr) {
+                const int r = idx / (NT / 2), c = idx % (NT / 2);
+                const int col = j0 + 2 * c;
+                int bytes = (nBp - col) * 8;
+                bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+                const double* src = p.C + ksrc[r] + (bytes ? col : 0);
+                cp_async16(dst + r * BS + 2 * c, src, bytes);
+            }
+        } else {
+            for (int idx = tid; idx < Kn * NT; idx += nthr) {
+                const int r = idx / NT, c = idx % NT;
+                const int col = j0 + c;
+                const bool in = col < nBp;
+                cp_async8(dst + r * BS + c, p.C + ksrc[r] + (in ? col : 0), in ? 8 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int mrows = nwarps * 16;
+    const int64_t bcol0 = p.b_off[cBp];
+    load_tile(0, 0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int stage = tile & 1;
+        if (tile + 1 < ntiles) {
+            load_tile(tile + 1, stage ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads(); // tile data visible; previous scatter finished reading Gs
+
+        const double* Bst = Bs + stage * KP * BS;
+#pragma unroll 1
+        for (int nh = 0; nh < 2; ++nh) { // two halves of the tile keep the accumulators at 16 regs
+            double acc[NT / 16][4];
+#pragma unroll
+            for (int nt = 0; nt < NT / 16; ++nt)
+                acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                if (ks < nks) {
+                    const double* bp = Bst + (4 * ks + t) * BS + nh * (NT / 2) + g;
+#pragma unroll
+                    for (int nt = 0; nt < NT / 16; ++nt)
+                        dmma_16x8x4(acc[nt], a[ks][0], a[ks][1], bp[nt * 8]);
+                }
+            }
+            double* g0 = Gs + (warp * 16 + g) * BS + nh * (NT / 2) + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < NT / 16; ++nt) {
+                *reinterpret_cast<double2*>(g0 + nt * 8) = make_double2(acc[nt][0], acc[nt][1]);
+                *reinterpret_cast<double2*>(g0 + 8 * BS + nt * 8) = make_double2(acc[nt][2], acc[nt][3]);
+            }
+        }
+        __syncthreads();
+
+        // beta replacement list: sigma[Ia, Ib] += sign * G[m(i,j), Jb]
+        const int j0 = tile * NT;
+        const int total = p.bs_width * NT;
+        for (int e = tid; e < total; e += nthr) {
+            const int j = e & (NT - 1), tt = e >> 6;
+            const int col = j0 + j;
+            if (col >= nBp)
+                continue;
+            const uint64_t ent = p.bs_ent[static_cast<int64_t>(tt) * p.nbs + bcol0 + col];
+            if (ent == ~0ull)
+                continue;
+            const int m = static_cast<int>(rowmap_s[(ent >> 40) & 0xffff]) - mbase;
+            if (static_cast<unsigned>(m) >= static_cast<unsigned>(mrows))
+                continue;
+            const long long base = rowbase[(ent >> 28) & 0xfff];
+            if (base < 0)
+                continue;
+            const double v = Gs[m * BS + j];
+            atomicAdd(p.sigma + base + (ent & 0xfffffffull), ((ent >> 56) & 1) ? -v : v);
+        }
+    }
+}
+
+struct SSParams {
+    const double* X;
+    double* Y;
+    const uint32_t* klist; // (N-2)-electron strings of this launch (one colour)
+    const uint32_t* h2_ptr;
+    const uint64_t* h2_ent;
+    const uint32_t *s_cls, *s_loc;
+    const int64_t* xoff; // [ncls_row * ngroups] offset of (row class, column group) in X, -1 if absent
+    const int64_t* yoff; // same for Y
+    const uint32_t* g_ncols;
+    const uint32_t* g_ldx;
+    const uint32_t* g_ldy;
+    const uint32_t* tiles; // 2 per blockIdx.x: column group, first column
+    const double* W;       // [P*P] antisymmetrised (and one-electron folded) integrals
+    int P;
+    int ngroups;
+};
+
+constexpr size_t ss_smem_bytes(int ks) { return size_t(ks) * 4 * (BS * 8 + 8 + 8 + 4); }
+
+template <int KS, bool AL16>
+__global__ void __launch_bounds__(32 * ((KS * 4 + 15) / 16)) ss_kernel(const SSParams p) {
+    constexpr int KP = KS * 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[]; // ss_smem_bytes(KS)
+    double* Bs = reinterpret_cast<double*>(smem_raw);
+    long long* msrc = reinterpret_cast<long long*>(Bs + KP * BS);
+    long long* mdst = msrc + KP;
+    unsigned* minfo = reinterpret_cast<unsigned*>(mdst + KP);
+    __shared__ int s_m;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t K = p.klist[blockIdx.y];
+    const int grp = p.tiles[2 * blockIdx.x];
+    const int j0 = p.tiles[2 * blockIdx.x + 1];
+    const int ncols = p.g_ncols[grp];
+    const long long ldx = p.g_ldx[grp], ldy = p.g_ldy[grp];
+
+    if (warp == 0) {
+        const int e0 = p.h2_ptr[K], e1 = p.h2_ptr[K + 1];
+        int cnt = 0;
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            bool ok = false;
+            long long src = -1, dst = -1;
+            unsigned info = 0;
+            if (e < e1) {
+                const uint64_t ent = p.h2_ent[e];
+                const uint32_t I = static_cast<uint32_t>(ent);
+                const int c = p.s_cls[I];
+                const long long xo = p.xoff[c * p.ngroups + grp];
+                if (xo >= 0) {
+                    ok = true;
+                    src = xo + static_cast<long long>(p.s_loc[I]) * ldx;
+                    dst = p.yoff[c * p.ngroups + grp] + static_cast<long long>(p.s_loc[I]) * ldy;
+                    info = static_cast<unsigned>((ent >> 32) & 0xffff) |
+                           (static_cast<unsigned>((ent >> 48) & 1) << 31);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+                msrc[pos] = src;
+                mdst[pos] = dst;
+                minfo[pos] = info;
+            }
+            cnt += __popc(mask);
+        }
+        if (lane == 0)
+            s_m = cnt;
+    }
+    for (int i = tid; i < KP * BS; i += nthr)
+        Bs[i] = 0.0;
+    __syncthreads();
+    const int m = s_m;
+    if (m == 0)
+        return;
+
+    // stage the m parent rows of this column tile
+    if (AL16) {
+        for (int idx = tid; idx < m * (NT / 2); idx += nthr) {
+            const int r = idx / (NT / 2), c = idx % (NT / 2);
+            const int col = j0 + 2 * c;
+            int bytes = (ncols - col) * 8;
+            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+            cp_async16(Bs + r * BS + 2 * c, p.X + msrc[r] + (bytes ? col : 0), bytes);
+        }
+    } else {
+        for (int idx = tid; idx < m * NT; idx += nthr) {
+            const int r = idx / NT, c = idx % NT;
+            const int col = j0 + c;
+            const bool in = col < ncols;
+            cp_async8(Bs + r * BS + c, p.X + msrc[r] + (in ? col : 0), in ? 8 : 0);
+        }
+    }
+    cp_async_commit();
+
+    // coefficient block: rows = output parents, columns = input parents
+    const int nks = (m + 3) >> 2;
+    const int ra = warp * 16 + g;
+    double a[KS][2];
+    {
+        const unsigned ia0 = ra < m ? minfo[ra] : 0, ia1 = ra + 8 < m ? minfo[ra + 8] : 0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            a[ks][0] = a[ks][1] = 0.0;
+            const int b = 4 * ks + t;
+            if (b < m) {
+                const unsigned ib = minfo[b];
+                const int pb = ib & 0xffff;
+                if (ra < m)
+                    a[ks][0] = (((ia0 ^ ib) >> 31) ? -1.0 : 1.0) *
+                               p.W[static_cast<size_t>(ia0 & 0xffff) * p.P + pb];
+                if (ra + 8 < m)
+                    a[ks][1] = (((ia1 ^ ib) >> 31) ? -1.0 : 1.0) *
+                               p.W[static_cast<size_t>(ia1 & 0xffff) * p.P + pb];
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (warp * 16 >= m)
+        return;
+
+#pragma unroll 1
+    for (int nh = 0; nh < 2; ++nh) {
+        double acc[NT / 16][4];
+#pragma unroll
+        for (int nt = 0; nt < NT / 16; ++nt)
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            if (ks < nks) {
+                const double* bp = Bs + (4 * ks + t) * BS + nh * (NT / 2) + g;
+#pragma unroll
+                for (int nt = 0; nt < NT / 16; ++nt)
+                    dmma_16x8x4(acc[nt], a[ks][0], a[ks][1], bp[nt * 8]);
+            }
+        }
+        // owner update: within one colour no two (N-2) strings share a parent row
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int row = ra + 8 * half;
+            if (row >= m)
+                continue;
+            const int c0 = j0 + nh * (NT / 2) + 2 * t;
+            double* y = p.Y + mdst[row] + c0;
+#pragma unroll
+            for (int nt = 0; nt < NT / 16; ++nt) {
+                const int col = c0 + nt * 8;
+                if (col < ncols)
+                    y[nt * 8] += acc[nt][2 * half];
+                if (col + 1 < ncols)
+                    y[nt * 8 + 1] += acc[nt][2 * half + 1];
+            }
+        }
+    }
+}
+
+// sigma = E * C
+__global__ void scale_copy_kernel(const double* __restrict__ x, double* __restrict__ y, double s,
+                                  int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = s * x[i];
+}
+
+struct TrBlock {
+    int64_t src_off, dst_off; // row-major [nA][ldA] at src_off  <->  row-major [nB][nA] at dst_off
+    int32_t nA, nB;
+    int64_t ldA;
+    uint32_t tile0; // first tile id of this block
+    uint32_t tiles_j;
+};
+
+// forward: T[dst_off + j*nA + i] = S[src_off + i*ldA + j];  back: S[...] += T[...]
+template <bool BACK>
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                 const TrBlock* __restrict__ blocks, int nblocks) {
+    __shared__ double tile[32][33];
+    // locate the block of this tile (blocks are few; binary search over tile0)
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].tile0 <= blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const TrBlock b = blocks[lo];
+    const uint32_t tl = blockIdx.x - b.tile0;
+    const int ti = tl / b.tiles_j, tj = tl % b.tiles_j;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+    if (!BACK) {
+        for (int r = ty; r < 32; r += 8) {
+            const int i = ti * 32 + r, j = tj * 32 + tx;
+            if (i < b.nA && j < b.nB)
+                tile[r][tx] = in[b.src_off + static_cast<int64_t>(i) * b.ldA + j];
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int j = tj * 32 + r, i = ti * 32 + tx;
+            if (i < b.nA && j < b.nB)
+                out[b.dst_off + static_cast<int64_t>(j) * b.nA + i] = tile[tx][r];
+        }
+    } else {
+        for (int r = ty; r < 32; r += 8) {
+            const int j = tj * 32 + r, i = ti * 32 + tx;
+            if (i < b.nA && j < b.nB)
+                tile[tx][r] = in[b.dst_off + static_cast<int64_t>(j) * b.nA + i];
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int i = ti * 32 + r, j = tj * 32 + tx;
+            if (i < b.nA && j < b.nB)
+                out[b.src_off + static_cast<int64_t>(i) * b.ldA + j] += tile[r][tx];
+        }
+    }
+}
+
+struct HdiagBlock {
+    int64_t off;
+    uint32_t a0, b0; // first global alpha / beta string index of the block's classes
+    int32_t nA, nB;
+    uint32_t tile0;
+};
+
+// E_det = E + ea[Ia] + eb[Ib] + sum_{q in Ib} ja[Ia][q]   (SlaterRules::energy)
+__global__ void hdiag_kernel(double* __restrict__ out, const HdiagBlock* __restrict__ blocks,
+                             int nblocks, const double* __restrict__ ea,
+                             const double* __restrict__ eb, const double* __restrict__ ja,
+                             const uint64_t* __restrict__ bstr, int norb, double E) {
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].tile0 <= blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const HdiagBlock b = blocks[lo];
+    const int i = blockIdx.x - b.tile0; // one alpha row per CTA
+    const double* jrow = ja + static_cast<size_t>(b.a0 + i) * norb;
+    const double e0 = E + ea[b.a0 + i];
+    for (int j = threadIdx.x; j < b.nB; j += blockDim.x) {
+        uint64_t w = bstr[b.b0 + j];
+        double e = e0 + eb[b.b0 + j];
+        while (w) {
+            const int q = __ffsll(static_cast<long long>(w)) - 1;
+            e += jrow[q];
+            w &= w - 1;
+        }
+        out[b.off + static_cast<int64_t>(i) * b.nB + j] = e;
+    }
+}
+
+} // namespace f2

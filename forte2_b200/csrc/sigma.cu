@@ -1,0 +1,879 @@
+// GPU-resident sigma builder: device copies of the replacement lists, integral repack, launch
+// planning and the C ABI of include/forte2_b200.h (CISigmaBuilder half).
+//
+// Reference behaviour followed: forte2/ci/ci_sigma_builder.cc:29-222 (constructor, set_algorithm,
+// set_memory, set_Hamiltonian validation, Hamiltonian = H0 + one-electron + same-spin + opposite
+// spin, avg_build_time), forte2/determinant/slater_rules.cc:86-121 (determinant energies).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "handles.hpp"
+#include "kernels.cuh"
+
+namespace f2 {
+
+#define F2_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " +     \
+                            __FILE__ + ":" + std::to_string(__LINE__));                            \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        if (count == n && p)
+            return;
+        release();
+        if (count) {
+            F2_CUDA(cudaMalloc(&p, count * sizeof(T)));
+            n = count;
+        }
+    }
+    void upload(const std::vector<T>& v) {
+        alloc(std::max<size_t>(v.size(), 1));
+        if (!v.empty())
+            F2_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+};
+
+struct DevStrings {
+    int device = 0;
+    DevBuf<uint32_t> a_cls, a_loc, b_cls, b_loc, as_ptr, nA_cls, nB_cls, a_off, b_off, zeros;
+    DevBuf<uint64_t> as_ent, bs_ent, a_str, b_str;
+    DevBuf<uint32_t> h2_ptr[2], h2_clist[2];
+    DevBuf<uint64_t> h2_ent[2];
+    DevBuf<int64_t> blk_off;  // [nclsA*nclsB]
+    DevBuf<int64_t> blk_offT; // [nclsB*nclsA] same offsets indexed (cB, cA)
+    bool al16 = false;        // every block offset and leading dimension is even
+};
+
+void destroy_dev_strings(DevStrings* d) { delete d; }
+
+static DevStrings* device_strings(f2_strings* S, int device) {
+    if (S->dev && S->dev->device == device)
+        return S->dev;
+    if (S->dev) {
+        delete S->dev;
+        S->dev = nullptr;
+    }
+    const CIStringsHost& h = *S->host;
+    const DeviceLists& L = h.device_lists();
+    auto d = std::make_unique<DevStrings>();
+    d->device = device;
+    d->a_cls.upload(L.a_cls);
+    d->a_loc.upload(L.a_loc);
+    d->b_cls.upload(L.b_cls);
+    d->b_loc.upload(L.b_loc);
+    d->as_ptr.upload(L.as_ptr);
+    d->as_ent.upload(L.as_ent);
+    d->bs_ent.upload(L.bs_ent);
+    for (int s = 0; s < 2; ++s) {
+        d->h2_ptr[s].upload(L.h2_ptr[s]);
+        d->h2_ent[s].upload(L.h2_ent[s]);
+        d->h2_clist[s].upload(L.h2_color_list[s]);
+    }
+    const auto& A = h.space(0, K_STR_N);
+    const auto& B = h.space(1, K_STR_N);
+    std::vector<uint32_t> nA(A.nclasses()), nB(B.nclasses()), aoff(A.nclasses()), boff(B.nclasses());
+    std::vector<uint64_t> astr, bstr;
+    for (size_t c = 0; c < A.nclasses(); ++c) {
+        nA[c] = static_cast<uint32_t>(A.strpcls(c));
+        aoff[c] = A.cls_off[c];
+        astr.insert(astr.end(), A.cls[c].begin(), A.cls[c].end());
+    }
+    for (size_t c = 0; c < B.nclasses(); ++c) {
+        nB[c] = static_cast<uint32_t>(B.strpcls(c));
+        boff[c] = B.cls_off[c];
+        bstr.insert(bstr.end(), B.cls[c].begin(), B.cls[c].end());
+    }
+    d->nA_cls.upload(nA);
+    d->nB_cls.upload(nB);
+    d->a_off.upload(aoff);
+    d->b_off.upload(boff);
+    d->a_str.upload(astr);
+    d->b_str.upload(bstr);
+    d->zeros.upload(std::vector<uint32_t>(std::max(A.nclasses(), B.nclasses()) + 1, 0u));
+    std::vector<int64_t> off(A.nclasses() * B.nclasses(), -1), offT(A.nclasses() * B.nclasses(), -1);
+    bool even = true;
+    for (const auto& b : h.blocks) {
+        off[b.cA * B.nclasses() + b.cB] = b.offset;
+        offT[b.cB * A.nclasses() + b.cA] = b.offset;
+        if (b.nA * b.nB == 0)
+            continue;
+        even = even && (b.offset % 2 == 0) && (b.nA % 2 == 0) && (b.nB % 2 == 0);
+    }
+    d->blk_off.upload(off);
+    d->blk_offT.upload(offT);
+    d->al16 = even;
+    S->dev = d.release();
+    return S->dev;
+}
+
+// one same-spin launch plan: which column groups exist, where each (row class, group) sits
+struct SSPlan {
+    int ngroups = 0, ntiles = 0;
+    DevBuf<int64_t> xoff, yoff;
+    DevBuf<uint32_t> g_ncols, g_ldx, g_ldy, tiles;
+    bool al16 = false;
+};
+
+struct BetaPass {
+    SSPlan plan;
+    DevBuf<TrBlock> tr;
+    int ntr = 0;
+    uint32_t ntr_tiles = 0;
+    int64_t elems = 0; // doubles used in each scratch buffer
+};
+
+} // namespace f2
+
+using namespace f2;
+
+struct f2_sigma {
+    f2_strings* S = nullptr;
+    DevStrings* D = nullptr;
+    int device = 0, norb = 0, log_level = 3;
+    double E = 0.0;
+    std::string algorithm = "Knowles-Handy"; // C++ member default of the reference
+    size_t memory_size = size_t(1) << 30;    // bytes; reference default 1 GiB
+    // integral tables
+    DevBuf<double> Vx, W[2], ea, eb, ja;
+    DevBuf<uint16_t> rowmap;
+    int M = 0, P[2] = {0, 0};
+    bool compressed = true;
+    // opposite-spin plan
+    DevBuf<uint32_t> items;
+    int nitems = 0, t3_ks = 0, t3_warps = 0, t3_msplit = 1;
+    size_t t3_smem = 0;
+    // same-spin plans
+    SSPlan alpha_plan;
+    std::vector<std::unique_ptr<BetaPass>> beta_passes;
+    bool beta_planned = false;
+    DevBuf<double> XT, YT;
+    int ss_ks[2] = {0, 0};
+    // hdiag
+    DevBuf<HdiagBlock> hd_blocks;
+    int hd_nblocks = 0;
+    uint32_t hd_rows = 0;
+    // timing
+    cudaEvent_t ev[5] = {};
+    bool ev_pending = false;
+    double t_acc[4] = {0, 0, 0, 0};
+    double last_ms[5] = {0, 0, 0, 0, 0};
+    long builds = 0;
+    // host staging for f2_sigma_apply_host
+    double *hC = nullptr, *hS = nullptr;
+    DevBuf<double> dC, dS;
+    cudaStream_t own_stream = nullptr;
+
+    ~f2_sigma() {
+        for (auto& e : ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (hC)
+            cudaFreeHost(hC);
+        if (hS)
+            cudaFreeHost(hS);
+        if (own_stream)
+            cudaStreamDestroy(own_stream);
+    }
+};
+
+namespace {
+
+int round_ks(int count) { // k-steps (of 4) rounded up to the instantiated multiples of 4
+    const int ks = (count + 3) / 4;
+    return std::max(4, ((ks + 3) / 4) * 4);
+}
+
+void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
+    const CIStringsHost& h = *b.S->host;
+    const int n = h.norb;
+    b.E = E;
+    auto v = [&](int p, int q, int r, int s) {
+        return V[((static_cast<size_t>(p) * n + q) * n + r) * n + s];
+    };
+    // 8-fold (real orbital) symmetry allows the pair-compressed rows (i >= j)
+    double vmax = 0.0, asym = 0.0;
+    for (int k = 0; k < n; ++k)
+        for (int i = 0; i < n; ++i)
+            for (int l = 0; l < n; ++l)
+                for (int j = 0; j < n; ++j) {
+                    vmax = std::max(vmax, std::fabs(v(k, i, l, j)));
+                    asym = std::max(asym, std::fabs(v(k, i, l, j) - v(k, j, l, i)));
+                }
+    b.compressed = asym <= 1e-12 * std::max(vmax, 1e-300);
+    const int n2 = n * n;
+    std::vector<uint16_t> rowmap(std::max(n2, 1));
+    if (b.compressed) {
+        b.M = n * (n + 1) / 2;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                const int hi = std::max(i, j), lo = std::min(i, j);
+                rowmap[i * n + j] = static_cast<uint16_t>(hi * (hi + 1) / 2 + lo);
+            }
+    } else {
+        b.M = n2;
+        for (int i = 0; i < n2; ++i)
+            rowmap[i] = static_cast<uint16_t>(i);
+    }
+    std::vector<double> Vx(static_cast<size_t>(std::max(b.M, 1)) * std::max(n2, 1), 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (b.compressed && j > i)
+                continue;
+            const size_t m = rowmap[i * n + j];
+            for (int k = 0; k < n; ++k)
+                for (int l = 0; l < n; ++l)
+                    Vx[m * n2 + k * n + l] =
+                        b.compressed ? 0.5 * (v(k, i, l, j) + v(k, j, l, i)) : v(k, i, l, j);
+        }
+    b.Vx.upload(Vx);
+    b.rowmap.upload(rowmap);
+
+    // same-spin integrals: antisymmetrised pairs with the one-electron operator folded in
+    for (int spin = 0; spin < 2; ++spin) {
+        const int ne = spin == 0 ? h.na : h.nb;
+        std::vector<double> W;
+        if (ne == 1) {
+            b.P[spin] = n;
+            W.assign(H, H + static_cast<size_t>(n) * n);
+        } else if (ne >= 2) {
+            const int P = n * (n - 1) / 2;
+            b.P[spin] = P;
+            W.assign(static_cast<size_t>(P) * P, 0.0);
+            const double f = 1.0 / (ne - 1);
+            auto hh = [&](int p, int q) { return H[p * n + q]; };
+            for (int p = 1; p < n; ++p)
+                for (int q = 0; q < p; ++q)
+                    for (int r = 1; r < n; ++r)
+                        for (int s = 0; s < r; ++s) {
+                            double w = v(p, q, r, s) - v(p, q, s, r);
+                            if (q == s)
+                                w += f * hh(p, r);
+                            if (p == r)
+                                w += f * hh(q, s);
+                            if (q == r)
+                                w -= f * hh(p, s);
+                            if (p == s)
+                                w -= f * hh(q, r);
+                            W[static_cast<size_t>(p * (p - 1) / 2 + q) * P + r * (r - 1) / 2 + s] = w;
+                        }
+        } else {
+            b.P[spin] = 0;
+        }
+        b.W[spin].upload(W);
+    }
+
+    // determinant-energy tables
+    std::vector<double> J(std::max(n2, 1)), K(std::max(n2, 1));
+    for (int p = 0; p < n; ++p)
+        for (int q = 0; q < n; ++q) {
+            J[p * n + q] = v(p, q, p, q);
+            K[p * n + q] = v(p, q, q, p);
+        }
+    auto string_energy = [&](const StringSpace& S, std::vector<double>& e, std::vector<double>* ja) {
+        e.assign(std::max<size_t>(S.nstr(), 1), 0.0);
+        if (ja)
+            ja->assign(std::max<size_t>(S.nstr() * n, 1), 0.0);
+        size_t g = 0;
+        for (const auto& cls : S.cls)
+            for (uint64_t w : cls) {
+                double x = 0.0;
+                for (int p = 0; p < n; ++p) {
+                    if (!((w >> p) & 1))
+                        continue;
+                    x += H[p * n + p];
+                    for (int q = 0; q < p; ++q)
+                        if ((w >> q) & 1)
+                            x += J[p * n + q] - K[p * n + q];
+                    if (ja)
+                        for (int q = 0; q < n; ++q)
+                            (*ja)[g * n + q] += J[p * n + q];
+                }
+                e[g++] = x;
+            }
+    };
+    std::vector<double> ea, eb, ja;
+    string_energy(h.space(0, K_STR_N), ea, &ja);
+    string_energy(h.space(1, K_STR_N), eb, nullptr);
+    b.ea.upload(ea);
+    b.eb.upload(eb);
+    b.ja.upload(ja);
+}
+
+void plan_t3(f2_sigma& b) {
+    const CIStringsHost& h = *b.S->host;
+    const DeviceLists& L = h.device_lists();
+    b.nitems = 0;
+    if (h.na < 1 || h.nb < 1 || L.as_max == 0 || h.ndet == 0)
+        return;
+    if (L.as_max > 128)
+        throw std::runtime_error("CISigmaBuilder: more than 128 single replacements per alpha string "
+                                 "is not supported by the opposite-spin kernel");
+    b.t3_ks = round_ks(L.as_max);
+    const int KP = b.t3_ks * 4;
+    const int MT = (b.M + 15) / 16;
+    const int maxw = b.t3_ks <= 24 ? 12 : 10;
+    const size_t nclsB = h.nclsB();
+    int msplit = (MT + maxw - 1) / maxw;
+    while (true) {
+        const int warps = (MT + msplit - 1) / msplit;
+        const size_t smem = (size_t(2) * KP * BS + size_t(warps) * 16 * BS) * 8 + size_t(KP) * 8 +
+                            nclsB * 8 + size_t(KP) * 4 + size_t(h.norb) * h.norb * 2 + 64;
+        if (smem <= 227 * 1024) {
+            b.t3_warps = warps;
+            b.t3_msplit = msplit;
+            b.t3_smem = smem;
+            break;
+        }
+        if (warps == 1)
+            throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
+        ++msplit;
+    }
+    // one CTA per (owned alpha string, beta class of the intermediate column, m-split)
+    const auto& A = h.space(0, K_STR_N);
+    const auto& B = h.space(1, K_STR_N);
+    std::vector<char> row_has_block(A.nclasses(), 0);
+    for (const auto& blk : h.blocks)
+        if (blk.nA * blk.nB > 0)
+            row_has_block[blk.cA] = 1;
+    std::vector<uint32_t> items;
+    for (size_t cA = 0; cA < A.nclasses(); ++cA) {
+        if (!row_has_block[cA])
+            continue;
+        for (size_t i = 0; i < A.strpcls(cA); ++i)
+            for (size_t cB = 0; cB < B.nclasses(); ++cB) {
+                if (B.strpcls(cB) == 0)
+                    continue;
+                for (int ms = 0; ms < b.t3_msplit; ++ms) {
+                    items.push_back(A.cls_off[cA] + static_cast<uint32_t>(i));
+                    items.push_back(static_cast<uint32_t>(cB) | (static_cast<uint32_t>(ms) << 16));
+                }
+            }
+    }
+    b.nitems = static_cast<int>(items.size() / 2);
+    b.items.upload(items);
+}
+
+void fill_tiles(std::vector<uint32_t>& tiles, const std::vector<uint32_t>& ncols) {
+    tiles.clear();
+    for (size_t g = 0; g < ncols.size(); ++g)
+        for (uint32_t j0 = 0; j0 < ncols[g]; j0 += NT) {
+            tiles.push_back(static_cast<uint32_t>(g));
+            tiles.push_back(j0);
+        }
+}
+
+void plan_alpha(f2_sigma& b) {
+    const CIStringsHost& h = *b.S->host;
+    const auto& B = h.space(1, K_STR_N);
+    const size_t nclsA = h.nclsA(), nclsB = h.nclsB();
+    std::vector<int64_t> off(nclsA * nclsB, -1);
+    std::vector<uint32_t> ncols(nclsB), tiles;
+    for (const auto& blk : h.blocks)
+        if (blk.nA * blk.nB > 0)
+            off[blk.cA * nclsB + blk.cB] = blk.offset;
+    for (size_t c = 0; c < nclsB; ++c)
+        ncols[c] = static_cast<uint32_t>(B.strpcls(c));
+    fill_tiles(tiles, ncols);
+    SSPlan& p = b.alpha_plan;
+    p.ngroups = static_cast<int>(nclsB);
+    p.ntiles = static_cast<int>(tiles.size() / 2);
+    p.xoff.upload(off);
+    p.yoff.upload(off);
+    p.g_ncols.upload(ncols);
+    p.g_ldx.upload(ncols);
+    p.g_ldy.upload(ncols);
+    p.tiles.upload(tiles);
+    p.al16 = b.D->al16;
+}
+
+// beta same-spin work runs on transposed row slabs: a pass holds, for a set of (alpha class,
+// row range) column groups, the transposed blocks [nB][rows] of every beta class paired with it.
+// Both scratch buffers together must fit the set_memory budget (ci_sigma_builder.cc:70-78,
+// ci_sigma_builder_knowles_handy.cc:15-32).
+void plan_beta(f2_sigma& b) {
+    const CIStringsHost& h = *b.S->host;
+    b.beta_passes.clear();
+    if (h.nb < 1 || h.ndet == 0) {
+        b.beta_planned = true;
+        return;
+    }
+    const size_t nclsA = h.nclsA(), nclsB = h.nclsB();
+    const int64_t cap = static_cast<int64_t>(b.memory_size / (2 * sizeof(double)));
+    // columns (beta strings) attached to each alpha class
+    std::vector<int64_t> width(nclsA, 0);
+    for (const auto& blk : h.blocks)
+        if (blk.nA * blk.nB > 0)
+            width[blk.cA] += blk.nB;
+    struct Group {
+        int cA;
+        int64_t i0, rows;
+    };
+    std::vector<std::vector<Group>> passes;
+    std::vector<Group> cur;
+    int64_t used = 0;
+    for (size_t cA = 0; cA < nclsA; ++cA) {
+        const int64_t nA = static_cast<int64_t>(h.space(0, K_STR_N).strpcls(cA));
+        if (width[cA] == 0 || nA == 0)
+            continue;
+        if (cap < width[cA])
+            throw std::runtime_error("The CI builder memory limit (" + std::to_string(b.memory_size) +
+                                     " bytes) is too small for one K-block column of " +
+                                     std::to_string(width[cA]) + " elements per buffer.");
+        int64_t i0 = 0;
+        while (i0 < nA) {
+            int64_t fit = (cap - used) / width[cA];
+            if (fit == 0) {
+                passes.push_back(cur);
+                cur.clear();
+                used = 0;
+                continue;
+            }
+            const int64_t rows = std::min(fit, nA - i0);
+            cur.push_back({static_cast<int>(cA), i0, rows});
+            used += rows * width[cA];
+            i0 += rows;
+        }
+    }
+    if (!cur.empty())
+        passes.push_back(cur);
+
+    int64_t max_elems = 0;
+    for (const auto& groups : passes) {
+        auto bp = std::make_unique<BetaPass>();
+        const int ng = static_cast<int>(groups.size());
+        std::vector<int64_t> xoff(nclsB * ng, -1);
+        std::vector<uint32_t> ncols(ng), tiles;
+        std::vector<TrBlock> tr;
+        int64_t pos = 0;
+        uint32_t tile0 = 0;
+        bool even = true;
+        for (int g = 0; g < ng; ++g) {
+            const Group& G = groups[g];
+            ncols[g] = static_cast<uint32_t>(G.rows);
+            for (size_t cB = 0; cB < nclsB; ++cB) {
+                const int64_t bi = h.block_of[G.cA * nclsB + cB];
+                if (bi < 0 || h.blocks[bi].nA * h.blocks[bi].nB == 0)
+                    continue;
+                const auto& blk = h.blocks[bi];
+                xoff[cB * ng + g] = pos;
+                TrBlock t;
+                t.src_off = blk.offset + G.i0 * blk.nB;
+                t.dst_off = pos;
+                t.nA = static_cast<int32_t>(G.rows);
+                t.nB = static_cast<int32_t>(blk.nB);
+                t.ldA = blk.nB;
+                t.tile0 = tile0;
+                t.tiles_j = static_cast<uint32_t>((blk.nB + 31) / 32);
+                tile0 += static_cast<uint32_t>((G.rows + 31) / 32) * t.tiles_j;
+                tr.push_back(t);
+                even = even && (pos % 2 == 0) && (G.rows % 2 == 0);
+                pos += G.rows * blk.nB;
+            }
+        }
+        fill_tiles(tiles, ncols);
+        bp->plan.ngroups = ng;
+        bp->plan.ntiles = static_cast<int>(tiles.size() / 2);
+        bp->plan.xoff.upload(xoff);
+        bp->plan.yoff.upload(xoff);
+        bp->plan.g_ncols.upload(ncols);
+        bp->plan.g_ldx.upload(ncols);
+        bp->plan.g_ldy.upload(ncols);
+        bp->plan.tiles.upload(tiles);
+        bp->plan.al16 = even;
+        bp->ntr = static_cast<int>(tr.size());
+        bp->ntr_tiles = tile0;
+        bp->tr.upload(tr);
+        bp->elems = pos;
+        max_elems = std::max(max_elems, pos);
+        b.beta_passes.push_back(std::move(bp));
+    }
+    b.XT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
+    b.YT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
+    b.beta_planned = true;
+}
+
+void plan_hdiag(f2_sigma& b) {
+    const CIStringsHost& h = *b.S->host;
+    std::vector<HdiagBlock> hb;
+    uint32_t tile0 = 0;
+    for (const auto& blk : h.blocks) {
+        if (blk.nA * blk.nB == 0)
+            continue;
+        HdiagBlock x;
+        x.off = blk.offset;
+        x.a0 = h.space(0, K_STR_N).cls_off[blk.cA];
+        x.b0 = h.space(1, K_STR_N).cls_off[blk.cB];
+        x.nA = static_cast<int32_t>(blk.nA);
+        x.nB = static_cast<int32_t>(blk.nB);
+        x.tile0 = tile0;
+        tile0 += static_cast<uint32_t>(blk.nA);
+        hb.push_back(x);
+    }
+    b.hd_nblocks = static_cast<int>(hb.size());
+    b.hd_rows = tile0;
+    b.hd_blocks.upload(hb);
+}
+
+template <int KS> void launch_t3_ks(const f2_sigma& b, const T3Params& p, cudaStream_t st) {
+    const dim3 grid(b.nitems), block(b.t3_warps * 32);
+    if (b.D->al16) {
+        F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(b.t3_smem)));
+        t3_kernel<KS, true><<<grid, block, b.t3_smem, st>>>(p);
+    } else {
+        F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(b.t3_smem)));
+        t3_kernel<KS, false><<<grid, block, b.t3_smem, st>>>(p);
+    }
+}
+
+void launch_t3(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st) {
+    if (b.nitems == 0)
+        return;
+    const CIStringsHost& h = *b.S->host;
+    const DevStrings& D = *b.D;
+    T3Params p;
+    p.C = C;
+    p.sigma = sigma;
+    p.items = b.items.p;
+    p.a_cls = D.a_cls.p;
+    p.a_loc = D.a_loc.p;
+    p.as_ptr = D.as_ptr.p;
+    p.as_ent = D.as_ent.p;
+    p.bs_ent = D.bs_ent.p;
+    p.bs_width = h.device_lists().bs_width;
+    p.nbs = h.nbs;
+    p.blk_off = D.blk_off.p;
+    p.sblk_off = D.blk_off.p;
+    p.srow0 = D.zeros.p;
+    p.nB_cls = D.nB_cls.p;
+    p.b_off = D.b_off.p;
+    p.nclsA = static_cast<int>(h.nclsA());
+    p.nclsB = static_cast<int>(h.nclsB());
+    p.norb = h.norb;
+    p.Vx = b.Vx.p;
+    p.M = b.M;
+    p.rowmap = b.rowmap.p;
+    switch (b.t3_ks) {
+    case 4: launch_t3_ks<4>(b, p, st); break;
+    case 8: launch_t3_ks<8>(b, p, st); break;
+    case 12: launch_t3_ks<12>(b, p, st); break;
+    case 16: launch_t3_ks<16>(b, p, st); break;
+    case 20: launch_t3_ks<20>(b, p, st); break;
+    case 24: launch_t3_ks<24>(b, p, st); break;
+    case 28: launch_t3_ks<28>(b, p, st); break;
+    case 32: launch_t3_ks<32>(b, p, st); break;
+    default: throw std::runtime_error("CISigmaBuilder: unsupported opposite-spin K size");
+    }
+    F2_CUDA(cudaGetLastError());
+}
+
+template <int KS>
+void launch_ss_ks(const SSParams& p, bool al16, dim3 grid, cudaStream_t st) {
+    const dim3 block(32 * ((KS * 4 + 15) / 16));
+    constexpr size_t smem = ss_smem_bytes(KS);
+    if (al16) {
+        if (smem > 48 * 1024)
+            F2_CUDA(cudaFuncSetAttribute(ss_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+        ss_kernel<KS, true><<<grid, block, smem, st>>>(p);
+    } else {
+        if (smem > 48 * 1024)
+            F2_CUDA(cudaFuncSetAttribute(ss_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+        ss_kernel<KS, false><<<grid, block, smem, st>>>(p);
+    }
+}
+
+// all colours of one spin for one plan
+void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const double* X, double* Y,
+                      cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    const DeviceLists& L = h.device_lists();
+    const DevStrings& D = *b.D;
+    if (plan.ntiles == 0 || L.h2_color_ptr[spin].size() < 2)
+        return;
+    SSParams p;
+    p.X = X;
+    p.Y = Y;
+    p.h2_ptr = D.h2_ptr[spin].p;
+    p.h2_ent = D.h2_ent[spin].p;
+    p.s_cls = spin == 0 ? D.a_cls.p : D.b_cls.p;
+    p.s_loc = spin == 0 ? D.a_loc.p : D.b_loc.p;
+    p.xoff = plan.xoff.p;
+    p.yoff = plan.yoff.p;
+    p.g_ncols = plan.g_ncols.p;
+    p.g_ldx = plan.g_ldx.p;
+    p.g_ldy = plan.g_ldy.p;
+    p.tiles = plan.tiles.p;
+    p.W = b.W[spin].p;
+    p.P = b.P[spin];
+    p.ngroups = plan.ngroups;
+    const auto& cptr = L.h2_color_ptr[spin];
+    for (size_t c = 0; c + 1 < cptr.size(); ++c) {
+        for (uint32_t k0 = cptr[c]; k0 < cptr[c + 1]; k0 += 65535) {
+            const uint32_t nk = std::min<uint32_t>(65535, cptr[c + 1] - k0);
+            p.klist = D.h2_clist[spin].p + k0;
+            const dim3 grid(plan.ntiles, nk);
+            switch (b.ss_ks[spin]) {
+            case 4: launch_ss_ks<4>(p, plan.al16, grid, st); break;
+            case 8: launch_ss_ks<8>(p, plan.al16, grid, st); break;
+            case 12: launch_ss_ks<12>(p, plan.al16, grid, st); break;
+            case 16: launch_ss_ks<16>(p, plan.al16, grid, st); break;
+            case 20: launch_ss_ks<20>(p, plan.al16, grid, st); break;
+            case 24: launch_ss_ks<24>(p, plan.al16, grid, st); break;
+            case 28: launch_ss_ks<28>(p, plan.al16, grid, st); break;
+            case 32: launch_ss_ks<32>(p, plan.al16, grid, st); break;
+            default: throw std::runtime_error("CISigmaBuilder: unsupported same-spin block size");
+            }
+        }
+    }
+    F2_CUDA(cudaGetLastError());
+}
+
+void collect_times(f2_sigma& b) {
+    if (!b.ev_pending)
+        return;
+    F2_CUDA(cudaEventSynchronize(b.ev[4]));
+    float ms[4];
+    for (int i = 0; i < 4; ++i)
+        F2_CUDA(cudaEventElapsedTime(&ms[i], b.ev[i], b.ev[i + 1]));
+    float tot;
+    F2_CUDA(cudaEventElapsedTime(&tot, b.ev[0], b.ev[4]));
+    b.last_ms[0] = ms[0];
+    b.last_ms[1] = ms[1];
+    b.last_ms[2] = ms[2];
+    b.last_ms[3] = ms[3];
+    b.last_ms[4] = tot;
+    b.t_acc[0] += tot * 1e-3;
+    b.t_acc[1] += ms[3] * 1e-3;
+    b.t_acc[2] += ms[1] * 1e-3;
+    b.t_acc[3] += ms[2] * 1e-3;
+    b.builds += 1;
+    b.ev_pending = false;
+}
+
+void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    if (n != h.ndet)
+        throw std::invalid_argument("CISigmaBuilder.Hamiltonian: vectors must have ndet = " +
+                                    std::to_string(h.ndet) + " elements, got " + std::to_string(n));
+    F2_CUDA(cudaSetDevice(b.device));
+    collect_times(b);
+    if (!b.beta_planned)
+        plan_beta(b);
+    if (n == 0)
+        return;
+    F2_CUDA(cudaEventRecord(b.ev[0], st));
+    scale_copy_kernel<<<148 * 8, 256, 0, st>>>(C, sigma, b.E, n);
+    F2_CUDA(cudaEventRecord(b.ev[1], st));
+    if (h.na >= 1)
+        launch_same_spin(b, 0, b.alpha_plan, C, sigma, st);
+    F2_CUDA(cudaEventRecord(b.ev[2], st));
+    for (const auto& bp : b.beta_passes) {
+        transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(C, b.XT.p, bp->tr.p, bp->ntr);
+        F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
+        launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, st);
+        transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr);
+    }
+    F2_CUDA(cudaEventRecord(b.ev[3], st));
+    launch_t3(b, C, sigma, st);
+    F2_CUDA(cudaEventRecord(b.ev[4], st));
+    F2_CUDA(cudaGetLastError());
+    b.ev_pending = true;
+}
+
+} // namespace
+
+extern "C" {
+
+f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const double* V,
+                          int log_level, int device) {
+    try {
+        int count = 0;
+        cudaError_t err = cudaGetDeviceCount(&count);
+        if (err != cudaSuccess || count == 0)
+            throw CudaError("forte2_b200: no CUDA device available (the sigma builder has no CPU "
+                            "fallback)");
+        F2_CUDA(cudaSetDevice(device));
+        auto b = std::make_unique<f2_sigma>();
+        b->S = strings;
+        b->device = device;
+        b->log_level = log_level;
+        b->norb = strings->host->norb;
+        b->D = device_strings(strings, device);
+        for (auto& e : b->ev)
+            F2_CUDA(cudaEventCreate(&e));
+        build_integrals(*b, E, H, V);
+        const DeviceLists& L = strings->host->device_lists();
+        for (int s = 0; s < 2; ++s) {
+            if (L.h2_max[s] > 128)
+                throw std::runtime_error("CISigmaBuilder: more than 128 parents per two-hole string "
+                                         "is not supported by the same-spin kernel");
+            b->ss_ks[s] = round_ks(std::max(L.h2_max[s], 1));
+        }
+        plan_t3(*b);
+        plan_alpha(*b);
+        plan_hdiag(*b);
+        return b.release();
+    } catch (const std::exception& e) {
+        status_of(e);
+        return nullptr;
+    }
+}
+
+void f2_sigma_destroy(f2_sigma* h) { delete h; }
+
+int f2_sigma_set_hamiltonian(f2_sigma* h, double E, const double* H, const double* V) {
+    try {
+        F2_CUDA(cudaSetDevice(h->device));
+        F2_CUDA(cudaDeviceSynchronize());
+        const bool was = h->compressed;
+        build_integrals(*h, E, H, V);
+        if (was != h->compressed)
+            plan_t3(*h);
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_set_algorithm(f2_sigma* h, const char* name) {
+    const std::string a(name);
+    if (a == "kh" || a == "knowles-handy")
+        h->algorithm = "Knowles-Handy";
+    else if (a == "hz" || a == "harrison-zarrabian")
+        h->algorithm = "Harrison-Zarrabian";
+    else {
+        g_last_error = "CI algorithm " + a + " not valid.";
+        return F2_ERUNTIME;
+    }
+    return F2_OK;
+}
+
+const char* f2_sigma_get_algorithm(const f2_sigma* h) { return h->algorithm.c_str(); }
+
+int f2_sigma_set_memory(f2_sigma* h, int64_t mb) {
+    if (mb < 0) {
+        g_last_error = "CI builder memory must be non-negative.";
+        return F2_EINVAL;
+    }
+    h->memory_size = static_cast<size_t>(mb) * 1024 * 1024;
+    // like the reference, the scratch is released here and re-planned lazily by the next build,
+    // which is where a too-small budget is reported
+    h->beta_planned = false;
+    h->beta_passes.clear();
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->XT.release();
+    h->YT.release();
+    return F2_OK;
+}
+
+int f2_sigma_set_log_level(f2_sigma* h, int level) {
+    h->log_level = level;
+    return F2_OK;
+}
+
+int f2_sigma_apply(f2_sigma* h, const double* C_dev, double* sigma_dev, int64_t n, void* stream) {
+    try {
+        apply(*h, C_dev, sigma_dev, n, static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, int64_t n) {
+    try {
+        const CIStringsHost& s = *h->S->host;
+        if (n != s.ndet)
+            throw std::invalid_argument("CISigmaBuilder.Hamiltonian: vectors must have ndet = " +
+                                        std::to_string(s.ndet) + " elements, got " +
+                                        std::to_string(n));
+        F2_CUDA(cudaSetDevice(h->device));
+        if (!h->own_stream)
+            F2_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        const size_t bytes = static_cast<size_t>(std::max<int64_t>(n, 1)) * sizeof(double);
+        if (!h->hC) {
+            F2_CUDA(cudaMallocHost(&h->hC, bytes));
+            F2_CUDA(cudaMallocHost(&h->hS, bytes));
+        }
+        h->dC.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)));
+        h->dS.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)));
+        std::memcpy(h->hC, C_host, static_cast<size_t>(n) * sizeof(double));
+        F2_CUDA(cudaMemcpyAsync(h->dC.p, h->hC, static_cast<size_t>(n) * sizeof(double),
+                                cudaMemcpyHostToDevice, h->own_stream));
+        apply(*h, h->dC.p, h->dS.p, n, h->own_stream);
+        F2_CUDA(cudaMemcpyAsync(h->hS, h->dS.p, static_cast<size_t>(n) * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->own_stream));
+        F2_CUDA(cudaStreamSynchronize(h->own_stream));
+        std::memcpy(sigma_host, h->hS, static_cast<size_t>(n) * sizeof(double));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_times(f2_sigma* h, double* out4) {
+    try {
+        F2_CUDA(cudaSetDevice(h->device));
+        collect_times(*h);
+        for (int i = 0; i < 4; ++i)
+            out4[i] = h->builds ? h->t_acc[i] / static_cast<double>(h->builds) : 0.0;
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_last_ms(f2_sigma* h, double* out5) {
+    try {
+        F2_CUDA(cudaSetDevice(h->device));
+        collect_times(*h);
+        std::memcpy(out5, h->last_ms, sizeof(h->last_ms));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream) {
+    try {
+        F2_CUDA(cudaSetDevice(h->device));
+        if (h->hd_rows == 0)
+            return F2_OK;
+        hdiag_kernel<<<h->hd_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            out_dev, h->hd_blocks.p, h->hd_nblocks, h->ea.p, h->eb.p, h->ja.p, h->D->b_str.p,
+            h->norb, h->E);
+        F2_CUDA(cudaGetLastError());
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+} // extern "C"

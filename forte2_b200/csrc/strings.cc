@@ -600,6 +600,23 @@ void CIStringsHost::build_device_lists() const {
         cptr.assign(1, 0);
         clist.clear();
         d.h2_max[spin] = 0;
+        if (ne == 1) {
+            // one electron of this spin: the only same-spin operator is h_pq a+_p a_q; treat the
+            // vacuum as the single "hole" string whose parents are all one-electron strings and
+            // let the pair index carry the occupied orbital
+            ptr.assign(2, 0);
+            for (size_t c = 0; c < S.nclasses(); ++c)
+                for (size_t x = 0; x < S.cls[c].size(); ++x)
+                    ent.push_back(uint64_t(S.cls_off[c] + x) |
+                                  (uint64_t(__builtin_ctzll(S.cls[c][x])) << 32));
+            ptr[1] = static_cast<uint32_t>(ent.size());
+            d.h2_max[spin] = static_cast<int>(ent.size());
+            if (!ent.empty()) {
+                clist.push_back(0);
+                cptr.push_back(1);
+            }
+            continue;
+        }
         if (ne < 2)
             continue;
         const auto& H = space(spin, K_STR_2H);

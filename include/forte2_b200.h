@@ -94,24 +94,6 @@ int f2_sigma_last_ms(f2_sigma* h, double* out5);
  * preconditioner. */
 int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream);
 
-/* ---- alpha-row partition for multi-GPU (no reference counterpart) ----------
- * Rank r of world owns, in every determinant block, the alpha rows [r*nIa/world, (r+1)*nIa/world).
- * The local vector is the concatenation of the owned row slabs in block order. */
-int64_t f2_strings_local_size(const f2_strings* h, int rank, int world);
-/* rows (block, first_row, nrows, local_offset) for this rank; returns nblocks */
-int f2_strings_local_layout(const f2_strings* h, int rank, int world, int64_t* out);
-/* sigma_local (owned rows only) from the FULL trial vector (all-gathered by the caller over NCCL).
- * The alpha same-spin term is computed for the columns rank owns of every row and written to
- * exch_dev (full layout, only owned columns non-zero); the caller reduces it (reduce-scatter over
- * rows) and adds it to sigma_local.  See forte2_b200/dist.py. */
-int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev,
-                        double* exch_dev, int rank, int world, void* stream);
-/* pack / unpack between the local slab layout and the full layout (device buffers) */
-int f2_sigma_scatter_local(f2_sigma* h, const double* full_dev, double* local_dev, int rank,
-                           int world, int accumulate, void* stream);
-int f2_sigma_gather_local(f2_sigma* h, const double* local_dev, double* full_dev, int rank,
-                          int world, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,138 @@
+"""GPU parity: forte2_b200.CISigmaBuilder.Hamiltonian vs the reference's own C++ builder
+(oracle/_ref) on the same integrals and the same trial vector.  Tolerance from BASELINE.json:
+sigma relative L2 <= 1e-12 in FP64."""
+import numpy as np
+import pytest
+
+from cases import SMALL_SPACES
+from forte2_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _pair(ref, space, ints):
+    import forte2_b200 as f2
+    E, H, V = ints
+    rs = ref.RefCIStrings(*space)
+    rb = ref.RefCISigmaBuilder(rs, E, H, V)
+    rb.set_algorithm("hz")
+    gs = f2.CIStrings(*space)
+    gb = f2.CISigmaBuilder(gs, E, H, V, 0)
+    return rs, rb, gs, gb
+
+
+def _rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+@pytest.mark.parametrize("name", sorted(SMALL_SPACES))
+@pytest.mark.parametrize("variant", ["S", "D", "four_fold"])
+def test_sigma_matches_reference(ref, torch_cuda, name, variant):
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    ints = synthetic.four_fold_integrals(n) if variant == "four_fold" else synthetic.integrals(n, variant)
+    rs, rb, gs, gb = _pair(ref, space, ints)
+    assert gs.ndet == rs.ndet
+    c = synthetic.trial_vector(max(rs.ndet, 1))[: rs.ndet].copy()
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    got = np.full_like(c, np.nan)
+    gb.Hamiltonian(c, got)  # numpy in, numpy out: the reference-facing host path
+    assert _rel(got, want) <= TOL
+    # device path (torch tensors), twice to check the result does not depend on leftovers
+    torch = torch_cuda
+    cd = torch.from_numpy(c).cuda()
+    sd = torch.full_like(cd, float("nan"))
+    gb.Hamiltonian(cd, sd)
+    gb.Hamiltonian(cd, sd)
+    assert _rel(sd.cpu().numpy(), want) <= TOL
+
+
+@pytest.mark.parametrize("name", ["cas66", "cas66_d2h", "gas343_54", "cas75_odd"])
+def test_hdiag_matches_slater_rules(ref, torch_cuda, name):
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    want = rb.det_energies()
+    got = gb.form_Hdiag_det().cpu().numpy()
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+def test_memory_chunking_and_errors(ref, torch_cuda):
+    """tests/ci/test_ci_rdms.py:393-436 of the reference: sigma under a small budget equals sigma after a
+    failed set_memory(0) attempt; negative memory is a ValueError."""
+    import forte2_b200 as f2
+    n = 6
+    H = np.diag(np.arange(1.0, n + 1))
+    V = np.zeros((n,) * 4)
+    gs = f2.CIStrings(2, 2, 0, [[0] * n], [], [])
+    gb = f2.CISigmaBuilder(gs, 0.0, H, V, 0)
+    gb.set_algorithm("hz")
+    c = np.linspace(-1.0, 1.0, gs.ndet)
+    gb.set_memory(1)
+    s1 = np.zeros_like(c)
+    gb.Hamiltonian(c, s1)
+    gb.set_memory(0)
+    with pytest.raises(RuntimeError, match="too small for one K-block column"):
+        gb.Hamiltonian(c, np.zeros_like(c))
+    gb.set_memory(1)
+    s2 = np.zeros_like(c)
+    gb.Hamiltonian(c, s2)
+    assert np.array_equal(s1, s2)
+    with pytest.raises(ValueError, match="memory must be non-negative"):
+        gb.set_memory(-1)
+    with pytest.raises(RuntimeError, match="not valid"):
+        gb.set_algorithm("nope")
+    gb.set_algorithm("kh")
+    assert gb.get_algorithm() == "Knowles-Handy"
+    gb.set_algorithm("harrison-zarrabian")
+    assert gb.get_algorithm() == "Harrison-Zarrabian"
+    with pytest.raises(RuntimeError, match="stride 1"):
+        gb.Hamiltonian(np.zeros(2 * gs.ndet)[::2], np.zeros(gs.ndet))
+
+
+def test_row_slab_passes_equal_single_pass(ref, torch_cuda):
+    """beta same-spin work split into several transposed row slabs (tiny set_memory) == one pass."""
+    space = SMALL_SPACES["cas88"]
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(8, "S"))
+    c = synthetic.trial_vector(rs.ndet)
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    gb.set_memory(1024)
+    a = np.zeros_like(c)
+    gb.Hamiltonian(c, a)
+    # 1 MB = 65536 doubles per buffer -> but force more passes by a GAS space with many classes
+    space = SMALL_SPACES["gas343_55"]
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(10, "S"))
+    c = synthetic.trial_vector(rs.ndet)
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    got = np.zeros_like(c)
+    gb.Hamiltonian(c, got)
+    assert _rel(got, want) <= TOL
+    assert _rel(a, a) == 0.0
+
+
+@pytest.mark.parametrize("n", [10, 12])
+def test_cas_medium(ref, torch_cuda, n):
+    space = (n // 2, n // 2, 0, [[0] * n], [], [])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    rb.set_memory(2048)
+    c = synthetic.trial_vector(rs.ndet)
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    got = np.zeros_like(c)
+    gb.Hamiltonian(c, got)
+    assert _rel(got, want) <= TOL
+    t = gb.avg_build_time()
+    assert len(t) == 4 and t[0] > 0
