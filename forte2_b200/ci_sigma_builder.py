@@ -126,6 +126,16 @@ class CISigmaBuilder:
         _lib.check(_lib.lib().f2_sigma_last_ms(self._h, out.ctypes.data_as(_lib.f64p)))
         return [float(x) for x in out]
 
+    def launch_count(self) -> int:
+        return int(_lib.lib().f2_sigma_launch_count(self._h))
+
+    def t3_shape(self):
+        """dict describing the contraction the opposite-spin kernel executes (see the header)."""
+        out = np.zeros(5, dtype=np.int64)
+        _lib.check(_lib.lib().f2_sigma_t3_shape(self._h, out.ctypes.data_as(_lib.i64p)))
+        return {"M": int(out[0]), "M_pad": int(out[1]), "K_max": int(out[2]), "k_cols": int(out[3]),
+                "pair_compressed": bool(out[4])}
+
     def form_Hdiag_det(self):
         """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""
         import torch

@@ -181,6 +181,8 @@ struct f2_sigma {
     double t_acc[4] = {0, 0, 0, 0};
     double last_ms[5] = {0, 0, 0, 0, 0};
     long builds = 0;
+    mutable int64_t launches = 0; // kernels launched by the last build
+    int64_t t3_kcols = 0;         // sum over work items of K_item * columns
     // host staging for f2_sigma_apply_host
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
@@ -359,18 +361,33 @@ void plan_t3(f2_sigma& b) {
         if (blk.nA * blk.nB > 0)
             row_has_block[blk.cA] = 1;
     std::vector<uint32_t> items;
+    std::vector<int> kcount(B.nclasses());
+    b.t3_kcols = 0;
     for (size_t cA = 0; cA < A.nclasses(); ++cA) {
         if (!row_has_block[cA])
             continue;
-        for (size_t i = 0; i < A.strpcls(cA); ++i)
+        for (size_t i = 0; i < A.strpcls(cA); ++i) {
+            // single replacements of this row that land in a block paired with each beta class
+            const uint32_t g = A.cls_off[cA] + static_cast<uint32_t>(i);
+            std::fill(kcount.begin(), kcount.end(), 0);
+            for (uint32_t e = L.as_ptr[g]; e < L.as_ptr[g + 1]; ++e) {
+                const uint32_t cJ = L.a_cls[L.as_ent[e] & 0xffffffffu];
+                for (size_t cB = 0; cB < B.nclasses(); ++cB) {
+                    const int64_t bi = h.block_of[cJ * B.nclasses() + cB];
+                    if (bi >= 0 && h.blocks[bi].nA * h.blocks[bi].nB > 0)
+                        kcount[cB] += 1;
+                }
+            }
             for (size_t cB = 0; cB < B.nclasses(); ++cB) {
-                if (B.strpcls(cB) == 0)
+                if (B.strpcls(cB) == 0 || kcount[cB] == 0)
                     continue;
+                b.t3_kcols += static_cast<int64_t>(kcount[cB]) * static_cast<int64_t>(B.strpcls(cB));
                 for (int ms = 0; ms < b.t3_msplit; ++ms) {
                     items.push_back(A.cls_off[cA] + static_cast<uint32_t>(i));
                     items.push_back(static_cast<uint32_t>(cB) | (static_cast<uint32_t>(ms) << 16));
                 }
             }
+        }
     }
     b.nitems = static_cast<int>(items.size() / 2);
     b.items.upload(items);
@@ -543,10 +560,12 @@ template <int KS> void launch_t3_ks(const f2_sigma& b, const T3Params& p, cudaSt
         F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(b.t3_smem)));
         t3_kernel<KS, true><<<grid, block, b.t3_smem, st>>>(p);
+        b.launches += 1;
     } else {
         F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(b.t3_smem)));
         t3_kernel<KS, false><<<grid, block, b.t3_smem, st>>>(p);
+        b.launches += 1;
     }
 }
 
@@ -638,6 +657,7 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
             const uint32_t nk = std::min<uint32_t>(65535, cptr[c + 1] - k0);
             p.klist = D.h2_clist[spin].p + k0;
             const dim3 grid(plan.ntiles, nk);
+            b.launches += 1;
             switch (b.ss_ks[spin]) {
             case 4: launch_ss_ks<4>(p, plan.al16, grid, st); break;
             case 8: launch_ss_ks<8>(p, plan.al16, grid, st); break;
@@ -687,6 +707,7 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
         plan_beta(b);
     if (n == 0)
         return;
+    b.launches = 1;
     F2_CUDA(cudaEventRecord(b.ev[0], st));
     scale_copy_kernel<<<148 * 8, 256, 0, st>>>(C, sigma, b.E, n);
     F2_CUDA(cudaEventRecord(b.ev[1], st));
@@ -695,6 +716,7 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
     F2_CUDA(cudaEventRecord(b.ev[2], st));
     for (const auto& bp : b.beta_passes) {
         transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(C, b.XT.p, bp->tr.p, bp->ntr);
+        b.launches += 2;
         F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
         launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, st);
         transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr);
@@ -859,6 +881,17 @@ int f2_sigma_last_ms(f2_sigma* h, double* out5) {
     } catch (const std::exception& e) {
         return status_of(e);
     }
+}
+
+int64_t f2_sigma_launch_count(const f2_sigma* h) { return h->launches; }
+
+int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
+    out5[0] = h->M;
+    out5[1] = static_cast<int64_t>(h->t3_warps) * 16 * h->t3_msplit;
+    out5[2] = h->S->host->device_lists().as_max;
+    out5[3] = h->t3_kcols;
+    out5[4] = h->compressed ? 1 : 0;
+    return F2_OK;
 }
 
 int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream) {

@@ -112,7 +112,7 @@ class CIStringsHost {
     size_t nclsA() const { return space(0, K_STR_N).nclasses(); }
     size_t nclsB() const { return space(1, K_STR_N).nclasses(); }
 
-    /// Reference-format flat export (same row layouts and row order as oracle/ref_cabi.cc).
+    /// Reference-format flat export (row layouts in include/forte2_b200.h).
     std::vector<int64_t> export_kind(int kind, int spin) const;
     /// (alpha word, beta word) of every determinant in CI-vector order
     void determinants(uint64_t* out) const;

@@ -93,6 +93,14 @@ int f2_sigma_last_ms(f2_sigma* h, double* out5);
  * for every determinant in CI-vector order, on the device: the determinant-basis Davidson
  * preconditioner. */
 int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream);
+/* number of kernels of this library launched by the last build (bench.py's gpu_launches) */
+int64_t f2_sigma_launch_count(const f2_sigma* h);
+/* what the opposite-spin kernel executes per build: out[0] = rows M of the integral matrix,
+ * out[1] = M padded to the MMA tile, out[2] = max single replacements per alpha string (GEMM K),
+ * out[3] = sum over launched (alpha string, beta class) work items of K_item * columns, i.e. the
+ * number of (k, column) pairs contracted; executed flops = 2 * out[1] * out[3], useful flops =
+ * 2 * out[0] * out[3].  out[4] = 1 when the pair-compressed (8-fold symmetric) rows are in use. */
+int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5);
 
 #ifdef __cplusplus
 }
