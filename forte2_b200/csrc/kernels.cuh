@@ -45,8 +45,7 @@ struct T3Params {
     const uint32_t* items; // 2 per CTA: alpha string (global index), beta class | m-split << 16
     const uint32_t *a_cls, *a_loc, *as_ptr;
     const uint64_t* as_ent;
-    const uint64_t* bs_ent;
-    int bs_width;
+    const uint32_t* tgt; // [M][nbs] beta replacement table: row m, source column Jb -> packed target
     int64_t nbs;
     const int64_t* blk_off;  // [nclsA*nclsB] offset of block (cA,cB) in C, -1 if not allowed
     const int64_t* sblk_off; // same for sigma (differs when sigma holds the owned rows only)
@@ -55,21 +54,29 @@ struct T3Params {
     int nclsA, nclsB, norb;
     const double* Vx; // [M][norb*norb]  Vx[m(i,j)][k*norb+l] = <k i | l j>
     int M;
-    const uint16_t* rowmap; // [norb*norb] (i,j) -> m
+    int tgt_pair; // 1: table rows and class offsets are even, two targets per 8-byte load
 };
 
-template <int KS, bool AL16>
+// packed beta replacement target: bit 31 sign, bits 20..30 class of Ib, bits 0..19 address of Ib in
+// its class; all ones = no replacement for this (row, column)
+constexpr uint32_t kNoTarget = 0xffffffffu;
+constexpr int TB = 68; // row stride of the staged C tile (== 4 mod 16: conflict-free B fragments)
+
+// Opposite-spin term.  One CTA per (output alpha string Ia, beta class of the intermediate column);
+// warp w owns rows [16w, 16w+16) of the integral matrix: its A fragments (signed columns of Vx picked
+// by the single replacements of Ia) stay in registers for the whole row, the B operand is the
+// gathered rows C[Ja_r, tile] staged by cp.async, and every accumulator element is added straight
+// from registers into sigma[Ia, Ib] through the replacement table (red.global.add.f64).
+template <int KS, bool AL16, int NS>
 __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3Params p) {
     constexpr int KP = KS * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthr >> 5, g = lane >> 2, t = lane & 3;
     double* Bs = reinterpret_cast<double*>(smem_raw);
-    double* Gs = Bs + 2 * KP * BS;
-    long long* ksrc = reinterpret_cast<long long*>(Gs + nwarps * 16 * BS);
+    long long* ksrc = reinterpret_cast<long long*>(Bs + NS * KP * TB);
     long long* rowbase = ksrc + KP;
     unsigned* kinfo = reinterpret_cast<unsigned*>(rowbase + p.nclsB);
-    unsigned short* rowmap_s = reinterpret_cast<unsigned short*>(kinfo + KP);
     __shared__ int s_Kn;
 
     const uint32_t Ia = p.items[2 * blockIdx.x];
@@ -117,9 +124,7 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
         const long long off = p.sblk_off[cA * p.nclsB + c];
         rowbase[c] = off >= 0 ? off + static_cast<long long>(ia - p.srow0[cA]) * p.nB_cls[c] : -1;
     }
-    for (int i = tid; i < p.norb * p.norb; i += nthr)
-        rowmap_s[i] = p.rowmap[i];
-    for (int i = tid; i < 2 * KP * BS; i += nthr)
+    for (int i = tid; i < NS * KP * TB; i += nthr)
         Bs[i] = 0.0;
     __syncthreads();
     const int Kn = s_Kn;
@@ -128,8 +133,7 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
     const int nks = (Kn + 3) >> 2;
 
     // A fragments: this warp owns rows [m0, m0+16) of the integral matrix for the whole row Ia
-    const int mbase = msp * nwarps * 16;
-    const int m0 = mbase + warp * 16;
+    const int m0 = (msp * nwarps + warp) * 16;
     const int ldv = p.norb * p.norb;
     double a[KS][2];
 #pragma unroll
@@ -149,45 +153,72 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
     }
 
     const int ntiles = (nBp + NT - 1) / NT;
-    auto load_tile = [&](int tile, int stage) {
-        const int j0 = tile * NT;
-        double* dst = Bs + stage * KP * BS;
-        if (AL16) {
-            for (int idx = tid; idx < Kn * (NT / 2); idx += nthr) {
-                const int r = idx / (NT / 2), c = idx % (NT / 2);
-                const int col = j0 + 2 * c;
-                int bytes = (nBp - col) * 8;
-                bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-                const double* src = p.C + ksrc[r] + (bytes ? col : 0);
-                cp_async16(dst + r * BS + 2 * c, src, bytes);
-            }
-        } else {
-            for (int idx = tid; idx < Kn * NT; idx += nthr) {
-                const int r = idx / NT, c = idx % NT;
-                const int col = j0 + c;
-                const bool in = col < nBp;
-                cp_async8(dst + r * BS + c, p.C + ksrc[r] + (in ? col : 0), in ? 8 : 0);
+    auto load_tile = [&](int tile) {
+        if (tile < ntiles) {
+            const int j0 = tile * NT;
+            double* dst = Bs + (tile % NS) * KP * TB;
+            if (AL16) {
+                for (int idx = tid; idx < Kn * (NT / 2); idx += nthr) {
+                    const int r = idx / (NT / 2), c = idx % (NT / 2);
+                    const int col = j0 + 2 * c;
+                    int bytes = (nBp - col) * 8;
+                    bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+                    cp_async16(dst + r * TB + 2 * c, p.C + ksrc[r] + (bytes ? col : 0), bytes);
+                }
+            } else {
+                for (int idx = tid; idx < Kn * NT; idx += nthr) {
+                    const int r = idx / NT, c = idx % NT;
+                    const int col = j0 + c;
+                    const bool in = col < nBp;
+                    cp_async8(dst + r * TB + c, p.C + ksrc[r] + (in ? col : 0), in ? 8 : 0);
+                }
             }
         }
-        cp_async_commit();
+        cp_async_commit(); // one group per call, empty past the end, keeps the wait count uniform
     };
 
-    const int mrows = nwarps * 16;
-    const int64_t bcol0 = p.b_off[cBp];
-    load_tile(0, 0);
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int stage = tile & 1;
-        if (tile + 1 < ntiles) {
-            load_tile(tile + 1, stage ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads(); // tile data visible; previous scatter finished reading Gs
+    // replacement-table rows of this thread's two accumulator rows
+    const bool row_ok[2] = {m0 + g < p.M, m0 + g + 8 < p.M};
+    const uint32_t* trow[2] = {p.tgt + static_cast<size_t>(row_ok[0] ? m0 + g : 0) * p.nbs + p.b_off[cBp],
+                               p.tgt + static_cast<size_t>(row_ok[1] ? m0 + g + 8 : 0) * p.nbs + p.b_off[cBp]};
 
-        const double* Bst = Bs + stage * KP * BS;
+#pragma unroll
+    for (int s = 0; s < NS - 1; ++s)
+        load_tile(s);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        cp_async_wait<NS - 2>();
+        __syncthreads(); // tile landed for every thread; stage (tile-1)%NS is no longer being read
+        load_tile(tile + NS - 1);
+        const double* Bst = Bs + (tile % NS) * KP * TB;
+        const int j0 = tile * NT;
 #pragma unroll 1
         for (int nh = 0; nh < 2; ++nh) { // two halves of the tile keep the accumulators at 16 regs
+            const int c0 = j0 + nh * (NT / 2) + 2 * t;
+            // fetch the replacement targets first: their latency hides behind the MMAs
+            uint32_t tg[NT / 16][2][2];
+#pragma unroll
+            for (int nt = 0; nt < NT / 16; ++nt) {
+                const int col = c0 + nt * 8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tg[nt][h][0] = kNoTarget;
+                    tg[nt][h][1] = kNoTarget;
+                    if (row_ok[h]) {
+                        if (p.tgt_pair) {
+                            if (col < nBp) { // nBp even: col + 1 is in range too
+                                const uint2 v = *reinterpret_cast<const uint2*>(trow[h] + col);
+                                tg[nt][h][0] = v.x;
+                                tg[nt][h][1] = v.y;
+                            }
+                        } else {
+                            if (col < nBp)
+                                tg[nt][h][0] = trow[h][col];
+                            if (col + 1 < nBp)
+                                tg[nt][h][1] = trow[h][col + 1];
+                        }
+                    }
+                }
+            }
             double acc[NT / 16][4];
 #pragma unroll
             for (int nt = 0; nt < NT / 16; ++nt)
@@ -195,40 +226,28 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 if (ks < nks) {
-                    const double* bp = Bst + (4 * ks + t) * BS + nh * (NT / 2) + g;
+                    const double* bp = Bst + (4 * ks + t) * TB + nh * (NT / 2) + g;
 #pragma unroll
                     for (int nt = 0; nt < NT / 16; ++nt)
                         dmma_16x8x4(acc[nt], a[ks][0], a[ks][1], bp[nt * 8]);
                 }
             }
-            double* g0 = Gs + (warp * 16 + g) * BS + nh * (NT / 2) + 2 * t;
+            // sigma[Ia, Ib] += sign * G[m, Jb], straight from the accumulators
 #pragma unroll
-            for (int nt = 0; nt < NT / 16; ++nt) {
-                *reinterpret_cast<double2*>(g0 + nt * 8) = make_double2(acc[nt][0], acc[nt][1]);
-                *reinterpret_cast<double2*>(g0 + 8 * BS + nt * 8) = make_double2(acc[nt][2], acc[nt][3]);
-            }
-        }
-        __syncthreads();
-
-        // beta replacement list: sigma[Ia, Ib] += sign * G[m(i,j), Jb]
-        const int j0 = tile * NT;
-        const int total = p.bs_width * NT;
-        for (int e = tid; e < total; e += nthr) {
-            const int j = e & (NT - 1), tt = e >> 6;
-            const int col = j0 + j;
-            if (col >= nBp)
-                continue;
-            const uint64_t ent = p.bs_ent[static_cast<int64_t>(tt) * p.nbs + bcol0 + col];
-            if (ent == ~0ull)
-                continue;
-            const int m = static_cast<int>(rowmap_s[(ent >> 40) & 0xffff]) - mbase;
-            if (static_cast<unsigned>(m) >= static_cast<unsigned>(mrows))
-                continue;
-            const long long base = rowbase[(ent >> 28) & 0xfff];
-            if (base < 0)
-                continue;
-            const double v = Gs[m * BS + j];
-            atomicAdd(p.sigma + base + (ent & 0xfffffffull), ((ent >> 56) & 1) ? -v : v);
+            for (int nt = 0; nt < NT / 16; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t x = tg[nt][h][c];
+                        if (x != kNoTarget) {
+                            const long long base = rowbase[(x >> 20) & 0x7ff];
+                            if (base >= 0) {
+                                const double v = acc[nt][2 * h + c];
+                                atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
+                            }
+                        }
+                    }
         }
     }
 }

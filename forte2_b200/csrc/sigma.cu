@@ -159,6 +159,9 @@ struct f2_sigma {
     // integral tables
     DevBuf<double> Vx, W[2], ea, eb, ja;
     DevBuf<uint16_t> rowmap;
+    DevBuf<uint32_t> tgt; // [M][nbs] beta replacement table
+    int tgt_pair = 0;
+    int t3_ns = 2;
     int M = 0, P[2] = {0, 0};
     bool compressed = true;
     // opposite-spin plan
@@ -253,6 +256,35 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
     b.Vx.upload(Vx);
     b.rowmap.upload(rowmap);
 
+    // beta replacement table: (row of the integral matrix, source string Jb) -> target string Ib.
+    // A row holds at most one replacement per source string (E_ij and E_ji exclude each other).
+    {
+        const DeviceLists& L = h.device_lists();
+        const auto& B = h.space(1, K_STR_N);
+        const size_t nbs = B.nstr();
+        if (B.nclasses() > 2046)
+            throw std::overflow_error("CISigmaBuilder: more than 2046 beta string classes");
+        for (size_t c = 0; c < B.nclasses(); ++c)
+            if (B.strpcls(c) > (size_t(1) << 20))
+                throw std::overflow_error("CISigmaBuilder: more than 2^20 beta strings in one class");
+        std::vector<uint32_t> T(std::max<size_t>(size_t(b.M) * nbs, 1), kNoTarget);
+        for (int t = 0; t < L.bs_width; ++t)
+            for (size_t gJ = 0; gJ < nbs; ++gJ) {
+                const uint64_t ent = L.bs_ent[size_t(t) * nbs + gJ];
+                if (ent == kNullEntry)
+                    continue;
+                const uint32_t m = rowmap[(ent >> 40) & 0xffff];
+                T[size_t(m) * nbs + gJ] = static_cast<uint32_t>(ent & 0xfffff) |
+                                          (static_cast<uint32_t>((ent >> 28) & 0x7ff) << 20) |
+                                          (static_cast<uint32_t>((ent >> 56) & 1) << 31);
+            }
+        b.tgt.upload(T);
+        bool pair = nbs % 2 == 0;
+        for (size_t c = 0; c < B.nclasses(); ++c)
+            pair = pair && (B.cls_off[c] % 2 == 0) && (B.strpcls(c) % 2 == 0);
+        b.tgt_pair = pair ? 1 : 0;
+    }
+
     // same-spin integrals: antisymmetrised pairs with the one-electron operator folded in
     for (int spin = 0; spin < 2; ++spin) {
         const int ne = spin == 0 ? h.na : h.nb;
@@ -338,21 +370,16 @@ void plan_t3(f2_sigma& b) {
     const int MT = (b.M + 15) / 16;
     const int maxw = b.t3_ks <= 24 ? 12 : 10;
     const size_t nclsB = h.nclsB();
-    int msplit = (MT + maxw - 1) / maxw;
-    while (true) {
-        const int warps = (MT + msplit - 1) / msplit;
-        const size_t smem = (size_t(2) * KP * BS + size_t(warps) * 16 * BS) * 8 + size_t(KP) * 8 +
-                            nclsB * 8 + size_t(KP) * 4 + size_t(h.norb) * h.norb * 2 + 64;
-        if (smem <= 227 * 1024) {
-            b.t3_warps = warps;
-            b.t3_msplit = msplit;
-            b.t3_smem = smem;
-            break;
-        }
-        if (warps == 1)
-            throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
-        ++msplit;
-    }
+    const int msplit = (MT + maxw - 1) / maxw;
+    b.t3_warps = (MT + msplit - 1) / msplit;
+    b.t3_msplit = msplit;
+    auto smem_for = [&](int ns) {
+        return size_t(ns) * KP * TB * 8 + size_t(KP) * 8 + nclsB * 8 + size_t(KP) * 4 + 64;
+    };
+    b.t3_ns = smem_for(3) <= 227 * 1024 ? 3 : 2;
+    b.t3_smem = smem_for(b.t3_ns);
+    if (b.t3_smem > 227 * 1024)
+        throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
     // one CTA per (owned alpha string, beta class of the intermediate column, m-split)
     const auto& A = h.space(0, K_STR_N);
     const auto& B = h.space(1, K_STR_N);
@@ -554,18 +581,26 @@ void plan_hdiag(f2_sigma& b) {
     b.hd_blocks.upload(hb);
 }
 
-template <int KS> void launch_t3_ks(const f2_sigma& b, const T3Params& p, cudaStream_t st) {
+template <int KS, bool AL16, int NS>
+void launch_t3_inst(const f2_sigma& b, const T3Params& p, cudaStream_t st) {
     const dim3 grid(b.nitems), block(b.t3_warps * 32);
+    F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, AL16, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(b.t3_smem)));
+    t3_kernel<KS, AL16, NS><<<grid, block, b.t3_smem, st>>>(p);
+    b.launches += 1;
+}
+
+template <int KS> void launch_t3_ks(const f2_sigma& b, const T3Params& p, cudaStream_t st) {
     if (b.D->al16) {
-        F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(b.t3_smem)));
-        t3_kernel<KS, true><<<grid, block, b.t3_smem, st>>>(p);
-        b.launches += 1;
+        if (b.t3_ns == 3)
+            launch_t3_inst<KS, true, 3>(b, p, st);
+        else
+            launch_t3_inst<KS, true, 2>(b, p, st);
     } else {
-        F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(b.t3_smem)));
-        t3_kernel<KS, false><<<grid, block, b.t3_smem, st>>>(p);
-        b.launches += 1;
+        if (b.t3_ns == 3)
+            launch_t3_inst<KS, false, 3>(b, p, st);
+        else
+            launch_t3_inst<KS, false, 2>(b, p, st);
     }
 }
 
@@ -582,8 +617,8 @@ void launch_t3(const f2_sigma& b, const double* C, double* sigma, cudaStream_t s
     p.a_loc = D.a_loc.p;
     p.as_ptr = D.as_ptr.p;
     p.as_ent = D.as_ent.p;
-    p.bs_ent = D.bs_ent.p;
-    p.bs_width = h.device_lists().bs_width;
+    p.tgt = b.tgt.p;
+    p.tgt_pair = b.tgt_pair;
     p.nbs = h.nbs;
     p.blk_off = D.blk_off.p;
     p.sblk_off = D.blk_off.p;
@@ -595,7 +630,6 @@ void launch_t3(const f2_sigma& b, const double* C, double* sigma, cudaStream_t s
     p.norb = h.norb;
     p.Vx = b.Vx.p;
     p.M = b.M;
-    p.rowmap = b.rowmap.p;
     switch (b.t3_ks) {
     case 4: launch_t3_ks<4>(b, p, st); break;
     case 8: launch_t3_ks<8>(b, p, st); break;
