@@ -55,6 +55,7 @@ struct T3Params {
     const double* Vx; // [M][norb*norb]  Vx[m(i,j)][k*norb+l] = <k i | l j>
     int M;
     int tgt_pair; // 1: table rows and class offsets are even, two targets per 8-byte load
+    int dbg;      // diagnosis only (F2_T3_DBG): bit 0 skip the atomics, bit 1 skip the table loads
 };
 
 // packed beta replacement target: bit 31 sign, bits 20..30 class of Ib, bits 0..19 address of Ib in
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
                 for (int h = 0; h < 2; ++h) {
                     tg[nt][h][0] = kNoTarget;
                     tg[nt][h][1] = kNoTarget;
-                    if (row_ok[h]) {
+                    if (row_ok[h] && !(p.dbg & 2)) {
                         if (p.tgt_pair) {
                             if (col < nBp) { // nBp even: col + 1 is in range too
                                 const uint2 v = *reinterpret_cast<const uint2*>(trow[h] + col);
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
                         const uint32_t x = tg[nt][h][c];
                         if (x != kNoTarget) {
                             const long long base = rowbase[(x >> 20) & 0x7ff];
-                            if (base >= 0) {
+                            if (base >= 0 && !(p.dbg & 1)) {
                                 const double v = acc[nt][2 * h + c];
                                 atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
                             }
@@ -420,13 +421,14 @@ __global__ void scale_copy_kernel(const double* __restrict__ x, double* __restri
 
 struct TrBlock {
     int64_t src_off, dst_off; // row-major [nA][ldA] at src_off  <->  row-major [nB][nA] at dst_off
+    int64_t sig_off;          // where the same rows sit in sigma (== src_off unless sigma is a local slab)
     int32_t nA, nB;
     int64_t ldA;
     uint32_t tile0; // first tile id of this block
     uint32_t tiles_j;
 };
 
-// forward: T[dst_off + j*nA + i] = S[src_off + i*ldA + j];  back: S[...] += T[...]
+// forward: T[dst_off + j*nA + i] = S[src_off + i*ldA + j];  back: Sigma[sig_off + i*ldA + j] += T[...]
 template <bool BACK>
 __global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out,
                                  const TrBlock* __restrict__ blocks, int nblocks) {
@@ -466,7 +468,37 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
         for (int r = ty; r < 32; r += 8) {
             const int i = ti * 32 + r, j = tj * 32 + tx;
             if (i < b.nA && j < b.nB)
-                out[b.src_off + static_cast<int64_t>(i) * b.ldA + j] += tile[r][tx];
+                out[b.sig_off + static_cast<int64_t>(i) * b.ldA + j] += tile[r][tx];
+        }
+    }
+}
+
+struct CopyPiece {
+    int64_t src_off, dst_off, n;
+    uint32_t cta0; // first CTA of this piece (1024 elements per CTA)
+};
+
+// dst[dst_off + i] (=|+=) s * src[src_off + i] for a list of contiguous pieces
+template <bool ACC>
+__global__ void piece_copy_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                  const CopyPiece* __restrict__ pieces, int npieces, double s) {
+    int lo = 0, hi = npieces - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (pieces[mid].cta0 <= blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const CopyPiece pc = pieces[lo];
+    const int64_t base = static_cast<int64_t>(blockIdx.x - pc.cta0) * 1024;
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+        const int64_t i = base + k;
+        if (i < pc.n) {
+            if (ACC)
+                dst[pc.dst_off + i] += s * src[pc.src_off + i];
+            else
+                dst[pc.dst_off + i] = s * src[pc.src_off + i];
         }
     }
 }

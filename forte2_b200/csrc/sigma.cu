@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -145,6 +146,28 @@ struct BetaPass {
     int64_t elems = 0; // doubles used in each scratch buffer
 };
 
+// Everything that depends on which alpha rows (and, for the alpha same-spin term, which beta
+// columns) this process owns.  rank 0 of world 1 is the single-GPU case.
+struct Part {
+    int rank = 0, world = 1;
+    std::vector<int64_t> lo, hi;  // per alpha class: owned rows [lo, hi)
+    std::vector<int64_t> cl, ch;  // per beta class: owned columns [cl, ch)
+    std::vector<int64_t> loc_off; // per block: offset of the owned row slab in the local vector
+    std::vector<int64_t> y_off;   // per block: offset of [nA][owned columns] in the exchange buffer
+    int64_t local_size = 0, y_size = 0;
+    DevBuf<int64_t> sblk_off;
+    DevBuf<uint32_t> srow0;
+    DevBuf<uint32_t> items;
+    int nitems = 0;
+    int64_t t3_kcols = 0;
+    SSPlan alpha_plan;
+    std::vector<std::unique_ptr<BetaPass>> beta_passes;
+    bool beta_planned = false;
+    DevBuf<CopyPiece> pieces; // owned row slabs: src = full layout, dst = local layout
+    int npieces = 0;
+    uint32_t piece_ctas = 0;
+};
+
 } // namespace f2
 
 using namespace f2;
@@ -164,14 +187,11 @@ struct f2_sigma {
     int t3_ns = 2;
     int M = 0, P[2] = {0, 0};
     bool compressed = true;
-    // opposite-spin plan
-    DevBuf<uint32_t> items;
-    int nitems = 0, t3_ks = 0, t3_warps = 0, t3_msplit = 1;
+    // opposite-spin kernel shape
+    int t3_ks = 0, t3_warps = 0, t3_msplit = 1;
     size_t t3_smem = 0;
-    // same-spin plans
-    SSPlan alpha_plan;
-    std::vector<std::unique_ptr<BetaPass>> beta_passes;
-    bool beta_planned = false;
+    // row/column ownership plans: the single-GPU one and the last multi-GPU one
+    std::unique_ptr<Part> single, shard;
     DevBuf<double> XT, YT;
     int ss_ks[2] = {0, 0};
     // hdiag
@@ -185,7 +205,6 @@ struct f2_sigma {
     double last_ms[5] = {0, 0, 0, 0, 0};
     long builds = 0;
     mutable int64_t launches = 0; // kernels launched by the last build
-    int64_t t3_kcols = 0;         // sum over work items of K_item * columns
     // host staging for f2_sigma_apply_host
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
@@ -356,10 +375,10 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
     b.ja.upload(ja);
 }
 
-void plan_t3(f2_sigma& b) {
+void plan_t3_shape(f2_sigma& b) {
     const CIStringsHost& h = *b.S->host;
     const DeviceLists& L = h.device_lists();
-    b.nitems = 0;
+    b.t3_ks = 0;
     if (h.na < 1 || h.nb < 1 || L.as_max == 0 || h.ndet == 0)
         return;
     if (L.as_max > 128)
@@ -380,44 +399,6 @@ void plan_t3(f2_sigma& b) {
     b.t3_smem = smem_for(b.t3_ns);
     if (b.t3_smem > 227 * 1024)
         throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
-    // one CTA per (owned alpha string, beta class of the intermediate column, m-split)
-    const auto& A = h.space(0, K_STR_N);
-    const auto& B = h.space(1, K_STR_N);
-    std::vector<char> row_has_block(A.nclasses(), 0);
-    for (const auto& blk : h.blocks)
-        if (blk.nA * blk.nB > 0)
-            row_has_block[blk.cA] = 1;
-    std::vector<uint32_t> items;
-    std::vector<int> kcount(B.nclasses());
-    b.t3_kcols = 0;
-    for (size_t cA = 0; cA < A.nclasses(); ++cA) {
-        if (!row_has_block[cA])
-            continue;
-        for (size_t i = 0; i < A.strpcls(cA); ++i) {
-            // single replacements of this row that land in a block paired with each beta class
-            const uint32_t g = A.cls_off[cA] + static_cast<uint32_t>(i);
-            std::fill(kcount.begin(), kcount.end(), 0);
-            for (uint32_t e = L.as_ptr[g]; e < L.as_ptr[g + 1]; ++e) {
-                const uint32_t cJ = L.a_cls[L.as_ent[e] & 0xffffffffu];
-                for (size_t cB = 0; cB < B.nclasses(); ++cB) {
-                    const int64_t bi = h.block_of[cJ * B.nclasses() + cB];
-                    if (bi >= 0 && h.blocks[bi].nA * h.blocks[bi].nB > 0)
-                        kcount[cB] += 1;
-                }
-            }
-            for (size_t cB = 0; cB < B.nclasses(); ++cB) {
-                if (B.strpcls(cB) == 0 || kcount[cB] == 0)
-                    continue;
-                b.t3_kcols += static_cast<int64_t>(kcount[cB]) * static_cast<int64_t>(B.strpcls(cB));
-                for (int ms = 0; ms < b.t3_msplit; ++ms) {
-                    items.push_back(A.cls_off[cA] + static_cast<uint32_t>(i));
-                    items.push_back(static_cast<uint32_t>(cB) | (static_cast<uint32_t>(ms) << 16));
-                }
-            }
-        }
-    }
-    b.nitems = static_cast<int>(items.size() / 2);
-    b.items.upload(items);
 }
 
 void fill_tiles(std::vector<uint32_t>& tiles, const std::vector<uint32_t>& ncols) {
@@ -429,39 +410,143 @@ void fill_tiles(std::vector<uint32_t>& tiles, const std::vector<uint32_t>& ncols
         }
 }
 
-void plan_alpha(f2_sigma& b) {
+// ownership: rank r of world owns rows [r nA / world, (r+1) nA / world) of every alpha class and,
+// for the alpha same-spin exchange, the same kind of slice of every beta class's columns
+std::unique_ptr<Part> make_part(f2_sigma& b, int rank, int world) {
     const CIStringsHost& h = *b.S->host;
+    const DeviceLists& L = h.device_lists();
+    const auto& A = h.space(0, K_STR_N);
     const auto& B = h.space(1, K_STR_N);
-    const size_t nclsA = h.nclsA(), nclsB = h.nclsB();
-    std::vector<int64_t> off(nclsA * nclsB, -1);
-    std::vector<uint32_t> ncols(nclsB), tiles;
-    for (const auto& blk : h.blocks)
-        if (blk.nA * blk.nB > 0)
-            off[blk.cA * nclsB + blk.cB] = blk.offset;
-    for (size_t c = 0; c < nclsB; ++c)
-        ncols[c] = static_cast<uint32_t>(B.strpcls(c));
-    fill_tiles(tiles, ncols);
-    SSPlan& p = b.alpha_plan;
-    p.ngroups = static_cast<int>(nclsB);
-    p.ntiles = static_cast<int>(tiles.size() / 2);
-    p.xoff.upload(off);
-    p.yoff.upload(off);
-    p.g_ncols.upload(ncols);
-    p.g_ldx.upload(ncols);
-    p.g_ldy.upload(ncols);
-    p.tiles.upload(tiles);
-    p.al16 = b.D->al16;
+    const size_t nclsA = A.nclasses(), nclsB = B.nclasses();
+    auto P = std::make_unique<Part>();
+    P->rank = rank;
+    P->world = world;
+    P->lo.resize(nclsA);
+    P->hi.resize(nclsA);
+    P->cl.resize(nclsB);
+    P->ch.resize(nclsB);
+    for (size_t c = 0; c < nclsA; ++c) {
+        const int64_t n = static_cast<int64_t>(A.strpcls(c));
+        P->lo[c] = n * rank / world;
+        P->hi[c] = n * (rank + 1) / world;
+    }
+    for (size_t c = 0; c < nclsB; ++c) {
+        const int64_t n = static_cast<int64_t>(B.strpcls(c));
+        P->cl[c] = n * rank / world;
+        P->ch[c] = n * (rank + 1) / world;
+    }
+    std::vector<int64_t> sblk(nclsA * nclsB, -1);
+    std::vector<uint32_t> srow0(nclsA + 1, 0);
+    std::vector<CopyPiece> pieces;
+    uint32_t cta0 = 0;
+    for (size_t c = 0; c < nclsA; ++c)
+        srow0[c] = static_cast<uint32_t>(P->lo[c]);
+    for (const auto& blk : h.blocks) {
+        const int64_t rows = P->hi[blk.cA] - P->lo[blk.cA];
+        const int64_t cols = P->ch[blk.cB] - P->cl[blk.cB];
+        P->loc_off.push_back(P->local_size);
+        P->y_off.push_back(P->y_size);
+        if (blk.nA * blk.nB > 0) {
+            sblk[blk.cA * nclsB + blk.cB] = P->local_size;
+            if (rows > 0) {
+                CopyPiece pc;
+                pc.src_off = blk.offset + P->lo[blk.cA] * blk.nB;
+                pc.dst_off = P->local_size;
+                pc.n = rows * blk.nB;
+                pc.cta0 = cta0;
+                cta0 += static_cast<uint32_t>((pc.n + 1023) / 1024);
+                pieces.push_back(pc);
+            }
+            P->local_size += rows * blk.nB;
+            P->y_size += blk.nA * cols;
+        }
+    }
+    P->sblk_off.upload(sblk);
+    P->srow0.upload(srow0);
+    P->npieces = static_cast<int>(pieces.size());
+    P->piece_ctas = cta0;
+    P->pieces.upload(pieces);
+
+    // ---- opposite-spin work items: (owned alpha string, beta class of the intermediate, m-split)
+    if (b.t3_ks > 0) {
+        std::vector<uint32_t> items;
+        std::vector<int> kcount(nclsB);
+        std::vector<char> row_has_block(nclsA, 0);
+        for (const auto& blk : h.blocks)
+            if (blk.nA * blk.nB > 0)
+                row_has_block[blk.cA] = 1;
+        for (size_t cA = 0; cA < nclsA; ++cA) {
+            if (!row_has_block[cA])
+                continue;
+            for (int64_t i = P->lo[cA]; i < P->hi[cA]; ++i) {
+                const uint32_t g = A.cls_off[cA] + static_cast<uint32_t>(i);
+                std::fill(kcount.begin(), kcount.end(), 0);
+                for (uint32_t e = L.as_ptr[g]; e < L.as_ptr[g + 1]; ++e) {
+                    const uint32_t cJ = L.a_cls[L.as_ent[e] & 0xffffffffu];
+                    for (size_t cB = 0; cB < nclsB; ++cB) {
+                        const int64_t bi = h.block_of[cJ * nclsB + cB];
+                        if (bi >= 0 && h.blocks[bi].nA * h.blocks[bi].nB > 0)
+                            kcount[cB] += 1;
+                    }
+                }
+                for (size_t cB = 0; cB < nclsB; ++cB) {
+                    if (B.strpcls(cB) == 0 || kcount[cB] == 0)
+                        continue;
+                    P->t3_kcols += static_cast<int64_t>(kcount[cB]) * static_cast<int64_t>(B.strpcls(cB));
+                    for (int ms = 0; ms < b.t3_msplit; ++ms) {
+                        items.push_back(g);
+                        items.push_back(static_cast<uint32_t>(cB) | (static_cast<uint32_t>(ms) << 16));
+                    }
+                }
+            }
+        }
+        P->nitems = static_cast<int>(items.size() / 2);
+        P->items.upload(items);
+    }
+
+    // ---- alpha same-spin plan: every row, owned columns; Y = sigma itself on one GPU, the exchange
+    // buffer ([nA][owned columns] per block) otherwise
+    {
+        std::vector<int64_t> xoff(nclsA * nclsB, -1), yoff(nclsA * nclsB, -1);
+        std::vector<uint32_t> ncols(nclsB), ldx(nclsB), ldy(nclsB), tiles;
+        bool even = b.D->al16;
+        for (size_t bi = 0; bi < h.blocks.size(); ++bi) {
+            const auto& blk = h.blocks[bi];
+            if (blk.nA * blk.nB == 0)
+                continue;
+            xoff[blk.cA * nclsB + blk.cB] = blk.offset + P->cl[blk.cB];
+            yoff[blk.cA * nclsB + blk.cB] = world == 1 ? blk.offset : P->y_off[bi];
+            even = even && (P->cl[blk.cB] % 2 == 0);
+        }
+        for (size_t c = 0; c < nclsB; ++c) {
+            ncols[c] = static_cast<uint32_t>(P->ch[c] - P->cl[c]);
+            ldx[c] = static_cast<uint32_t>(B.strpcls(c));
+            ldy[c] = world == 1 ? ldx[c] : ncols[c];
+        }
+        fill_tiles(tiles, ncols);
+        SSPlan& p = P->alpha_plan;
+        p.ngroups = static_cast<int>(nclsB);
+        p.ntiles = static_cast<int>(tiles.size() / 2);
+        p.xoff.upload(xoff);
+        p.yoff.upload(yoff);
+        p.g_ncols.upload(ncols);
+        p.g_ldx.upload(ldx);
+        p.g_ldy.upload(ldy);
+        p.tiles.upload(tiles);
+        p.al16 = even;
+    }
+    return P;
 }
 
 // beta same-spin work runs on transposed row slabs: a pass holds, for a set of (alpha class,
 // row range) column groups, the transposed blocks [nB][rows] of every beta class paired with it.
 // Both scratch buffers together must fit the set_memory budget (ci_sigma_builder.cc:70-78,
 // ci_sigma_builder_knowles_handy.cc:15-32).
-void plan_beta(f2_sigma& b) {
+void plan_beta(f2_sigma& b, Part& P) {
     const CIStringsHost& h = *b.S->host;
-    b.beta_passes.clear();
+    P.beta_passes.clear();
     if (h.nb < 1 || h.ndet == 0) {
-        b.beta_planned = true;
+        P.beta_planned = true;
         return;
     }
     const size_t nclsA = h.nclsA(), nclsB = h.nclsB();
@@ -479,15 +564,14 @@ void plan_beta(f2_sigma& b) {
     std::vector<Group> cur;
     int64_t used = 0;
     for (size_t cA = 0; cA < nclsA; ++cA) {
-        const int64_t nA = static_cast<int64_t>(h.space(0, K_STR_N).strpcls(cA));
-        if (width[cA] == 0 || nA == 0)
+        if (width[cA] == 0 || P.hi[cA] == P.lo[cA])
             continue;
         if (cap < width[cA])
             throw std::runtime_error("The CI builder memory limit (" + std::to_string(b.memory_size) +
                                      " bytes) is too small for one K-block column of " +
                                      std::to_string(width[cA]) + " elements per buffer.");
-        int64_t i0 = 0;
-        while (i0 < nA) {
+        int64_t i0 = P.lo[cA];
+        while (i0 < P.hi[cA]) {
             int64_t fit = (cap - used) / width[cA];
             if (fit == 0) {
                 passes.push_back(cur);
@@ -495,7 +579,7 @@ void plan_beta(f2_sigma& b) {
                 used = 0;
                 continue;
             }
-            const int64_t rows = std::min(fit, nA - i0);
+            const int64_t rows = std::min(fit, P.hi[cA] - i0);
             cur.push_back({static_cast<int>(cA), i0, rows});
             used += rows * width[cA];
             i0 += rows;
@@ -525,6 +609,7 @@ void plan_beta(f2_sigma& b) {
                 xoff[cB * ng + g] = pos;
                 TrBlock t;
                 t.src_off = blk.offset + G.i0 * blk.nB;
+                t.sig_off = P.world == 1 ? t.src_off : P.loc_off[bi] + (G.i0 - P.lo[G.cA]) * blk.nB;
                 t.dst_off = pos;
                 t.nA = static_cast<int32_t>(G.rows);
                 t.nB = static_cast<int32_t>(blk.nB);
@@ -552,11 +637,13 @@ void plan_beta(f2_sigma& b) {
         bp->tr.upload(tr);
         bp->elems = pos;
         max_elems = std::max(max_elems, pos);
-        b.beta_passes.push_back(std::move(bp));
+        P.beta_passes.push_back(std::move(bp));
     }
-    b.XT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
-    b.YT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
-    b.beta_planned = true;
+    if (static_cast<size_t>(std::max<int64_t>(max_elems, 1)) > b.XT.n) {
+        b.XT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
+        b.YT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
+    }
+    P.beta_planned = true;
 }
 
 void plan_hdiag(f2_sigma& b) {
@@ -582,47 +669,52 @@ void plan_hdiag(f2_sigma& b) {
 }
 
 template <int KS, bool AL16, int NS>
-void launch_t3_inst(const f2_sigma& b, const T3Params& p, cudaStream_t st) {
-    const dim3 grid(b.nitems), block(b.t3_warps * 32);
+void launch_t3_inst(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
+    const dim3 grid(nitems), block(b.t3_warps * 32);
     F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, AL16, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(b.t3_smem)));
     t3_kernel<KS, AL16, NS><<<grid, block, b.t3_smem, st>>>(p);
     b.launches += 1;
 }
 
-template <int KS> void launch_t3_ks(const f2_sigma& b, const T3Params& p, cudaStream_t st) {
+template <int KS>
+void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
     if (b.D->al16) {
         if (b.t3_ns == 3)
-            launch_t3_inst<KS, true, 3>(b, p, st);
+            launch_t3_inst<KS, true, 3>(b, p, nitems, st);
         else
-            launch_t3_inst<KS, true, 2>(b, p, st);
+            launch_t3_inst<KS, true, 2>(b, p, nitems, st);
     } else {
         if (b.t3_ns == 3)
-            launch_t3_inst<KS, false, 3>(b, p, st);
+            launch_t3_inst<KS, false, 3>(b, p, nitems, st);
         else
-            launch_t3_inst<KS, false, 2>(b, p, st);
+            launch_t3_inst<KS, false, 2>(b, p, nitems, st);
     }
 }
 
-void launch_t3(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st) {
-    if (b.nitems == 0)
+void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma, cudaStream_t st) {
+    if (P.nitems == 0)
         return;
     const CIStringsHost& h = *b.S->host;
     const DevStrings& D = *b.D;
     T3Params p;
     p.C = C;
     p.sigma = sigma;
-    p.items = b.items.p;
+    p.items = P.items.p;
     p.a_cls = D.a_cls.p;
     p.a_loc = D.a_loc.p;
     p.as_ptr = D.as_ptr.p;
     p.as_ent = D.as_ent.p;
     p.tgt = b.tgt.p;
     p.tgt_pair = b.tgt_pair;
+    {
+        const char* e = std::getenv("F2_T3_DBG");
+        p.dbg = e ? std::atoi(e) : 0;
+    }
     p.nbs = h.nbs;
     p.blk_off = D.blk_off.p;
-    p.sblk_off = D.blk_off.p;
-    p.srow0 = D.zeros.p;
+    p.sblk_off = P.sblk_off.p;
+    p.srow0 = P.srow0.p;
     p.nB_cls = D.nB_cls.p;
     p.b_off = D.b_off.p;
     p.nclsA = static_cast<int>(h.nclsA());
@@ -631,14 +723,14 @@ void launch_t3(const f2_sigma& b, const double* C, double* sigma, cudaStream_t s
     p.Vx = b.Vx.p;
     p.M = b.M;
     switch (b.t3_ks) {
-    case 4: launch_t3_ks<4>(b, p, st); break;
-    case 8: launch_t3_ks<8>(b, p, st); break;
-    case 12: launch_t3_ks<12>(b, p, st); break;
-    case 16: launch_t3_ks<16>(b, p, st); break;
-    case 20: launch_t3_ks<20>(b, p, st); break;
-    case 24: launch_t3_ks<24>(b, p, st); break;
-    case 28: launch_t3_ks<28>(b, p, st); break;
-    case 32: launch_t3_ks<32>(b, p, st); break;
+    case 4: launch_t3_ks<4>(b, p, P.nitems, st); break;
+    case 8: launch_t3_ks<8>(b, p, P.nitems, st); break;
+    case 12: launch_t3_ks<12>(b, p, P.nitems, st); break;
+    case 16: launch_t3_ks<16>(b, p, P.nitems, st); break;
+    case 20: launch_t3_ks<20>(b, p, P.nitems, st); break;
+    case 24: launch_t3_ks<24>(b, p, P.nitems, st); break;
+    case 28: launch_t3_ks<28>(b, p, P.nitems, st); break;
+    case 32: launch_t3_ks<32>(b, p, P.nitems, st); break;
     default: throw std::runtime_error("CISigmaBuilder: unsupported opposite-spin K size");
     }
     F2_CUDA(cudaGetLastError());
@@ -730,25 +822,35 @@ void collect_times(f2_sigma& b) {
     b.ev_pending = false;
 }
 
-void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t st) {
+// sigma (the owned rows) from the full trial vector.  On one GPU yexch is unused; otherwise the
+// alpha same-spin term of the owned columns of every row is left in yexch for the caller to exchange.
+void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, cudaStream_t st) {
     const CIStringsHost& h = *b.S->host;
-    if (n != h.ndet)
-        throw std::invalid_argument("CISigmaBuilder.Hamiltonian: vectors must have ndet = " +
-                                    std::to_string(h.ndet) + " elements, got " + std::to_string(n));
     F2_CUDA(cudaSetDevice(b.device));
     collect_times(b);
-    if (!b.beta_planned)
-        plan_beta(b);
-    if (n == 0)
+    if (!P.beta_planned)
+        plan_beta(b, P);
+    if (h.ndet == 0)
         return;
-    b.launches = 1;
+    b.launches = 0;
     F2_CUDA(cudaEventRecord(b.ev[0], st));
-    scale_copy_kernel<<<148 * 8, 256, 0, st>>>(C, sigma, b.E, n);
+    if (P.world == 1) {
+        scale_copy_kernel<<<148 * 8, 256, 0, st>>>(C, sigma, b.E, h.ndet);
+        b.launches += 1;
+    } else if (P.piece_ctas) {
+        piece_copy_kernel<false><<<P.piece_ctas, 256, 0, st>>>(C, sigma, P.pieces.p, P.npieces, b.E);
+        b.launches += 1;
+    }
     F2_CUDA(cudaEventRecord(b.ev[1], st));
-    if (h.na >= 1)
-        launch_same_spin(b, 0, b.alpha_plan, C, sigma, st);
+    if (h.na >= 1) {
+        if (P.world > 1)
+            F2_CUDA(cudaMemsetAsync(yexch, 0, static_cast<size_t>(P.y_size) * sizeof(double), st));
+        launch_same_spin(b, 0, P.alpha_plan, C, P.world == 1 ? sigma : yexch, st);
+    }
     F2_CUDA(cudaEventRecord(b.ev[2], st));
-    for (const auto& bp : b.beta_passes) {
+    for (const auto& bp : P.beta_passes) {
+        if (bp->ntr_tiles == 0)
+            continue;
         transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(C, b.XT.p, bp->tr.p, bp->ntr);
         b.launches += 2;
         F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
@@ -756,10 +858,31 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
         transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
-    launch_t3(b, C, sigma, st);
+    launch_t3(b, P, C, sigma, st);
     F2_CUDA(cudaEventRecord(b.ev[4], st));
     F2_CUDA(cudaGetLastError());
     b.ev_pending = true;
+}
+
+void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    if (n != h.ndet)
+        throw std::invalid_argument("CISigmaBuilder.Hamiltonian: vectors must have ndet = " +
+                                    std::to_string(h.ndet) + " elements, got " + std::to_string(n));
+    apply(b, *b.single, C, sigma, nullptr, st);
+}
+
+Part& shard_of(f2_sigma& b, int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world)
+        throw std::invalid_argument("CISigmaBuilder: invalid rank/world");
+    if (world == 1)
+        return *b.single;
+    if (!b.shard || b.shard->rank != rank || b.shard->world != world) {
+        F2_CUDA(cudaSetDevice(b.device));
+        F2_CUDA(cudaDeviceSynchronize());
+        b.shard = make_part(b, rank, world);
+    }
+    return *b.shard;
 }
 
 } // namespace
@@ -791,8 +914,8 @@ f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const 
                                          "is not supported by the same-spin kernel");
             b->ss_ks[s] = round_ks(std::max(L.h2_max[s], 1));
         }
-        plan_t3(*b);
-        plan_alpha(*b);
+        plan_t3_shape(*b);
+        b->single = make_part(*b, 0, 1);
         plan_hdiag(*b);
         return b.release();
     } catch (const std::exception& e) {
@@ -809,8 +932,11 @@ int f2_sigma_set_hamiltonian(f2_sigma* h, double E, const double* H, const doubl
         F2_CUDA(cudaDeviceSynchronize());
         const bool was = h->compressed;
         build_integrals(*h, E, H, V);
-        if (was != h->compressed)
-            plan_t3(*h);
+        if (was != h->compressed) {
+            plan_t3_shape(*h);
+            h->single = make_part(*h, 0, 1);
+            h->shard.reset();
+        }
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);
@@ -840,8 +966,11 @@ int f2_sigma_set_memory(f2_sigma* h, int64_t mb) {
     h->memory_size = static_cast<size_t>(mb) * 1024 * 1024;
     // like the reference, the scratch is released here and re-planned lazily by the next build,
     // which is where a too-small budget is reported
-    h->beta_planned = false;
-    h->beta_passes.clear();
+    for (Part* P : {h->single.get(), h->shard.get()})
+        if (P) {
+            P->beta_planned = false;
+            P->beta_passes.clear();
+        }
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->XT.release();
@@ -919,11 +1048,44 @@ int f2_sigma_last_ms(f2_sigma* h, double* out5) {
 
 int64_t f2_sigma_launch_count(const f2_sigma* h) { return h->launches; }
 
+int f2_sigma_part_layout(f2_sigma* h, int rank, int world, int64_t* sizes2, int64_t* rows6) {
+    try {
+        Part& P = shard_of(*h, rank, world);
+        sizes2[0] = P.local_size;
+        sizes2[1] = P.y_size;
+        const auto& blocks = h->S->host->blocks;
+        for (size_t bi = 0; bi < blocks.size(); ++bi) {
+            const auto& blk = blocks[bi];
+            int64_t* o = rows6 + 6 * bi;
+            o[0] = P.lo[blk.cA];
+            o[1] = P.hi[blk.cA] - P.lo[blk.cA];
+            o[2] = P.loc_off[bi];
+            o[3] = P.cl[blk.cB];
+            o[4] = P.ch[blk.cB] - P.cl[blk.cB];
+            o[5] = P.y_off[bi];
+        }
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev, double* exch_dev,
+                        int rank, int world, void* stream) {
+    try {
+        Part& P = shard_of(*h, rank, world);
+        apply(*h, P, C_full_dev, sigma_local_dev, exch_dev, static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
     out5[0] = h->M;
     out5[1] = static_cast<int64_t>(h->t3_warps) * 16 * h->t3_msplit;
     out5[2] = h->S->host->device_lists().as_max;
-    out5[3] = h->t3_kcols;
+    out5[3] = h->single ? h->single->t3_kcols : 0;
     out5[4] = h->compressed ? 1 : 0;
     return F2_OK;
 }

@@ -1,0 +1,160 @@
+"""Multi-GPU sigma build: the CI vector and sigma are partitioned by alpha-string rows over the ranks
+of one torch.distributed group (one process per GPU, NCCL over NVLink on the B200 box).
+
+No reference counterpart exists (forte2 is single-process); correctness is
+defined as equality with the single-GPU / reference result.
+
+Per sigma build
+  1. all-gather of the trial vector (each rank contributes its owned row slabs)            -- NCCL
+  2. local work through the C ABI (f2_sigma_apply_part): H0, beta same-spin and the opposite-spin term
+     for the owned ROWS (these only write owned rows), and the alpha same-spin term, which couples
+     rows, for the owned COLUMNS of every row
+  3. exchange of the alpha same-spin partial results to the row owners (all-to-all) and add  -- NCCL
+Rank r owns rows [r*nIa/world, (r+1)*nIa/world) of every determinant block (same rule for columns).
+The local vector is the concatenation of the owned row slabs in block order.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class Layout:
+    """Ownership arithmetic, identical to make_part() in csrc/sigma.cu (checked in the GPU tests)."""
+
+    def __init__(self, blocks: np.ndarray, rank: int, world: int):
+        self.rank, self.world = rank, world
+        self.blocks = [(int(off), int(nA), int(nB)) for _, _, off, nA, nB in blocks]
+        self.rows, self.cols = [], []  # per block: (first, count, offset in local vector / exchange buffer)
+        loc = y = 0
+        for off, nA, nB in self.blocks:
+            lo, hi = nA * rank // world, nA * (rank + 1) // world
+            cl, ch = nB * rank // world, nB * (rank + 1) // world
+            self.rows.append((lo, hi - lo, loc))
+            self.cols.append((cl, ch - cl, y))
+            if nA * nB > 0:
+                loc += (hi - lo) * nB
+                y += nA * (ch - cl)
+        self.local_size, self.exchange_size = loc, y
+        self.ndet = sum(nA * nB for _, nA, nB in self.blocks)
+
+
+class CudaEngine:
+    """Local work on one GPU through the C ABI."""
+
+    def __init__(self, builder):
+        self.builder = builder
+
+    def apply_part(self, c_full, sigma_loc, yexch, rank, world):
+        stream = torch.cuda.current_stream(self.builder.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_apply_part(self.builder._h, c_full.data_ptr(), sigma_loc.data_ptr(),
+                                                  yexch.data_ptr(), rank, world, stream))
+
+    def layout_from_library(self, nblocks, rank, world):
+        sizes = np.zeros(2, dtype=np.int64)
+        rows = np.zeros((nblocks, 6), dtype=np.int64)
+        _lib.check(_lib.lib().f2_sigma_part_layout(self.builder._h, rank, world, sizes.ctypes.data_as(_lib.i64p),
+                                                   rows.ctypes.data_as(_lib.i64p)))
+        return sizes, rows
+
+
+class ShardedSigma:
+    """sigma = H C with C and sigma sharded by alpha rows.  `engine` does the local work: CudaEngine on
+    the GPU box; the gloo tests pass a CPU stand-in with the same apply_part signature."""
+
+    def __init__(self, builder=None, rank=None, world=None, group=None, engine=None, blocks=None, device=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.engine = engine if engine is not None else CudaEngine(builder)
+        if blocks is None:
+            blocks = builder.ci_strings.blocks()
+        self.layouts = [Layout(blocks, q, self.world) for q in range(self.world)]
+        self.layout = self.layouts[self.rank]
+        self.local_size = self.layout.local_size
+        self.ndet = self.layout.ndet
+        self.device = device if device is not None else (
+            torch.device("cuda", builder.device) if builder is not None else torch.device("cpu"))
+        self._max_local = max(lay.local_size for lay in self.layouts)
+        kw = dict(dtype=torch.float64, device=self.device)
+        self._full = torch.empty(self.ndet, **kw)
+        self._gather = [torch.empty(self._max_local, **kw) for _ in range(self.world)]
+        self._pad = torch.zeros(self._max_local, **kw)
+        self._yexch = torch.zeros(max(self.layout.exchange_size, 1), **kw)
+        if isinstance(self.engine, CudaEngine):
+            sizes, rows = self.engine.layout_from_library(len(self.layout.blocks), self.rank, self.world)
+            assert int(sizes[0]) == self.layout.local_size and int(sizes[1]) == self.layout.exchange_size
+            for b, (lo, n, off) in enumerate(self.layout.rows):
+                assert (int(rows[b, 0]), int(rows[b, 1])) == (lo, n)
+
+    # ---- layout helpers ----
+    def scatter_full(self, full: torch.Tensor) -> torch.Tensor:
+        """owned row slabs of a full-layout vector (for tests and initial guesses)"""
+        out = torch.empty(self.local_size, dtype=full.dtype, device=full.device)
+        for (off, nA, nB), (lo, n, loc) in zip(self.layout.blocks, self.layout.rows):
+            if nA * nB > 0 and n > 0:
+                out[loc:loc + n * nB] = full[off + lo * nB: off + (lo + n) * nB]
+        return out
+
+    def all_gather_full(self, c_loc: torch.Tensor) -> torch.Tensor:
+        """full-layout copy of a sharded vector on every rank (step 1)"""
+        if self.world == 1:
+            self._full.copy_(c_loc)
+            return self._full
+        self._pad[: self.local_size].copy_(c_loc)
+        dist.all_gather(self._gather, self._pad, group=self.group)
+        for q, lay in enumerate(self.layouts):
+            for (off, nA, nB), (lo, n, loc) in zip(lay.blocks, lay.rows):
+                if nA * nB > 0 and n > 0:
+                    self._full[off + lo * nB: off + (lo + n) * nB].copy_(self._gather[q][loc:loc + n * nB])
+        return self._full
+
+    def _exchange_add(self, sigma_loc: torch.Tensor):
+        """send the alpha same-spin partials [rows of q][my columns] to q, add what arrives (step 3)"""
+        me = self.layout
+        send, recv = [], []
+        for q, lay in enumerate(self.layouts):
+            parts, n_recv = [], 0
+            for b, (off, nA, nB) in enumerate(me.blocks):
+                if nA * nB == 0:
+                    continue
+                cl, nc, yoff = me.cols[b]
+                lo_q, n_q, _ = lay.rows[b]
+                if nc > 0 and n_q > 0:
+                    parts.append(self._yexch[yoff + lo_q * nc: yoff + (lo_q + n_q) * nc])
+                n_recv += me.rows[b][1] * lay.cols[b][1]
+            send.append(torch.cat(parts) if parts else self._yexch[:0])
+            recv.append(torch.empty(n_recv, dtype=torch.float64, device=self.device))
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                recv[q].copy_(send[q])
+                continue
+            if send[q].numel():
+                ops.append(dist.P2POp(dist.isend, send[q].contiguous(), q, group=self.group))
+            if recv[q].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[q], q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for q, lay in enumerate(self.layouts):
+            pos = 0
+            for b, (off, nA, nB) in enumerate(me.blocks):
+                if nA * nB == 0:
+                    continue
+                lo, n, loc = me.rows[b]
+                cl_q, nc_q, _ = lay.cols[b]
+                if n > 0 and nc_q > 0:
+                    blk = sigma_loc[loc:loc + n * nB].view(n, nB)
+                    blk[:, cl_q:cl_q + nc_q] += recv[q][pos:pos + n * nc_q].view(n, nc_q)
+                pos += n * nc_q
+
+    def Hamiltonian(self, c_loc: torch.Tensor, sigma_loc: torch.Tensor) -> None:
+        assert c_loc.numel() == self.local_size and sigma_loc.numel() == self.local_size
+        full = self.all_gather_full(c_loc)
+        self.engine.apply_part(full, sigma_loc, self._yexch, self.rank, self.world)
+        if self.world > 1:
+            self._exchange_add(sigma_loc)

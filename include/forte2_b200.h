@@ -102,6 +102,20 @@ int64_t f2_sigma_launch_count(const f2_sigma* h);
  * 2 * out[0] * out[3].  out[4] = 1 when the pair-compressed (8-fold symmetric) rows are in use. */
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5);
 
+/* ---- alpha-row partition for multi-GPU (no reference counterpart) ----------
+ * Rank r of world owns, in every determinant block, the alpha rows [r*nIa/world, (r+1)*nIa/world); its
+ * local vector is the concatenation of the owned row slabs in block order.  For the alpha same-spin
+ * term (which couples rows) it owns the same kind of slice of every block's beta columns.
+ * sizes2 = {local vector length, exchange buffer length}; rows6 = per block
+ * (first_row, nrows, local_offset, first_col, ncols, exchange_offset). */
+int f2_sigma_part_layout(f2_sigma* h, int rank, int world, int64_t* sizes2, int64_t* rows6);
+/* sigma_local (owned rows) from the FULL trial vector (all-gathered by the caller over NCCL):
+ * H0 + beta same-spin + opposite-spin are complete on return; the alpha same-spin term of the owned
+ * COLUMNS of every row is left in exch_dev, laid out per block as [nIa][ncols], for the caller to
+ * send to the row owners (all-to-all) and add.  Device pointers; stream = cudaStream_t. */
+int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev, double* exch_dev,
+                        int rank, int world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ def port_lib():
         dp, up = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
         L.port_sigma.restype = C.c_int
         L.port_sigma.argtypes = [C.c_int64, up, C.c_int, C.c_double, dp, dp, dp, dp]
+        L.port_sigma_parts.restype = C.c_int
+        L.port_sigma_parts.argtypes = [C.c_int64, up, C.c_int, C.c_double, dp, dp, dp, dp, C.c_int]
         L.port_energies.argtypes = [C.c_int64, up, C.c_int, C.c_double, dp, dp, dp]
         _port = L
     return _port
@@ -37,14 +39,17 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def port_sigma(dets, E, H, V, c):
+PART_SCALAR, PART_ALPHA, PART_BETA, PART_ALPHA_BETA, PART_ALL = 1, 2, 4, 8, 15
+
+
+def port_sigma(dets, E, H, V, c, parts=PART_ALL):
     dets = np.ascontiguousarray(dets, dtype=np.uint64)
     H = np.ascontiguousarray(H, dtype=np.float64)
     V = np.ascontiguousarray(V, dtype=np.float64)
     c = np.ascontiguousarray(c, dtype=np.float64)
     out = np.zeros_like(c)
-    rc = port_lib().port_sigma(len(c), dets.ctypes.data_as(C.POINTER(C.c_uint64)), H.shape[0], float(E), _dp(H),
-                               _dp(V), _dp(c), _dp(out))
+    rc = port_lib().port_sigma_parts(len(c), dets.ctypes.data_as(C.POINTER(C.c_uint64)), H.shape[0], float(E),
+                                     _dp(H), _dp(V), _dp(c), _dp(out), int(parts))
     assert rc == 0
     return out
 

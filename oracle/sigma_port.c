@@ -54,20 +54,27 @@ static double sign_below(uint64_t w, int n) {
 
 #define V4(p, q, r, s) V[(((size_t)(p) * n + (q)) * n + (r)) * n + (s)]
 
-/* <I|H|I>, slater_rules.cc:86-121 */
-static double port_energy(int n, double E, const double* H, const double* V, uint64_t a, uint64_t b) {
-    double e = E;
+/* term selection for the multi-process tests: the Hamiltonian is the sum of these four parts */
+enum { PART_SCALAR = 1, PART_ALPHA = 2, PART_BETA = 4, PART_ALPHA_BETA = 8, PART_ALL = 15 };
+
+/* <I|H|I>, slater_rules.cc:86-121, split into scalar / alpha same-spin / beta same-spin / alpha-beta */
+static double port_energy_parts(int n, double E, const double* H, const double* V, uint64_t a, uint64_t b,
+                                int parts) {
+    double e = (parts & PART_SCALAR) ? E : 0.0;
     for (int p = 0; p < n; ++p) {
         if ((a >> p) & 1) {
-            e += H[p * n + p];
-            for (int q = 0; q < p; ++q)
-                if ((a >> q) & 1)
-                    e += V4(q, p, q, p) - V4(q, p, p, q);
-            for (int q = 0; q < n; ++q)
-                if ((b >> q) & 1)
-                    e += V4(p, q, p, q);
+            if (parts & PART_ALPHA) {
+                e += H[p * n + p];
+                for (int q = 0; q < p; ++q)
+                    if ((a >> q) & 1)
+                        e += V4(q, p, q, p) - V4(q, p, p, q);
+            }
+            if (parts & PART_ALPHA_BETA)
+                for (int q = 0; q < n; ++q)
+                    if ((b >> q) & 1)
+                        e += V4(p, q, p, q);
         }
-        if ((b >> p) & 1) {
+        if (((b >> p) & 1) && (parts & PART_BETA)) {
             e += H[p * n + p];
             for (int q = 0; q < p; ++q)
                 if ((b >> q) & 1)
@@ -77,22 +84,26 @@ static double port_energy(int n, double E, const double* H, const double* V, uin
     return e;
 }
 
+static double port_energy(int n, double E, const double* H, const double* V, uint64_t a, uint64_t b) {
+    return port_energy_parts(n, E, H, V, a, b, PART_ALL);
+}
+
 /* h(i,a) + sum_j same-spin (<ij|aj> - <ij|ja>) + sum_j other-spin <ij|aj>, slater_rules.cc:127-143 */
 static double single_coupling(int n, const double* H, const double* V, int i, int a, uint64_t same,
-                              uint64_t other) {
-    double c = H[i * n + a];
+                              uint64_t other, int want_same, int want_other) {
+    double c = want_same ? H[i * n + a] : 0.0;
     for (int j = 0; j < n; ++j) {
-        if ((same >> j) & 1)
+        if (want_same && ((same >> j) & 1))
             c += V4(i, j, a, j) - V4(i, j, j, a);
-        if ((other >> j) & 1)
+        if (want_other && ((other >> j) & 1))
             c += V4(i, j, a, j);
     }
     return c;
 }
 
 /* sigma[I] = sum_J <I|H|J> C[J] over the ndet determinants dets[2*I] (alpha), dets[2*I+1] (beta) */
-int port_sigma(int64_t ndet, const uint64_t* dets, int n, double E, const double* H, const double* V,
-               const double* C, double* sigma) {
+int port_sigma_parts(int64_t ndet, const uint64_t* dets, int n, double E, const double* H, const double* V,
+                     const double* C, double* sigma, int parts) {
     det_key* keys = (det_key*)malloc((size_t)(ndet > 0 ? ndet : 1) * sizeof(det_key));
     if (!keys)
         return 1;
@@ -104,9 +115,11 @@ int port_sigma(int64_t ndet, const uint64_t* dets, int n, double E, const double
     qsort(keys, (size_t)ndet, sizeof(det_key), cmp_key);
     for (int64_t I = 0; I < ndet; ++I) {
         const uint64_t a = dets[2 * I], b = dets[2 * I + 1];
-        double acc = port_energy(n, E, H, V, a, b) * C[I];
+        double acc = port_energy_parts(n, E, H, V, a, b, parts) * C[I];
         for (int spin = 0; spin < 2; ++spin) {
             const uint64_t s = spin == 0 ? a : b, o = spin == 0 ? b : a;
+            const int want_same = parts & (spin == 0 ? PART_ALPHA : PART_BETA);
+            const int want_ab = parts & PART_ALPHA_BETA;
             /* single replacements i -> x of this spin (slater_rules.cc:186-198) */
             for (int i = 0; i < n; ++i) {
                 if (!((s >> i) & 1))
@@ -119,10 +132,10 @@ int port_sigma(int64_t ndet, const uint64_t* dets, int n, double E, const double
                     const uint64_t s2 = s1 | (1ull << x);
                     const double sg = si * sign_below(s1, x);
                     const int64_t J = spin == 0 ? find_det(keys, ndet, s2, o) : find_det(keys, ndet, o, s2);
-                    if (J >= 0)
-                        acc += sg * single_coupling(n, H, V, i, x, s, o) * C[J];
+                    if (J >= 0 && (want_same || want_ab))
+                        acc += sg * single_coupling(n, H, V, i, x, s, o, want_same, want_ab) * C[J];
                     /* same-spin double replacements (i,j) -> (x,y), i<j, x<y (slater_rules.cc:174-184) */
-                    for (int j = i + 1; j < n; ++j) {
+                    for (int j = i + 1; j < n && want_same; ++j) {
                         if (!((s2 >> j) & 1) || j == x)
                             continue;
                         const uint64_t s3 = s2 & ~(1ull << j);
@@ -142,7 +155,7 @@ int port_sigma(int64_t ndet, const uint64_t* dets, int n, double E, const double
                     }
                     /* opposite-spin double replacement, counted once from the alpha side
                      * (slater_rules.cc:166-172): <i j|x y> with i,x alpha and j,y beta */
-                    if (spin == 0) {
+                    if (spin == 0 && want_ab) {
                         for (int j = 0; j < n; ++j) {
                             if (!((b >> j) & 1))
                                 continue;
@@ -165,6 +178,11 @@ int port_sigma(int64_t ndet, const uint64_t* dets, int n, double E, const double
     }
     free(keys);
     return 0;
+}
+
+int port_sigma(int64_t ndet, const uint64_t* dets, int n, double E, const double* H, const double* V,
+               const double* C, double* sigma) {
+    return port_sigma_parts(ndet, dets, n, E, H, V, C, sigma, PART_ALL);
 }
 
 /* determinant energies for every determinant (SlaterRules::energies, slater_rules.cc:145-152) */

@@ -1,0 +1,91 @@
+"""world_size = 2 and 3 over gloo on CPU: the row partition, the all-gather, the column-owned alpha
+same-spin exchange and the add, with the oracle port standing in for the GPU's local work.  The GPU
+version of the same check (NCCL, the real C ABI) is tests/test_dist_gpu.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cases import SMALL_SPACES
+from forte2_b200 import synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class PortEngine:
+    """CPU stand-in for CudaEngine: same contract as f2_sigma_apply_part, computed with oracle/sigma_port.c
+    (scalar + beta + alpha-beta terms for the owned rows; alpha same-spin term for the owned columns)."""
+
+    def __init__(self, dets, ints, layouts):
+        self.dets, self.ints, self.layouts = dets, ints, layouts
+
+    def apply_part(self, c_full, sigma_loc, yexch, rank, world):
+        from oracle import checker
+        E, H, V = self.ints
+        c = c_full.numpy()
+        rows_part = checker.port_sigma(self.dets, E, H, V, c, checker.PART_SCALAR | checker.PART_BETA |
+                                       checker.PART_ALPHA_BETA)
+        alpha_part = checker.port_sigma(self.dets, E, H, V, c, checker.PART_ALPHA)
+        lay = self.layouts[rank]
+        out = sigma_loc.numpy()
+        y = yexch.numpy()
+        for (off, nA, nB), (lo, n, loc), (cl, nc, yoff) in zip(lay.blocks, lay.rows, lay.cols):
+            if nA * nB == 0:
+                continue
+            out[loc:loc + n * nB] = rows_part[off + lo * nB: off + (lo + n) * nB]
+            if world > 1:
+                y[yoff:yoff + nA * nc] = alpha_part[off:off + nA * nB].reshape(nA, nB)[:, cl:cl + nc].reshape(-1)
+            else:
+                out[loc:loc + n * nB] += alpha_part[off + lo * nB: off + (lo + n) * nB]
+
+
+def _worker(rank, world, port, name, result_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import forte2_b200 as f2
+        from forte2_b200.dist import ShardedSigma
+        from oracle import checker
+        space = SMALL_SPACES[name]
+        n = sum(len(s) for s in space[3])
+        ints = synthetic.integrals(n, "S")
+        strings = f2.CIStrings(*space)
+        dets = strings.make_determinants()
+        sh = ShardedSigma(rank=rank, world=world, engine=PortEngine(dets, ints, None),
+                          blocks=strings.blocks(), device=torch.device("cpu"))
+        sh.engine.layouts = sh.layouts
+        c_full = torch.from_numpy(synthetic.trial_vector(strings.ndet))
+        c_loc = sh.scatter_full(c_full)
+        sigma_loc = torch.zeros_like(c_loc)
+        sh.Hamiltonian(c_loc, sigma_loc)
+        got = sh.all_gather_full(sigma_loc).clone().numpy()
+        want = checker.port_sigma(dets, *ints, c_full.numpy())
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert sum(lay.local_size for lay in sh.layouts) == strings.ndet
+        np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array([err]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("name,world", [("cas66", 2), ("gas343_54", 2), ("cas66_d2h", 3), ("cas75_odd", 3)])
+def test_sharded_sigma_over_gloo(tmp_path, name, world):
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        err = float(np.load(tmp_path / f"err_{r}.npy")[0])
+        assert err <= 1e-13, (r, err)

@@ -1,0 +1,63 @@
+"""N = 2 GPUs over NCCL (skipped with fewer): sharded sigma through the real C ABI equals the
+single-GPU sigma and the reference to 1e-12 relative L2."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, spaces, result_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import forte2_b200 as f2
+        from forte2_b200 import synthetic
+        from forte2_b200.dist import ShardedSigma
+        errs = []
+        for space in spaces:
+            n = sum(len(s) for s in space[3])
+            E, H, V = synthetic.integrals(n, "S")
+            strings = f2.CIStrings(*space)
+            builder = f2.CISigmaBuilder(strings, E, H, V, 0, device=rank)
+            c_full = torch.from_numpy(synthetic.trial_vector(strings.ndet)).cuda()
+            want = torch.empty_like(c_full)
+            builder.Hamiltonian(c_full, want)  # single-GPU result on this rank
+            sh = ShardedSigma(builder, rank, world)
+            c_loc = sh.scatter_full(c_full)
+            sigma_loc = torch.full_like(c_loc, float("nan"))
+            sh.Hamiltonian(c_loc, sigma_loc)
+            got = sh.all_gather_full(sigma_loc).clone()
+            errs.append(float((got - want).norm() / want.norm()))
+        np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array(errs))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_sharded_sigma_two_gpus(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    spaces = [(3, 3, 0, [[0] * 6], [], []), (5, 4, 0, [[0] * 3, [0] * 4, [0] * 3], [4, 0, 0], [6, 8, 2]),
+              (3, 3, 0, [[0, 5, 2, 3, 6, 7]], [], []), (5, 5, 0, [[0] * 10], [], []), (4, 3, 0, [[0] * 7], [], [])]
+    mp.spawn(_worker, args=(2, _free_port(), spaces, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        errs = np.load(tmp_path / f"err_{r}.npy")
+        assert np.all(errs <= 1e-12), (r, errs)
