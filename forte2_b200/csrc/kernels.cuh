@@ -56,6 +56,11 @@ struct T3Params {
     int M;
     int tgt_pair; // 1: table rows and class offsets are even, two targets per 8-byte load
     int dbg;      // diagnosis only (F2_T3_DBG): bit 0 skip the atomics, bit 1 skip the table loads
+    // alpha same-spin folding (complete alpha string space, one GPU): the accumulators hold
+    // Z = G + 2 kk C[Ia] and every row m = (ij) is also added, halved, to sigma[E_ij Ia, :]
+    int fold;
+    const double* kk2;      // [M] 2 kk_ij / na, added to the diagonal (k = l) columns of A
+    const uint16_t* rowmap; // [norb*norb] (i,j) -> m
 };
 
 // packed beta replacement target: bit 31 sign, bits 20..30 class of Ib, bits 0..19 address of Ib in
@@ -63,21 +68,37 @@ struct T3Params {
 constexpr uint32_t kNoTarget = 0xffffffffu;
 constexpr int TB = 68; // row stride of the staged C tile (== 4 mod 16: conflict-free B fragments)
 
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a0, double b0) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a0), "d"(b0));
+}
+
+constexpr size_t t3_smem_bytes(int ks, int ns, int nclsB, int rows) {
+    return size_t(ns) * ks * 4 * TB * 8 + size_t(ks) * 4 * (8 + 8 + 4) + size_t(nclsB) * 8 + size_t(rows) * 2 + 64;
+}
+
 // Opposite-spin term.  One CTA per (output alpha string Ia, beta class of the intermediate column);
 // warp w owns rows [16w, 16w+16) of the integral matrix: its A fragments (signed columns of Vx picked
 // by the single replacements of Ia) stay in registers for the whole row, the B operand is the
 // gathered rows C[Ja_r, tile] staged by cp.async, and every accumulator element is added straight
-// from registers into sigma[Ia, Ib] through the replacement table (red.global.add.f64).
-template <int KS, bool AL16, int NS>
-__global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3Params p) {
+// from registers into sigma through the replacement table (red.global.add.f64).
+// TAIL: the last (at most 8) rows of the integral matrix do not get a warp of their own -- that would
+// leave one SM sub-partition with an extra warp of tensor work -- but are spread over the warps, each
+// taking an 8-row x (64/nwarps)-column strip (m8n8k4).
+template <int KS, bool AL16, int NS, bool TAIL>
+__global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_kernel(const T3Params p) {
     constexpr int KP = KS * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthr >> 5, g = lane >> 2, t = lane & 3;
+    const int rows_cta = nwarps * 16 + (TAIL ? 8 : 0);
     double* Bs = reinterpret_cast<double*>(smem_raw);
     long long* ksrc = reinterpret_cast<long long*>(Bs + NS * KP * TB);
-    long long* rowbase = ksrc + KP;
+    long long* krow = ksrc + KP; // sigma row of Ja_r in the block paired with this column class
+    long long* rowbase = krow + KP;
     unsigned* kinfo = reinterpret_cast<unsigned*>(rowbase + p.nclsB);
+    short* arow = reinterpret_cast<short*>(kinfo + KP); // local row m -> replacement r with E_ij Ia = Ja_r
     __shared__ int s_Kn;
 
     const uint32_t Ia = p.items[2 * blockIdx.x];
@@ -86,6 +107,7 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
     const int cA = p.a_cls[Ia];
     const uint32_t ia = p.a_loc[Ia];
     const int nBp = p.nB_cls[cBp];
+    const int mbase = msp * nwarps * 16;
 
     if (warp == 0) {
         const int e0 = p.as_ptr[Ia], e1 = p.as_ptr[Ia + 1];
@@ -93,15 +115,18 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
         for (int base = e0; base < e1; base += 32) {
             const int e = base + lane;
             bool ok = false;
-            long long src = -1;
+            long long src = -1, dst = -1;
             unsigned info = 0;
             if (e < e1) {
                 const uint64_t ent = p.as_ent[e];
                 const uint32_t Ja = static_cast<uint32_t>(ent);
-                const long long off = p.blk_off[p.a_cls[Ja] * p.nclsB + cBp];
+                const int cJ = p.a_cls[Ja];
+                const long long off = p.blk_off[cJ * p.nclsB + cBp];
                 if (off >= 0) {
                     ok = true;
                     src = off + static_cast<long long>(p.a_loc[Ja]) * nBp;
+                    const long long so = p.sblk_off[cJ * p.nclsB + cBp];
+                    dst = so >= 0 ? so + (static_cast<long long>(p.a_loc[Ja]) - p.srow0[cJ]) * nBp : -1;
                     info = static_cast<unsigned>((ent >> 32) & 0xffff) |
                            (static_cast<unsigned>((ent >> 48) & 1) << 31);
                 }
@@ -110,12 +135,14 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
             if (ok) {
                 const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
                 ksrc[pos] = src;
+                krow[pos] = dst;
                 kinfo[pos] = info;
             }
             cnt += __popc(mask);
         }
         for (int r = cnt + lane; r < KP; r += 32) {
             ksrc[r] = -1;
+            krow[r] = -1;
             kinfo[r] = 0;
         }
         if (lane == 0)
@@ -125,6 +152,8 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
         const long long off = p.sblk_off[cA * p.nclsB + c];
         rowbase[c] = off >= 0 ? off + static_cast<long long>(ia - p.srow0[cA]) * p.nB_cls[c] : -1;
     }
+    for (int i = tid; i < rows_cta; i += nthr)
+        arow[i] = -1;
     for (int i = tid; i < NS * KP * TB; i += nthr)
         Bs[i] = 0.0;
     __syncthreads();
@@ -132,24 +161,43 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
     if (Kn == 0)
         return;
     const int nks = (Kn + 3) >> 2;
+    if (p.fold) {
+        // <Ia|E_kl|Ja_r> = s_r  <=>  E_lk Ia = s_r Ja_r : row m(l,k) of the accumulators goes to row Ja_r
+        for (int r = tid; r < Kn; r += nthr) {
+            const int kl = kinfo[r] & 0xffff;
+            const int k = kl / p.norb, l = kl - k * p.norb;
+            const int m = static_cast<int>(p.rowmap[l * p.norb + k]) - mbase;
+            if (m >= 0 && m < rows_cta)
+                arow[m] = static_cast<short>(r);
+        }
+        __syncthreads();
+    }
 
     // A fragments: this warp owns rows [m0, m0+16) of the integral matrix for the whole row Ia
-    const int m0 = (msp * nwarps + warp) * 16;
+    const int m0 = mbase + warp * 16;
+    const int mt = mbase + nwarps * 16 + g; // TAIL: row of the shared 8-row strip held by this lane
     const int ldv = p.norb * p.norb;
     double a[KS][2];
+    double at[TAIL ? KS : 1];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         a[ks][0] = 0.0;
         a[ks][1] = 0.0;
+        if constexpr (TAIL)
+            at[ks] = 0.0;
         const int r = 4 * ks + t;
         if (r < Kn) {
             const unsigned info = kinfo[r];
             const double sg = (info >> 31) ? -1.0 : 1.0;
             const int kl = info & 0xffff;
+            const bool diag = p.fold && (kl / p.norb == kl % p.norb);
             if (m0 + g < p.M)
-                a[ks][0] = sg * p.Vx[static_cast<size_t>(m0 + g) * ldv + kl];
+                a[ks][0] = sg * p.Vx[static_cast<size_t>(m0 + g) * ldv + kl] + (diag ? p.kk2[m0 + g] : 0.0);
             if (m0 + g + 8 < p.M)
-                a[ks][1] = sg * p.Vx[static_cast<size_t>(m0 + g + 8) * ldv + kl];
+                a[ks][1] = sg * p.Vx[static_cast<size_t>(m0 + g + 8) * ldv + kl] + (diag ? p.kk2[m0 + g + 8] : 0.0);
+            if constexpr (TAIL)
+                if (mt < p.M)
+                    at[ks] = sg * p.Vx[static_cast<size_t>(mt) * ldv + kl] + (diag ? p.kk2[mt] : 0.0);
         }
     }
 
@@ -178,10 +226,59 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
         cp_async_commit(); // one group per call, empty past the end, keeps the wait count uniform
     };
 
-    // replacement-table rows of this thread's two accumulator rows
-    const bool row_ok[2] = {m0 + g < p.M, m0 + g + 8 < p.M};
-    const uint32_t* trow[2] = {p.tgt + static_cast<size_t>(row_ok[0] ? m0 + g : 0) * p.nbs + p.b_off[cBp],
-                               p.tgt + static_cast<size_t>(row_ok[1] ? m0 + g + 8 : 0) * p.nbs + p.b_off[cBp]};
+    // per accumulator row of this lane: replacement-table row (beta scatter) and, when folding, the
+    // sigma row and sign of the alpha replacement E_ij Ia
+    constexpr int NR = TAIL ? 3 : 2;
+    const int rowm[3] = {m0 + g, m0 + g + 8, mt};
+    bool row_ok[NR];
+    const uint32_t* trow[NR];
+    long long abase[NR];
+    double ahalf[NR];
+#pragma unroll
+    for (int h = 0; h < NR; ++h) {
+        row_ok[h] = rowm[h] < p.M;
+        trow[h] = p.tgt + static_cast<size_t>(row_ok[h] ? rowm[h] : 0) * p.nbs + p.b_off[cBp];
+        abase[h] = -1;
+        ahalf[h] = 0.5;
+        if (p.fold && row_ok[h]) {
+            const int r = arow[rowm[h] - mbase];
+            if (r >= 0) {
+                abase[h] = krow[r];
+                ahalf[h] = (kinfo[r] >> 31) ? -0.5 : 0.5;
+            }
+        }
+    }
+
+    auto fetch = [&](uint32_t (&tg)[2], int h, int col) {
+        tg[0] = kNoTarget;
+        tg[1] = kNoTarget;
+        if (row_ok[h] && !(p.dbg & 2)) {
+            if (p.tgt_pair) {
+                if (col < nBp) { // nBp even: col + 1 is in range too
+                    const uint2 v = *reinterpret_cast<const uint2*>(trow[h] + col);
+                    tg[0] = v.x;
+                    tg[1] = v.y;
+                }
+            } else {
+                if (col < nBp)
+                    tg[0] = trow[h][col];
+                if (col + 1 < nBp)
+                    tg[1] = trow[h][col + 1];
+            }
+        }
+    };
+    // sigma[Ia, Ib] += sign * Z[m, Jb]  (beta replacement), sigma[E_ij Ia, Jb] += sign/2 * Z[m, Jb]
+    auto emit = [&](double v, uint32_t x, int h, int col) {
+        if (p.dbg & 1)
+            return;
+        if (x != kNoTarget) {
+            const long long base = rowbase[(x >> 20) & 0x7ff];
+            if (base >= 0)
+                atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
+        }
+        if (abase[h] >= 0 && col < nBp)
+            atomicAdd(p.sigma + abase[h] + col, ahalf[h] * v);
+    };
 
 #pragma unroll
     for (int s = 0; s < NS - 1; ++s)
@@ -198,28 +295,10 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
             // fetch the replacement targets first: their latency hides behind the MMAs
             uint32_t tg[NT / 16][2][2];
 #pragma unroll
-            for (int nt = 0; nt < NT / 16; ++nt) {
-                const int col = c0 + nt * 8;
+            for (int nt = 0; nt < NT / 16; ++nt)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tg[nt][h][0] = kNoTarget;
-                    tg[nt][h][1] = kNoTarget;
-                    if (row_ok[h] && !(p.dbg & 2)) {
-                        if (p.tgt_pair) {
-                            if (col < nBp) { // nBp even: col + 1 is in range too
-                                const uint2 v = *reinterpret_cast<const uint2*>(trow[h] + col);
-                                tg[nt][h][0] = v.x;
-                                tg[nt][h][1] = v.y;
-                            }
-                        } else {
-                            if (col < nBp)
-                                tg[nt][h][0] = trow[h][col];
-                            if (col + 1 < nBp)
-                                tg[nt][h][1] = trow[h][col + 1];
-                        }
-                    }
-                }
-            }
+                for (int h = 0; h < 2; ++h)
+                    fetch(tg[nt][h], h, c0 + nt * 8);
             double acc[NT / 16][4];
 #pragma unroll
             for (int nt = 0; nt < NT / 16; ++nt)
@@ -233,22 +312,31 @@ __global__ void __launch_bounds__((KS <= 24 ? 384 : 320), 1) t3_kernel(const T3P
                         dmma_16x8x4(acc[nt], a[ks][0], a[ks][1], bp[nt * 8]);
                 }
             }
-            // sigma[Ia, Ib] += sign * G[m, Jb], straight from the accumulators
 #pragma unroll
             for (int nt = 0; nt < NT / 16; ++nt)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint32_t x = tg[nt][h][c];
-                        if (x != kNoTarget) {
-                            const long long base = rowbase[(x >> 20) & 0x7ff];
-                            if (base >= 0 && !(p.dbg & 1)) {
-                                const double v = acc[nt][2 * h + c];
-                                atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
-                            }
-                        }
-                    }
+                    for (int c = 0; c < 2; ++c)
+                        emit(acc[nt][2 * h + c], tg[nt][h][c], h, c0 + nt * 8 + c);
+        }
+        if constexpr (TAIL) {
+            // this warp's strip of the shared 8-row tail: columns [cw, cw + 64/nwarps)
+            const int per = NT / 8 / nwarps; // n8 tiles per warp (1 for 8 warps, 2 for 4)
+#pragma unroll 1
+            for (int q = 0; q < per; ++q) {
+                const int cw = (warp * per + q) * 8;
+                const int col = j0 + cw + 2 * t;
+                uint32_t tg[2];
+                fetch(tg, 2, col);
+                double acc[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    if (ks < nks)
+                        dmma_8x8x4(acc, at[ks], Bst[(4 * ks + t) * TB + cw + g]);
+                emit(acc[0], tg[0], 2, col);
+                emit(acc[1], tg[1], 2, col + 1);
+            }
         }
     }
 }

@@ -185,6 +185,9 @@ struct f2_sigma {
     DevBuf<uint32_t> tgt; // [M][nbs] beta replacement table
     int tgt_pair = 0;
     int t3_ns = 2;
+    bool t3_tail = false;  // last <= 8 integral rows spread over the warps
+    bool fold_ok = false;  // alpha same-spin term can ride in the opposite-spin kernel (one GPU)
+    DevBuf<double> kk2, Wfold; // 2 kk_ij / na per integral row; beta W with h - 2 kk folded
     int M = 0, P[2] = {0, 0};
     bool compressed = true;
     // opposite-spin kernel shape
@@ -304,10 +307,34 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
         b.tgt_pair = pair ? 1 : 0;
     }
 
-    // same-spin integrals: antisymmetrised pairs with the one-electron operator folded in
-    for (int spin = 0; spin < 2; ++spin) {
+    // kk_ij = h_ij - 1/2 sum_m (im|mj): the one-electron operator of the E_ij E_kl form
+    std::vector<double> kk(std::max(n2, 1), 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double x = H[i * n + j];
+            for (int m = 0; m < n; ++m)
+                x -= 0.5 * v(i, m, m, j);
+            kk[i * n + j] = x;
+        }
+    {
+        std::vector<double> kk2(std::max(b.M, 1), 0.0);
+        if (h.na >= 1)
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j)
+                    kk2[rowmap[i * n + j]] = 2.0 * kk[i * n + j] / h.na;
+        b.kk2.upload(kk2);
+    }
+
+    // same-spin integrals: antisymmetrised pairs with the one-electron operator folded in.
+    // variant 2 (beta only): one-electron matrix h - 2 kk, used when the opposite-spin kernel also
+    // carries the alpha same-spin term (its beta scatter then leaves an extra 2 kk one-electron term)
+    for (int variant = 0; variant < 3; ++variant) {
+        const int spin = variant == 0 ? 0 : 1;
         const int ne = spin == 0 ? h.na : h.nb;
-        std::vector<double> W;
+        std::vector<double> W, h1(std::max(n2, 1));
+        for (int i = 0; i < n2; ++i)
+            h1[i] = variant == 2 ? H[i] - 2.0 * kk[i] : H[i];
+        const double* H = h1.data();
         if (ne == 1) {
             b.P[spin] = n;
             W.assign(H, H + static_cast<size_t>(n) * n);
@@ -335,7 +362,10 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
         } else {
             b.P[spin] = 0;
         }
-        b.W[spin].upload(W);
+        if (variant == 2)
+            b.Wfold.upload(W);
+        else
+            b.W[spin].upload(W);
     }
 
     // determinant-energy tables
@@ -385,18 +415,24 @@ void plan_t3_shape(f2_sigma& b) {
         throw std::runtime_error("CISigmaBuilder: more than 128 single replacements per alpha string "
                                  "is not supported by the opposite-spin kernel");
     b.t3_ks = round_ks(L.as_max);
-    const int KP = b.t3_ks * 4;
     const int MT = (b.M + 15) / 16;
     const int maxw = b.t3_ks <= 24 ? 12 : 10;
     const size_t nclsB = h.nclsB();
     const int msplit = (MT + maxw - 1) / maxw;
     b.t3_warps = (MT + msplit - 1) / msplit;
     b.t3_msplit = msplit;
-    auto smem_for = [&](int ns) {
-        return size_t(ns) * KP * TB * 8 + size_t(KP) * 8 + nclsB * 8 + size_t(KP) * 4 + 64;
-    };
-    b.t3_ns = smem_for(3) <= 227 * 1024 ? 3 : 2;
-    b.t3_smem = smem_for(b.t3_ns);
+    // a last tile of at most 8 rows is spread over the other warps when that balances the four SM
+    // sub-partitions (4 or 8 warps left)
+    b.t3_tail = msplit == 1 && (b.M - (MT - 1) * 16) <= 8 && (MT - 1 == 4 || MT - 1 == 8);
+    if (b.t3_tail)
+        b.t3_warps = MT - 1;
+    const int rows = b.t3_warps * 16 + (b.t3_tail ? 8 : 0);
+    b.t3_ns = t3_smem_bytes(b.t3_ks, 3, static_cast<int>(nclsB), rows) <= 227 * 1024 ? 3 : 2;
+    b.t3_smem = t3_smem_bytes(b.t3_ks, b.t3_ns, static_cast<int>(nclsB), rows);
+    // the alpha same-spin term can be folded in when every single replacement of every alpha string
+    // stays in the string space (no GAS restriction), so that E_ij E_kl needs no outside intermediate
+    b.fold_ok = L.as_ent.size() == static_cast<size_t>(h.nas) * (h.na * (h.norb - h.na) + h.na) &&
+                std::getenv("F2_NO_FOLD") == nullptr;
     if (b.t3_smem > 227 * 1024)
         throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
 }
@@ -668,31 +704,42 @@ void plan_hdiag(f2_sigma& b) {
     b.hd_blocks.upload(hb);
 }
 
-template <int KS, bool AL16, int NS>
+template <int KS, bool AL16, int NS, bool TAIL>
 void launch_t3_inst(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
     const dim3 grid(nitems), block(b.t3_warps * 32);
-    F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, AL16, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, AL16, NS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(b.t3_smem)));
-    t3_kernel<KS, AL16, NS><<<grid, block, b.t3_smem, st>>>(p);
+    t3_kernel<KS, AL16, NS, TAIL><<<grid, block, b.t3_smem, st>>>(p);
     b.launches += 1;
+}
+
+template <int KS, bool AL16>
+void launch_t3_al(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
+    if (b.t3_tail) {
+        if constexpr (KS <= 24) { // the tail strip costs KS more registers; 8 warps keep that affordable
+            if (b.t3_ns == 3)
+                launch_t3_inst<KS, AL16, 3, true>(b, p, nitems, st);
+            else
+                launch_t3_inst<KS, AL16, 2, true>(b, p, nitems, st);
+            return;
+        }
+    }
+    if (b.t3_ns == 3)
+        launch_t3_inst<KS, AL16, 3, false>(b, p, nitems, st);
+    else
+        launch_t3_inst<KS, AL16, 2, false>(b, p, nitems, st);
 }
 
 template <int KS>
 void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
-    if (b.D->al16) {
-        if (b.t3_ns == 3)
-            launch_t3_inst<KS, true, 3>(b, p, nitems, st);
-        else
-            launch_t3_inst<KS, true, 2>(b, p, nitems, st);
-    } else {
-        if (b.t3_ns == 3)
-            launch_t3_inst<KS, false, 3>(b, p, nitems, st);
-        else
-            launch_t3_inst<KS, false, 2>(b, p, nitems, st);
-    }
+    if (b.D->al16)
+        launch_t3_al<KS, true>(b, p, nitems, st);
+    else
+        launch_t3_al<KS, false>(b, p, nitems, st);
 }
 
-void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma, cudaStream_t st) {
+void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma, bool fold,
+               cudaStream_t st) {
     if (P.nitems == 0)
         return;
     const CIStringsHost& h = *b.S->host;
@@ -707,6 +754,9 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     p.as_ent = D.as_ent.p;
     p.tgt = b.tgt.p;
     p.tgt_pair = b.tgt_pair;
+    p.fold = fold ? 1 : 0;
+    p.kk2 = b.kk2.p;
+    p.rowmap = b.rowmap.p;
     {
         const char* e = std::getenv("F2_T3_DBG");
         p.dbg = e ? std::atoi(e) : 0;
@@ -755,7 +805,7 @@ void launch_ss_ks(const SSParams& p, bool al16, dim3 grid, cudaStream_t st) {
 
 // all colours of one spin for one plan
 void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const double* X, double* Y,
-                      cudaStream_t st) {
+                      const double* W, cudaStream_t st) {
     const CIStringsHost& h = *b.S->host;
     const DeviceLists& L = h.device_lists();
     const DevStrings& D = *b.D;
@@ -774,7 +824,7 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
     p.g_ldx = plan.g_ldx.p;
     p.g_ldy = plan.g_ldy.p;
     p.tiles = plan.tiles.p;
-    p.W = b.W[spin].p;
+    p.W = W;
     p.P = b.P[spin];
     p.ngroups = plan.ngroups;
     const auto& cptr = L.h2_color_ptr[spin];
@@ -842,10 +892,11 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         b.launches += 1;
     }
     F2_CUDA(cudaEventRecord(b.ev[1], st));
-    if (h.na >= 1) {
+    const bool fold = b.fold_ok && P.world == 1 && P.nitems > 0;
+    if (h.na >= 1 && !fold) {
         if (P.world > 1)
             F2_CUDA(cudaMemsetAsync(yexch, 0, static_cast<size_t>(P.y_size) * sizeof(double), st));
-        launch_same_spin(b, 0, P.alpha_plan, C, P.world == 1 ? sigma : yexch, st);
+        launch_same_spin(b, 0, P.alpha_plan, C, P.world == 1 ? sigma : yexch, b.W[0].p, st);
     }
     F2_CUDA(cudaEventRecord(b.ev[2], st));
     for (const auto& bp : P.beta_passes) {
@@ -854,11 +905,11 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(C, b.XT.p, bp->tr.p, bp->ntr);
         b.launches += 2;
         F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
-        launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, st);
+        launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, fold ? b.Wfold.p : b.W[1].p, st);
         transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
-    launch_t3(b, P, C, sigma, st);
+    launch_t3(b, P, C, sigma, fold, st);
     F2_CUDA(cudaEventRecord(b.ev[4], st));
     F2_CUDA(cudaGetLastError());
     b.ev_pending = true;
