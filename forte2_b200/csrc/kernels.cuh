@@ -39,6 +39,19 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// red.global.add.f64 executed only where the predicate holds (no branch, no return value)
+__device__ __forceinline__ void red_add_if(double* addr, double v, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}"
+                 ::"l"(addr), "d"(v), "r"(static_cast<int>(ok))
+                 : "memory");
+}
+// same, valid where the packed replacement target x is not the all-ones filler
+__device__ __forceinline__ void red_add_target(double* addr, double v, uint32_t x) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0xffffffff;\n\t@p red.global.add.f64 [%0], %1;\n\t}"
+                 ::"l"(addr), "d"(v), "r"(x)
+                 : "memory");
+}
+
 struct T3Params {
     const double* C;
     double* sigma;
@@ -55,7 +68,6 @@ struct T3Params {
     const double* Vx; // [M][norb*norb]  Vx[m(i,j)][k*norb+l] = <k i | l j>
     int M;
     int tgt_pair; // 1: table rows and class offsets are even, two targets per 8-byte load
-    int dbg;      // diagnosis only (F2_T3_DBG): bit 0 skip the atomics, bit 1 skip the table loads
     // alpha same-spin folding (complete alpha string space, one GPU): the accumulators hold
     // Z = G + 2 kk C[Ia] and every row m = (ij) is also added, halved, to sigma[E_ij Ia, :]
     int fold;
@@ -86,7 +98,9 @@ constexpr size_t t3_smem_bytes(int ks, int ns, int nclsB, int rows) {
 // TAIL: the last (at most 8) rows of the integral matrix do not get a warp of their own -- that would
 // leave one SM sub-partition with an extra warp of tensor work -- but are spread over the warps, each
 // taking an 8-row x (64/nwarps)-column strip (m8n8k4).
-template <int KS, bool AL16, int NS, bool TAIL>
+// ONEB: a single beta class (no symmetry / GAS split of the beta strings) and paired table loads: the
+// scatter target is sigma[Ia, :] itself, so an emit is mask + address + sign flip + predicated RED.
+template <int KS, bool AL16, int NS, bool TAIL, bool ONEB>
 __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_kernel(const T3Params p) {
     constexpr int KP = KS * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -230,30 +244,33 @@ __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_k
     // sigma row and sign of the alpha replacement E_ij Ia
     constexpr int NR = TAIL ? 3 : 2;
     const int rowm[3] = {m0 + g, m0 + g + 8, mt};
-    bool row_ok[NR];
+    bool row_ok[NR], aok[NR];
     const uint32_t* trow[NR];
-    long long abase[NR];
+    double* aptr[NR];
     double ahalf[NR];
 #pragma unroll
     for (int h = 0; h < NR; ++h) {
         row_ok[h] = rowm[h] < p.M;
         trow[h] = p.tgt + static_cast<size_t>(row_ok[h] ? rowm[h] : 0) * p.nbs + p.b_off[cBp];
-        abase[h] = -1;
+        aok[h] = false;
+        aptr[h] = p.sigma;
         ahalf[h] = 0.5;
         if (p.fold && row_ok[h]) {
             const int r = arow[rowm[h] - mbase];
-            if (r >= 0) {
-                abase[h] = krow[r];
+            if (r >= 0 && krow[r] >= 0) {
+                aok[h] = true;
+                aptr[h] = p.sigma + krow[r];
                 ahalf[h] = (kinfo[r] >> 31) ? -0.5 : 0.5;
             }
         }
     }
+    double* const srow = p.sigma + (ONEB ? rowbase[0] : 0); // ONEB: the host guarantees the block exists
 
     auto fetch = [&](uint32_t (&tg)[2], int h, int col) {
         tg[0] = kNoTarget;
         tg[1] = kNoTarget;
-        if (row_ok[h] && !(p.dbg & 2)) {
-            if (p.tgt_pair) {
+        if (row_ok[h]) {
+            if (ONEB || p.tgt_pair) {
                 if (col < nBp) { // nBp even: col + 1 is in range too
                     const uint2 v = *reinterpret_cast<const uint2*>(trow[h] + col);
                     tg[0] = v.x;
@@ -267,17 +284,32 @@ __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_k
             }
         }
     };
-    // sigma[Ia, Ib] += sign * Z[m, Jb]  (beta replacement), sigma[E_ij Ia, Jb] += sign/2 * Z[m, Jb]
-    auto emit = [&](double v, uint32_t x, int h, int col) {
-        if (p.dbg & 1)
-            return;
-        if (x != kNoTarget) {
-            const long long base = rowbase[(x >> 20) & 0x7ff];
-            if (base >= 0)
-                atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
+    // beta replacement: sigma[Ia, Ib] += sign * Z[m, Jb]
+    auto emit = [&](double v, uint32_t x) {
+        if constexpr (ONEB) {
+            // address = row + 8 * (x & 0xfffff) in one mad.wide; sign = bit 31 of x onto bit 63 of v
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, lo, hi;\n\t.reg .b64 a;\n\t.reg .f64 sv;\n\t"
+                         "setp.ne.u32 p, %2, 0xffffffff;\n\t"
+                         "and.b32 t, %2, 0xfffff;\n\t"
+                         "mad.wide.u32 a, t, 8, %0;\n\t"
+                         "mov.b64 {lo, hi}, %1;\n\t"
+                         "and.b32 t, %2, 0x80000000;\n\t"
+                         "xor.b32 hi, hi, t;\n\t"
+                         "mov.b64 sv, {lo, hi};\n\t"
+                         "@p red.global.add.f64 [a], sv;\n\t}"
+                         ::"l"(srow), "d"(v), "r"(x)
+                         : "memory");
+        } else {
+            if (x != kNoTarget) {
+                const long long base = rowbase[(x >> 20) & 0x7ff];
+                if (base >= 0)
+                    atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
+            }
         }
-        if (abase[h] >= 0 && col < nBp)
-            atomicAdd(p.sigma + abase[h] + col, ahalf[h] * v);
+    };
+    // folded alpha replacement: sigma[E_ij Ia, Jb] += sign/2 * Z[m, Jb]
+    auto emit_fold = [&](double v, int h, int col, bool full) {
+        red_add_if(aptr[h] + col, ahalf[h] * v, aok[h] && (full || col < nBp));
     };
 
 #pragma unroll
@@ -289,6 +321,7 @@ __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_k
         load_tile(tile + NS - 1);
         const double* Bst = Bs + (tile % NS) * KP * TB;
         const int j0 = tile * NT;
+        const bool full = j0 + NT <= nBp;
 #pragma unroll 1
         for (int nh = 0; nh < 2; ++nh) { // two halves of the tile keep the accumulators at 16 regs
             const int c0 = j0 + nh * (NT / 2) + 2 * t;
@@ -318,7 +351,29 @@ __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_k
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        emit(acc[nt][2 * h + c], tg[nt][h][c], h, c0 + nt * 8 + c);
+                        emit(acc[nt][2 * h + c], tg[nt][h][c]);
+            if (p.fold) {
+                if (full) { // one (divergent) branch per row, then unconditional REDs at fixed offsets
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (aok[h]) {
+                            double* dst = aptr[h] + c0;
+#pragma unroll
+                            for (int nt = 0; nt < NT / 16; ++nt)
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+                                    atomicAdd(dst + nt * 8 + c, ahalf[h] * acc[nt][2 * h + c]);
+                        }
+                } else {
+#pragma unroll
+                    for (int nt = 0; nt < NT / 16; ++nt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                emit_fold(acc[nt][2 * h + c], h, c0 + nt * 8 + c, false);
+                }
+            }
         }
         if constexpr (TAIL) {
             // this warp's strip of the shared 8-row tail: columns [cw, cw + 64/nwarps)
@@ -334,8 +389,12 @@ __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_k
                 for (int ks = 0; ks < KS; ++ks)
                     if (ks < nks)
                         dmma_8x8x4(acc, at[ks], Bst[(4 * ks + t) * TB + cw + g]);
-                emit(acc[0], tg[0], 2, col);
-                emit(acc[1], tg[1], 2, col + 1);
+                emit(acc[0], tg[0]);
+                emit(acc[1], tg[1]);
+                if (p.fold) {
+                    emit_fold(acc[0], 2, col, full);
+                    emit_fold(acc[1], 2, col + 1, full);
+                }
             }
         }
     }

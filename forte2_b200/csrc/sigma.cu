@@ -704,13 +704,24 @@ void plan_hdiag(f2_sigma& b) {
     b.hd_blocks.upload(hb);
 }
 
+template <int KS, bool AL16, int NS, bool TAIL, bool ONEB>
+void launch_t3_oneb(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
+    const dim3 grid(nitems), block(b.t3_warps * 32);
+    F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, AL16, NS, TAIL, ONEB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(b.t3_smem)));
+    t3_kernel<KS, AL16, NS, TAIL, ONEB><<<grid, block, b.t3_smem, st>>>(p);
+    b.launches += 1;
+}
+
 template <int KS, bool AL16, int NS, bool TAIL>
 void launch_t3_inst(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
-    const dim3 grid(nitems), block(b.t3_warps * 32);
-    F2_CUDA(cudaFuncSetAttribute(t3_kernel<KS, AL16, NS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(b.t3_smem)));
-    t3_kernel<KS, AL16, NS, TAIL><<<grid, block, b.t3_smem, st>>>(p);
-    b.launches += 1;
+    if constexpr (AL16) { // the single-beta-class fast emit needs the paired table loads
+        if (p.nclsB == 1 && p.tgt_pair) {
+            launch_t3_oneb<KS, AL16, NS, TAIL, true>(b, p, nitems, st);
+            return;
+        }
+    }
+    launch_t3_oneb<KS, AL16, NS, TAIL, false>(b, p, nitems, st);
 }
 
 template <int KS, bool AL16>
@@ -757,10 +768,6 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     p.fold = fold ? 1 : 0;
     p.kk2 = b.kk2.p;
     p.rowmap = b.rowmap.p;
-    {
-        const char* e = std::getenv("F2_T3_DBG");
-        p.dbg = e ? std::atoi(e) : 0;
-    }
     p.nbs = h.nbs;
     p.blk_off = D.blk_off.p;
     p.sblk_off = P.sblk_off.p;
@@ -1134,7 +1141,7 @@ int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_loc
 
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
     out5[0] = h->M;
-    out5[1] = static_cast<int64_t>(h->t3_warps) * 16 * h->t3_msplit;
+    out5[1] = (static_cast<int64_t>(h->t3_warps) * 16 + (h->t3_tail ? 8 : 0)) * h->t3_msplit;
     out5[2] = h->S->host->device_lists().as_max;
     out5[3] = h->single ? h->single->t3_kcols : 0;
     out5[4] = h->compressed ? 1 : 0;

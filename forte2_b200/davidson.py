@@ -1,0 +1,440 @@
+"""Device-resident Davidson-Liu eigensolver: the GPU counterpart of forte2's
+`forte2.helpers.davidsonliu.DavidsonLiuSolver` (forte2/helpers/davidsonliu.py:12-484).
+
+Same constructor arguments, same `add_sigma_builder / add_h_diag / add_guesses / add_project_out /
+solve` calls, same iteration (subspace matrix, Ritz pairs, preconditioned residuals, collapse,
+iterated Gram-Schmidt with the reference's thresholds), but
+
+* every vector lives in HBM as a contiguous row of a `(max_subspace, size)` torch CUDA tensor (the
+  reference keeps `(size, max_subspace)` numpy arrays whose columns are strided,
+  davidsonliu.py:75-83), so the sigma builder receives contiguous device vectors;
+* every O(size) step is one streaming CUDA kernel of the C ABI (`f2_dl_dots`, `f2_dl_combine`,
+  `f2_dl_residual`, `f2_dl_scale`; forte2_b200/csrc/davidson.cu); only the (<= 16 x 16) subspace
+  problem is solved on the host;
+* with `comm` (a torch.distributed process group) the vectors are the rank's row slab of the CI
+  vector and the small reductions are all-reduced.
+
+`sigma_builder(basis_block, sigma_block)` receives two `(m, size)` CUDA tensors (row i = vector i).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class DavidsonLiuParams:
+    """forte2/base_classes/params.py:107-146 (same names, defaults and validation)."""
+    guess_per_root: int = 2
+    ndets_per_guess: int = 10
+    collapse_per_root: int = 2
+    basis_per_root: int = 4
+    maxiter: int = 100
+    e_tol: float = 1e-12
+    r_tol: float = 1e-6
+
+    def __post_init__(self):
+        if self.collapse_per_root < 1:
+            raise ValueError(f"Davidson-Liu solver: collapse_per_root ({self.collapse_per_root}) must be greater "
+                             "than or equal to 1.")
+        if self.basis_per_root < self.collapse_per_root + 1:
+            raise ValueError(f"Davidson-Liu solver: basis_per_root ({self.basis_per_root}) must be greater than or "
+                             f"equal to collapse_per_root + 1 ({self.collapse_per_root + 1}).")
+
+
+class _Kernels:
+    """Thin typed wrappers over the f2_dl_* entry points for row-major (nvec, size) CUDA tensors."""
+
+    def __init__(self, torch, device, comm=None):
+        self.torch, self.device, self.comm = torch, device, comm
+        self.L = _lib.lib()
+        self.work = torch.empty(int(self.L.f2_dl_workspace_doubles()), dtype=torch.float64, device=device)
+        self.small = torch.empty(256, dtype=torch.float64, device=device)
+        self.launches = 0
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _reduce(self, t):
+        if self.comm is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm)
+        return t.cpu().numpy().copy()
+
+    @staticmethod
+    def _rows(t):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype.is_floating_point and t.element_size() == 8
+        return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else t.shape[1]), t.shape[0], t.shape[1]
+
+    def dots(self, A, X):
+        """(p, q) numpy matrix of <A_i | X_j>, summed over ranks."""
+        ap, lda, p, n = self._rows(A)
+        xp, ldx, q, n2 = self._rows(X)
+        assert n == n2
+        out = np.zeros((p, q))
+        for i0 in range(0, p, 16):
+            pc = min(16, p - i0)
+            for j0 in range(0, q, 16):
+                qc = min(16, q - j0)
+                res = self.small[: pc * qc]
+                _lib.check(self.L.f2_dl_dots(ap + 8 * lda * i0, lda, pc, xp + 8 * ldx * j0, ldx, qc, n,
+                                             res.data_ptr(), self.work.data_ptr(), self._stream()))
+                self.launches += 2 * ((qc + 3) // 4)
+                out[i0:i0 + pc, j0:j0 + qc] = self._reduce(res).reshape(pc, qc)
+        return out
+
+    def combine(self, A, coef, Y, beta=0.0, want_sumsq=False):
+        """Y_j = beta Y_j + sum_i coef[i, j] A_i; rows of Y may alias rows of A. Returns |Y_j|^2 or None."""
+        yp, ldy, k, n = self._rows(Y)
+        if A is None or A.shape[0] == 0:
+            ap, lda, p = yp, ldy, 0
+            coef = np.zeros((1, k))
+        else:
+            ap, lda, p, n2 = self._rows(A)
+            assert n == n2
+        assert p <= 16 and k <= 16
+        coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(max(p, 1), k)
+        ss = self.small[:k] if want_sumsq else None
+        _lib.check(self.L.f2_dl_combine(ap, lda, p, coef.ctypes.data_as(_lib.f64p), yp, ldy, k, float(beta), n,
+                                        ss.data_ptr() if want_sumsq else None, self.work.data_ptr(),
+                                        self._stream()))
+        self.launches += 2 if want_sumsq else 1
+        return self._reduce(ss) if want_sumsq else None
+
+    def residual(self, B, S, alpha, lam, hdiag, R, thresh):
+        bp, ld, m, n = self._rows(B)
+        sp, lds, m2, _ = self._rows(S)
+        rp, ldr, k, _ = self._rows(R)
+        assert m == m2 and (ld == lds or m == 1) and m <= 16 and k <= 16
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(m, k)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(k)
+        out = self.small[:k]
+        _lib.check(self.L.f2_dl_residual(bp, sp, ld, m, alpha.ctypes.data_as(_lib.f64p),
+                                         lam.ctypes.data_as(_lib.f64p),
+                                         hdiag.data_ptr() if hdiag is not None else None, rp, ldr, k,
+                                         float(thresh), n, out.data_ptr(), self.work.data_ptr(), self._stream()))
+        self.launches += 2
+        return self._reduce(out)
+
+    def scale(self, v, s):
+        assert v.dim() == 1 and v.stride(0) == 1
+        _lib.check(self.L.f2_dl_scale(v.data_ptr(), float(s), v.shape[0], self._stream()))
+        self.launches += 1
+
+
+class DavidsonLiuSolver:
+    """Davidson-Liu on device vectors. See the module docstring; reference: davidsonliu.py:12-484."""
+
+    def __init__(self, size, nroot, davidson_liu_params=None, energy_shift=None, log_level=3, dtype=np.float64,
+                 device=None, comm=None, global_size=None, log=None, _kernels=None):
+        import torch
+        self.torch = torch
+        self.size, self.nroot = int(size), int(nroot)
+        self.davidson_liu_params = davidson_liu_params or DavidsonLiuParams()
+        self.energy_shift, self.log_level, self.comm = energy_shift, log_level, comm
+        self.global_size = int(global_size) if global_size is not None else self.size
+        if np.dtype(dtype) != np.float64:
+            raise TypeError("the device Davidson-Liu solver is float64 only")
+        p = self.davidson_liu_params
+        self.collapse_per_root, self.basis_per_root = p.collapse_per_root, p.basis_per_root
+        self.maxiter, self.e_tol, self.r_tol = p.maxiter, p.e_tol, p.r_tol
+        if self.global_size <= 0:
+            raise ValueError("Davidson-Liu solver called with space of dimension smaller than 1.")
+        if self.nroot <= 0:
+            raise ValueError("Davidson-Liu solver called with zero roots.")
+        self.collapse_size = min(self.collapse_per_root * self.nroot, self.global_size)
+        self.max_subspace_size = min(self.basis_per_root * self.nroot, self.global_size)
+        if self.max_subspace_size > 16:
+            raise ValueError("the device Davidson-Liu solver holds at most 16 subspace vectors "
+                             f"(basis_per_root * nroot = {self.max_subspace_size})")
+        # _kernels: test hook (tests/ inject a host stand-in for the four streaming kernels to exercise the
+        # iteration logic without a GPU); the product path below has no CPU fallback
+        if _kernels is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("forte2_b200: no CUDA device available (the Davidson-Liu solver has no CPU "
+                                   "fallback)")
+            if device is None:
+                device = torch.cuda.current_device()
+            self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        else:
+            self.device = torch.device(device if device is not None else "cpu")
+        kw = dict(dtype=torch.float64, device=self.device)
+        self.b = torch.zeros((self.max_subspace_size, self.size), **kw)
+        self.sigma = torch.zeros((self.max_subspace_size, self.size), **kw)
+        self.r = torch.zeros((self.nroot, self.size), **kw)
+        self.h_diag = None
+        self.G = np.zeros((self.max_subspace_size, self.max_subspace_size))
+        self.alpha = np.zeros_like(self.G)
+        self.lam = np.zeros(self.max_subspace_size)
+        self.lam_old = np.zeros_like(self.lam)
+        self.schmidt_discard_threshold = 1e-8
+        self.schmidt_orthogonality_threshold = 1e-12
+        self.preconditioner_denom_threshold = 1e-8
+        self.basis_size = 0
+        self.sigma_size = 0
+        self._build_sigma = None
+        self._executed = False
+        self._guesses = None
+        self._proj_out = None
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(20261017)
+        self.k = _kernels if _kernels is not None else _Kernels(torch, self.device, comm)
+        self._log = log
+        self.iter_times = []
+        self.history = []
+
+    # ---- reference interface ------------------------------------------------------------------
+    def add_sigma_builder(self, sigma_builder):
+        self._build_sigma = sigma_builder
+
+    def add_h_diag(self, h_diag):
+        t = self._as_device(h_diag)
+        if t.shape != (self.size,):
+            raise ValueError("h_diag must be shape (size,)")
+        self.h_diag = t.contiguous()
+
+    def add_guesses(self, guesses):
+        """numpy (size, n_guess) as the reference takes them, or a CUDA tensor (n_guess, size)."""
+        torch = self.torch
+        if isinstance(guesses, np.ndarray):
+            if guesses.ndim != 2 or guesses.shape[0] != self.size:
+                raise ValueError("guesses must be shape (size, n_guess)")
+            g = torch.from_numpy(np.ascontiguousarray(guesses.T, dtype=np.float64)).to(self.device)
+        else:
+            g = guesses
+            if g.dim() != 2 or g.shape[1] != self.size:
+                raise ValueError("device guesses must be shape (n_guess, size)")
+        if not 1 <= g.shape[0] <= self.max_subspace_size:
+            raise ValueError("between 1 and max_subspace_size guesses are needed")
+        self._guesses = g
+
+    def add_project_out(self, project_out):
+        """Vectors to project out of sigma and of the corrections (davidsonliu.py:147-182); each may be
+        shorter than `size` (zero padded).  Orthonormalised on the host like the reference (QR)."""
+        if len(project_out) == 0:
+            return
+        if self.comm is not None:
+            raise NotImplementedError("project_out is not supported with sharded vectors")
+        arrs = [np.asarray(v.cpu() if hasattr(v, "cpu") else v, dtype=np.float64) for v in project_out]
+        for v in arrs:
+            if len(v) > self.size:
+                raise ValueError(f"Each project_out vector must have length at most {self.size}, but got {len(v)}")
+        Q, _ = np.linalg.qr(np.stack(arrs, axis=1), mode="reduced")
+        self._proj_out = self.torch.from_numpy(np.ascontiguousarray(Q.T)).to(self.device)
+
+    def do_project_out(self, rows):
+        if self._proj_out is None or rows.shape[0] == 0:
+            return
+        psize = self._proj_out.shape[1]
+        sub = rows[:, :psize]
+        for u in self._proj_out:
+            u2 = u.unsqueeze(0)
+            for j in range(rows.shape[0]):
+                tgt = sub[j:j + 1]
+                c = self.k.dots(u2, tgt)
+                self.k.combine(u2, -c, tgt, beta=1.0)
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _as_device(self, x):
+        torch = self.torch
+        if isinstance(x, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
+        return x.to(self.device, dtype=torch.float64)
+
+    def _say(self, msg):
+        if self._log is not None:
+            self._log(msg)
+
+    def _add_and_orthonormalize(self, cand_rows):
+        """davidsonliu.py:415-484: candidates (rows) are orthonormalised one by one against
+        b[:basis_size] and the rows accepted so far, and appended to b.  Returns the number added.
+        Classical Gram-Schmidt with re-orthogonalisation: each cycle is one f2_dl_dots and one
+        f2_dl_combine pass; the normalisation is carried as a pending factor and folded into the
+        next pass."""
+        added = 0
+        self._accepted = [False] * cand_rows.shape[0]
+        for j in range(cand_rows.shape[0]):
+            cur = self.basis_size + added
+            if cur >= self.max_subspace_size:
+                break
+            slot = self.b[cur:cur + 1]
+            slot.copy_(cand_rows[j:j + 1])
+            basis = self.b[:cur]
+            s = 1.0        # the candidate is s * slot
+            ok = False
+            normalised = False
+            for cycle in range(10):
+                if cur > 0:
+                    c = self.k.dots(basis, slot)[:, 0] * s
+                else:
+                    c = np.zeros(0)
+                if normalised and (cur == 0 or np.abs(c).max() < self.schmidt_orthogonality_threshold):
+                    ok = True
+                    break
+                ss = self.k.combine(basis if cur > 0 else None, -c.reshape(-1, 1), slot, beta=s, want_sumsq=True)
+                normv = float(np.sqrt(ss[0]))
+                if not np.isfinite(normv) or normv < self.schmidt_discard_threshold:
+                    break
+                s = 1.0 / normv
+                normalised = True
+            if ok:
+                if s != 1.0:
+                    self.k.scale(slot[0], s)
+                added += 1
+                self._accepted[j] = True
+        return added
+
+    def _events(self):
+        if self.device.type == "cuda":
+            return self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+
+        class _Wall:  # host stand-in used with the test hook
+            def record(self):
+                self.t = time.perf_counter()
+
+            def synchronize(self):
+                pass
+
+            def elapsed_time(self, other):
+                return (other.t - self.t) * 1e3
+        return _Wall(), _Wall()
+
+    def _random_rows(self, n):
+        t = self.torch.rand((n, self.size), dtype=self.torch.float64, device=self.device, generator=self._gen)
+        return t * 2.0 - 1.0
+
+    # ---- the solver ---------------------------------------------------------------------------
+    def solve(self):
+        torch = self.torch
+        if self._build_sigma is None:
+            raise ValueError("Sigma builder function is not set.")
+        if self.h_diag is None:
+            raise ValueError("Hamiltonian diagonal is not set.")
+        nroot = self.nroot
+
+        if not self._executed:
+            G = self._guesses if self._guesses is not None else self._random_rows(nroot)
+            G = G.clone()
+            self.do_project_out(G)
+            self.basis_size = 0
+            self.sigma_size = 0
+            self.basis_size = self._add_and_orthonormalize(G)
+            if self.basis_size == 0:
+                raise ValueError("no linearly independent guess vector")
+            self.lam_old[:] = 0.0
+            self.G[:] = 0.0
+        self.iter = 0
+        self.converged = False
+        self.iter_times = []
+        self.history = []
+        g_valid = self.sigma_size  # rows/columns of self.G that are up to date
+
+        for self.iter in range(self.maxiter):
+            t0 = time.perf_counter()
+            ev0, ev1 = self._events()
+            ev0.record()
+            # 2. sigma for the new basis vectors
+            m_new = self.basis_size - self.sigma_size
+            if m_new > 0:
+                Bblock = self.b[self.sigma_size:self.basis_size]
+                Sblock = self.sigma[self.sigma_size:self.basis_size]
+                self._build_sigma(Bblock, Sblock)
+                self.do_project_out(Sblock)
+                self.sigma_size = self.basis_size
+            m = self.basis_size
+            Bblk, Sblk = self.b[:m], self.sigma[:m]
+            # 3. subspace matrix: only the new columns are computed (the reference recomputes B^T S)
+            if g_valid < m:
+                cols = self.k.dots(Bblk, self.sigma[g_valid:m])  # (m, m - g_valid)
+                self.G[:m, g_valid:m] = cols
+                self.G[g_valid:m, :g_valid] = cols[:g_valid].T
+                g_valid = m
+            Gm = 0.5 * (self.G[:m, :m] + self.G[:m, :m].T)
+            lam, alpha = np.linalg.eigh(Gm)
+            if self.energy_shift is not None:
+                idx = np.argsort(np.abs(lam - self.energy_shift))
+                lam, alpha = lam[idx], alpha[:, idx]
+            self.lam[:m] = lam
+            self.alpha[:m, :m] = alpha
+            kr = min(nroot, m)
+            ar, lamr = alpha[:, :kr], lam[:kr]
+
+            # 4. residuals, their norms and the preconditioned corrections in one pass
+            rn2 = self.k.residual(Bblk, Sblk, ar, lamr, self.h_diag, self.r[:kr],
+                                  self.preconditioner_denom_threshold)
+            rnorms = np.sqrt(rn2)
+            avg_e = float(lamr.mean())
+            max_de = float(np.max(np.abs(lamr - self.lam_old[:kr])))
+            max_r = float(rnorms.max())
+            conv = (max_de < self.e_tol and max_r < self.r_tol) or (m == self.global_size)
+            if conv or self.iter == self.maxiter - 1:
+                self.converged = bool(conv)
+                ev1.record()
+                ev1.synchronize()
+                self.iter_times.append(ev0.elapsed_time(ev1) * 1e-3)
+                self.history.append((self.iter, avg_e, max_de, max_r, m, m_new))
+                break
+            # Root locking (a deliberate difference from davidsonliu.py:306-366): the reference adds a
+            # correction for every root and replaces a discarded one (norm < 1e-8 after projection, i.e. a
+            # root converged far below r_tol) by a random vector, which costs a sigma build and perturbs the
+            # other roots.  Here only roots that are not converged yet get a correction, the subspace is
+            # collapsed only when those do not fit, and a random vector replaces a discarded correction of
+            # an unconverged root only.  With every root active this is the reference's iteration.
+            de = np.abs(lamr - self.lam_old[:kr])
+            active = [j for j in range(kr) if rnorms[j] >= self.r_tol or de[j] >= self.e_tol]
+            self.lam_old[:kr] = lamr
+
+            # 5. collapse
+            if self.basis_size + len(active) > self.max_subspace_size:
+                k = min(self.collapse_size, self.basis_size)
+                ak = alpha[:, :k]
+                self.k.combine(Bblk, ak, self.b[:k])
+                self.k.combine(Sblk, ak, self.sigma[:k])
+                Gk = ak.T @ Gm @ ak
+                self.G[:] = 0.0
+                self.G[:k, :k] = Gk
+                self.basis_size = self.sigma_size = g_valid = k
+                m = k
+
+            # 6. corrections: project out, orthonormalise against the basis, append
+            to_add = min(len(active), self.max_subspace_size - self.basis_size)
+            if to_add == 0:
+                self.converged = True
+                break
+            if active[:to_add] != list(range(to_add)):
+                for dst, src in enumerate(active[:to_add]):  # dst <= src: compact the active rows
+                    if dst != src:
+                        self.r[dst].copy_(self.r[src])
+            R0 = self.r[:to_add]
+            self.do_project_out(R0)
+            added = self._add_and_orthonormalize(R0)
+            self.basis_size += added
+            msg = ""
+            missing = to_add - added
+            if missing > 0:
+                temp = self._random_rows(missing)
+                self.do_project_out(temp)
+                added2 = self._add_and_orthonormalize(temp)
+                self.basis_size += added2
+                msg = f"+{added2} rand"
+            ev1.record()
+            ev1.synchronize()
+            self.iter_times.append(ev0.elapsed_time(ev1) * 1e-3)
+            self.history.append((self.iter, avg_e, max_de, max_r, self.basis_size, m_new))
+            self._say(f"{self.iter:4d} {avg_e:20.12f} {max_de:+12.4e} {max_r:+12.4e} {self.basis_size:4d} "
+                      f"{time.perf_counter() - t0:10.4f} {msg}")
+
+        # final Ritz vectors, in place in the first nroot rows of b
+        m = self.basis_size
+        kr = min(nroot, m)
+        lamr = self.lam[:kr].copy()
+        self.k.combine(self.b[:m], self.alpha[:m, :kr], self.b[:kr])
+        evecs = self.b[:kr]
+        self.basis_size = kr
+        self.sigma_size = 0
+        self._executed = True
+        return lamr, evecs

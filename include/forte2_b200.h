@@ -116,6 +116,36 @@ int f2_sigma_part_layout(f2_sigma* h, int rank, int world, int64_t* sizes2, int6
 int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev, double* exch_dev,
                         int rank, int world, void* stream);
 
+/* <I|H|J> for the n determinants at the given CI-vector addresses, n x n row-major, on the HOST
+ * (SlaterRules::slater_rules, forte2/determinant/slater_rules.cc:123-245): the guess Hamiltonian of
+ * forte2/ci/ci.py:411-452.  H, V as in f2_sigma_create.  Needs no GPU. */
+int f2_slater_matrix(const f2_strings* h, double E, const double* H, const double* V,
+                     const int64_t* addresses, int n, double* out);
+
+/* ---- Davidson-Liu device primitives (forte2/helpers/davidsonliu.py:184-484) ----------------------
+ * The reference solver is numpy on (size, max_subspace) arrays; these are the streaming passes of
+ * its iteration on DEVICE vectors stored as contiguous rows (row i at base + i*ld).  At most 16
+ * vectors per side of a call.  work_dev: device scratch of f2_dl_workspace_doubles() doubles.
+ * Small coefficient matrices are HOST pointers (row-major), results of reductions are written to
+ * DEVICE memory (the caller all-reduces them across ranks when the vectors are sharded). */
+int64_t f2_dl_workspace_doubles(void);
+/* out_dev[i*q + j] = <A_i | X_j>   (subspace matrix B^T S, davidsonliu.py:257; Gram-Schmidt
+ * overlaps, davidsonliu.py:445-468) */
+int f2_dl_dots(const double* A, int64_t lda, int p, const double* X, int64_t ldx, int q, int64_t n,
+               double* out_dev, double* work_dev, void* stream);
+/* Y_j = beta*Y_j + sum_i coef[i*k + j] A_i, j < k; rows of Y may alias rows of A (in-place collapse,
+ * davidsonliu.py:389-413; Ritz vectors :376-378; projection against the basis :317).  sumsq_dev
+ * (may be NULL) receives |Y_j|^2. */
+int f2_dl_combine(const double* A, int64_t lda, int p, const double* coef_host, double* Y, int64_t ldy,
+                  int k, double beta, int64_t n, double* sumsq_dev, double* work_dev, void* stream);
+/* R_j = sum_i alpha[i*k+j] (S_i - lam_j B_i); rnorm2_dev[j] = |R_j|^2; then the preconditioner
+ * R_j <- R_j / (lam_j - hdiag) where |lam_j - hdiag| > denom_threshold, else 0
+ * (davidsonliu.py:266-283).  hdiag = NULL skips the preconditioner. */
+int f2_dl_residual(const double* B, const double* S, int64_t ld, int m, const double* alpha_host,
+                   const double* lam_host, const double* hdiag, double* R, int64_t ldr, int k,
+                   double denom_threshold, int64_t n, double* rnorm2_dev, double* work_dev, void* stream);
+int f2_dl_scale(double* v, double s, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

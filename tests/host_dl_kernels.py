@@ -1,0 +1,45 @@
+"""TEST INFRASTRUCTURE: a host (torch CPU) stand-in for the four streaming kernels of
+forte2_b200/csrc/davidson.cu, with the same call signatures as forte2_b200.davidson._Kernels.  It lets
+the CPU test-suite exercise the Davidson-Liu iteration logic (and, over gloo, its sharded form) without
+a GPU.  Never imported by the product."""
+import numpy as np
+import torch
+
+
+class HostKernels:
+    def __init__(self, comm=None):
+        self.comm = comm
+        self.launches = 0
+
+    def _reduce(self, arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        if self.comm is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm)
+        return t.numpy().copy()
+
+    def dots(self, A, X):
+        return self._reduce((A @ X.T).numpy())
+
+    def combine(self, A, coef, Y, beta=0.0, want_sumsq=False):
+        k = Y.shape[0]
+        new = beta * Y if beta != 0.0 else torch.zeros_like(Y)
+        if A is not None and A.shape[0] > 0:
+            c = torch.from_numpy(np.ascontiguousarray(coef, dtype=np.float64).reshape(A.shape[0], k))
+            new = new + c.T @ A
+        Y.copy_(new)
+        return self._reduce((Y * Y).sum(dim=1).numpy()) if want_sumsq else None
+
+    def residual(self, B, S, alpha, lam, hdiag, R, thresh):
+        a = torch.from_numpy(np.ascontiguousarray(alpha, dtype=np.float64).reshape(B.shape[0], R.shape[0]))
+        l = torch.from_numpy(np.ascontiguousarray(lam, dtype=np.float64))
+        r = a.T @ S - l[:, None] * (a.T @ B)
+        rn2 = (r * r).sum(dim=1).numpy()
+        if hdiag is not None:
+            d = l[:, None] - hdiag[None, :]
+            r = torch.where(d.abs() > thresh, r / d, torch.zeros_like(r))
+        R.copy_(r)
+        return self._reduce(rn2)
+
+    def scale(self, v, s):
+        v.mul_(s)
