@@ -185,6 +185,16 @@ struct f2_sigma {
     DevBuf<uint32_t> tgt; // [M][nbs] beta replacement table
     int tgt_pair = 0;
     int t3_ns = 2;
+    // gather-form opposite-spin kernel (t3g_kernel): single determinant block whose rows fit in smem
+    bool t3g = false;
+    int t3g_nm16 = 0, t3g_has8 = 0, t3g_astride = 0, t3g_mpad = 0;
+    int64_t t3g_gld = 0;
+    size_t t3g_smem = 0;
+    DevBuf<uint32_t> gsrc;
+    DevBuf<double> VxT;
+    bool t3_v4 = false;    // warp-specialised opposite-spin kernel (t3v4_kernel) is applicable
+    int t3_v4_ns = 3;
+    size_t t3_v4_smem = 0;
     bool t3_tail = false;  // last <= 8 integral rows spread over the warps
     bool fold_ok = false;  // alpha same-spin term can ride in the opposite-spin kernel (one GPU)
     DevBuf<double> kk2, Wfold; // 2 kk_ij / na per integral row; beta W with h - 2 kk folded
@@ -277,6 +287,13 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
         }
     b.Vx.upload(Vx);
     b.rowmap.upload(rowmap);
+    {
+        std::vector<double> VxT(Vx.size());
+        for (int m = 0; m < b.M; ++m)
+            for (int kl = 0; kl < n2; ++kl)
+                VxT[static_cast<size_t>(kl) * b.M + m] = Vx[static_cast<size_t>(m) * n2 + kl];
+        b.VxT.upload(VxT);
+    }
 
     // beta replacement table: (row of the integral matrix, source string Jb) -> target string Ib.
     // A row holds at most one replacement per source string (E_ij and E_ji exclude each other).
@@ -301,6 +318,27 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
                                           (static_cast<uint32_t>((ent >> 56) & 1) << 31);
             }
         b.tgt.upload(T);
+        // inverse table for the gather form: (row m, target Ib) -> source Jb with <Ib|E_m|Jb> = sign;
+        // "no source" points at the zero slot behind the staged row (index nbs).  Single beta class only.
+        b.gsrc.release();
+        if (B.nclasses() == 1 && h.nclsA() == 1 && nbs < (size_t(1) << 20)) {
+            const int Mpad = (b.M + 3) / 4 * 4;
+            const size_t gld = (nbs + 15) / 16 * 16;
+            std::vector<uint32_t> Gt(std::max<size_t>(size_t(Mpad) * gld, 1), static_cast<uint32_t>(nbs));
+            for (int m = 0; m < b.M; ++m)
+                for (size_t gJ = 0; gJ < nbs; ++gJ) {
+                    const uint32_t x = T[size_t(m) * nbs + gJ];
+                    if (x == kNoTarget)
+                        continue;
+                    const size_t Ib = x & 0xfffffu;
+                    // E_m Jb = sign Ib.  With pair-compressed rows E_ij and E_ji share row m; otherwise the
+                    // gather row of <Ib|E_ij|Jb> is the row of (i, j) itself
+                    Gt[size_t(m) * gld + Ib] = static_cast<uint32_t>(gJ) | (x & 0x80000000u);
+                }
+            b.gsrc.upload(Gt);
+            b.t3g_mpad = Mpad;
+            b.t3g_gld = static_cast<int64_t>(gld);
+        }
         bool pair = nbs % 2 == 0;
         for (size_t c = 0; c < B.nclasses(); ++c)
             pair = pair && (B.cls_off[c] % 2 == 0) && (B.strpcls(c) % 2 == 0);
@@ -435,6 +473,34 @@ void plan_t3_shape(f2_sigma& b) {
                 std::getenv("F2_NO_FOLD") == nullptr;
     if (b.t3_smem > 227 * 1024)
         throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
+    // gather form: one determinant block, rows of C (and the A' block) fit in shared memory
+    b.t3g = false;
+    if (b.gsrc.p && b.D->al16 && h.nbs % 2 == 0 && b.M >= 33 && std::getenv("F2_NO_T3G") == nullptr) {
+        const int kn = L.as_max;
+        const int nm16 = kn / 16, rem = kn % 16;
+        b.t3g_nm16 = nm16 + (rem > 8 ? 1 : 0);
+        b.t3g_has8 = (rem > 0 && rem <= 8) ? 1 : 0;
+        const int rows = b.t3g_nm16 * 16 + b.t3g_has8 * 8;
+        int S = b.t3g_mpad;
+        while (S % 16 != 4)
+            ++S;
+        b.t3g_astride = S;
+        b.t3g_smem = t3g_smem_bytes(h.nbs, rows, S);
+        b.t3g = b.t3g_nm16 >= 1 && b.t3g_nm16 <= 5 && b.t3g_smem <= 227 * 1024;
+    }
+    // warp-specialised kernel: 8 MMA warps cover up to 128 rows (+ the 8-row tail strip), even layout
+    b.t3_v4 = false;
+    if (b.D->al16 && b.M >= 33 && b.M <= V4_ROWS && std::getenv("F2_V4") != nullptr) {
+        for (int ns : {3, 2}) {
+            const size_t need = t3v4_smem_bytes(b.t3_ks, ns, static_cast<int>(nclsB));
+            if (need <= 227 * 1024) {
+                b.t3_v4 = true;
+                b.t3_v4_ns = ns;
+                b.t3_v4_smem = need;
+                break;
+            }
+        }
+    }
 }
 
 void fill_tiles(std::vector<uint32_t>& tiles, const std::vector<uint32_t>& ncols) {
@@ -741,12 +807,73 @@ void launch_t3_al(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t
         launch_t3_inst<KS, AL16, 2, false>(b, p, nitems, st);
 }
 
+template <int KS, bool TAIL>
+void launch_t3v4_inst(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
+    F2_CUDA(cudaFuncSetAttribute(t3v4_kernel<KS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(b.t3_v4_smem)));
+    t3v4_kernel<KS, TAIL><<<nitems, V4_THREADS, b.t3_v4_smem, st>>>(p, b.t3_v4_ns);
+    b.launches += 1;
+}
+
 template <int KS>
 void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
-    if (b.D->al16)
+    // the bulk copies of the warp-specialised kernel need 16-byte aligned rows of C
+    if (b.t3_v4 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+        if (b.M > V4_MMA_WARPS * 16)
+            launch_t3v4_inst<KS, true>(b, p, nitems, st);
+        else
+            launch_t3v4_inst<KS, false>(b, p, nitems, st);
+        return;
+    }
+    if (b.D->al16 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0)
         launch_t3_al<KS, true>(b, p, nitems, st);
     else
         launch_t3_al<KS, false>(b, p, nitems, st);
+}
+
+
+template <int NM16, bool HAS8>
+void launch_t3g_inst(const f2_sigma& b, const T3GParams& p, int nrows, cudaStream_t st) {
+    F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(b.t3g_smem)));
+    t3g_kernel<NM16, HAS8><<<nrows, T3G_THREADS, b.t3g_smem, st>>>(p);
+    b.launches += 1;
+}
+
+// gather-form opposite-spin term over all input alpha strings (single block, single GPU)
+void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    const DevStrings& D = *b.D;
+    T3GParams p;
+    p.C = C;
+    p.sigma = sigma;
+    p.as_ptr = D.as_ptr.p;
+    p.as_ent = D.as_ent.p;
+    p.gsrc = b.gsrc.p;
+    p.VxT = b.VxT.p;
+    p.nbs = h.nbs;
+    p.gld = b.t3g_gld;
+    p.M = b.M;
+    p.Mpad = b.t3g_mpad;
+    p.norb = h.norb;
+    p.first = 0;
+    p.astride = b.t3g_astride;
+    const int nrows = static_cast<int>(h.nas);
+    const int key = b.t3g_nm16 * 2 + b.t3g_has8;
+    switch (key) {
+    case 2: launch_t3g_inst<1, false>(b, p, nrows, st); break;
+    case 3: launch_t3g_inst<1, true>(b, p, nrows, st); break;
+    case 4: launch_t3g_inst<2, false>(b, p, nrows, st); break;
+    case 5: launch_t3g_inst<2, true>(b, p, nrows, st); break;
+    case 6: launch_t3g_inst<3, false>(b, p, nrows, st); break;
+    case 7: launch_t3g_inst<3, true>(b, p, nrows, st); break;
+    case 8: launch_t3g_inst<4, false>(b, p, nrows, st); break;
+    case 9: launch_t3g_inst<4, true>(b, p, nrows, st); break;
+    case 10: launch_t3g_inst<5, false>(b, p, nrows, st); break;
+    case 11: launch_t3g_inst<5, true>(b, p, nrows, st); break;
+    default: throw std::runtime_error("CISigmaBuilder: unsupported gather-form shape");
+    }
+    F2_CUDA(cudaGetLastError());
 }
 
 void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma, bool fold,
@@ -899,7 +1026,8 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         b.launches += 1;
     }
     F2_CUDA(cudaEventRecord(b.ev[1], st));
-    const bool fold = b.fold_ok && P.world == 1 && P.nitems > 0;
+    const bool gather = b.t3g && P.world == 1 && P.nitems > 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    const bool fold = !gather && b.fold_ok && P.world == 1 && P.nitems > 0;
     if (h.na >= 1 && !fold) {
         if (P.world > 1)
             F2_CUDA(cudaMemsetAsync(yexch, 0, static_cast<size_t>(P.y_size) * sizeof(double), st));
@@ -916,7 +1044,10 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
-    launch_t3(b, P, C, sigma, fold, st);
+    if (gather)
+        launch_t3g(b, C, sigma, st);
+    else
+        launch_t3(b, P, C, sigma, fold, st);
     F2_CUDA(cudaEventRecord(b.ev[4], st));
     F2_CUDA(cudaGetLastError());
     b.ev_pending = true;
@@ -1141,7 +1272,18 @@ int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_loc
 
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
     out5[0] = h->M;
-    out5[1] = (static_cast<int64_t>(h->t3_warps) * 16 + (h->t3_tail ? 8 : 0)) * h->t3_msplit;
+    if (h->t3g) { // rows of A' actually multiplied, expressed per column of the GEMM K dimension of the list
+        const int rows = h->t3g_nm16 * 16 + h->t3g_has8 * 8;
+        const int kmax = std::max(h->S->host->device_lists().as_max, 1);
+        out5[0] = h->M;
+        out5[1] = (static_cast<int64_t>(h->t3g_mpad) * rows + kmax - 1) / kmax;
+        out5[2] = kmax;
+        out5[3] = h->single ? h->single->t3_kcols : 0;
+        out5[4] = h->compressed ? 1 : 0;
+        return F2_OK;
+    }
+    out5[1] = h->t3_v4 ? (h->M > V4_MMA_WARPS * 16 ? V4_ROWS : V4_MMA_WARPS * 16)
+                        : (static_cast<int64_t>(h->t3_warps) * 16 + (h->t3_tail ? 8 : 0)) * h->t3_msplit;
     out5[2] = h->S->host->device_lists().as_max;
     out5[3] = h->single ? h->single->t3_kcols : 0;
     out5[4] = h->compressed ? 1 : 0;
