@@ -860,11 +860,14 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
             for (int nt = 0; nt < 2; ++nt)
                 acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
         acc8[0][0] = acc8[0][1] = acc8[1][0] = acc8[1][1] = 0.0;
-        // lane (g, t) feeds B[k = t][n = g] of both n8 tiles; tile nt holds actual column n0 + 2g + nt
-        const uint32_t* gp = p.gsrc + static_cast<size_t>(t) * p.gld + n0 + 2 * g;
+        // lane (g, t) feeds B[k = t][n = g] of both n8 tiles; n index gg of tile nt is the actual column
+        // n0 + 8 nt + (gg >> 1) + 4 (gg & 1), so that the four lanes of an accumulator row hold four
+        // consecutive columns (one full 32-byte sector per reduction instruction and row)
+        const uint32_t* gp = p.gsrc + static_cast<size_t>(t) * p.gld + n0 + (g >> 1) + 4 * (g & 1);
         const size_t gstep = static_cast<size_t>(4) * p.gld;
         auto table = [&](int ks) { // entries of k-step ks (clamped: never used past the end)
-            return __ldg(reinterpret_cast<const uint2*>(gp + (ks < nks ? ks : 0) * gstep));
+            const uint32_t* q = gp + (ks < nks ? ks : 0) * gstep;
+            return make_uint2(__ldg(q), __ldg(q + 8));
         };
         auto gather = [&](uint32_t e) {
             const double v = row[e & 0xfffffu];
@@ -901,9 +904,8 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
                 dmma_8x8x4(acc8[1], a0, b1);
             }
         }
-        // sigma[Ia_r, n0 + 4t + 2c + nt] += acc[..][nt][2h + c]
-        const int c0 = n0 + 4 * t;
-        const bool full = c0 + 3 < p.nbs;
+        // accumulator (row, tile nt, n index 2t + c) is column n0 + 8 nt + 4 c + t
+        const int c0 = n0 + t;
 #pragma unroll
         for (int i = 0; i < NM16; ++i)
 #pragma unroll
@@ -911,27 +913,24 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
                 const long long ro = rowoff[16 * i + g + 8 * h];
                 if (ro >= 0) {
                     double* dst = p.sigma + ro + c0;
-                    if (full) {
-                        atomicAdd(dst + 0, acc[i][0][2 * h + 0]);
-                        atomicAdd(dst + 1, acc[i][1][2 * h + 0]);
-                        atomicAdd(dst + 2, acc[i][0][2 * h + 1]);
-                        atomicAdd(dst + 3, acc[i][1][2 * h + 1]);
-                    } else {
-                        if (c0 + 0 < p.nbs) atomicAdd(dst + 0, acc[i][0][2 * h + 0]);
-                        if (c0 + 1 < p.nbs) atomicAdd(dst + 1, acc[i][1][2 * h + 0]);
-                        if (c0 + 2 < p.nbs) atomicAdd(dst + 2, acc[i][0][2 * h + 1]);
-                        if (c0 + 3 < p.nbs) atomicAdd(dst + 3, acc[i][1][2 * h + 1]);
-                    }
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (c0 + 8 * nt + 4 * c < p.nbs)
+                                atomicAdd(dst + 8 * nt + 4 * c, acc[i][nt][2 * h + c]);
                 }
             }
         if constexpr (HAS8) {
             const long long ro = rowoff[16 * NM16 + g];
             if (ro >= 0) {
                 double* dst = p.sigma + ro + c0;
-                if (c0 + 0 < p.nbs) atomicAdd(dst + 0, acc8[0][0]);
-                if (c0 + 1 < p.nbs) atomicAdd(dst + 1, acc8[1][0]);
-                if (c0 + 2 < p.nbs) atomicAdd(dst + 2, acc8[0][1]);
-                if (c0 + 3 < p.nbs) atomicAdd(dst + 3, acc8[1][1]);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (c0 + 8 * nt + 4 * c < p.nbs)
+                            atomicAdd(dst + 8 * nt + 4 * c, acc8[nt][c]);
             }
         }
     }
@@ -940,7 +939,7 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
 struct SSParams {
     const double* X;
     double* Y;
-    const uint32_t* klist; // (N-2)-electron strings of this launch (one colour)
+    const uint32_t* klist; // (N-2)-electron strings of this launch (blockIdx.x)
     const uint32_t* h2_ptr;
     const uint64_t* h2_ent;
     const uint32_t *s_cls, *s_loc;
@@ -949,32 +948,65 @@ struct SSParams {
     const uint32_t* g_ncols;
     const uint32_t* g_ldx;
     const uint32_t* g_ldy;
-    const uint32_t* tiles; // 2 per blockIdx.x: column group, first column
+    const uint32_t* tiles; // 2 per blockIdx.y: column group, first column of the SSG_TW-wide panel
     const double* W;       // [P*P] antisymmetrised (and one-electron folded) integrals
     int P;
     int ngroups;
+    int nk; // number of strings in klist
 };
 
-constexpr size_t ss_smem_bytes(int ks) { return size_t(ks) * 4 * (BS * 8 + 8 + 8 + 4); }
+constexpr int SSG_TW = 256; // columns per CTA: a panel of all rows x SSG_TW columns of X and Y stays in L2
+constexpr int SSG_KG = 8;   // (N-2)-electron strings per CTA, software-pipelined
+__host__ __device__ constexpr int ssg_astride(int rows) { // smallest stride >= rows, == 4 (mod 16)
+    int s = rows;
+    while (s % 16 != 4)
+        ++s;
+    return s;
+}
+constexpr size_t ssg_smem_bytes(int rows) {
+    return 2 * size_t(rows) * ssg_astride(rows) * 8 + 3 * size_t(rows) * (8 + 8 + 4) + 16;
+}
 
-template <int KS, bool AL16>
-__global__ void __launch_bounds__(32 * ((KS * 4 + 15) / 16)) ss_kernel(const SSParams p) {
-    constexpr int KP = KS * 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[]; // ss_smem_bytes(KS)
-    double* Bs = reinterpret_cast<double*>(smem_raw);
-    long long* msrc = reinterpret_cast<long long*>(Bs + KP * BS);
-    long long* mdst = msrc + KP;
-    unsigned* minfo = reinterpret_cast<unsigned*>(mdst + KP);
-    __shared__ int s_m;
-    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ double flip_sign(double v, unsigned signbit31) {
+    return __hiloint2double(__double2hiint(v) ^ static_cast<int>(signbit31 & 0x80000000u), __double2loint(v));
+}
+
+// Same-spin term (one- and two-electron) through the (N-2)-electron strings K, reduction form.
+// One CTA per (group of SSG_KG strings K, panel of SSG_TW columns).  Per K the m x m block
+// W[pair_a, pair_b] of antisymmetrised integrals is copied into shared memory with cp.async while the
+// previous K multiplies (the phases s_a s_b are applied to the B operand and to the result instead of
+// the block, so the copy needs no registers).  Every warp takes 16-column chunks: B fragments are the
+// parent rows X[I_b, chunk] loaded straight from global memory into registers (full 32-byte sectors,
+// no staging), A fragments come from the shared block, and the m x 16 result is added to Y[I_a, chunk]
+// with red.global.add.f64.  No colouring, no read of Y: one launch per spin and operand; K varies
+// fastest over the grid so that a column panel of X and Y is reused out of L2 by all K.
+// Reference counterpart: CISigmaBuilder::H2_hz_same_spin and H1_hz
+// (ci_sigma_builder_harrison_zarrabian.cc:14-195).
+template <int NM16, bool HAS8, bool AL16>
+__global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
+    constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
+    constexpr int S = ssg_astride(ROWS);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Abuf = reinterpret_cast<double*>(smem_raw); // [2][ROWS][S]
+    long long* msrc3 = reinterpret_cast<long long*>(Abuf + 2 * ROWS * S); // [3][ROWS]
+    long long* mdst3 = msrc3 + 3 * ROWS;
+    unsigned* minfo3 = reinterpret_cast<unsigned*>(mdst3 + 3 * ROWS);
+    __shared__ int s_m[3];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t K = p.klist[blockIdx.y];
-    const int grp = p.tiles[2 * blockIdx.x];
-    const int j0 = p.tiles[2 * blockIdx.x + 1];
+    const int grp = p.tiles[2 * blockIdx.y];
+    const int j0 = p.tiles[2 * blockIdx.y + 1];
     const int ncols = p.g_ncols[grp];
     const long long ldx = p.g_ldx[grp], ldy = p.g_ldy[grp];
+    const int k_first = blockIdx.x * SSG_KG;
+    const int k_cnt = p.nk - k_first < SSG_KG ? p.nk - k_first : SSG_KG;
 
-    if (warp == 0) {
+    auto decode = [&](int j) { // warp 0: parent list of the j-th string of this CTA into slot j % 3
+        const int slot = j % 3;
+        long long* msrc = msrc3 + slot * ROWS;
+        long long* mdst = mdst3 + slot * ROWS;
+        unsigned* minfo = minfo3 + slot * ROWS;
+        const uint32_t K = p.klist[k_first + j];
         const int e0 = p.h2_ptr[K], e1 = p.h2_ptr[K + 1];
         int cnt = 0;
         for (int base = e0; base < e1; base += 32) {
@@ -998,100 +1030,156 @@ __global__ void __launch_bounds__(32 * ((KS * 4 + 15) / 16)) ss_kernel(const SSP
             const unsigned mask = __ballot_sync(0xffffffffu, ok);
             if (ok) {
                 const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-                msrc[pos] = src;
-                mdst[pos] = dst;
-                minfo[pos] = info;
+                if (pos < ROWS) {
+                    msrc[pos] = src;
+                    mdst[pos] = dst;
+                    minfo[pos] = info;
+                }
             }
             cnt += __popc(mask);
         }
+        cnt = cnt < ROWS ? cnt : ROWS;
+        for (int r = cnt + lane; r < ROWS; r += 32) {
+            msrc[r] = -1;
+            mdst[r] = -1;
+            minfo[r] = 0;
+        }
         if (lane == 0)
-            s_m = cnt;
+            s_m[slot] = cnt;
+    };
+    auto copy_block = [&](int j) { // all threads: W[pair_a, pair_b] of string j into buffer j % 2 (async)
+        const unsigned* minfo = minfo3 + (j % 3) * ROWS;
+        const int m = s_m[j % 3];
+        double* A = Abuf + (j & 1) * ROWS * S;
+        for (int idx = tid; idx < ROWS * S; idx += 256) {
+            const int a = idx / S, b = idx - a * S;
+            const bool in = a < m && b < m;
+            const double* src = in ? p.W + static_cast<size_t>(minfo[a] & 0xffff) * p.P + (minfo[b] & 0xffff) : p.W;
+            cp_async8(A + idx, src, in ? 8 : 0);
+        }
+        cp_async_commit();
+    };
+
+    if (warp == 0) {
+        decode(0);
+        if (k_cnt > 1)
+            decode(1);
     }
-    for (int i = tid; i < KP * BS; i += nthr)
-        Bs[i] = 0.0;
     __syncthreads();
-    const int m = s_m;
-    if (m == 0)
-        return;
-
-    // stage the m parent rows of this column tile
-    if (AL16) {
-        for (int idx = tid; idx < m * (NT / 2); idx += nthr) {
-            const int r = idx / (NT / 2), c = idx % (NT / 2);
-            const int col = j0 + 2 * c;
-            int bytes = (ncols - col) * 8;
-            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-            cp_async16(Bs + r * BS + 2 * c, p.X + msrc[r] + (bytes ? col : 0), bytes);
-        }
-    } else {
-        for (int idx = tid; idx < m * NT; idx += nthr) {
-            const int r = idx / NT, c = idx % NT;
-            const int col = j0 + c;
-            const bool in = col < ncols;
-            cp_async8(Bs + r * BS + c, p.X + msrc[r] + (in ? col : 0), in ? 8 : 0);
-        }
-    }
-    cp_async_commit();
-
-    // coefficient block: rows = output parents, columns = input parents
-    const int nks = (m + 3) >> 2;
-    const int ra = warp * 16 + g;
-    double a[KS][2];
-    {
-        const unsigned ia0 = ra < m ? minfo[ra] : 0, ia1 = ra + 8 < m ? minfo[ra + 8] : 0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            a[ks][0] = a[ks][1] = 0.0;
-            const int b = 4 * ks + t;
-            if (b < m) {
-                const unsigned ib = minfo[b];
-                const int pb = ib & 0xffff;
-                if (ra < m)
-                    a[ks][0] = (((ia0 ^ ib) >> 31) ? -1.0 : 1.0) *
-                               p.W[static_cast<size_t>(ia0 & 0xffff) * p.P + pb];
-                if (ra + 8 < m)
-                    a[ks][1] = (((ia1 ^ ib) >> 31) ? -1.0 : 1.0) *
-                               p.W[static_cast<size_t>(ia1 & 0xffff) * p.P + pb];
-            }
-        }
-    }
+    copy_block(0);
     cp_async_wait<0>();
     __syncthreads();
-    if (warp * 16 >= m)
-        return;
 
-#pragma unroll 1
-    for (int nh = 0; nh < 2; ++nh) {
-        double acc[NT / 16][4];
+    const int jend = j0 + SSG_TW < ncols ? j0 + SSG_TW : ncols;
+    const int nchunks = (jend - j0 + 15) >> 4;
+    for (int j = 0; j < k_cnt; ++j) {
+        if (j + 1 < k_cnt)
+            copy_block(j + 1);
+        if (warp == 0 && j + 2 < k_cnt)
+            decode(j + 2);
+        const int m = s_m[j % 3];
+        const long long* msrc = msrc3 + (j % 3) * ROWS;
+        const long long* mdst = mdst3 + (j % 3) * ROWS;
+        const unsigned* minfo = minfo3 + (j % 3) * ROWS;
+        const int nks = (m + 3) >> 2;
+        const double* ap = Abuf + (j & 1) * ROWS * S + g * S + t;
+        for (int chunk = warp; chunk < nchunks && m > 0; chunk += 8) {
+            const int n0 = j0 + (chunk << 4);
+            // B operand: n8 tile nt, n index gg holds column n0 + 8 nt + (gg >> 1) + 4 (gg & 1), so that the
+            // four lanes of an accumulator row hold four consecutive columns (one full sector per reduction)
+            const int cb = n0 + (g >> 1) + 4 * (g & 1);
+            double acc[NM16 > 0 ? NM16 : 1][2][4];
+            double acc8[2][2];
 #pragma unroll
-        for (int nt = 0; nt < NT / 16; ++nt)
-            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0;
+            for (int i = 0; i < NM16; ++i)
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            if (ks < nks) {
-                const double* bp = Bs + (4 * ks + t) * BS + nh * (NT / 2) + g;
+                for (int nt = 0; nt < 2; ++nt)
+                    acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
+            acc8[0][0] = acc8[0][1] = acc8[1][0] = acc8[1][1] = 0.0;
+            constexpr int PFB = 2; // k-steps per register batch; the next batch loads while this one multiplies
+            double cur[PFB][2], nxt[PFB][2];
+            unsigned scur[PFB], snxt[PFB];
+            auto loadb = [&](int ks, double (&v)[2], unsigned& sg) { // parent row 4ks + t, columns cb, cb + 8
+                v[0] = 0.0;
+                v[1] = 0.0;
+                sg = 0;
+                const int b = 4 * ks + t;
+                if (ks < nks && b < m) {
+                    const double* src = p.X + msrc[b] + cb;
+                    sg = minfo[b];
+                    if (cb < jend)
+                        v[0] = __ldg(src);
+                    if (cb + 8 < jend)
+                        v[1] = __ldg(src + 8);
+                }
+            };
 #pragma unroll
-                for (int nt = 0; nt < NT / 16; ++nt)
-                    dmma_16x8x4(acc[nt], a[ks][0], a[ks][1], bp[nt * 8]);
+            for (int i = 0; i < PFB; ++i)
+                loadb(i, cur[i], scur[i]);
+            for (int kb = 0; kb < nks; kb += PFB) {
+#pragma unroll
+                for (int i = 0; i < PFB; ++i)
+                    loadb(kb + PFB + i, nxt[i], snxt[i]);
+#pragma unroll
+                for (int i = 0; i < PFB; ++i) {
+                    const int ks = kb + i;
+                    if (ks < nks) {
+                        const double b0 = flip_sign(cur[i][0], scur[i]), b1 = flip_sign(cur[i][1], scur[i]);
+                        const double* a = ap + 4 * ks;
+#pragma unroll
+                        for (int mt = 0; mt < NM16; ++mt) {
+                            const double a0 = a[(16 * mt) * S], a1 = a[(16 * mt + 8) * S];
+                            dmma_16x8x4(acc[mt][0], a0, a1, b0);
+                            dmma_16x8x4(acc[mt][1], a0, a1, b1);
+                        }
+                        if constexpr (HAS8) {
+                            const double a0 = a[(16 * NM16) * S];
+                            dmma_8x8x4(acc8[0], a0, b0);
+                            dmma_8x8x4(acc8[1], a0, b1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < PFB; ++i) {
+                    cur[i][0] = nxt[i][0];
+                    cur[i][1] = nxt[i][1];
+                    scur[i] = snxt[i];
+                }
+            }
+            // accumulator (row, tile nt, n index 2t + c) is column n0 + 8 nt + 4 c + t
+            const int c0 = n0 + t;
+#pragma unroll
+            for (int mt = 0; mt < NM16; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int a = 16 * mt + g + 8 * h;
+                    if (a < m) {
+                        double* dst = p.Y + mdst[a] + c0;
+                        const unsigned sg = minfo[a];
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                if (c0 + 8 * nt + 4 * c < jend)
+                                    atomicAdd(dst + 8 * nt + 4 * c, flip_sign(acc[mt][nt][2 * h + c], sg));
+                    }
+                }
+            if constexpr (HAS8) {
+                const int a = 16 * NM16 + g;
+                if (a < m) {
+                    double* dst = p.Y + mdst[a] + c0;
+                    const unsigned sg = minfo[a];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (c0 + 8 * nt + 4 * c < jend)
+                                atomicAdd(dst + 8 * nt + 4 * c, flip_sign(acc8[nt][c], sg));
+                }
             }
         }
-        // owner update: within one colour no two (N-2) strings share a parent row
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int row = ra + 8 * half;
-            if (row >= m)
-                continue;
-            const int c0 = j0 + nh * (NT / 2) + 2 * t;
-            double* y = p.Y + mdst[row] + c0;
-#pragma unroll
-            for (int nt = 0; nt < NT / 16; ++nt) {
-                const int col = c0 + nt * 8;
-                if (col < ncols)
-                    y[nt * 8] += acc[nt][2 * half];
-                if (col + 1 < ncols)
-                    y[nt * 8 + 1] += acc[nt][2 * half + 1];
-            }
-        }
+        cp_async_wait<0>();
+        __syncthreads();
     }
 }
 

@@ -506,7 +506,7 @@ void plan_t3_shape(f2_sigma& b) {
 void fill_tiles(std::vector<uint32_t>& tiles, const std::vector<uint32_t>& ncols) {
     tiles.clear();
     for (size_t g = 0; g < ncols.size(); ++g)
-        for (uint32_t j0 = 0; j0 < ncols[g]; j0 += NT) {
+        for (uint32_t j0 = 0; j0 < ncols[g]; j0 += SSG_TW) {
             tiles.push_back(static_cast<uint32_t>(g));
             tiles.push_back(j0);
         }
@@ -920,30 +920,30 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     F2_CUDA(cudaGetLastError());
 }
 
-template <int KS>
-void launch_ss_ks(const SSParams& p, bool al16, dim3 grid, cudaStream_t st) {
-    const dim3 block(32 * ((KS * 4 + 15) / 16));
-    constexpr size_t smem = ss_smem_bytes(KS);
+template <int NM16, bool HAS8>
+void launch_ssg_inst(const SSParams& p, bool al16, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = ssg_smem_bytes(NM16 * 16 + (HAS8 ? 8 : 0));
     if (al16) {
         if (smem > 48 * 1024)
-            F2_CUDA(cudaFuncSetAttribute(ss_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            F2_CUDA(cudaFuncSetAttribute(ssg_kernel<NM16, HAS8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-        ss_kernel<KS, true><<<grid, block, smem, st>>>(p);
+        ssg_kernel<NM16, HAS8, true><<<grid, 256, smem, st>>>(p);
     } else {
         if (smem > 48 * 1024)
-            F2_CUDA(cudaFuncSetAttribute(ss_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            F2_CUDA(cudaFuncSetAttribute(ssg_kernel<NM16, HAS8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-        ss_kernel<KS, false><<<grid, block, smem, st>>>(p);
+        ssg_kernel<NM16, HAS8, false><<<grid, 256, smem, st>>>(p);
     }
 }
 
-// all colours of one spin for one plan
+// every (N-2)-electron string of one spin for one plan, one launch (reductions into Y commute)
 void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const double* X, double* Y,
                       const double* W, cudaStream_t st) {
     const CIStringsHost& h = *b.S->host;
     const DeviceLists& L = h.device_lists();
     const DevStrings& D = *b.D;
-    if (plan.ntiles == 0 || L.h2_color_ptr[spin].size() < 2)
+    const size_t nk = L.h2_color_list[spin].size();
+    if (plan.ntiles == 0 || nk == 0)
         return;
     SSParams p;
     p.X = X;
@@ -957,26 +957,39 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
     p.g_ncols = plan.g_ncols.p;
     p.g_ldx = plan.g_ldx.p;
     p.g_ldy = plan.g_ldy.p;
-    p.tiles = plan.tiles.p;
     p.W = W;
     p.P = b.P[spin];
     p.ngroups = plan.ngroups;
-    const auto& cptr = L.h2_color_ptr[spin];
-    for (size_t c = 0; c + 1 < cptr.size(); ++c) {
-        for (uint32_t k0 = cptr[c]; k0 < cptr[c + 1]; k0 += 65535) {
-            const uint32_t nk = std::min<uint32_t>(65535, cptr[c + 1] - k0);
-            p.klist = D.h2_clist[spin].p + k0;
-            const dim3 grid(plan.ntiles, nk);
+    const bool al16 = plan.al16 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    const int mmax = std::max(L.h2_max[spin], 1);
+    const int nm16 = mmax / 16 + (mmax % 16 > 8 ? 1 : 0), has8 = (mmax % 16 > 0 && mmax % 16 <= 8) ? 1 : 0;
+    // grid: x = K (fastest: all K of a column panel run together, the panel stays in L2), y = panel
+    for (size_t k0 = 0; k0 < nk; k0 += size_t(1) << 30) {
+        const uint32_t nkk = static_cast<uint32_t>(std::min<size_t>(size_t(1) << 30, nk - k0));
+        p.klist = D.h2_clist[spin].p + k0;
+        p.nk = static_cast<int>(nkk);
+        for (int t0 = 0; t0 < plan.ntiles; t0 += 65535) {
+            const int nt = std::min(65535, plan.ntiles - t0);
+            p.tiles = plan.tiles.p + 2 * static_cast<size_t>(t0);
+            const dim3 grid((nkk + SSG_KG - 1) / SSG_KG, nt);
             b.launches += 1;
-            switch (b.ss_ks[spin]) {
-            case 4: launch_ss_ks<4>(p, plan.al16, grid, st); break;
-            case 8: launch_ss_ks<8>(p, plan.al16, grid, st); break;
-            case 12: launch_ss_ks<12>(p, plan.al16, grid, st); break;
-            case 16: launch_ss_ks<16>(p, plan.al16, grid, st); break;
-            case 20: launch_ss_ks<20>(p, plan.al16, grid, st); break;
-            case 24: launch_ss_ks<24>(p, plan.al16, grid, st); break;
-            case 28: launch_ss_ks<28>(p, plan.al16, grid, st); break;
-            case 32: launch_ss_ks<32>(p, plan.al16, grid, st); break;
+            switch (nm16 * 2 + has8) {
+            case 1: launch_ssg_inst<0, true>(p, al16, grid, st); break;
+            case 2: launch_ssg_inst<1, false>(p, al16, grid, st); break;
+            case 3: launch_ssg_inst<1, true>(p, al16, grid, st); break;
+            case 4: launch_ssg_inst<2, false>(p, al16, grid, st); break;
+            case 5: launch_ssg_inst<2, true>(p, al16, grid, st); break;
+            case 6: launch_ssg_inst<3, false>(p, al16, grid, st); break;
+            case 7: launch_ssg_inst<3, true>(p, al16, grid, st); break;
+            case 8: launch_ssg_inst<4, false>(p, al16, grid, st); break;
+            case 9: launch_ssg_inst<4, true>(p, al16, grid, st); break;
+            case 10: launch_ssg_inst<5, false>(p, al16, grid, st); break;
+            case 11: launch_ssg_inst<5, true>(p, al16, grid, st); break;
+            case 12: launch_ssg_inst<6, false>(p, al16, grid, st); break;
+            case 13: launch_ssg_inst<6, true>(p, al16, grid, st); break;
+            case 14: launch_ssg_inst<7, false>(p, al16, grid, st); break;
+            case 15: launch_ssg_inst<7, true>(p, al16, grid, st); break;
+            case 16: launch_ssg_inst<8, false>(p, al16, grid, st); break;
             default: throw std::runtime_error("CISigmaBuilder: unsupported same-spin block size");
             }
         }
