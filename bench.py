@@ -10,8 +10,10 @@ flush is needed between steps).  For N > 1 the CI vector is sharded by alpha-str
 (strong scaling: the same sigma build is split over N GPUs, one NCCL all-gather of C per step).
 
 The JSON line carries, beside the driver contract's keys:
-  roofline     the opposite-spin kernel (t3_kernel) against the FP64 tensor peak measured in this run
-               with a cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
+  roofline     the opposite-spin kernel (t3g_kernel on one GPU, t3_kernel when sharded) against the FP64
+               tensor peak measured in this run with a cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
+  davidson     (N = 1) time of one Davidson-Liu iteration of a 3-root solve on the same workload: 3 sigma
+               builds + the device solver's streaming passes (forte2_b200/davidson.py)
   cpu_baseline the reference's own C++ CISigmaBuilder::Hamiltonian (oracle/_ref) timed on the host cores
                on a bounded sample, scaled to the workload by the reference's own GEMM flop count
   e2e          the same metric through the numpy-facing call (host buffers in, host buffers out)
@@ -217,6 +219,30 @@ def workload_config(workload, gpus):
             "l2_policy": "inputs (C, sigma: %.2f GB each) larger than L2; no flush" % (ndet * 8 / 1e9)}
 
 
+def davidson_leg(torch, strings, builder, E, H, V, nroot=3, iters=5):
+    """Device Davidson-Liu (forte2_b200/davidson.py) on the bench workload: `iters` iterations of an
+    nroot-root solve from the reference's guess (forte2/ci/ci.py:411-452); iteration 0 builds
+    guess_per_root * nroot sigma vectors, every later one nroot.  Times are CUDA-event times per iteration."""
+    from forte2_b200.ci_solver import CISolver
+    from forte2_b200.davidson import DavidsonLiuParams
+    solver = CISolver(strings, E, H, V, nroot=nroot, davidson_liu_params=DavidsonLiuParams(maxiter=iters),
+                      log_level=0, builder=builder)
+    solver.run()
+    ds = solver.eigensolver
+    steady = [t for t, h in zip(ds.iter_times, ds.history) if h[5] == nroot]
+    steady.sort()
+    med = steady[len(steady) // 2] if steady else None
+    out = {"nroot": nroot, "iterations_run": len(ds.iter_times),
+           "iter_ms_all": [round(t * 1e3, 3) for t in ds.iter_times],
+           "sigma_builds_per_iter": [h[5] for h in ds.history],
+           "iter_ms_steady": med * 1e3 if med else None,
+           "solver_launches": int(ds.k.launches),
+           "note": "steady = iterations that build nroot sigma vectors; solver overhead = iter - nroot * sigma"}
+    del solver, ds
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -302,7 +328,9 @@ def run_ours(args):
     survey_flops = 2.0 * (n * (n + 1) / 2) ** 2 * ndet * frac_work
     t3_s = last[3] * 1e-3
     roofline = {
-        "bound": "tensor", "kernel": "t3_kernel (opposite-spin, DMMA)",
+        "bound": "tensor",
+        "kernel": ("t3g_kernel (opposite-spin, gather form, DMMA)" if shape["form"] == "gather" and world == 1
+                   else "t3_kernel (opposite-spin, scatter form, DMMA)"),
         "achieved": useful_flops / t3_s / 1e12, "peak": peak, "unit": "TFLOP/s",
         "frac": useful_flops / t3_s / 1e12 / peak,
         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
@@ -319,7 +347,7 @@ def run_ours(args):
         hbm_peak = 6650.0
     same_spin_ms = last[1] + last[2]
     same_spin = {
-        "bound": "hbm", "kernels": "ss_kernel x colours + transposes (same-spin alpha + beta, one-electron folded)",
+        "bound": "hbm", "kernels": "ssg_kernel (alpha) + transposes + ssg_kernel (beta), one-electron folded",
         "algorithmic_bytes": 2 * 24.0 * ndet * frac_work, "ms": same_spin_ms,
         "achieved": (2 * 24.0 * ndet * frac_work) / (same_spin_ms * 1e-3) / 1e9 if same_spin_ms else None,
         "peak": hbm_peak, "unit": "GB/s",
@@ -344,6 +372,14 @@ def run_ours(args):
         e2e = {"value": value, "unit": "sigma builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "sharded vectors live on the GPUs; no host path at N>1"}
 
+    # ---- one Davidson-Liu iteration of a 3-root solve (N = 1): the caller on either side of sigma ----
+    davidson = None
+    if world == 1 and not args.no_davidson:
+        try:
+            davidson = davidson_leg(torch, strings, builder, E, H, V)
+        except torch.cuda.OutOfMemoryError as e:  # the 3-root subspace needs 27 vectors
+            davidson = {"error": f"out of memory: {e}"[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -359,6 +395,7 @@ def run_ours(args):
         "term_ms_last_step": {"H0": last[0], "same_spin_alpha": last[1], "same_spin_beta": last[2],
                               "opposite_spin": last[3], "total": last[4]},
         "roofline": roofline, "roofline_same_spin": same_spin, "cpu_baseline": cpu, "e2e": e2e,
+        "davidson": davidson,
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)
@@ -374,6 +411,7 @@ def main():
     ap.add_argument("--workload", default="cas16", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-davidson", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

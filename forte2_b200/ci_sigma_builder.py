@@ -131,10 +131,10 @@ class CISigmaBuilder:
 
     def t3_shape(self):
         """dict describing the contraction the opposite-spin kernel executes (see the header)."""
-        out = np.zeros(5, dtype=np.int64)
+        out = np.zeros(6, dtype=np.int64)
         _lib.check(_lib.lib().f2_sigma_t3_shape(self._h, out.ctypes.data_as(_lib.i64p)))
         return {"M": int(out[0]), "M_pad": int(out[1]), "K_max": int(out[2]), "k_cols": int(out[3]),
-                "pair_compressed": bool(out[4])}
+                "pair_compressed": bool(out[4]), "form": "gather" if out[5] else "scatter"}
 
     def form_Hdiag_det(self):
         """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""

@@ -40,14 +40,14 @@ class CISolver:
     """
 
     def __init__(self, strings: CIStrings, E, H, V, nroot=1, davidson_liu_params=None, ci_algorithm="hz",
-                 ci_builder_memory=1024, energy_shift=None, log_level=3, device=None, log=None):
+                 ci_builder_memory=1024, energy_shift=None, log_level=3, device=None, log=None, builder=None):
         self.ci_strings = strings
         self.E0, self.H, self.V = float(E), np.asarray(H, dtype=np.float64), np.asarray(V, dtype=np.float64)
         self.nroot = int(nroot)
         self.davidson_liu_params = davidson_liu_params or DavidsonLiuParams()
         self.ci_algorithm, self.ci_builder_memory = ci_algorithm, int(ci_builder_memory)
         self.energy_shift, self.log_level, self.device, self._log = energy_shift, log_level, device, log
-        self.ci_sigma_builder = None
+        self.ci_sigma_builder = builder  # an existing CISigmaBuilder for the same strings/integrals may be reused
         self.eigensolver = None
         self.executed = False
 
@@ -73,9 +73,10 @@ class CISolver:
         s = self.ci_strings
         if s.ndet == 0:
             raise ValueError("No determinants could be generated for the given state and orbitals.")
-        self.ci_sigma_builder = CISigmaBuilder(s, self.E0, self.H, self.V, self.log_level, device=self.device)
+        if self.ci_sigma_builder is None:
+            self.ci_sigma_builder = CISigmaBuilder(s, self.E0, self.H, self.V, self.log_level, device=self.device)
+            self.ci_sigma_builder.set_memory(self.ci_builder_memory)
         b = self.ci_sigma_builder
-        b.set_memory(self.ci_builder_memory)
         b.set_algorithm(self.ci_algorithm.lower())
         hdiag = b.form_Hdiag_det()
         if s.ndet == 1:

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -222,8 +223,11 @@ struct f2_sigma {
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
     cudaStream_t own_stream = nullptr;
+    std::vector<cudaEvent_t> piece_ev;
 
     ~f2_sigma() {
+        for (auto& e : piece_ev)
+            cudaEventDestroy(e);
         for (auto& e : ev)
             if (e)
                 cudaEventDestroy(e);
@@ -237,6 +241,25 @@ struct f2_sigma {
 };
 
 namespace {
+
+// host-to-host copy split over a few threads (one memcpy stream does not saturate the memory system)
+void parallel_copy(double* dst, const double* src, size_t count) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthr = std::min<size_t>(std::min<unsigned>(hw, 8), std::max<size_t>(1, count >> 18));
+    if (nthr <= 1) {
+        std::memcpy(dst, src, count * sizeof(double));
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = (count + nthr - 1) / nthr;
+    for (size_t t = 0; t < nthr; ++t) {
+        const size_t lo = t * per, hi = std::min(count, lo + per);
+        if (lo < hi)
+            pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, (hi - lo) * sizeof(double)); });
+    }
+    for (auto& th : pool)
+        th.join();
+}
 
 int round_ks(int count) { // k-steps (of 4) rounded up to the instantiated multiples of 4
     const int ks = (count + 3) / 4;
@@ -1211,14 +1234,35 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
         }
         h->dC.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)));
         h->dS.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)));
-        std::memcpy(h->hC, C_host, static_cast<size_t>(n) * sizeof(double));
-        F2_CUDA(cudaMemcpyAsync(h->dC.p, h->hC, static_cast<size_t>(n) * sizeof(double),
-                                cudaMemcpyHostToDevice, h->own_stream));
+        // pageable user memory -> pinned staging -> device in 64 MB pieces: the host copy of piece i + 1
+        // (several threads) overlaps the DMA of piece i; the way back mirrors it
+        const size_t total = static_cast<size_t>(n), piece = size_t(8) << 20;
+        for (size_t off = 0; off < total; off += piece) {
+            const size_t cnt = std::min(piece, total - off);
+            parallel_copy(h->hC + off, C_host + off, cnt);
+            F2_CUDA(cudaMemcpyAsync(h->dC.p + off, h->hC + off, cnt * sizeof(double), cudaMemcpyHostToDevice,
+                                    h->own_stream));
+        }
         apply(*h, h->dC.p, h->dS.p, n, h->own_stream);
-        F2_CUDA(cudaMemcpyAsync(h->hS, h->dS.p, static_cast<size_t>(n) * sizeof(double),
-                                cudaMemcpyDeviceToHost, h->own_stream));
+        const size_t npieces = (total + piece - 1) / piece;
+        if (h->piece_ev.size() < npieces) {
+            const size_t old = h->piece_ev.size();
+            h->piece_ev.resize(npieces);
+            for (size_t i = old; i < npieces; ++i)
+                F2_CUDA(cudaEventCreateWithFlags(&h->piece_ev[i], cudaEventDisableTiming));
+        }
+        for (size_t i = 0; i < npieces; ++i) {
+            const size_t off = i * piece, cnt = std::min(piece, total - off);
+            F2_CUDA(cudaMemcpyAsync(h->hS + off, h->dS.p + off, cnt * sizeof(double), cudaMemcpyDeviceToHost,
+                                    h->own_stream));
+            F2_CUDA(cudaEventRecord(h->piece_ev[i], h->own_stream));
+        }
+        for (size_t i = 0; i < npieces; ++i) {
+            const size_t off = i * piece, cnt = std::min(piece, total - off);
+            F2_CUDA(cudaEventSynchronize(h->piece_ev[i]));
+            parallel_copy(sigma_host + off, h->hS + off, cnt);
+        }
         F2_CUDA(cudaStreamSynchronize(h->own_stream));
-        std::memcpy(sigma_host, h->hS, static_cast<size_t>(n) * sizeof(double));
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);
@@ -1284,6 +1328,7 @@ int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_loc
 }
 
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
+    out5[5] = h->t3g ? 1 : 0;
     out5[0] = h->M;
     if (h->t3g) { // rows of A' actually multiplied, expressed per column of the GEMM K dimension of the list
         const int rows = h->t3g_nm16 * 16 + h->t3g_has8 * 8;

@@ -99,8 +99,10 @@ int64_t f2_sigma_launch_count(const f2_sigma* h);
  * out[1] = M padded to the MMA tile, out[2] = max single replacements per alpha string (GEMM K),
  * out[3] = sum over launched (alpha string, beta class) work items of K_item * columns, i.e. the
  * number of (k, column) pairs contracted; executed flops = 2 * out[1] * out[3], useful flops =
- * 2 * out[0] * out[3].  out[4] = 1 when the pair-compressed (8-fold symmetric) rows are in use. */
-int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5);
+ * 2 * out[0] * out[3].  out[4] = 1 when the pair-compressed (8-fold symmetric) rows are in use.
+ * out[5] = 1 when the single-GPU build uses the gather form (t3g_kernel: one CTA per input alpha string,
+ * rows of C staged in shared memory), 0 for the scatter form (t3_kernel).  out has 6 entries. */
+int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out6);
 
 /* ---- alpha-row partition for multi-GPU (no reference counterpart) ----------
  * Rank r of world owns, in every determinant block, the alpha rows [r*nIa/world, (r+1)*nIa/world); its
