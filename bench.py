@@ -7,10 +7,12 @@ A "step" is one CISigmaBuilder.Hamiltonian(C, sigma) on synthetic 8-fold symmetr
 (forte2_b200/synthetic.py, variant S, seed 20261017) with C resident in HBM.  Workload at every N:
 CAS(16e,16o) singlet, 165 636 900 determinants (C = 1.33 GB, far larger than the 126 MB L2, so no L2
 flush is needed between steps).  For N > 1 the CI vector is sharded by alpha-string rows
-(strong scaling: the same sigma build is split over N GPUs, one NCCL all-gather of C per step).
+(strong scaling: the same sigma build is split over N GPUs; forte2_b200/dist.py picks the rows form --
+all-to-all of a column slab of C, reduce-scatter of the opposite-spin term -- when the gather-form
+kernel serves the space, else the full form with one NCCL all-gather of C per step).
 
 The JSON line carries, beside the driver contract's keys:
-  roofline     the opposite-spin kernel (t3g_kernel on one GPU, t3_kernel when sharded) against the FP64
+  roofline     the opposite-spin kernel (t3g_kernel; t3_kernel where the gather form does not fit) against the FP64
                tensor peak measured in this run with a cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
   davidson     (N = 1) time of one Davidson-Liu iteration of a 3-root solve on the same workload: 3 sigma
                builds + the device solver's streaming passes (forte2_b200/davidson.py)
@@ -215,7 +217,7 @@ def workload_config(workload, gpus):
     return {"workload": f"CASCI({na + nb}e,{n}o) singlet sigma build, {ndet} determinants, synthetic 8-fold symmetric "
                         f"integrals (variant S, seed 20261017)",
             "ndet": ndet, "norb": n, "na": na, "nb": nb,
-            "partition": "single GPU" if gpus == 1 else f"alpha-string rows over {gpus} GPUs, NCCL all-gather of C",
+            "partition": "single GPU" if gpus == 1 else f"alpha-string rows over {gpus} GPUs, NCCL",
             "l2_policy": "inputs (C, sigma: %.2f GB each) larger than L2; no flush" % (ndet * 8 / 1e9)}
 
 
@@ -278,7 +280,7 @@ def run_ours(args):
             builder.Hamiltonian(c, sigma)
     else:
         from forte2_b200.dist import ShardedSigma
-        sharded = ShardedSigma(builder, rank, world)
+        sharded = ShardedSigma(builder, rank, world, form=args.form)
         c_loc = torch.randn(sharded.local_size, dtype=torch.float64, device=dev, generator=gen)
         sigma_loc = torch.empty_like(c_loc)
 
@@ -329,7 +331,8 @@ def run_ours(args):
     t3_s = last[3] * 1e-3
     roofline = {
         "bound": "tensor",
-        "kernel": ("t3g_kernel (opposite-spin, gather form, DMMA)" if shape["form"] == "gather" and world == 1
+        "kernel": ("t3g_kernel (opposite-spin, gather form, DMMA)"
+                   if shape["form"] == "gather" and (world == 1 or sharded.form == "rows")
                    else "t3_kernel (opposite-spin, scatter form, DMMA)"),
         "achieved": useful_flops / t3_s / 1e12, "peak": peak, "unit": "TFLOP/s",
         "frac": useful_flops / t3_s / 1e12 / peak,
@@ -371,6 +374,7 @@ def run_ours(args):
     else:
         e2e = {"value": value, "unit": "sigma builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "sharded vectors live on the GPUs; no host path at N>1"}
+        comm_ms = ms_per_step - last[4]
 
     # ---- one Davidson-Liu iteration of a 3-root solve (N = 1): the caller on either side of sigma ----
     davidson = None
@@ -396,6 +400,10 @@ def run_ours(args):
                               "opposite_spin": last[3], "total": last[4]},
         "roofline": roofline, "roofline_same_spin": same_spin, "cpu_baseline": cpu, "e2e": e2e,
         "davidson": davidson,
+        "sharded": None if world == 1 else {
+            "form": sharded.form, "local_compute_ms_rank0": last[4], "exchange_ms_rank0": comm_ms,
+            "note": "exchange = step time minus rank 0's kernel time: the NCCL collectives of "
+                    "forte2_b200/dist.py and their pack/unpack copies"},
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)
@@ -412,6 +420,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-davidson", action="store_true")
+    ap.add_argument("--form", default="auto", choices=["auto", "full", "rows"],
+                    help="N > 1: communication form of forte2_b200/dist.py")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

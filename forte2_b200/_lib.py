@@ -50,6 +50,10 @@ SIGNATURES = {
     "f2_sigma_part_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p, i64p]),
     "f2_sigma_apply_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p]),
+    "f2_sigma_hdiag_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "f2_sigma_rows_form": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p]),
+    "f2_sigma_apply_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p]),
     "f2_slater_matrix": (C.c_int, [C.c_void_p, C.c_double, f64p, f64p, i64p, C.c_int, f64p]),
     "f2_dl_workspace_doubles": (C.c_int64, []),
     "f2_dl_dots": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int64,

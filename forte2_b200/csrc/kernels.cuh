@@ -780,6 +780,9 @@ struct T3GParams {
     int M, Mpad, norb;
     int first; // first alpha string of this launch
     int astride;
+    // sharded build: sigma row of alpha string Ia in the reduce-scatter layout (world slots of equal
+    // size, slot q = the rows rank q owns); NULL = row Ia itself
+    const uint32_t* rowpad;
 };
 
 constexpr size_t t3g_smem_bytes(int64_t nbs, int rows, int astride) {
@@ -826,7 +829,7 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
             const int kl = static_cast<int>((ent >> 32) & 0xffff);
             const int k = kl / p.norb, l = kl - k * p.norb;
             s_kl[r] = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
-            rowoff[r] = static_cast<long long>(Iar) * p.nbs;
+            rowoff[r] = static_cast<long long>(p.rowpad ? p.rowpad[Iar] : Iar) * p.nbs;
         } else {
             s_kl[r] = -1;
             rowoff[r] = -1;
@@ -1201,9 +1204,10 @@ struct TrBlock {
 };
 
 // forward: T[dst_off + j*nA + i] = S[src_off + i*ldA + j];  back: Sigma[sig_off + i*ldA + j] += T[...]
+// local_src (forward only): `in` is the local row-slab vector, rows sit at sig_off instead of src_off
 template <bool BACK>
 __global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                 const TrBlock* __restrict__ blocks, int nblocks) {
+                                 const TrBlock* __restrict__ blocks, int nblocks, bool local_src) {
     __shared__ double tile[32][33];
     // locate the block of this tile (blocks are few; binary search over tile0)
     int lo = 0, hi = nblocks - 1;
@@ -1222,7 +1226,7 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
         for (int r = ty; r < 32; r += 8) {
             const int i = ti * 32 + r, j = tj * 32 + tx;
             if (i < b.nA && j < b.nB)
-                tile[r][tx] = in[b.src_off + static_cast<int64_t>(i) * b.ldA + j];
+                tile[r][tx] = in[(local_src ? b.sig_off : b.src_off) + static_cast<int64_t>(i) * b.ldA + j];
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {

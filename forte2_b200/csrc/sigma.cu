@@ -162,6 +162,12 @@ struct Part {
     int nitems = 0;
     int64_t t3_kcols = 0;
     SSPlan alpha_plan;
+    // rows form (sharded build without a full copy of C): alpha same-spin plan whose operand is the
+    // exchanged column slab [nIa][owned columns], and the reduce-scatter row layout of the gather-form
+    // opposite-spin kernel
+    SSPlan alpha_cols_plan;
+    DevBuf<uint32_t> rowpad;
+    int64_t slot_rows = 0; // rows per reduce-scatter slot (max over ranks of the owned row count)
     std::vector<std::unique_ptr<BetaPass>> beta_passes;
     bool beta_planned = false;
     DevBuf<CopyPiece> pieces; // owned row slabs: src = full layout, dst = local layout
@@ -660,6 +666,33 @@ std::unique_ptr<Part> make_part(f2_sigma& b, int rank, int world) {
         p.tiles.upload(tiles);
         p.al16 = even;
     }
+    // ---- rows form (single determinant block only): column-slab alpha plan and reduce-scatter layout
+    if (world > 1 && nclsA == 1 && nclsB == 1 && h.blocks.size() == 1 && h.ndet > 0) {
+        const uint32_t nc = static_cast<uint32_t>(P->ch[0] - P->cl[0]);
+        std::vector<int64_t> off(1, 0);
+        std::vector<uint32_t> ncols(1, nc), tiles;
+        fill_tiles(tiles, ncols);
+        SSPlan& p = P->alpha_cols_plan;
+        p.ngroups = 1;
+        p.ntiles = static_cast<int>(tiles.size() / 2);
+        p.xoff.upload(off);
+        p.yoff.upload(off);
+        p.g_ncols.upload(ncols);
+        p.g_ldx.upload(ncols);
+        p.g_ldy.upload(ncols);
+        p.tiles.upload(tiles);
+        p.al16 = false;
+        const int64_t nA = static_cast<int64_t>(A.strpcls(0));
+        int64_t slot = 0;
+        for (int q = 0; q < world; ++q)
+            slot = std::max(slot, nA * (q + 1) / world - nA * q / world);
+        P->slot_rows = slot;
+        std::vector<uint32_t> rowpad(static_cast<size_t>(nA));
+        for (int q = 0; q < world; ++q)
+            for (int64_t i = nA * q / world; i < nA * (q + 1) / world; ++i)
+                rowpad[static_cast<size_t>(i)] = static_cast<uint32_t>(q * slot + (i - nA * q / world));
+        P->rowpad.upload(rowpad);
+    }
     return P;
 }
 
@@ -863,8 +896,11 @@ void launch_t3g_inst(const f2_sigma& b, const T3GParams& p, int nrows, cudaStrea
     b.launches += 1;
 }
 
-// gather-form opposite-spin term over all input alpha strings (single block, single GPU)
-void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st) {
+// gather-form opposite-spin term over the input alpha strings [first, first + nrows) (single block).
+// C points at row 0 of the block (rows outside the range are never read); rowpad (may be NULL) maps
+// output rows into the reduce-scatter layout of a sharded build.
+void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st, int first = 0,
+                int nrows = -1, const uint32_t* rowpad = nullptr) {
     const CIStringsHost& h = *b.S->host;
     const DevStrings& D = *b.D;
     T3GParams p;
@@ -879,9 +915,13 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
     p.M = b.M;
     p.Mpad = b.t3g_mpad;
     p.norb = h.norb;
-    p.first = 0;
+    p.first = first;
     p.astride = b.t3g_astride;
-    const int nrows = static_cast<int>(h.nas);
+    p.rowpad = rowpad;
+    if (nrows < 0)
+        nrows = static_cast<int>(h.nas);
+    if (nrows == 0)
+        return;
     const int key = b.t3g_nm16 * 2 + b.t3g_has8;
     switch (key) {
     case 2: launch_t3g_inst<1, false>(b, p, nrows, st); break;
@@ -1073,11 +1113,11 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
     for (const auto& bp : P.beta_passes) {
         if (bp->ntr_tiles == 0)
             continue;
-        transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(C, b.XT.p, bp->tr.p, bp->ntr);
+        transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(C, b.XT.p, bp->tr.p, bp->ntr, false);
         b.launches += 2;
         F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
         launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, fold ? b.Wfold.p : b.W[1].p, st);
-        transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr);
+        transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr, false);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
     if (gather)
@@ -1095,6 +1135,59 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
         throw std::invalid_argument("CISigmaBuilder.Hamiltonian: vectors must have ndet = " +
                                     std::to_string(h.ndet) + " elements, got " + std::to_string(n));
     apply(b, *b.single, C, sigma, nullptr, st);
+}
+
+// Rows form of the sharded build (single determinant block, gather-form opposite-spin kernel): no
+// rank ever holds the full trial vector.
+//   sigma_loc  = E C_loc + beta same-spin term of the owned rows                 (complete)
+//   ycols      = alpha same-spin term of [all rows][owned columns], from xcols    (caller: all-to-all, add)
+//   scatter    = opposite-spin contributions of the owned INPUT rows to every sigma row, world slots of
+//                slot_rows x nbs (caller: reduce-scatter, add)
+void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, double* sigma, double* ycols,
+                double* scatter, cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    F2_CUDA(cudaSetDevice(b.device));
+    collect_times(b);
+    if (!P.beta_planned)
+        plan_beta(b, P);
+    if (h.ndet == 0)
+        return;
+    const int64_t rows = P.hi[0] - P.lo[0];
+    b.launches = 0;
+    F2_CUDA(cudaEventRecord(b.ev[0], st));
+    if (P.local_size > 0) {
+        scale_copy_kernel<<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
+        b.launches += 1;
+    }
+    F2_CUDA(cudaEventRecord(b.ev[1], st));
+    F2_CUDA(cudaMemsetAsync(ycols, 0, static_cast<size_t>(std::max<int64_t>(P.y_size, 1)) * sizeof(double), st));
+    if (h.na >= 1)
+        launch_same_spin(b, 0, P.alpha_cols_plan, xcols, ycols, b.W[0].p, st);
+    F2_CUDA(cudaEventRecord(b.ev[2], st));
+    for (const auto& bp : P.beta_passes) {
+        if (bp->ntr_tiles == 0)
+            continue;
+        transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(Cloc, b.XT.p, bp->tr.p, bp->ntr, true);
+        b.launches += 2;
+        F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
+        launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, b.W[1].p, st);
+        transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr, false);
+    }
+    F2_CUDA(cudaEventRecord(b.ev[3], st));
+    F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_rows * h.nbs * sizeof(double), st));
+    if (h.na >= 1 && h.nb >= 1 && rows > 0)
+        launch_t3g(b, Cloc - P.lo[0] * h.nbs, scatter, st, static_cast<int>(P.lo[0]), static_cast<int>(rows),
+                   P.rowpad.p);
+    F2_CUDA(cudaEventRecord(b.ev[4], st));
+    F2_CUDA(cudaGetLastError());
+    b.ev_pending = true;
+}
+
+// the rows form needs the gather-form kernel and 16-byte aligned row slabs (even nbs)
+bool rows_form_ok(const f2_sigma& b) {
+    const CIStringsHost& h = *b.S->host;
+    return b.t3g && h.blocks.size() == 1 && h.nclsA() == 1 && h.nclsB() == 1 && h.nbs % 2 == 0 &&
+           std::getenv("F2_NO_ROWS_FORM") == nullptr;
 }
 
 Part& shard_of(f2_sigma& b, int rank, int world) {
@@ -1327,6 +1420,43 @@ int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_loc
     }
 }
 
+int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4) {
+    try {
+        if (!h || !out4)
+            throw std::invalid_argument("null argument");
+        out4[0] = out4[1] = out4[2] = out4[3] = 0;
+        if (world > 1 && rows_form_ok(*h)) {
+            Part& P = shard_of(*h, rank, world);
+            out4[0] = 1;
+            out4[1] = P.slot_rows;
+            out4[2] = h->S->host->nbs;
+            out4[3] = P.y_size;
+        }
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xcols_dev, double* sigma_local_dev,
+                        double* ycols_dev, double* scatter_dev, int rank, int world, void* stream) {
+    try {
+        if (!h || !C_local_dev || !xcols_dev || !sigma_local_dev || !ycols_dev || !scatter_dev)
+            throw std::invalid_argument("null argument");
+        if (world <= 1 || !rows_form_ok(*h))
+            throw std::runtime_error("CISigmaBuilder: the rows form of the sharded build is not available for "
+                                     "this string space (f2_sigma_rows_form)");
+        if ((reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
+            throw std::invalid_argument("CISigmaBuilder: the local trial vector must be 16-byte aligned");
+        Part& P = shard_of(*h, rank, world);
+        apply_rows(*h, P, C_local_dev, xcols_dev, sigma_local_dev, ycols_dev, scatter_dev,
+                   static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
     out5[5] = h->t3g ? 1 : 0;
     out5[0] = h->M;
@@ -1357,6 +1487,45 @@ int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream) {
             out_dev, h->hd_blocks.p, h->hd_nblocks, h->ea.p, h->eb.p, h->ja.p, h->D->b_str.p,
             h->norb, h->E);
         F2_CUDA(cudaGetLastError());
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream) {
+    try {
+        if (!h || !out_local_dev)
+            throw std::invalid_argument("null argument");
+        F2_CUDA(cudaSetDevice(h->device));
+        Part& P = shard_of(*h, rank, world);
+        const CIStringsHost& hs = *h->S->host;
+        std::vector<HdiagBlock> hb;
+        uint32_t tile0 = 0;
+        for (size_t bi = 0; bi < hs.blocks.size(); ++bi) {
+            const auto& blk = hs.blocks[bi];
+            const int64_t rows = P.hi[blk.cA] - P.lo[blk.cA];
+            if (blk.nA * blk.nB == 0 || rows == 0)
+                continue;
+            HdiagBlock x;
+            x.off = world == 1 ? blk.offset : P.loc_off[bi];
+            x.a0 = hs.space(0, K_STR_N).cls_off[blk.cA] + static_cast<uint32_t>(P.lo[blk.cA]);
+            x.b0 = hs.space(1, K_STR_N).cls_off[blk.cB];
+            x.nA = static_cast<int32_t>(rows);
+            x.nB = static_cast<int32_t>(blk.nB);
+            x.tile0 = tile0;
+            tile0 += static_cast<uint32_t>(rows);
+            hb.push_back(x);
+        }
+        if (tile0 == 0)
+            return F2_OK;
+        DevBuf<HdiagBlock> dev;
+        dev.upload(hb);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        hdiag_kernel<<<tile0, 256, 0, st>>>(out_local_dev, dev.p, static_cast<int>(hb.size()), h->ea.p, h->eb.p,
+                                            h->ja.p, h->D->b_str.p, h->norb, h->E);
+        F2_CUDA(cudaGetLastError());
+        F2_CUDA(cudaStreamSynchronize(st)); // the block table is freed on return
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);

@@ -4,14 +4,25 @@ of one torch.distributed group (one process per GPU, NCCL over NVLink on the B20
 No reference counterpart exists (forte2 is single-process); correctness is
 defined as equality with the single-GPU / reference result.
 
-Per sigma build
+Rank r owns rows [r*nIa/world, (r+1)*nIa/world) of every determinant block (same rule for columns).
+The local vector is the concatenation of the owned row slabs in block order.
+
+Full form (any string space), per sigma build
   1. all-gather of the trial vector (each rank contributes its owned row slabs)            -- NCCL
   2. local work through the C ABI (f2_sigma_apply_part): H0, beta same-spin and the opposite-spin term
      for the owned ROWS (these only write owned rows), and the alpha same-spin term, which couples
      rows, for the owned COLUMNS of every row
   3. exchange of the alpha same-spin partial results to the row owners (all-to-all) and add  -- NCCL
-Rank r owns rows [r*nIa/world, (r+1)*nIa/world) of every determinant block (same rule for columns).
-The local vector is the concatenation of the owned row slabs in block order.
+
+Rows form (one determinant block served by the gather-form opposite-spin kernel; no rank ever holds the
+full vector), per sigma build
+  1. all-to-all of C: rank r sends C[rows of r, columns of q] to q and assembles the column slab
+     [all rows][columns of r]                                                                -- NCCL, ndet/world doubles
+  2. local work (f2_sigma_apply_rows): H0 and beta same-spin term of the owned rows from the local
+     slab; alpha same-spin term of the column slab; opposite-spin term of the owned INPUT rows,
+     scattered to every sigma row in a buffer of world equal slots
+  3. all-to-all of the alpha same-spin result back to the row owners, add                      -- NCCL
+  4. reduce-scatter of the opposite-spin buffer, add                                          -- NCCL, ndet doubles
 """
 from __future__ import annotations
 
@@ -53,6 +64,18 @@ class CudaEngine:
         _lib.check(_lib.lib().f2_sigma_apply_part(self.builder._h, c_full.data_ptr(), sigma_loc.data_ptr(),
                                                   yexch.data_ptr(), rank, world, stream))
 
+    def rows_form(self, rank, world):
+        """(available, slot_rows, nbs) of the rows form (f2_sigma_rows_form)"""
+        out = np.zeros(4, dtype=np.int64)
+        _lib.check(_lib.lib().f2_sigma_rows_form(self.builder._h, rank, world, out.ctypes.data_as(_lib.i64p)))
+        return bool(out[0]), int(out[1]), int(out[2])
+
+    def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world):
+        stream = torch.cuda.current_stream(self.builder.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_apply_rows(self.builder._h, c_loc.data_ptr(), xcols.data_ptr(),
+                                                  sigma_loc.data_ptr(), ycols.data_ptr(), scatter.data_ptr(),
+                                                  rank, world, stream))
+
     def layout_from_library(self, nblocks, rank, world):
         sizes = np.zeros(2, dtype=np.int64)
         rows = np.zeros((nblocks, 6), dtype=np.int64)
@@ -65,7 +88,8 @@ class ShardedSigma:
     """sigma = H C with C and sigma sharded by alpha rows.  `engine` does the local work: CudaEngine on
     the GPU box; the gloo tests pass a CPU stand-in with the same apply_part signature."""
 
-    def __init__(self, builder=None, rank=None, world=None, group=None, engine=None, blocks=None, device=None):
+    def __init__(self, builder=None, rank=None, world=None, group=None, engine=None, blocks=None, device=None,
+                 form="auto"):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -79,11 +103,23 @@ class ShardedSigma:
         self.device = device if device is not None else (
             torch.device("cuda", builder.device) if builder is not None else torch.device("cpu"))
         self._max_local = max(lay.local_size for lay in self.layouts)
-        kw = dict(dtype=torch.float64, device=self.device)
-        self._full = torch.empty(self.ndet, **kw)
-        self._gather = [torch.empty(self._max_local, **kw) for _ in range(self.world)]
-        self._pad = torch.zeros(self._max_local, **kw)
+        self._kw = kw = dict(dtype=torch.float64, device=self.device)
+        self._full = self._gather = self._pad = None  # full-layout buffers, allocated on first use
         self._yexch = torch.zeros(max(self.layout.exchange_size, 1), **kw)
+        # rows form: wanted unless form == "full", used when the engine offers it for this space
+        self.form = "full"
+        if form not in ("auto", "full", "rows"):
+            raise ValueError("form must be 'auto', 'full' or 'rows'")
+        if form != "full" and self.world > 1 and hasattr(self.engine, "rows_form"):
+            ok, slot_rows, nbs = self.engine.rows_form(self.rank, self.world)
+            if ok:
+                self.form = "rows"
+                self._slot = slot_rows * nbs
+                self._xcols = torch.zeros(max(self.layout.exchange_size, 1), **kw)
+                self._scatter = torch.empty(self.world * self._slot, **kw)
+                self._rs_out = torch.empty(self._slot, **kw)
+        if form == "rows" and self.form != "rows" and self.world > 1:
+            raise RuntimeError("the rows form of the sharded build is not available for this string space")
         if isinstance(self.engine, CudaEngine):
             sizes, rows = self.engine.layout_from_library(len(self.layout.blocks), self.rank, self.world)
             assert int(sizes[0]) == self.layout.local_size and int(sizes[1]) == self.layout.exchange_size
@@ -101,9 +137,14 @@ class ShardedSigma:
 
     def all_gather_full(self, c_loc: torch.Tensor) -> torch.Tensor:
         """full-layout copy of a sharded vector on every rank (step 1)"""
+        if self._full is None:
+            self._full = torch.empty(self.ndet, **self._kw)
         if self.world == 1:
             self._full.copy_(c_loc)
             return self._full
+        if self._gather is None:
+            self._gather = [torch.empty(self._max_local, **self._kw) for _ in range(self.world)]
+            self._pad = torch.zeros(self._max_local, **self._kw)
         self._pad[: self.local_size].copy_(c_loc)
         dist.all_gather(self._gather, self._pad, group=self.group)
         for q, lay in enumerate(self.layouts):
@@ -152,8 +193,46 @@ class ShardedSigma:
                     blk[:, cl_q:cl_q + nc_q] += recv[q][pos:pos + n * nc_q].view(n, nc_q)
                 pos += n * nc_q
 
+    def _exchange_cols(self, c_loc: torch.Tensor):
+        """rows form, step 1: column slab [all rows][my columns] of C from the row slabs (one block)"""
+        me = self.layout
+        (off, nA, nB), (lo, n, _), (cl, nc, _) = me.blocks[0], me.rows[0], me.cols[0]
+        mine = c_loc.view(n, nB)
+        slab = self._xcols[: nA * nc].view(nA, nc)
+        ops, keep = [], []
+        for q, lay in enumerate(self.layouts):
+            lo_q, n_q, _ = lay.rows[0]
+            cl_q, nc_q, _ = lay.cols[0]
+            if q == self.rank:
+                slab[lo:lo + n].copy_(mine[:, cl:cl + nc])
+                continue
+            if n > 0 and nc_q > 0:
+                piece = mine[:, cl_q:cl_q + nc_q].contiguous()
+                keep.append(piece)
+                ops.append(dist.P2POp(dist.isend, piece, q, group=self.group))
+            if n_q > 0 and nc > 0:
+                ops.append(dist.P2POp(dist.irecv, slab[lo_q:lo_q + n_q], q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _reduce_scatter_add(self, sigma_loc: torch.Tensor):
+        """rows form, step 4: sum over ranks of slot `rank` of the opposite-spin buffers, added to sigma"""
+        if dist.get_backend(self.group) == "nccl":
+            dist.reduce_scatter_tensor(self._rs_out, self._scatter, op=dist.ReduceOp.SUM, group=self.group)
+            sigma_loc += self._rs_out[: self.local_size]
+        else:  # gloo (CPU tests): no reduce-scatter, reduce everything and take the own slot
+            dist.all_reduce(self._scatter, op=dist.ReduceOp.SUM, group=self.group)
+            sigma_loc += self._scatter[self.rank * self._slot: self.rank * self._slot + self.local_size]
+
     def Hamiltonian(self, c_loc: torch.Tensor, sigma_loc: torch.Tensor) -> None:
         assert c_loc.numel() == self.local_size and sigma_loc.numel() == self.local_size
+        if self.form == "rows":
+            self._exchange_cols(c_loc)
+            self.engine.apply_rows(c_loc, self._xcols, sigma_loc, self._yexch, self._scatter, self.rank, self.world)
+            self._reduce_scatter_add(sigma_loc)
+            self._exchange_add(sigma_loc)
+            return
         full = self.all_gather_full(c_loc)
         self.engine.apply_part(full, sigma_loc, self._yexch, self.rank, self.world)
         if self.world > 1:

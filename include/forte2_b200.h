@@ -118,6 +118,23 @@ int f2_sigma_part_layout(f2_sigma* h, int rank, int world, int64_t* sizes2, int6
 int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev, double* exch_dev,
                         int rank, int world, void* stream);
 
+/* determinant energies of the owned rows, in the local (row slab) layout; synchronises the stream */
+int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream);
+
+/* Rows form of the sharded build: no rank holds the full trial vector.  Available when the CI space is
+ * one determinant block served by the gather-form opposite-spin kernel (f2_sigma_t3_shape out[5]).
+ * out4 = {available (0/1), slot_rows, nbs, column-slab length}: the reduce-scatter buffer has world
+ * slots of slot_rows*nbs doubles, slot q holding the sigma rows rank q owns. */
+int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4);
+/* C_local: owned rows of C.  xcols: [nIa][owned columns] of C, assembled by the caller with an
+ * all-to-all of the row slabs.  On return sigma_local = H0 + beta same-spin term of the owned rows;
+ * ycols = alpha same-spin term of [nIa][owned columns] (caller: all-to-all back to the row owners, add);
+ * scatter = opposite-spin contributions of the owned INPUT rows to every sigma row in the slot layout
+ * above (caller: reduce-scatter over NCCL, add).  Device pointers; stream = cudaStream_t. */
+int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xcols_dev,
+                        double* sigma_local_dev, double* ycols_dev, double* scatter_dev, int rank, int world,
+                        void* stream);
+
 /* <I|H|J> for the n determinants at the given CI-vector addresses, n x n row-major, on the HOST
  * (SlaterRules::slater_rules, forte2/determinant/slater_rules.cc:123-245): the guess Hamiltonian of
  * forte2/ci/ci.py:411-452.  H, V as in f2_sigma_create.  Needs no GPU. */

@@ -1,6 +1,8 @@
-"""world_size = 2 and 3 over gloo on CPU: the row partition, the all-gather, the column-owned alpha
-same-spin exchange and the add, with the oracle port standing in for the GPU's local work.  The GPU
-version of the same check (NCCL, the real C ABI) is tests/test_dist_gpu.py."""
+"""world_size = 2 and 3 over gloo on CPU: the row partition and both communication forms of
+forte2_b200/dist.py (full: all-gather + column-owned alpha same-spin exchange; rows: all-to-all of the
+column slab, exchange back, reduce-scatter of the opposite-spin term), with the oracle port standing in
+for the GPU's local work.  The GPU version of the same check (NCCL, the real C ABI) is
+tests/test_dist_gpu.py."""
 import os
 import socket
 import sys
@@ -44,7 +46,38 @@ class PortEngine:
                 out[loc:loc + n * nB] += alpha_part[off + lo * nB: off + (lo + n) * nB]
 
 
-def _worker(rank, world, port, name, result_dir):
+    # ---- rows form: same contract as f2_sigma_rows_form / f2_sigma_apply_rows (single block) ----
+    def rows_form(self, rank, world):
+        lay = self.layouts[rank]
+        if len(lay.blocks) != 1:
+            return False, 0, 0
+        _, nA, nB = lay.blocks[0]
+        slot_rows = max(L.rows[0][1] for L in self.layouts)
+        return True, slot_rows, nB
+
+    def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world):
+        from oracle import checker
+        E, H, V = self.ints
+        lay = self.layouts[rank]
+        (off, nA, nB), (lo, n, _), (cl, nc, _) = lay.blocks[0], lay.rows[0], lay.cols[0]
+        rows_only = np.zeros(nA * nB)
+        rows_only[lo * nB:(lo + n) * nB] = c_loc.numpy()
+        cols_only = np.zeros((nA, nB))
+        cols_only[:, cl:cl + nc] = xcols.numpy()[: nA * nc].reshape(nA, nc)
+        local = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_SCALAR | checker.PART_BETA)
+        sigma_loc.numpy()[:] = local[lo * nB:(lo + n) * nB]
+        alpha = checker.port_sigma(self.dets, E, H, V, cols_only.reshape(-1), checker.PART_ALPHA)
+        ycols.numpy()[: nA * nc] = alpha.reshape(nA, nB)[:, cl:cl + nc].reshape(-1)
+        t3 = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_ALPHA_BETA).reshape(nA, nB)
+        _, slot_rows, _ = self.rows_form(rank, world)
+        out = scatter.numpy()
+        out[:] = 0.0
+        for q, L in enumerate(self.layouts):
+            lo_q, n_q, _ = L.rows[0]
+            out[q * slot_rows * nB: q * slot_rows * nB + n_q * nB] = t3[lo_q:lo_q + n_q].reshape(-1)
+
+
+def _worker(rank, world, port, name, form, result_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -59,9 +92,11 @@ def _worker(rank, world, port, name, result_dir):
         ints = synthetic.integrals(n, "S")
         strings = f2.CIStrings(*space)
         dets = strings.make_determinants()
-        sh = ShardedSigma(rank=rank, world=world, engine=PortEngine(dets, ints, None),
-                          blocks=strings.blocks(), device=torch.device("cpu"))
-        sh.engine.layouts = sh.layouts
+        from forte2_b200.dist import Layout
+        engine = PortEngine(dets, ints, [Layout(strings.blocks(), q, world) for q in range(world)])
+        sh = ShardedSigma(rank=rank, world=world, engine=engine, blocks=strings.blocks(),
+                          device=torch.device("cpu"), form=form)
+        assert sh.form == form
         c_full = torch.from_numpy(synthetic.trial_vector(strings.ndet))
         c_loc = sh.scatter_full(c_full)
         sigma_loc = torch.zeros_like(c_loc)
@@ -83,9 +118,11 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("name,world", [("cas66", 2), ("gas343_54", 2), ("cas66_d2h", 3), ("cas75_odd", 3)])
-def test_sharded_sigma_over_gloo(tmp_path, name, world):
-    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("name,world,form", [("cas66", 2, "full"), ("gas343_54", 2, "full"), ("cas66_d2h", 3, "full"),
+                                             ("cas75_odd", 3, "full"), ("cas66", 2, "rows"), ("cas75_odd", 3, "rows"),
+                                             ("cas88", 3, "rows")])
+def test_sharded_sigma_over_gloo(tmp_path, name, world, form):
+    mp.spawn(_worker, args=(world, _free_port(), name, form, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         err = float(np.load(tmp_path / f"err_{r}.npy")[0])
         assert err <= 1e-13, (r, err)

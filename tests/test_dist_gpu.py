@@ -32,12 +32,20 @@ def _worker(rank, world, port, spaces, result_dir):
             c_full = torch.from_numpy(synthetic.trial_vector(strings.ndet)).cuda()
             want = torch.empty_like(c_full)
             builder.Hamiltonian(c_full, want)  # single-GPU result on this rank
-            sh = ShardedSigma(builder, rank, world)
-            c_loc = sh.scatter_full(c_full)
-            sigma_loc = torch.full_like(c_loc, float("nan"))
-            sh.Hamiltonian(c_loc, sigma_loc)
-            got = sh.all_gather_full(sigma_loc).clone()
-            errs.append(float((got - want).norm() / want.norm()))
+            forms = []
+            for form in ("full", "auto"):
+                sh = ShardedSigma(builder, rank, world, form=form)
+                if form == "auto" and sh.form == "full":
+                    continue  # the rows form does not exist for this space; "full" is already checked
+                forms.append(sh.form)
+                c_loc = sh.scatter_full(c_full)
+                sigma_loc = torch.full_like(c_loc, float("nan"))
+                sh.Hamiltonian(c_loc, sigma_loc)
+                sh.Hamiltonian(c_loc, sigma_loc)  # twice: no dependence on leftovers
+                got = sh.all_gather_full(sigma_loc).clone()
+                errs.append(float((got - want).norm() / want.norm()))
+            if n >= 8 and len(space[3]) == 1 and strings.nbs % 2 == 0 and strings.nas % 2 == 0:
+                assert "rows" in forms, forms
         np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array(errs))
     finally:
         dist.destroy_process_group()
@@ -56,7 +64,8 @@ def test_sharded_sigma_two_gpus(tmp_path):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     spaces = [(3, 3, 0, [[0] * 6], [], []), (5, 4, 0, [[0] * 3, [0] * 4, [0] * 3], [4, 0, 0], [6, 8, 2]),
-              (3, 3, 0, [[0, 5, 2, 3, 6, 7]], [], []), (5, 5, 0, [[0] * 10], [], []), (4, 3, 0, [[0] * 7], [], [])]
+              (3, 3, 0, [[0, 5, 2, 3, 6, 7]], [], []), (5, 5, 0, [[0] * 10], [], []), (4, 3, 0, [[0] * 7], [], []),
+              (6, 6, 0, [[0] * 12], [], [])]
     mp.spawn(_worker, args=(2, _free_port(), spaces, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         errs = np.load(tmp_path / f"err_{r}.npy")

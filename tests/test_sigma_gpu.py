@@ -136,3 +136,38 @@ def test_cas_medium(ref, torch_cuda, n):
     assert _rel(got, want) <= TOL
     t = gb.avg_build_time()
     assert len(t) == 4 and t[0] > 0
+
+
+@pytest.mark.parametrize("n,world", [(8, 2), (10, 3), (10, 4)])
+def test_rows_form_parts_emulated_on_one_gpu(ref, torch_cuda, n, world):
+    """f2_sigma_apply_rows (the sharded build that never holds the full vector) for every rank of a world,
+    run one after the other on this GPU, the three exchanges of forte2_b200/dist.py done by hand:
+    the sum equals the single-GPU sigma and the reference.  The NCCL version is tests/test_dist_gpu.py."""
+    torch = torch_cuda
+    from forte2_b200.dist import CudaEngine, Layout
+    space = (n // 2, n // 2, 0, [[0] * n], [], [])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    c = synthetic.trial_vector(rs.ndet)
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    eng = CudaEngine(gb)
+    nA, nB = gs.nas, gs.nbs
+    C = torch.from_numpy(c).cuda().view(nA, nB)
+    lays = [Layout(gs.blocks(), q, world) for q in range(world)]
+    ok, slot_rows, nbs = eng.rows_form(0, world)
+    assert ok and nbs == nB and slot_rows == max(L.rows[0][1] for L in lays)
+    total = torch.zeros(nA, nB, dtype=torch.float64, device="cuda")
+    for q, L in enumerate(lays):
+        (lo, nr, _), (cl, nc, _) = L.rows[0], L.cols[0]
+        c_loc = C[lo:lo + nr].contiguous().view(-1)
+        xcols = C[:, cl:cl + nc].contiguous().view(-1)
+        sigma_loc = torch.full_like(c_loc, float("nan"))
+        ycols = torch.full((max(nA * nc, 1),), float("nan"), dtype=torch.float64, device="cuda")
+        scatter = torch.full((world * slot_rows * nB,), float("nan"), dtype=torch.float64, device="cuda")
+        eng.apply_rows(c_loc, xcols, sigma_loc, ycols, scatter, q, world)
+        total[lo:lo + nr] += sigma_loc.view(nr, nB)
+        total[:, cl:cl + nc] += ycols[: nA * nc].view(nA, nc)
+        for r, Lr in enumerate(lays):
+            lo_r, n_r, _ = Lr.rows[0]
+            total[lo_r:lo_r + n_r] += scatter[r * slot_rows * nB: r * slot_rows * nB + n_r * nB].view(n_r, nB)
+    assert _rel(total.view(-1).cpu().numpy(), want) <= TOL
