@@ -313,6 +313,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     last = builder.last_build_ms()  # [H0, same-spin alpha, same-spin beta, opposite spin, total]
+    phases = None
+    if world > 1:  # every rank takes part: one extra build with a CUDA event at each phase boundary
+        phases = [(name, round(ms, 3)) for name, ms in sharded.profile_phases(c_loc, sigma_loc)]
     ms_per_step = ms_total / args.steps
     value = 1e3 / ms_per_step
 
@@ -402,6 +405,7 @@ def run_ours(args):
         "davidson": davidson,
         "sharded": None if world == 1 else {
             "form": sharded.form, "local_compute_ms_rank0": last[4], "exchange_ms_rank0": comm_ms,
+            "phases_ms_rank0_one_extra_build": phases,
             "note": "exchange = step time minus rank 0's kernel time: the NCCL collectives of "
                     "forte2_b200/dist.py and their pack/unpack copies"},
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks.summary(),

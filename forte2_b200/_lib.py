@@ -22,6 +22,7 @@ f64p = C.POINTER(C.c_double)
 # name -> (restype, argtypes); must list every symbol of include/forte2_b200.h
 SIGNATURES = {
     "f2_last_error": (C.c_char_p, []),
+    "f2_last_status": (C.c_int, []),
     "f2_abi_version": (C.c_int, []),
     "f2_strings_create": (C.c_void_p, [C.c_int64, C.c_int64, C.c_int, C.c_int, i32p, i32p, C.c_int, i32p,
                                        C.c_int, i32p]),
@@ -55,6 +56,16 @@ SIGNATURES = {
     "f2_sigma_apply_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p]),
     "f2_slater_matrix": (C.c_int, [C.c_void_p, C.c_double, f64p, f64p, i64p, C.c_int, f64p]),
+    "f2_adapter_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
+    "f2_adapter_destroy": (None, [C.c_void_p]),
+    "f2_adapter_info": (C.c_int, [C.c_void_p, i64p]),
+    "f2_adapter_table": (C.c_int64, [C.c_void_p, i64p, i64p, f64p, C.c_int64]),
+    "f2_adapter_conf_ranges": (C.c_int, [C.c_void_p, i64p]),
+    "f2_adapter_csf_to_det": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "f2_adapter_det_to_csf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "f2_adapter_csf_to_det_host": (C.c_int, [C.c_void_p, f64p, C.c_int64, f64p, C.c_int64]),
+    "f2_adapter_det_to_csf_host": (C.c_int, [C.c_void_p, f64p, C.c_int64, f64p, C.c_int64]),
+    "f2_adapter_hdiag_csf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "f2_dl_workspace_doubles": (C.c_int64, []),
     "f2_dl_dots": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                              C.c_void_p, C.c_void_p, C.c_void_p]),

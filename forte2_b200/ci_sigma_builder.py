@@ -136,6 +136,33 @@ class CISigmaBuilder:
         return {"M": int(out[0]), "M_pad": int(out[1]), "K_max": int(out[2]), "k_cols": int(out[3]),
                 "pair_compressed": bool(out[4]), "form": "gather" if out[5] else "scatter"}
 
+    def form_Hdiag_det_part(self, rank: int, world: int, local_size: int):
+        """determinant energies of the alpha rows rank `rank` of `world` owns, in the local layout of
+        forte2_b200/dist.py (f2_sigma_hdiag_part)"""
+        import torch
+        out = torch.empty(local_size, dtype=torch.float64, device=f"cuda:{self.device}")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_hdiag_part(self._h, out.data_ptr(), rank, world, stream))
+        return out
+
+    def form_Hdiag_csf(self, dets, spin_adapter, spin_adapt_full_preconditioner: bool = False):
+        """Davidson preconditioner in the CSF basis (CISigmaBuilder::form_Hdiag_csf,
+        forte2/ci/ci_sigma_builder.cc:317-370) as a CUDA tensor of ncsf doubles.  `dets` is accepted for
+        signature compatibility and not used (the adapter knows its determinants).  Only the default
+        form H_II ~ sum_d c_dI^2 <d|H|d> exists on the device; the exact form (which the reference itself
+        calls too slow to use) is refused."""
+        import torch
+        if spin_adapt_full_preconditioner:
+            raise NotImplementedError("spin_adapt_full_preconditioner=True is not available on the device")
+        if spin_adapter.ci_strings is not self.ci_strings and spin_adapter.ndet != self.ci_strings.ndet:
+            raise ValueError("the spin adapter was prepared for a different determinant space")
+        e_det = self.form_Hdiag_det()
+        out = torch.empty(spin_adapter.ncsf, dtype=torch.float64, device=e_det.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().f2_adapter_hdiag_csf(spin_adapter._h, e_det.data_ptr(), out.data_ptr(), self.device,
+                                                   stream))
+        return out
+
     def form_Hdiag_det(self):
         """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""
         import torch

@@ -37,10 +37,18 @@ class CISolver:
 
     Parameters follow forte2/ci/ci.py:30-79 where they exist there: `nroot`, `davidson_liu_params`,
     `ci_algorithm` ("hz" | "kh" ...), `ci_builder_memory` (MB), `energy_shift`, `log_level`.
+
+    With `spin_adapter` (a prepared forte2_b200.CISpinAdapter) the solve runs in the CSF basis exactly as
+    forte2's default path does (forte2/ci/ci.py:147-165, 214-235): the Davidson vectors have ncsf elements,
+    the preconditioner is form_Hdiag_csf, and every sigma build is csf_C_to_det_C -> Hamiltonian ->
+    det_C_to_csf_C, all on device vectors.  Without it the solve runs in the determinant basis
+    (forte2/ci/rel_ci.py:96-114), which is the only option once the coupling table no longer fits.
     """
 
     def __init__(self, strings: CIStrings, E, H, V, nroot=1, davidson_liu_params=None, ci_algorithm="hz",
-                 ci_builder_memory=1024, energy_shift=None, log_level=3, device=None, log=None, builder=None):
+                 ci_builder_memory=1024, energy_shift=None, log_level=3, device=None, log=None, builder=None,
+                 spin_adapter=None):
+        self.spin_adapter = spin_adapter
         self.ci_strings = strings
         self.E0, self.H, self.V = float(E), np.asarray(H, dtype=np.float64), np.asarray(V, dtype=np.float64)
         self.nroot = int(nroot)
@@ -68,6 +76,75 @@ class CISolver:
         guess[:, indices] = coeff
         return guess
 
+    # forte2/ci/ci.py:405-452 with _basis_matrix_element = slater_rules_csf
+    def _build_guess_vectors_csf(self, hdiag):
+        import torch
+        sa = self.spin_adapter
+        p = self.davidson_liu_params
+        self.num_guess_states = min(p.guess_per_root * self.nroot, sa.ncsf)
+        nguess = min(p.ndets_per_guess * self.num_guess_states, sa.ncsf)
+        key = hdiag if self.energy_shift is None else (hdiag - self.energy_shift).abs()
+        indices = torch.topk(key, nguess, largest=False, sorted=True).indices
+        rows = [sa.csf(int(i)) for i in indices.cpu().numpy()]
+        dets = sorted({d for row in rows for d, _ in row})
+        pos = {d: k for k, d in enumerate(dets)}
+        C = np.zeros((len(dets), nguess))
+        for j, row in enumerate(rows):
+            for d, c in row:
+                C[pos[d], j] += c
+        Hdet = slater_matrix(self.ci_strings, self.E0, self.H, self.V, np.array(dets, dtype=np.int64))
+        Hguess = C.T @ Hdet @ C
+        _, evecs = np.linalg.eigh(0.5 * (Hguess + Hguess.T))
+        guess = torch.zeros((self.num_guess_states, sa.ncsf), dtype=torch.float64, device=hdiag.device)
+        coeff = torch.from_numpy(np.ascontiguousarray(evecs[:, : self.num_guess_states].T)).to(hdiag.device)
+        guess[:, indices] = coeff
+        return guess
+
+    def evecs_det(self):
+        """the converged roots in the determinant basis, (nroot, ndet) CUDA tensor"""
+        import torch
+        if self.spin_adapter is None:
+            return self.evecs
+        out = torch.empty((self.evecs.shape[0], self.ci_strings.ndet), dtype=torch.float64, device=self.evecs.device)
+        for i in range(self.evecs.shape[0]):
+            self.spin_adapter.csf_C_to_det_C(self.evecs[i].contiguous(), out[i])
+        return out
+
+    def _run_csf(self, b):
+        import torch
+        s, sa = self.ci_strings, self.spin_adapter
+        if sa.ndet != s.ndet:
+            raise ValueError("the spin adapter was prepared for a different determinant space")
+        if sa.ncsf == 0:
+            raise ValueError("No CSFs could be generated for the given state and orbitals.")
+        hdiag = b.form_Hdiag_csf(None, sa)
+        if sa.ncsf == 1:
+            self.evals = self.E = hdiag[:1].cpu().numpy()
+            self.evecs = torch.ones((1, 1), dtype=torch.float64, device=hdiag.device)
+            self.converged = self.executed = True
+            return self
+        if self.eigensolver is None:
+            self.eigensolver = DavidsonLiuSolver(
+                size=sa.ncsf, nroot=self.nroot, davidson_liu_params=self.davidson_liu_params,
+                energy_shift=self.energy_shift, log_level=self.log_level, device=b.device, log=self._log)
+            self.eigensolver.add_guesses(self._build_guess_vectors_csf(hdiag))
+        self.eigensolver.add_h_diag(hdiag)
+        b_det = torch.empty(s.ndet, dtype=torch.float64, device=hdiag.device)
+        sigma_det = torch.empty_like(b_det)
+
+        def sigma_builder(Bblock, Sblock):  # forte2/ci/ci.py:228-233
+            for i in range(Bblock.shape[0]):
+                sa.csf_C_to_det_C(Bblock[i], b_det)
+                b.Hamiltonian(b_det, sigma_det)
+                sa.det_C_to_csf_C(sigma_det, Sblock[i])
+
+        self.eigensolver.add_sigma_builder(sigma_builder)
+        self.evals, self.evecs = self.eigensolver.solve()
+        self.E = self.evals
+        self.converged = self.eigensolver.converged
+        self.executed = True
+        return self
+
     def run(self):
         import torch
         s = self.ci_strings
@@ -78,6 +155,8 @@ class CISolver:
             self.ci_sigma_builder.set_memory(self.ci_builder_memory)
         b = self.ci_sigma_builder
         b.set_algorithm(self.ci_algorithm.lower())
+        if self.spin_adapter is not None:
+            return self._run_csf(b)
         hdiag = b.form_Hdiag_det()
         if s.ndet == 1:
             self.evals = hdiag[:1].cpu().numpy()
@@ -95,6 +174,110 @@ class CISolver:
         def sigma_builder(Bblock, Sblock):
             for i in range(Bblock.shape[0]):
                 b.Hamiltonian(Bblock[i], Sblock[i])
+
+        self.eigensolver.add_sigma_builder(sigma_builder)
+        self.evals, self.evecs = self.eigensolver.solve()
+        self.E = self.evals
+        self.converged = self.eigensolver.converged
+        self.executed = True
+        return self
+
+
+class ShardedCISolver:
+    """The same solve with the CI vector sharded by alpha-string rows over the ranks of a
+    torch.distributed process group (one process per GPU; forte2_b200/dist.py).  No reference
+    counterpart (forte2 is single-process); the roots equal the single-GPU roots.
+
+    Every O(ndet) object (Hdiag, guesses, the Davidson subspace, sigma) exists only as the rank's row
+    slab; the ranks agree on the guess determinants through an all-gather of their local candidates.
+    """
+
+    def __init__(self, strings: CIStrings, E, H, V, nroot=1, davidson_liu_params=None, ci_algorithm="hz",
+                 ci_builder_memory=1024, log_level=3, device=None, log=None, builder=None, group=None,
+                 form="auto", _sharded=None, _hdiag=None, _kernels=None):
+        # _sharded / _hdiag / _kernels: test hooks (tests/ run the host logic over gloo with CPU stand-ins
+        # for the GPU work); the product path below has no CPU fallback
+        import torch.distributed as dist
+        self.ci_strings = strings
+        self.E0, self.H, self.V = float(E), np.asarray(H, dtype=np.float64), np.asarray(V, dtype=np.float64)
+        self.nroot = int(nroot)
+        self.davidson_liu_params = davidson_liu_params or DavidsonLiuParams()
+        self.ci_algorithm, self.ci_builder_memory = ci_algorithm, int(ci_builder_memory)
+        self.log_level, self.device, self._log = log_level, device, log
+        self.ci_sigma_builder = builder
+        # the Davidson kernels treat comm=None as "not sharded": always hand them a real group
+        self.group, self.form = (group if group is not None else dist.group.WORLD), form
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.eigensolver = None
+        self.sharded = _sharded
+        self._hdiag, self._kernels = _hdiag, _kernels
+        self.executed = False
+
+    def _build_guess_vectors(self, hdiag_loc):
+        """forte2/ci/ci.py:411-452 on sharded vectors: the nguess lowest-energy determinants are the
+        lowest of the union of every rank's nguess lowest."""
+        import torch
+        import torch.distributed as dist
+        lay = self.sharded.layout
+        ndet = self.ci_strings.ndet
+        p = self.davidson_liu_params
+        self.num_guess_states = min(p.guess_per_root * self.nroot, ndet)
+        nguess_dets = min(p.ndets_per_guess * self.num_guess_states, ndet)
+        k = min(nguess_dets, hdiag_loc.numel())
+        vals = torch.full((nguess_dets,), float("inf"), dtype=torch.float64, device=hdiag_loc.device)
+        addr = torch.full((nguess_dets,), -1, dtype=torch.int64, device=hdiag_loc.device)
+        if k > 0:
+            top = torch.topk(hdiag_loc, k, largest=False, sorted=True)
+            vals[:k] = top.values
+            addr[:k] = torch.from_numpy(lay.global_of_local(top.indices.cpu().numpy())).to(addr.device)
+        all_vals = [torch.empty_like(vals) for _ in range(self.world)]
+        all_addr = [torch.empty_like(addr) for _ in range(self.world)]
+        dist.all_gather(all_vals, vals, group=self.group)
+        dist.all_gather(all_addr, addr, group=self.group)
+        v = torch.cat(all_vals).cpu().numpy()
+        a = torch.cat(all_addr).cpu().numpy()
+        keep = a >= 0
+        v, a = v[keep], a[keep]
+        order = np.lexsort((a, v))[:nguess_dets]  # by energy, ties by address: identical on every rank
+        idx = a[order].astype(np.int64)
+        Hguess = slater_matrix(self.ci_strings, self.E0, self.H, self.V, idx)
+        _, evecs = np.linalg.eigh(Hguess)
+        guess = torch.zeros((self.num_guess_states, lay.local_size), dtype=torch.float64, device=hdiag_loc.device)
+        local = lay.local_of_global(idx)
+        mine = np.nonzero(local >= 0)[0]
+        if mine.size:
+            coeff = np.ascontiguousarray(evecs[mine, : self.num_guess_states].T)
+            guess[:, torch.from_numpy(local[mine]).to(guess.device)] = torch.from_numpy(coeff).to(guess.device)
+        return guess
+
+    def run(self):
+        from .dist import ShardedSigma
+        s = self.ci_strings
+        if s.ndet == 0:
+            raise ValueError("No determinants could be generated for the given state and orbitals.")
+        b = self.ci_sigma_builder
+        if self.sharded is None or self._hdiag is None:
+            if b is None:
+                b = self.ci_sigma_builder = CISigmaBuilder(s, self.E0, self.H, self.V, self.log_level,
+                                                           device=self.device)
+                b.set_memory(self.ci_builder_memory)
+            b.set_algorithm(self.ci_algorithm.lower())
+        if self.sharded is None:
+            self.sharded = ShardedSigma(b, self.rank, self.world, group=self.group, form=self.form)
+        sh = self.sharded
+        hdiag = self._hdiag if self._hdiag is not None else b.form_Hdiag_det_part(self.rank, self.world,
+                                                                                  sh.local_size)
+        if self.eigensolver is None:
+            self.eigensolver = DavidsonLiuSolver(
+                size=sh.local_size, nroot=self.nroot, davidson_liu_params=self.davidson_liu_params,
+                log_level=self.log_level, device=hdiag.device, comm=self.group, global_size=s.ndet, log=self._log,
+                _kernels=self._kernels)
+            self.eigensolver.add_guesses(self._build_guess_vectors(hdiag))
+        self.eigensolver.add_h_diag(hdiag)
+
+        def sigma_builder(Bblock, Sblock):
+            for i in range(Bblock.shape[0]):
+                sh.Hamiltonian(Bblock[i], Sblock[i])
 
         self.eigensolver.add_sigma_builder(sigma_builder)
         self.evals, self.evecs = self.eigensolver.solve()

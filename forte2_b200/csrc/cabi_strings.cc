@@ -8,18 +8,21 @@
 
 namespace f2 {
 thread_local std::string g_last_error;
+thread_local int g_last_status = F2_OK;
 
 int status_of(const std::exception& e) {
     g_last_error = e.what();
+    int st = F2_ERUNTIME;
     if (dynamic_cast<const std::invalid_argument*>(&e))
-        return F2_EINVAL;
-    if (dynamic_cast<const std::overflow_error*>(&e))
-        return F2_EOVERFLOW;
-    if (dynamic_cast<const std::out_of_range*>(&e))
-        return F2_EINDEX;
-    if (dynamic_cast<const CudaError*>(&e))
-        return F2_ECUDA;
-    return F2_ERUNTIME;
+        st = F2_EINVAL;
+    else if (dynamic_cast<const std::overflow_error*>(&e))
+        st = F2_EOVERFLOW;
+    else if (dynamic_cast<const std::out_of_range*>(&e))
+        st = F2_EINDEX;
+    else if (dynamic_cast<const CudaError*>(&e))
+        st = F2_ECUDA;
+    g_last_status = st;
+    return st;
 }
 } // namespace f2
 
@@ -28,6 +31,7 @@ using namespace f2;
 extern "C" {
 
 const char* f2_last_error(void) { return g_last_error.c_str(); }
+int f2_last_status(void) { return g_last_status; }
 int f2_abi_version(void) { return 1; }
 
 f2_strings* f2_strings_create(int64_t na, int64_t nb, int symmetry, int ngas, const int* gas_sizes,

@@ -1186,12 +1186,13 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
     }
 }
 
-// sigma = E * C
+// sigma = E * C  (ACC: sigma += E * C, when the opposite-spin term has already been streamed in)
+template <bool ACC>
 __global__ void scale_copy_kernel(const double* __restrict__ x, double* __restrict__ y, double s,
                                   int64_t n) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-        y[i] = s * x[i];
+        y[i] = ACC ? y[i] + s * x[i] : s * x[i];
 }
 
 struct TrBlock {

@@ -228,7 +228,8 @@ struct f2_sigma {
     // host staging for f2_sigma_apply_host
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr;
     std::vector<cudaEvent_t> piece_ev;
 
     ~f2_sigma() {
@@ -243,6 +244,10 @@ struct f2_sigma {
             cudaFreeHost(hS);
         if (own_stream)
             cudaStreamDestroy(own_stream);
+        if (copy_stream)
+            cudaStreamDestroy(copy_stream);
+        if (copy_ev)
+            cudaEventDestroy(copy_ev);
     }
 };
 
@@ -1084,7 +1089,10 @@ void collect_times(f2_sigma& b) {
 
 // sigma (the owned rows) from the full trial vector.  On one GPU yexch is unused; otherwise the
 // alpha same-spin term of the owned columns of every row is left in yexch for the caller to exchange.
-void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, cudaStream_t st) {
+// t3_streamed (one GPU, host path): the gather-form opposite-spin term has already been added into a
+// zeroed sigma while C was arriving; H0 then accumulates and the opposite-spin launch is skipped.
+void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, cudaStream_t st,
+           bool t3_streamed = false) {
     const CIStringsHost& h = *b.S->host;
     F2_CUDA(cudaSetDevice(b.device));
     collect_times(b);
@@ -1095,7 +1103,10 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
     b.launches = 0;
     F2_CUDA(cudaEventRecord(b.ev[0], st));
     if (P.world == 1) {
-        scale_copy_kernel<<<148 * 8, 256, 0, st>>>(C, sigma, b.E, h.ndet);
+        if (t3_streamed)
+            scale_copy_kernel<true><<<148 * 8, 256, 0, st>>>(C, sigma, b.E, h.ndet);
+        else
+            scale_copy_kernel<false><<<148 * 8, 256, 0, st>>>(C, sigma, b.E, h.ndet);
         b.launches += 1;
     } else if (P.piece_ctas) {
         piece_copy_kernel<false><<<P.piece_ctas, 256, 0, st>>>(C, sigma, P.pieces.p, P.npieces, b.E);
@@ -1104,6 +1115,8 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
     F2_CUDA(cudaEventRecord(b.ev[1], st));
     const bool gather = b.t3g && P.world == 1 && P.nitems > 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
     const bool fold = !gather && b.fold_ok && P.world == 1 && P.nitems > 0;
+    if (t3_streamed && !gather)
+        throw std::logic_error("streamed opposite-spin term without the gather form");
     if (h.na >= 1 && !fold) {
         if (P.world > 1)
             F2_CUDA(cudaMemsetAsync(yexch, 0, static_cast<size_t>(P.y_size) * sizeof(double), st));
@@ -1120,7 +1133,9 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr, false);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
-    if (gather)
+    if (t3_streamed)
+        ; // done by the caller, piece by piece
+    else if (gather)
         launch_t3g(b, C, sigma, st);
     else
         launch_t3(b, P, C, sigma, fold, st);
@@ -1156,7 +1171,7 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
     b.launches = 0;
     F2_CUDA(cudaEventRecord(b.ev[0], st));
     if (P.local_size > 0) {
-        scale_copy_kernel<<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
+        scale_copy_kernel<false><<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
         b.launches += 1;
     }
     F2_CUDA(cudaEventRecord(b.ev[1], st));
@@ -1327,16 +1342,51 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
         }
         h->dC.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)));
         h->dS.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)));
-        // pageable user memory -> pinned staging -> device in 64 MB pieces: the host copy of piece i + 1
-        // (several threads) overlaps the DMA of piece i; the way back mirrors it
-        const size_t total = static_cast<size_t>(n), piece = size_t(8) << 20;
+        // pageable user memory -> pinned staging -> device in 64 MB pieces on a copy stream: the host copy
+        // of piece i + 1 (several threads) overlaps the DMA of piece i.  With the gather-form kernel the
+        // opposite-spin term of the alpha rows that have arrived is launched every few pieces, so the
+        // tensor work starts while most of C is still crossing PCIe; the way back mirrors the staging.
+        size_t piece = size_t(8) << 20;
+        if (const char* e = std::getenv("F2_HOST_PIECE")) // test hook: piece size in doubles
+            piece = std::max<size_t>(16, static_cast<size_t>(std::atoll(e)));
+        const size_t total = static_cast<size_t>(n);
+        const bool streamed = h->t3g && h->single->nitems > 0 && s.nbs > 0 &&
+                              std::getenv("F2_NO_STREAMED_HOST") == nullptr;
+        if (!h->copy_stream)
+            F2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (!h->copy_ev)
+            F2_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
+        if (streamed) {
+            collect_times(*h);
+            F2_CUDA(cudaMemsetAsync(h->dS.p, 0, bytes, h->own_stream));
+        }
+        int64_t rows_done = 0;
+        int64_t streamed_launches = 0;
+        const size_t group = 4 * piece; // launch granularity: >= 17 waves of CTAs at CAS(16,16)
+        size_t next_launch = group;
         for (size_t off = 0; off < total; off += piece) {
             const size_t cnt = std::min(piece, total - off);
             parallel_copy(h->hC + off, C_host + off, cnt);
             F2_CUDA(cudaMemcpyAsync(h->dC.p + off, h->hC + off, cnt * sizeof(double), cudaMemcpyHostToDevice,
-                                    h->own_stream));
+                                    h->copy_stream));
+            const size_t arrived = off + cnt;
+            if (streamed && (arrived >= next_launch || arrived == total)) {
+                const int64_t rows_in = arrived == total ? s.nas : static_cast<int64_t>(arrived / s.nbs);
+                if (rows_in > rows_done) {
+                    F2_CUDA(cudaEventRecord(h->copy_ev, h->copy_stream));
+                    F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->copy_ev, 0));
+                    launch_t3g(*h, h->dC.p, h->dS.p, h->own_stream, static_cast<int>(rows_done),
+                               static_cast<int>(rows_in - rows_done));
+                    streamed_launches += 1;
+                    rows_done = rows_in;
+                }
+                next_launch = arrived + group;
+            }
         }
-        apply(*h, h->dC.p, h->dS.p, n, h->own_stream);
+        F2_CUDA(cudaEventRecord(h->copy_ev, h->copy_stream));
+        F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->copy_ev, 0));
+        apply(*h, *h->single, h->dC.p, h->dS.p, nullptr, h->own_stream, streamed);
+        h->launches += streamed_launches;
         const size_t npieces = (total + piece - 1) / piece;
         if (h->piece_ev.size() < npieces) {
             const size_t old = h->piece_ev.size();

@@ -51,6 +51,26 @@ class Layout:
                 y += nA * (ch - cl)
         self.local_size, self.exchange_size = loc, y
         self.ndet = sum(nA * nB for _, nA, nB in self.blocks)
+        # owned pieces: (first local index, first CI-vector address, length), ascending in both
+        self.pieces = [(loc_b, off + lo * nB, n * nB) for (off, nA, nB), (lo, n, loc_b) in zip(self.blocks, self.rows)
+                       if nA * nB > 0 and n > 0]
+
+    def global_of_local(self, idx: np.ndarray) -> np.ndarray:
+        """CI-vector addresses of local indices"""
+        idx = np.asarray(idx, dtype=np.int64)
+        starts = np.array([p[0] for p in self.pieces], dtype=np.int64)
+        k = np.searchsorted(starts, idx, side="right") - 1
+        shift = np.array([p[1] - p[0] for p in self.pieces], dtype=np.int64)
+        return idx + shift[k]
+
+    def local_of_global(self, addr: np.ndarray) -> np.ndarray:
+        """local indices of CI-vector addresses, -1 where this rank does not own the determinant"""
+        addr = np.asarray(addr, dtype=np.int64)
+        out = np.full(addr.shape, -1, dtype=np.int64)
+        for loc_b, g0, n in self.pieces:
+            m = (addr >= g0) & (addr < g0 + n)
+            out[m] = addr[m] - g0 + loc_b
+        return out
 
 
 class CudaEngine:
@@ -104,6 +124,7 @@ class ShardedSigma:
             torch.device("cuda", builder.device) if builder is not None else torch.device("cpu"))
         self._max_local = max(lay.local_size for lay in self.layouts)
         self._kw = kw = dict(dtype=torch.float64, device=self.device)
+        self._phase_events = None
         self._full = self._gather = self._pad = None  # full-layout buffers, allocated on first use
         self._yexch = torch.zeros(max(self.layout.exchange_size, 1), **kw)
         # rows form: wanted unless form == "full", used when the engine offers it for this space
@@ -225,15 +246,39 @@ class ShardedSigma:
             dist.all_reduce(self._scatter, op=dist.ReduceOp.SUM, group=self.group)
             sigma_loc += self._scatter[self.rank * self._slot: self.rank * self._slot + self.local_size]
 
+    def _mark(self, name):
+        """phase boundary for profile_phases(): a CUDA event on the current stream"""
+        if self._phase_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._phase_events.append((name, ev))
+
+    def profile_phases(self, c_loc, sigma_loc):
+        """one build with a CUDA event at every phase boundary; returns [(phase, ms)] (device time on
+        this rank's stream, NCCL kernels included)"""
+        self._phase_events = []
+        self._mark("start")
+        self.Hamiltonian(c_loc, sigma_loc)
+        torch.cuda.synchronize()
+        ev, self._phase_events = self._phase_events, None
+        return [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(ev[:-1], ev[1:])]
+
     def Hamiltonian(self, c_loc: torch.Tensor, sigma_loc: torch.Tensor) -> None:
         assert c_loc.numel() == self.local_size and sigma_loc.numel() == self.local_size
         if self.form == "rows":
             self._exchange_cols(c_loc)
+            self._mark("all-to-all of C (column slab)")
             self.engine.apply_rows(c_loc, self._xcols, sigma_loc, self._yexch, self._scatter, self.rank, self.world)
+            self._mark("local kernels")
             self._reduce_scatter_add(sigma_loc)
+            self._mark("reduce-scatter + add")
             self._exchange_add(sigma_loc)
+            self._mark("all-to-all of the alpha same-spin term + add")
             return
         full = self.all_gather_full(c_loc)
+        self._mark("all-gather of C")
         self.engine.apply_part(full, sigma_loc, self._yexch, self.rank, self.world)
+        self._mark("local kernels")
         if self.world > 1:
             self._exchange_add(sigma_loc)
+            self._mark("all-to-all of the alpha same-spin term + add")

@@ -19,6 +19,7 @@ extern "C" {
 
 typedef struct f2_strings f2_strings;
 typedef struct f2_sigma f2_sigma;
+typedef struct f2_adapter f2_adapter;
 
 enum { F2_OK = 0, F2_EINVAL = 1, F2_ERUNTIME = 2, F2_EOVERFLOW = 3, F2_EINDEX = 4, F2_ECUDA = 5 };
 
@@ -29,6 +30,8 @@ enum {
 };
 
 const char* f2_last_error(void);
+/* status code of the failure f2_last_error() describes (for the functions that return a NULL handle) */
+int f2_last_status(void);
 int f2_abi_version(void);
 
 /* ---- CIStrings: forte2/ci/ci_strings.h:15, ctor forte2/ci/ci_strings.cc:26-184 ------------------
@@ -140,6 +143,34 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
  * forte2/ci/ci.py:411-452.  H, V as in f2_sigma_create.  Needs no GPU. */
 int f2_slater_matrix(const f2_strings* h, double E, const double* H, const double* V,
                      const int64_t* addresses, int n, double* out);
+
+/* ---- CISpinAdapter: forte2/determinant/ci_spin_adapter.h:48, forte2/api/ci_helpers_api.cc:190-201 ----
+ * CSF <-> determinant transform of the CI vector, executed before and after every sigma build of a
+ * spin-adapted CI (forte2/ci/ci.py:228-233).  f2_adapter_create is prepare_couplings
+ * (ci_spin_adapter.cc:137-200) over the determinants of `strings` in CI-vector order and needs no GPU;
+ * the coupling table goes to the device on the first transform.  twoMs must equal na - nb. */
+f2_adapter* f2_adapter_create(const f2_strings* strings, int twoS, int twoMs);
+void f2_adapter_destroy(f2_adapter* h);
+/* out4 = nconf, ncsf, ndet, ncoupling (properties of ci_helpers_api.cc:196-197) */
+int f2_adapter_info(const f2_adapter* h, int64_t* out4);
+/* the table CSF(i) = sum_j coeff_ij Determinant(det_ij) in the reference's order
+ * (csf_to_det_bounds_ / csf_to_det_coeff_, ci_spin_adapter.h:189-191): bounds[ncsf+1], det[ncoupling],
+ * coeff[ncoupling]; returns ncoupling (det/coeff may be NULL to size) */
+int64_t f2_adapter_table(const f2_adapter* h, int64_t* bounds, int64_t* det, double* coeff, int64_t cap);
+/* first CSF of every configuration, nconf + 1 entries (conf_to_csfs_range, ci_spin_adapter.h:76) */
+int f2_adapter_conf_ranges(const f2_adapter* h, int64_t* out);
+/* csf_C_to_det_C / det_C_to_csf_C (ci_spin_adapter.cc:69-97) on DEVICE vectors; the output is
+ * overwritten.  device = CUDA ordinal of the buffers, stream = cudaStream_t. */
+int f2_adapter_csf_to_det(f2_adapter* h, const double* csf_dev, double* det_dev, int device, void* stream);
+int f2_adapter_det_to_csf(f2_adapter* h, const double* det_dev, double* csf_dev, int device, void* stream);
+/* the same on HOST vectors (the reference's numpy-facing methods): staged through the device */
+int f2_adapter_csf_to_det_host(f2_adapter* h, const double* csf_host, int64_t ncsf, double* det_host, int64_t ndet);
+int f2_adapter_det_to_csf_host(f2_adapter* h, const double* det_host, int64_t ndet, double* csf_host, int64_t ncsf);
+/* Davidson preconditioner in the CSF basis, H_II ~ sum_d c_dI^2 <d|H|d> (CISigmaBuilder::form_Hdiag_csf
+ * with spin_adapt_full_preconditioner = false, ci_sigma_builder.cc:331-367), from the determinant
+ * energies of f2_sigma_hdiag; device vectors */
+int f2_adapter_hdiag_csf(f2_adapter* h, const double* det_energies_dev, double* out_csf_dev, int device,
+                         void* stream);
 
 /* ---- Davidson-Liu device primitives (forte2/helpers/davidsonliu.py:184-484) ----------------------
  * The reference solver is numpy on (size, max_subspace) arrays; these are the streaming passes of

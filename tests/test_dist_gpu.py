@@ -51,6 +51,21 @@ def _worker(rank, world, port, spaces, result_dir):
         dist.destroy_process_group()
 
 
+def _spawn(fn, args, nprocs, timeout=300):
+    """mp.spawn with a deadline: a collective mismatch would otherwise hang the GPU box until NCCL's
+    watchdog fires"""
+    import time
+    import torch.multiprocessing as mp
+    ctx = mp.spawn(fn, args=args, nprocs=nprocs, join=False)
+    deadline = time.time() + timeout
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            pytest.fail(f"{fn.__name__}: {nprocs} ranks did not finish within {timeout} s")
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -62,11 +77,50 @@ def _free_port():
 def test_sharded_sigma_two_gpus(tmp_path):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
     spaces = [(3, 3, 0, [[0] * 6], [], []), (5, 4, 0, [[0] * 3, [0] * 4, [0] * 3], [4, 0, 0], [6, 8, 2]),
               (3, 3, 0, [[0, 5, 2, 3, 6, 7]], [], []), (5, 5, 0, [[0] * 10], [], []), (4, 3, 0, [[0] * 7], [], []),
               (6, 6, 0, [[0] * 12], [], [])]
-    mp.spawn(_worker, args=(2, _free_port(), spaces, str(tmp_path)), nprocs=2, join=True)
+    _spawn(_worker, (2, _free_port(), spaces, str(tmp_path)), 2)
     for r in range(2):
         errs = np.load(tmp_path / f"err_{r}.npy")
         assert np.all(errs <= 1e-12), (r, errs)
+
+
+def _solver_worker(rank, world, port, result_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import forte2_b200 as f2
+        from forte2_b200 import synthetic
+        from forte2_b200.ci_solver import CISolver, ShardedCISolver
+        from forte2_b200.davidson import DavidsonLiuParams
+        out = []
+        for space, form in [((5, 5, 0, [[0] * 10], [], []), "auto"), ((5, 5, 0, [[0] * 10], [], []), "full"),
+                            ((5, 4, 0, [[0] * 3, [0] * 4, [0] * 3], [4, 0, 0], [6, 8, 2]), "auto")]:
+            n = sum(len(s) for s in space[3])
+            E, H, V = synthetic.integrals(n, "D")
+            strings = f2.CIStrings(*space)
+            params = DavidsonLiuParams(e_tol=1e-12, r_tol=1e-8)
+            single = CISolver(strings, E, H, V, nroot=3, davidson_liu_params=params, log_level=0, device=rank).run()
+            sharded = ShardedCISolver(strings, E, H, V, nroot=3, davidson_liu_params=params, log_level=0,
+                                      device=rank, form=form).run()
+            out.append(np.concatenate([np.asarray(single.E), np.asarray(sharded.E)]))
+        np.save(os.path.join(result_dir, f"roots_{rank}.npy"), np.array(out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_davidson_roots_two_gpus(tmp_path):
+    """3-root Davidson-Liu with every vector sharded over 2 GPUs == the single-GPU roots to 1e-10 Eh
+    (BASELINE.json), in both communication forms and on a GAS space."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _spawn(_solver_worker, (2, _free_port(), str(tmp_path)), 2)
+    for r in range(2):
+        roots = np.load(tmp_path / f"roots_{r}.npy")
+        for row in roots:
+            assert np.max(np.abs(row[:3] - row[3:])) <= 1e-10, (r, row)

@@ -171,3 +171,25 @@ def test_rows_form_parts_emulated_on_one_gpu(ref, torch_cuda, n, world):
             lo_r, n_r, _ = Lr.rows[0]
             total[lo_r:lo_r + n_r] += scatter[r * slot_rows * nB: r * slot_rows * nB + n_r * nB].view(n_r, nB)
     assert _rel(total.view(-1).cpu().numpy(), want) <= TOL
+
+
+def test_host_path_streams_the_opposite_spin_term(ref, torch_cuda, monkeypatch):
+    """numpy in / numpy out with the trial vector crossing PCIe in many small pieces: the gather-form
+    opposite-spin kernel is launched on the rows that have arrived (f2_sigma_apply_host); same sigma as
+    the one-piece path and as the reference."""
+    n = 10
+    space = (n // 2, n // 2, 0, [[0] * n], [], [])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    c = synthetic.trial_vector(rs.ndet)
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    assert gb.t3_shape()["form"] == "gather"
+    monkeypatch.setenv("F2_HOST_PIECE", "1000")  # 63504 determinants -> 64 pieces, 16 launches
+    got = np.full_like(c, np.nan)
+    gb.Hamiltonian(c, got)
+    assert _rel(got, want) <= TOL
+    assert gb.launch_count() > 12
+    monkeypatch.setenv("F2_NO_STREAMED_HOST", "1")
+    got2 = np.full_like(c, np.nan)
+    gb.Hamiltonian(c, got2)
+    assert _rel(got2, want) <= TOL

@@ -123,3 +123,23 @@ def test_large_space_sizes():
     assert (s.nas, s.ndet) == (3432, 11778624)
     s = f2.CIStrings(10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2])
     assert (s.nas, s.nbs, s.ndet, s.nblocks) == (29932, 29932, 22065484, 36)
+
+
+def test_shard_layout_index_maps():
+    """forte2_b200/dist.py Layout: local <-> CI-vector address maps of the alpha-row partition are
+    inverse to each other and the ranks' pieces tile the vector exactly once."""
+    import forte2_b200 as f2
+    from forte2_b200.dist import Layout
+    for name in ["cas66", "gas343_54", "cas66_d2h", "cas75_odd", "gas2_sym4"]:
+        strings = f2.CIStrings(*SMALL_SPACES[name])
+        for world in (1, 2, 3, 5):
+            seen = np.zeros(strings.ndet, dtype=np.int64)
+            for rank in range(world):
+                lay = Layout(strings.blocks(), rank, world)
+                loc = np.arange(lay.local_size)
+                glob = lay.global_of_local(loc)
+                seen[glob] += 1
+                assert np.array_equal(lay.local_of_global(glob), loc)
+                others = np.setdiff1d(np.arange(strings.ndet), glob)
+                assert np.all(lay.local_of_global(others) == -1)
+            assert np.all(seen == 1)
