@@ -1075,22 +1075,42 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
 
     const int jend = j0 + SSG_TW < ncols ? j0 + SSG_TW : ncols;
     const int nchunks = (jend - j0 + 15) >> 4;
+    constexpr int PFB = 2; // k-steps per register batch; the next batch loads while this one multiplies
+    double cur[PFB][2], nxt[PFB][2];
+    unsigned scur[PFB], snxt[PFB];
+    // parent row 4ks + t of the string in slot `slot`, columns cb and cb + 8 (zeros past the end)
+    auto loadb = [&](int slot, int ks, int cb, double (&v)[2], unsigned& sg) {
+        v[0] = 0.0;
+        v[1] = 0.0;
+        sg = 0;
+        const int b = 4 * ks + t;
+        if (b < s_m[slot]) {
+            const double* src = p.X + msrc3[slot * ROWS + b] + cb;
+            sg = minfo3[slot * ROWS + b];
+            if (cb < jend)
+                v[0] = __ldg(src);
+            if (cb + 8 < jend)
+                v[1] = __ldg(src + 8);
+        }
+    };
+    // B operand: n8 tile nt, n index gg holds column n0 + 8 nt + (gg >> 1) + 4 (gg & 1), so that the
+    // four lanes of an accumulator row hold four consecutive columns (one full sector per reduction)
+    const int cboff = (g >> 1) + 4 * (g & 1);
+    bool primed = false; // cur already holds the first batch of the next (string, chunk) of this warp
     for (int j = 0; j < k_cnt; ++j) {
         if (j + 1 < k_cnt)
             copy_block(j + 1);
         if (warp == 0 && j + 2 < k_cnt)
             decode(j + 2);
-        const int m = s_m[j % 3];
-        const long long* msrc = msrc3 + (j % 3) * ROWS;
-        const long long* mdst = mdst3 + (j % 3) * ROWS;
-        const unsigned* minfo = minfo3 + (j % 3) * ROWS;
+        const int slot = j % 3;
+        const int m = s_m[slot];
+        const long long* mdst = mdst3 + slot * ROWS;
+        const unsigned* minfo = minfo3 + slot * ROWS;
         const int nks = (m + 3) >> 2;
         const double* ap = Abuf + (j & 1) * ROWS * S + g * S + t;
         for (int chunk = warp; chunk < nchunks && m > 0; chunk += 8) {
             const int n0 = j0 + (chunk << 4);
-            // B operand: n8 tile nt, n index gg holds column n0 + 8 nt + (gg >> 1) + 4 (gg & 1), so that the
-            // four lanes of an accumulator row hold four consecutive columns (one full sector per reduction)
-            const int cb = n0 + (g >> 1) + 4 * (g & 1);
+            const int cb = n0 + cboff;
             double acc[NM16 > 0 ? NM16 : 1][2][4];
             double acc8[2][2];
 #pragma unroll
@@ -1099,30 +1119,29 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
                 for (int nt = 0; nt < 2; ++nt)
                     acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
             acc8[0][0] = acc8[0][1] = acc8[1][0] = acc8[1][1] = 0.0;
-            constexpr int PFB = 2; // k-steps per register batch; the next batch loads while this one multiplies
-            double cur[PFB][2], nxt[PFB][2];
-            unsigned scur[PFB], snxt[PFB];
-            auto loadb = [&](int ks, double (&v)[2], unsigned& sg) { // parent row 4ks + t, columns cb, cb + 8
-                v[0] = 0.0;
-                v[1] = 0.0;
-                sg = 0;
-                const int b = 4 * ks + t;
-                if (ks < nks && b < m) {
-                    const double* src = p.X + msrc[b] + cb;
-                    sg = minfo[b];
-                    if (cb < jend)
-                        v[0] = __ldg(src);
-                    if (cb + 8 < jend)
-                        v[1] = __ldg(src + 8);
-                }
-            };
-#pragma unroll
-            for (int i = 0; i < PFB; ++i)
-                loadb(i, cur[i], scur[i]);
-            for (int kb = 0; kb < nks; kb += PFB) {
+            if (!primed) {
 #pragma unroll
                 for (int i = 0; i < PFB; ++i)
-                    loadb(kb + PFB + i, nxt[i], snxt[i]);
+                    loadb(slot, i, cb, cur[i], scur[i]);
+            }
+            // the work item after this one: next chunk of the same string, else the first chunk of the
+            // next string (its parent list was decoded two strings ahead and is visible since the last
+            // barrier); its first batch is loaded during the last multiplications of this one, so the
+            // L2 latency of a new chunk hides behind the reductions, the barrier and the tensor work
+            const bool same = chunk + 8 < nchunks;
+            const bool has_next = same || (j + 1 < k_cnt && s_m[(j + 1) % 3] > 0);
+            const int nslot = same ? slot : (j + 1) % 3;
+            const int ncb = j0 + ((same ? chunk + 8 : warp) << 4) + cboff;
+            for (int kb = 0; kb < nks; kb += PFB) {
+                if (kb + PFB < nks) {
+#pragma unroll
+                    for (int i = 0; i < PFB; ++i)
+                        loadb(slot, kb + PFB + i, cb, nxt[i], snxt[i]);
+                } else if (has_next) {
+#pragma unroll
+                    for (int i = 0; i < PFB; ++i)
+                        loadb(nslot, i, ncb, nxt[i], snxt[i]);
+                }
 #pragma unroll
                 for (int i = 0; i < PFB; ++i) {
                     const int ks = kb + i;
@@ -1149,6 +1168,7 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
                     scur[i] = snxt[i];
                 }
             }
+            primed = has_next;
             // accumulator (row, tile nt, n index 2t + c) is column n0 + 8 nt + 4 c + t
             const int c0 = n0 + t;
 #pragma unroll
