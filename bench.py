@@ -211,6 +211,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` summary of this workload (profiles/, written by scripts/ncu_summary.py), or None."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel}_{workload}.md"))):
+        text = open(path).read()
+        rd = re.search(r"\| dram__bytes_read\.sum \| ([0-9.]+) \| (\w+) \|", text)
+        wr = re.search(r"\| dram__bytes_write\.sum \| ([0-9.]+) \| (\w+) \|", text)
+        if rd and wr:
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+            best = {"bytes": float(rd.group(1)) * scale[rd.group(2)] + float(wr.group(1)) * scale[wr.group(2)],
+                    "source": os.path.relpath(path, ROOT)}
+    return best
+
+
 def workload_config(workload, gpus):
     n, na, nb = WORKLOADS[workload]
     ndet = comb(n, na) * comb(n, nb)
@@ -346,6 +363,12 @@ def run_ours(args):
         "kernel_ms": last[3], "kernel_share_of_step": last[3] / last[4] if last[4] else None,
         "traffic": None,
     }
+    if world == 1 and shape["form"] == "gather":
+        tr = ncu_traffic(args.workload, "t3g")
+        if tr:
+            roofline["traffic"] = tr["bytes"]
+            roofline["traffic_source"] = tr["source"] + " (ncu --set full, one launch)"
+            roofline["algorithmic_hbm_bytes"] = 16.0 * ndet
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -142,6 +143,7 @@ struct SSPlan {
 struct BetaPass {
     SSPlan plan;
     DevBuf<TrBlock> tr;
+    std::vector<TrBlock> tr_host; // the same blocks: which sigma rows this pass completes
     int ntr = 0;
     uint32_t ntr_tiles = 0;
     int64_t elems = 0; // doubles used in each scratch buffer
@@ -212,6 +214,9 @@ struct f2_sigma {
     size_t t3_smem = 0;
     // row/column ownership plans: the single-GPU one and the last multi-GPU one
     std::unique_ptr<Part> single, shard;
+    // host path: the single-GPU partition with the beta same-spin term cut into about eight row slabs,
+    // so that finished sigma rows leave for the host while the next slab is computed
+    std::unique_ptr<Part> host_part;
     DevBuf<double> XT, YT;
     int ss_ks[2] = {0, 0};
     // hdiag
@@ -219,8 +224,13 @@ struct f2_sigma {
     int hd_nblocks = 0;
     uint32_t hd_rows = 0;
     // timing
-    cudaEvent_t ev[5] = {};
-    bool ev_pending = false;
+    // per-term timing events: a ring of sets so that the host never has to wait for the previous build
+    // before launching the next one (it may run up to kEvSets - 1 builds ahead of the device)
+    static constexpr int kEvSets = 4;
+    cudaEvent_t evs[kEvSets][5] = {};
+    cudaEvent_t* ev = evs[0];
+    int ev_idx = 0;
+    bool set_pending[kEvSets] = {false, false, false, false};
     double t_acc[4] = {0, 0, 0, 0};
     double last_ms[5] = {0, 0, 0, 0, 0};
     long builds = 0;
@@ -229,15 +239,16 @@ struct f2_sigma {
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t copy_ev = nullptr;
+    cudaEvent_t copy_ev = nullptr, pass_ev = nullptr;
     std::vector<cudaEvent_t> piece_ev;
 
     ~f2_sigma() {
         for (auto& e : piece_ev)
             cudaEventDestroy(e);
-        for (auto& e : ev)
-            if (e)
-                cudaEventDestroy(e);
+        for (auto& set : evs)
+            for (auto& e : set)
+                if (e)
+                    cudaEventDestroy(e);
         if (hC)
             cudaFreeHost(hC);
         if (hS)
@@ -248,6 +259,8 @@ struct f2_sigma {
             cudaStreamDestroy(copy_stream);
         if (copy_ev)
             cudaEventDestroy(copy_ev);
+        if (pass_ev)
+            cudaEventDestroy(pass_ev);
     }
 };
 
@@ -256,7 +269,7 @@ namespace {
 // host-to-host copy split over a few threads (one memcpy stream does not saturate the memory system)
 void parallel_copy(double* dst, const double* src, size_t count) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nthr = std::min<size_t>(std::min<unsigned>(hw, 8), std::max<size_t>(1, count >> 18));
+    const size_t nthr = std::min<size_t>(std::min<unsigned>(hw, 12), std::max<size_t>(1, count >> 18));
     if (nthr <= 1) {
         std::memcpy(dst, src, count * sizeof(double));
         return;
@@ -705,7 +718,7 @@ std::unique_ptr<Part> make_part(f2_sigma& b, int rank, int world) {
 // row range) column groups, the transposed blocks [nB][rows] of every beta class paired with it.
 // Both scratch buffers together must fit the set_memory budget (ci_sigma_builder.cc:70-78,
 // ci_sigma_builder_knowles_handy.cc:15-32).
-void plan_beta(f2_sigma& b, Part& P) {
+void plan_beta(f2_sigma& b, Part& P, int64_t cap_elems = 0) {
     const CIStringsHost& h = *b.S->host;
     P.beta_passes.clear();
     if (h.nb < 1 || h.ndet == 0) {
@@ -713,12 +726,18 @@ void plan_beta(f2_sigma& b, Part& P) {
         return;
     }
     const size_t nclsA = h.nclsA(), nclsB = h.nclsB();
-    const int64_t cap = static_cast<int64_t>(b.memory_size / (2 * sizeof(double)));
+    int64_t cap = static_cast<int64_t>(b.memory_size / (2 * sizeof(double)));
     // columns (beta strings) attached to each alpha class
     std::vector<int64_t> width(nclsA, 0);
     for (const auto& blk : h.blocks)
         if (blk.nA * blk.nB > 0)
             width[blk.cA] += blk.nB;
+    if (cap_elems > 0) { // a smaller slab on request, never below one row of the widest class
+        int64_t wmax = 1;
+        for (int64_t w : width)
+            wmax = std::max(wmax, w);
+        cap = std::min(cap, std::max(cap_elems, wmax));
+    }
     struct Group {
         int cA;
         int64_t i0, rows;
@@ -798,6 +817,7 @@ void plan_beta(f2_sigma& b, Part& P) {
         bp->ntr = static_cast<int>(tr.size());
         bp->ntr_tiles = tile0;
         bp->tr.upload(tr);
+        bp->tr_host = tr;
         bp->elems = pos;
         max_elems = std::max(max_elems, pos);
         P.beta_passes.push_back(std::move(bp));
@@ -1065,15 +1085,16 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
     F2_CUDA(cudaGetLastError());
 }
 
-void collect_times(f2_sigma& b) {
-    if (!b.ev_pending)
+void collect_set(f2_sigma& b, int set) {
+    if (!b.set_pending[set])
         return;
-    F2_CUDA(cudaEventSynchronize(b.ev[4]));
+    cudaEvent_t* ev = b.evs[set];
+    F2_CUDA(cudaEventSynchronize(ev[4]));
     float ms[4];
     for (int i = 0; i < 4; ++i)
-        F2_CUDA(cudaEventElapsedTime(&ms[i], b.ev[i], b.ev[i + 1]));
+        F2_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     float tot;
-    F2_CUDA(cudaEventElapsedTime(&tot, b.ev[0], b.ev[4]));
+    F2_CUDA(cudaEventElapsedTime(&tot, ev[0], ev[4]));
     b.last_ms[0] = ms[0];
     b.last_ms[1] = ms[1];
     b.last_ms[2] = ms[2];
@@ -1084,18 +1105,33 @@ void collect_times(f2_sigma& b) {
     b.t_acc[2] += ms[1] * 1e-3;
     b.t_acc[3] += ms[2] * 1e-3;
     b.builds += 1;
-    b.ev_pending = false;
+    b.set_pending[set] = false;
+}
+
+// every build that has not been accounted for yet, oldest first (waits for the newest one)
+void collect_times(f2_sigma& b) {
+    for (int k = 1; k <= f2_sigma::kEvSets; ++k)
+        collect_set(b, (b.ev_idx + k) % f2_sigma::kEvSets);
+}
+
+// next event set of the ring; the build that used it kEvSets builds ago is accounted for first
+void begin_build(f2_sigma& b) {
+    b.ev_idx = (b.ev_idx + 1) % f2_sigma::kEvSets;
+    collect_set(b, b.ev_idx);
+    b.ev = b.evs[b.ev_idx];
 }
 
 // sigma (the owned rows) from the full trial vector.  On one GPU yexch is unused; otherwise the
 // alpha same-spin term of the owned columns of every row is left in yexch for the caller to exchange.
 // t3_streamed (one GPU, host path): the gather-form opposite-spin term has already been added into a
 // zeroed sigma while C was arriving; H0 then accumulates and the opposite-spin launch is skipped.
+// after_beta_pass (host path): called after the launches of every beta row slab; with the streamed
+// opposite-spin term that slab's sigma rows are final once those launches have run.
 void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, cudaStream_t st,
-           bool t3_streamed = false) {
+           bool t3_streamed = false, const std::function<void(const BetaPass&)>* after_beta_pass = nullptr) {
     const CIStringsHost& h = *b.S->host;
     F2_CUDA(cudaSetDevice(b.device));
-    collect_times(b);
+    begin_build(b);
     if (!P.beta_planned)
         plan_beta(b, P);
     if (h.ndet == 0)
@@ -1131,6 +1167,8 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
         launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, fold ? b.Wfold.p : b.W[1].p, st);
         transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr, false);
+        if (after_beta_pass)
+            (*after_beta_pass)(*bp);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
     if (t3_streamed)
@@ -1141,7 +1179,7 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         launch_t3(b, P, C, sigma, fold, st);
     F2_CUDA(cudaEventRecord(b.ev[4], st));
     F2_CUDA(cudaGetLastError());
-    b.ev_pending = true;
+    b.set_pending[b.ev_idx] = true;
 }
 
 void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t st) {
@@ -1162,7 +1200,7 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
                 double* scatter, cudaStream_t st) {
     const CIStringsHost& h = *b.S->host;
     F2_CUDA(cudaSetDevice(b.device));
-    collect_times(b);
+    begin_build(b);
     if (!P.beta_planned)
         plan_beta(b, P);
     if (h.ndet == 0)
@@ -1195,7 +1233,7 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
                    P.rowpad.p);
     F2_CUDA(cudaEventRecord(b.ev[4], st));
     F2_CUDA(cudaGetLastError());
-    b.ev_pending = true;
+    b.set_pending[b.ev_idx] = true;
 }
 
 // the rows form needs the gather-form kernel and 16-byte aligned row slabs (even nbs)
@@ -1237,8 +1275,9 @@ f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const 
         b->log_level = log_level;
         b->norb = strings->host->norb;
         b->D = device_strings(strings, device);
-        for (auto& e : b->ev)
-            F2_CUDA(cudaEventCreate(&e));
+        for (auto& set : b->evs)
+            for (auto& e : set)
+                F2_CUDA(cudaEventCreate(&e));
         build_integrals(*b, E, H, V);
         const DeviceLists& L = strings->host->device_lists();
         for (int s = 0; s < 2; ++s) {
@@ -1299,7 +1338,7 @@ int f2_sigma_set_memory(f2_sigma* h, int64_t mb) {
     h->memory_size = static_cast<size_t>(mb) * 1024 * 1024;
     // like the reference, the scratch is released here and re-planned lazily by the next build,
     // which is where a too-small budget is reported
-    for (Part* P : {h->single.get(), h->shard.get()})
+    for (Part* P : {h->single.get(), h->shard.get(), h->host_part.get()})
         if (P) {
             P->beta_planned = false;
             P->beta_passes.clear();
@@ -1356,10 +1395,8 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
             F2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         if (!h->copy_ev)
             F2_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
-        if (streamed) {
-            collect_times(*h);
+        if (streamed)
             F2_CUDA(cudaMemsetAsync(h->dS.p, 0, bytes, h->own_stream));
-        }
         int64_t rows_done = 0;
         int64_t streamed_launches = 0;
         const size_t group = 4 * piece; // launch granularity: >= 17 waves of CTAs at CAS(16,16)
@@ -1385,26 +1422,59 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
         }
         F2_CUDA(cudaEventRecord(h->copy_ev, h->copy_stream));
         F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->copy_ev, 0));
-        apply(*h, *h->single, h->dC.p, h->dS.p, nullptr, h->own_stream, streamed);
+        // the way back: sigma rows travel in pieces, each followed by an event the unstaging copy waits for
+        struct Piece {
+            size_t off, cnt;
+        };
+        std::vector<Piece> out;
+        auto piece_event = [&](size_t i) {
+            if (h->piece_ev.size() <= i) {
+                const size_t old = h->piece_ev.size();
+                h->piece_ev.resize(i + 1);
+                for (size_t k = old; k <= i; ++k)
+                    F2_CUDA(cudaEventCreateWithFlags(&h->piece_ev[k], cudaEventDisableTiming));
+            }
+            return h->piece_ev[i];
+        };
+        auto send_back = [&](size_t off, size_t cnt, cudaStream_t st) {
+            for (size_t o = off; o < off + cnt; o += piece) {
+                const size_t c = std::min(piece, off + cnt - o);
+                F2_CUDA(cudaMemcpyAsync(h->hS + o, h->dS.p + o, c * sizeof(double), cudaMemcpyDeviceToHost, st));
+                F2_CUDA(cudaEventRecord(piece_event(out.size()), st));
+                out.push_back({o, c});
+            }
+        };
+        if (streamed && s.nb >= 1) {
+            // beta same-spin term last, in about eight row slabs: the rows of a finished slab are final and
+            // cross PCIe on the copy stream while the next slab is computed
+            if (!h->host_part)
+                h->host_part = make_part(*h, 0, 1);
+            if (!h->host_part->beta_planned)
+                plan_beta(*h, *h->host_part, (s.ndet + 7) / 8);
+            if (!h->pass_ev)
+                F2_CUDA(cudaEventCreateWithFlags(&h->pass_ev, cudaEventDisableTiming));
+            const std::function<void(const BetaPass&)> after = [&](const BetaPass& bp) {
+                F2_CUDA(cudaEventRecord(h->pass_ev, h->own_stream));
+                F2_CUDA(cudaStreamWaitEvent(h->copy_stream, h->pass_ev, 0));
+                for (const TrBlock& t : bp.tr_host)
+                    send_back(static_cast<size_t>(t.sig_off), static_cast<size_t>(t.nA) * static_cast<size_t>(t.nB),
+                              h->copy_stream);
+            };
+            apply(*h, *h->host_part, h->dC.p, h->dS.p, nullptr, h->own_stream, true, &after);
+        } else {
+            apply(*h, *h->single, h->dC.p, h->dS.p, nullptr, h->own_stream, streamed);
+            send_back(0, total, h->own_stream);
+        }
         h->launches += streamed_launches;
-        const size_t npieces = (total + piece - 1) / piece;
-        if (h->piece_ev.size() < npieces) {
-            const size_t old = h->piece_ev.size();
-            h->piece_ev.resize(npieces);
-            for (size_t i = old; i < npieces; ++i)
-                F2_CUDA(cudaEventCreateWithFlags(&h->piece_ev[i], cudaEventDisableTiming));
-        }
-        for (size_t i = 0; i < npieces; ++i) {
-            const size_t off = i * piece, cnt = std::min(piece, total - off);
-            F2_CUDA(cudaMemcpyAsync(h->hS + off, h->dS.p + off, cnt * sizeof(double), cudaMemcpyDeviceToHost,
-                                    h->own_stream));
-            F2_CUDA(cudaEventRecord(h->piece_ev[i], h->own_stream));
-        }
-        for (size_t i = 0; i < npieces; ++i) {
-            const size_t off = i * piece, cnt = std::min(piece, total - off);
+        size_t returned = 0;
+        for (size_t i = 0; i < out.size(); ++i) {
             F2_CUDA(cudaEventSynchronize(h->piece_ev[i]));
-            parallel_copy(sigma_host + off, h->hS + off, cnt);
+            parallel_copy(sigma_host + out[i].off, h->hS + out[i].off, out[i].cnt);
+            returned += out[i].cnt;
         }
+        if (returned != total)
+            throw std::logic_error("f2_sigma_apply_host: sigma pieces do not cover the vector");
+        F2_CUDA(cudaStreamSynchronize(h->copy_stream));
         F2_CUDA(cudaStreamSynchronize(h->own_stream));
         return F2_OK;
     } catch (const std::exception& e) {

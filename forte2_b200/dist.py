@@ -174,45 +174,65 @@ class ShardedSigma:
                     self._full[off + lo * nB: off + (lo + n) * nB].copy_(self._gather[q][loc:loc + n * nB])
         return self._full
 
-    def _exchange_add(self, sigma_loc: torch.Tensor):
-        """send the alpha same-spin partials [rows of q][my columns] to q, add what arrives (step 3)"""
+    def _exchange_plan(self):
+        """per peer q: the slices of the exchange buffer that go to q, the receive buffer, and where the
+        received pieces are added (computed once; the buffers are reused by every build)"""
+        if getattr(self, "_xplan", None) is not None:
+            return self._xplan
         me = self.layout
-        send, recv = [], []
+        plan = []
         for q, lay in enumerate(self.layouts):
-            parts, n_recv = [], 0
+            send_slices, adds, n_recv = [], [], 0
             for b, (off, nA, nB) in enumerate(me.blocks):
                 if nA * nB == 0:
                     continue
                 cl, nc, yoff = me.cols[b]
                 lo_q, n_q, _ = lay.rows[b]
                 if nc > 0 and n_q > 0:
-                    parts.append(self._yexch[yoff + lo_q * nc: yoff + (lo_q + n_q) * nc])
-                n_recv += me.rows[b][1] * lay.cols[b][1]
-            send.append(torch.cat(parts) if parts else self._yexch[:0])
-            recv.append(torch.empty(n_recv, dtype=torch.float64, device=self.device))
-        ops = []
-        for q in range(self.world):
-            if q == self.rank:
-                recv[q].copy_(send[q])
-                continue
-            if send[q].numel():
-                ops.append(dist.P2POp(dist.isend, send[q].contiguous(), q, group=self.group))
-            if recv[q].numel():
-                ops.append(dist.P2POp(dist.irecv, recv[q], q, group=self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for q, lay in enumerate(self.layouts):
-            pos = 0
-            for b, (off, nA, nB) in enumerate(me.blocks):
-                if nA * nB == 0:
-                    continue
+                    send_slices.append((yoff + lo_q * nc, yoff + (lo_q + n_q) * nc))
                 lo, n, loc = me.rows[b]
                 cl_q, nc_q, _ = lay.cols[b]
                 if n > 0 and nc_q > 0:
-                    blk = sigma_loc[loc:loc + n * nB].view(n, nB)
-                    blk[:, cl_q:cl_q + nc_q] += recv[q][pos:pos + n * nc_q].view(n, nc_q)
-                pos += n * nc_q
+                    adds.append((loc, n, nB, cl_q, nc_q, n_recv))
+                n_recv += n * nc_q
+            n_send = sum(hi - lo for lo, hi in send_slices)
+            # one contiguous slice needs no packing; several (symmetry / GAS blocks) are packed into a buffer
+            send_buf = torch.empty(n_send, **self._kw) if len(send_slices) > 1 else None
+            recv_buf = torch.empty(n_recv, **self._kw) if q != self.rank else None
+            plan.append((send_slices, send_buf, recv_buf, adds))
+        self._xplan = plan
+        return plan
+
+    def _exchange_add(self, sigma_loc: torch.Tensor):
+        """send the alpha same-spin partials [rows of q][my columns] to q, add what arrives (step 3)"""
+        plan = self._exchange_plan()
+        ops, sends = [], []
+        for q, (send_slices, send_buf, recv_buf, adds) in enumerate(plan):
+            if len(send_slices) == 1:
+                send = self._yexch[send_slices[0][0]:send_slices[0][1]]
+            elif send_slices:
+                pos = 0
+                for lo, hi in send_slices:
+                    send_buf[pos:pos + hi - lo].copy_(self._yexch[lo:hi])
+                    pos += hi - lo
+                send = send_buf
+            else:
+                send = self._yexch[:0]
+            sends.append(send)
+            if q == self.rank:
+                continue
+            if send.numel():
+                ops.append(dist.P2POp(dist.isend, send, q, group=self.group))
+            if recv_buf.numel():
+                ops.append(dist.P2POp(dist.irecv, recv_buf, q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for q, (send_slices, send_buf, recv_buf, adds) in enumerate(plan):
+            src = sends[q] if q == self.rank else recv_buf
+            for loc, n, nB, cl_q, nc_q, pos in adds:
+                blk = sigma_loc[loc:loc + n * nB].view(n, nB)
+                blk[:, cl_q:cl_q + nc_q] += src[pos:pos + n * nc_q].view(n, nc_q)
 
     def _exchange_cols(self, c_loc: torch.Tensor):
         """rows form, step 1: column slab [all rows][my columns] of C from the row slabs (one block)"""
