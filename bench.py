@@ -385,7 +385,10 @@ def run_ours(args):
 
     # ---- end to end through the numpy-facing call (host buffers, H2D + D2H inside) ----
     e2e = None
-    if world == 1:
+    if world == 1 and args.no_e2e:
+        e2e = {"value": None, "unit": "sigma builds/s", "h2d_bytes_per_step": ndet * 8, "d2h_bytes_per_step": ndet * 8,
+               "note": "skipped (--no-e2e)"}
+    elif world == 1:
         c_host = c.cpu().numpy()
         s_host = np.empty_like(c_host)
         builder.Hamiltonian(c_host, s_host)  # warm-up: allocates the pinned staging buffers
@@ -447,6 +450,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-davidson", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (needs 2 x 8 ndet bytes of pinned memory)")
     ap.add_argument("--form", default="auto", choices=["auto", "full", "rows"],
                     help="N > 1: communication form of forte2_b200/dist.py")
     args = ap.parse_args()

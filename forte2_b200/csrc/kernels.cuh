@@ -783,46 +783,50 @@ struct T3GParams {
     // sharded build: sigma row of alpha string Ia in the reduce-scatter layout (world slots of equal
     // size, slot q = the rows rank q owns); NULL = row Ia itself
     const uint32_t* rowpad;
+    // columns of the row of C staged in shared memory; the rest (long rows, e.g. CAS(18,18): 389 KB) is
+    // gathered from global memory, where the row stays L2-resident while its CTA runs
+    int nsm;
 };
 
-constexpr size_t t3g_smem_bytes(int64_t nbs, int rows, int astride) {
-    return size_t(nbs + 2) * 8 + size_t(rows) * astride * 8 + size_t(rows) * 8 + 64;
+constexpr size_t t3g_smem_bytes(int64_t nsm, int rows, int astride) {
+    return size_t(nsm + 2) * 8 + size_t(rows) * astride * 8 + size_t(rows) * 8 + 64;
 }
 
-constexpr int T3G_THREADS = 384; // 12 warps, three per SM sub-partition
-
-template <int NM16, bool HAS8>
-__global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) {
+// LONG = false: the whole row is staged (nsm == nbs).  THREADS: 384 (12 warps) up to 88 output rows,
+// 256 above (the accumulators of 96 rows need more than 170 registers per thread).
+template <int NM16, bool HAS8, bool LONG, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
     constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int S = p.astride;
-    double* row = reinterpret_cast<double*>(smem_raw);            // [nbs + 2], last two are zero
-    double* Asm = row + p.nbs + 2;                                // [ROWS][S]
+    const int nsm = p.nsm;
+    double* row = reinterpret_cast<double*>(smem_raw);            // [nsm + 2], last two are zero
+    double* Asm = row + nsm + 2;                                  // [ROWS][S]
     long long* rowoff = reinterpret_cast<long long*>(Asm + ROWS * S); // [ROWS] sigma offset of Ia_r, -1
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(rowoff + ROWS);
     __shared__ int s_kl[ROWS]; // (l_r * norb + k_r) | sign << 31, -1 for padding rows
 
     const uint32_t Ja = p.first + blockIdx.x;
+    const double* src = p.C + static_cast<int64_t>(Ja) * p.nbs;
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const unsigned total = static_cast<unsigned>(p.nbs * 8);
+        const unsigned total = static_cast<unsigned>(nsm) * 8u;
         mbar_expect_tx(bar, total);
-        const double* src = p.C + static_cast<int64_t>(Ja) * p.nbs;
         for (unsigned off = 0; off < total; off += 32768u) {
             const unsigned n = total - off < 32768u ? total - off : 32768u;
             bulk_g2s(reinterpret_cast<unsigned char*>(row) + off,
                      reinterpret_cast<const unsigned char*>(src) + off, n, bar);
         }
-        row[p.nbs] = 0.0;
-        row[p.nbs + 1] = 0.0;
+        row[nsm] = 0.0;
+        row[nsm + 1] = 0.0;
     }
     // the single replacements of Ja, read as <Ia_r| E_{lk} |Ja> = s_r from the list of Ja as an output row
     const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
     const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;
-    for (int r = tid; r < ROWS; r += T3G_THREADS) {
+    for (int r = tid; r < ROWS; r += THREADS) {
         if (r < Kn) {
             const uint64_t ent = p.as_ent[e0 + r];
             const uint32_t Iar = static_cast<uint32_t>(ent);
@@ -837,7 +841,7 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
     }
     __syncthreads();
     // A'[r][m] = s_r VxT[lk_r][m]; columns m >= M and rows r >= Kn are zero
-    for (int idx = tid; idx < ROWS * S; idx += T3G_THREADS) {
+    for (int idx = tid; idx < ROWS * S; idx += THREADS) {
         const int r = idx / S, m = idx - r * S;
         double v = 0.0;
         const int e = s_kl[r];
@@ -853,7 +857,8 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
 
     const int nks = p.Mpad >> 2;
     const int nchunks = static_cast<int>((p.nbs + 15) >> 4);
-    for (int chunk = warp; chunk < nchunks; chunk += T3G_THREADS / 32) {
+    const uint32_t nbs32 = static_cast<uint32_t>(p.nbs);
+    for (int chunk = warp; chunk < nchunks; chunk += THREADS / 32) {
         const int n0 = chunk << 4;
         double acc[NM16][2][4];
         double acc8[2][2];
@@ -873,27 +878,40 @@ __global__ void __launch_bounds__(T3G_THREADS, 1) t3g_kernel(const T3GParams p) 
             return make_uint2(__ldg(q), __ldg(q + 8));
         };
         auto gather = [&](uint32_t e) {
-            const double v = row[e & 0xfffffu];
+            const uint32_t idx = e & 0xfffffu;
+            double v;
+            if constexpr (LONG) {
+                // staged part from shared memory (index nsm = the zero slot), the rest of the row from L2
+                v = row[idx < static_cast<uint32_t>(nsm) ? idx : static_cast<uint32_t>(nsm)];
+                if (idx >= static_cast<uint32_t>(nsm) && idx < nbs32)
+                    v = __ldg(src + idx);
+            } else {
+                v = row[idx];
+            }
             return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
         };
-        // table entries run four k-steps ahead of the MMAs, gathered operands one k-step ahead
-        uint2 q0 = table(1), q1 = table(2), q2 = table(3), q3 = table(4);
-        double bn0, bn1;
+        // table entries run five k-steps ahead of the MMAs, gathered operands one (LONG: two) ahead
+        uint2 q0 = table(2), q1 = table(3), q2 = table(4), q3 = table(5);
+        double bn0, bn1, bm0, bm1;
         {
-            const uint2 x0 = table(0);
+            const uint2 x0 = table(0), x1 = table(1);
             bn0 = gather(x0.x);
             bn1 = gather(x0.y);
+            bm0 = gather(x1.x);
+            bm1 = gather(x1.y);
         }
         const double* ap = Asm + g * S + t;
 #pragma unroll 4
         for (int ks = 0; ks < nks; ++ks) {
             const double b0 = bn0, b1 = bn1;
-            bn0 = gather(q0.x);
-            bn1 = gather(q0.y);
+            bn0 = bm0;
+            bn1 = bm1;
+            bm0 = gather(q0.x);
+            bm1 = gather(q0.y);
             q0 = q1;
             q1 = q2;
             q2 = q3;
-            q3 = table(ks + 5);
+            q3 = table(ks + 6);
             const double* a = ap + 4 * ks;
 #pragma unroll
             for (int i = 0; i < NM16; ++i) {

@@ -196,6 +196,8 @@ struct f2_sigma {
     int t3_ns = 2;
     // gather-form opposite-spin kernel (t3g_kernel): single determinant block whose rows fit in smem
     bool t3g = false;
+    bool t3g_long = false; // the row of C does not fit in shared memory: part staged, the rest gathered from L2
+    int t3g_nsm = 0;       // staged columns
     int t3g_nm16 = 0, t3g_has8 = 0, t3g_astride = 0, t3g_mpad = 0;
     int64_t t3g_gld = 0;
     size_t t3g_smem = 0;
@@ -533,7 +535,29 @@ void plan_t3_shape(f2_sigma& b) {
             ++S;
         b.t3g_astride = S;
         b.t3g_smem = t3g_smem_bytes(h.nbs, rows, S);
-        b.t3g = b.t3g_nm16 >= 1 && b.t3g_nm16 <= 5 && b.t3g_smem <= 227 * 1024;
+        b.t3g_long = false;
+        b.t3g_nsm = static_cast<int>(h.nbs);
+        const bool shape_ok = b.t3g_nm16 >= 1 && b.t3g_nm16 <= 6 && !(b.t3g_nm16 == 6 && b.t3g_has8);
+        if (shape_ok && b.t3g_smem > 227 * 1024 - 2048 && std::getenv("F2_NO_T3G_LONG") == nullptr) {
+            // long rows: stage as many columns as fit beside the A' block, gather the rest from L2
+            const int64_t fixed = static_cast<int64_t>(t3g_smem_bytes(0, rows, S));
+            int64_t nsm = (int64_t(227) * 1024 - 2048 - fixed) / 8; // 2 KB left for the kernel's static arrays
+            nsm -= nsm % 2;
+            if (const char* e = std::getenv("F2_T3G_NSM")) // tuning / test hook
+                nsm = std::min<int64_t>(nsm, std::max<int64_t>(0, std::atoll(e)) & ~int64_t(1));
+            if (nsm >= 0) {
+                b.t3g_long = true;
+                b.t3g_nsm = static_cast<int>(std::min<int64_t>(nsm, h.nbs));
+                b.t3g_smem = t3g_smem_bytes(b.t3g_nsm, rows, S);
+            }
+        } else if (shape_ok && std::getenv("F2_T3G_NSM") != nullptr) {
+            // test hook: exercise the long-row path on a small space
+            const int64_t nsm = std::min<int64_t>(h.nbs, std::max<int64_t>(0, std::atoll(std::getenv("F2_T3G_NSM"))) & ~int64_t(1));
+            b.t3g_long = true;
+            b.t3g_nsm = static_cast<int>(nsm);
+            b.t3g_smem = t3g_smem_bytes(b.t3g_nsm, rows, S);
+        }
+        b.t3g = shape_ok && b.t3g_smem <= 227 * 1024 - 2048;
     }
     // warp-specialised kernel: 8 MMA warps cover up to 128 rows (+ the 8-row tail strip), even layout
     b.t3_v4 = false;
@@ -915,9 +939,16 @@ void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t
 
 template <int NM16, bool HAS8>
 void launch_t3g_inst(const f2_sigma& b, const T3GParams& p, int nrows, cudaStream_t st) {
-    F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(b.t3g_smem)));
-    t3g_kernel<NM16, HAS8><<<nrows, T3G_THREADS, b.t3g_smem, st>>>(p);
+    constexpr int THREADS = NM16 >= 6 ? 256 : 384;
+    if (b.t3g_long) {
+        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, true, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(b.t3g_smem)));
+        t3g_kernel<NM16, HAS8, true, THREADS><<<nrows, THREADS, b.t3g_smem, st>>>(p);
+    } else {
+        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, false, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(b.t3g_smem)));
+        t3g_kernel<NM16, HAS8, false, THREADS><<<nrows, THREADS, b.t3g_smem, st>>>(p);
+    }
     b.launches += 1;
 }
 
@@ -943,6 +974,7 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
     p.first = first;
     p.astride = b.t3g_astride;
     p.rowpad = rowpad;
+    p.nsm = b.t3g_nsm;
     if (nrows < 0)
         nrows = static_cast<int>(h.nas);
     if (nrows == 0)
@@ -959,6 +991,7 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
     case 9: launch_t3g_inst<4, true>(b, p, nrows, st); break;
     case 10: launch_t3g_inst<5, false>(b, p, nrows, st); break;
     case 11: launch_t3g_inst<5, true>(b, p, nrows, st); break;
+    case 12: launch_t3g_inst<6, false>(b, p, nrows, st); break;
     default: throw std::runtime_error("CISigmaBuilder: unsupported gather-form shape");
     }
     F2_CUDA(cudaGetLastError());

@@ -193,3 +193,26 @@ def test_host_path_streams_the_opposite_spin_term(ref, torch_cuda, monkeypatch):
     got2 = np.full_like(c, np.nan)
     gb.Hamiltonian(c, got2)
     assert _rel(got2, want) <= TOL
+
+
+@pytest.mark.parametrize("nsm", [0, 100, 250])
+def test_gather_form_with_partially_staged_rows(ref, torch_cuda, monkeypatch, nsm):
+    """Long rows of C (CAS(18,18): 389 KB) do not fit in shared memory: the gather-form kernel stages the
+    first columns and gathers the rest from global memory.  Forced here on CAS(10,10) (252 columns) with
+    0, 100 and 250 staged columns; device, host-streamed and sharded (rows form, emulated) paths."""
+    torch = torch_cuda
+    monkeypatch.setenv("F2_T3G_NSM", str(nsm))
+    n = 10
+    space = (5, 5, 0, [[0] * n], [], [])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    assert gb.t3_shape()["form"] == "gather"
+    c = synthetic.trial_vector(rs.ndet)
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    cd = torch.from_numpy(c).cuda()
+    sd = torch.full_like(cd, float("nan"))
+    gb.Hamiltonian(cd, sd)
+    assert _rel(sd.cpu().numpy(), want) <= TOL
+    got = np.full_like(c, np.nan)
+    gb.Hamiltonian(c, got)
+    assert _rel(got, want) <= TOL
