@@ -233,6 +233,7 @@ struct f2_sigma {
     cudaEvent_t* ev = evs[0];
     int ev_idx = 0;
     bool set_pending[kEvSets] = {false, false, false, false};
+    bool t3_first[kEvSets] = {false, false, false, false}; // rows form: the opposite-spin term runs first
     double t_acc[4] = {0, 0, 0, 0};
     double last_ms[5] = {0, 0, 0, 0, 0};
     long builds = 0;
@@ -1128,6 +1129,13 @@ void collect_set(f2_sigma& b, int set) {
         F2_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     float tot;
     F2_CUDA(cudaEventElapsedTime(&tot, ev[0], ev[4]));
+    if (b.t3_first[set]) { // intervals are [opposite spin, H0, alpha, beta]
+        const float t3 = ms[0];
+        ms[0] = ms[1];
+        ms[1] = ms[2];
+        ms[2] = ms[3];
+        ms[3] = t3;
+    }
     b.last_ms[0] = ms[0];
     b.last_ms[1] = ms[1];
     b.last_ms[2] = ms[2];
@@ -1152,6 +1160,7 @@ void begin_build(f2_sigma& b) {
     b.ev_idx = (b.ev_idx + 1) % f2_sigma::kEvSets;
     collect_set(b, b.ev_idx);
     b.ev = b.evs[b.ev_idx];
+    b.t3_first[b.ev_idx] = false;
 }
 
 // sigma (the owned rows) from the full trial vector.  On one GPU yexch is unused; otherwise the
@@ -1229,44 +1238,54 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
 //   ycols      = alpha same-spin term of [all rows][owned columns], from xcols    (caller: all-to-all, add)
 //   scatter    = opposite-spin contributions of the owned INPUT rows to every sigma row, world slots of
 //                slot_rows x nbs (caller: reduce-scatter, add)
+// phases: 1 = the opposite-spin term into `scatter` (first, so that the caller can start the
+// reduce-scatter while phase 2 runs), 2 = H0 and the two same-spin terms, 3 = both.
 void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, double* sigma, double* ycols,
-                double* scatter, cudaStream_t st) {
+                double* scatter, int phases, cudaStream_t st) {
     const CIStringsHost& h = *b.S->host;
     F2_CUDA(cudaSetDevice(b.device));
-    begin_build(b);
+    if (phases & 1) {
+        begin_build(b);
+        b.t3_first[b.ev_idx] = true;
+        b.launches = 0;
+    }
     if (!P.beta_planned)
         plan_beta(b, P);
     if (h.ndet == 0)
         return;
     const int64_t rows = P.hi[0] - P.lo[0];
-    b.launches = 0;
-    F2_CUDA(cudaEventRecord(b.ev[0], st));
-    if (P.local_size > 0) {
-        scale_copy_kernel<false><<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
-        b.launches += 1;
+    // event order of this form: start, [opposite spin], e1, [H0], e2, [alpha], e3, [beta], e4
+    if (phases & 1) {
+        F2_CUDA(cudaEventRecord(b.ev[0], st));
+        F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_rows * h.nbs * sizeof(double), st));
+        if (h.na >= 1 && h.nb >= 1 && rows > 0)
+            launch_t3g(b, Cloc - P.lo[0] * h.nbs, scatter, st, static_cast<int>(P.lo[0]), static_cast<int>(rows),
+                       P.rowpad.p);
+        F2_CUDA(cudaEventRecord(b.ev[1], st));
     }
-    F2_CUDA(cudaEventRecord(b.ev[1], st));
-    F2_CUDA(cudaMemsetAsync(ycols, 0, static_cast<size_t>(std::max<int64_t>(P.y_size, 1)) * sizeof(double), st));
-    if (h.na >= 1)
-        launch_same_spin(b, 0, P.alpha_cols_plan, xcols, ycols, b.W[0].p, st);
-    F2_CUDA(cudaEventRecord(b.ev[2], st));
-    for (const auto& bp : P.beta_passes) {
-        if (bp->ntr_tiles == 0)
-            continue;
-        transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(Cloc, b.XT.p, bp->tr.p, bp->ntr, true);
-        b.launches += 2;
-        F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
-        launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, b.W[1].p, st);
-        transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr, false);
+    if (phases & 2) {
+        if (P.local_size > 0) {
+            scale_copy_kernel<false><<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
+            b.launches += 1;
+        }
+        F2_CUDA(cudaEventRecord(b.ev[2], st));
+        F2_CUDA(cudaMemsetAsync(ycols, 0, static_cast<size_t>(std::max<int64_t>(P.y_size, 1)) * sizeof(double), st));
+        if (h.na >= 1)
+            launch_same_spin(b, 0, P.alpha_cols_plan, xcols, ycols, b.W[0].p, st);
+        F2_CUDA(cudaEventRecord(b.ev[3], st));
+        for (const auto& bp : P.beta_passes) {
+            if (bp->ntr_tiles == 0)
+                continue;
+            transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(Cloc, b.XT.p, bp->tr.p, bp->ntr, true);
+            b.launches += 2;
+            F2_CUDA(cudaMemsetAsync(b.YT.p, 0, static_cast<size_t>(bp->elems) * sizeof(double), st));
+            launch_same_spin(b, 1, bp->plan, b.XT.p, b.YT.p, b.W[1].p, st);
+            transpose_kernel<true><<<bp->ntr_tiles, 256, 0, st>>>(b.YT.p, sigma, bp->tr.p, bp->ntr, false);
+        }
+        F2_CUDA(cudaEventRecord(b.ev[4], st));
+        b.set_pending[b.ev_idx] = true;
     }
-    F2_CUDA(cudaEventRecord(b.ev[3], st));
-    F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_rows * h.nbs * sizeof(double), st));
-    if (h.na >= 1 && h.nb >= 1 && rows > 0)
-        launch_t3g(b, Cloc - P.lo[0] * h.nbs, scatter, st, static_cast<int>(P.lo[0]), static_cast<int>(rows),
-                   P.rowpad.p);
-    F2_CUDA(cudaEventRecord(b.ev[4], st));
     F2_CUDA(cudaGetLastError());
-    b.set_pending[b.ev_idx] = true;
 }
 
 // the rows form needs the gather-form kernel and 16-byte aligned row slabs (even nbs)
@@ -1592,7 +1611,7 @@ int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4) {
 }
 
 int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xcols_dev, double* sigma_local_dev,
-                        double* ycols_dev, double* scatter_dev, int rank, int world, void* stream) {
+                        double* ycols_dev, double* scatter_dev, int rank, int world, int phases, void* stream) {
     try {
         if (!h || !C_local_dev || !xcols_dev || !sigma_local_dev || !ycols_dev || !scatter_dev)
             throw std::invalid_argument("null argument");
@@ -1601,8 +1620,10 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
                                      "this string space (f2_sigma_rows_form)");
         if ((reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
             throw std::invalid_argument("CISigmaBuilder: the local trial vector must be 16-byte aligned");
+        if (phases < 1 || phases > 3)
+            throw std::invalid_argument("CISigmaBuilder: phases must be 1, 2 or 3");
         Part& P = shard_of(*h, rank, world);
-        apply_rows(*h, P, C_local_dev, xcols_dev, sigma_local_dev, ycols_dev, scatter_dev,
+        apply_rows(*h, P, C_local_dev, xcols_dev, sigma_local_dev, ycols_dev, scatter_dev, phases,
                    static_cast<cudaStream_t>(stream));
         return F2_OK;
     } catch (const std::exception& e) {

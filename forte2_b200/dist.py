@@ -90,11 +90,11 @@ class CudaEngine:
         _lib.check(_lib.lib().f2_sigma_rows_form(self.builder._h, rank, world, out.ctypes.data_as(_lib.i64p)))
         return bool(out[0]), int(out[1]), int(out[2])
 
-    def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world):
+    def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world, phases=3):
         stream = torch.cuda.current_stream(self.builder.device).cuda_stream
         _lib.check(_lib.lib().f2_sigma_apply_rows(self.builder._h, c_loc.data_ptr(), xcols.data_ptr(),
                                                   sigma_loc.data_ptr(), ycols.data_ptr(), scatter.data_ptr(),
-                                                  rank, world, stream))
+                                                  rank, world, phases, stream))
 
     def layout_from_library(self, nblocks, rank, world):
         sizes = np.zeros(2, dtype=np.int64)
@@ -257,14 +257,21 @@ class ShardedSigma:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
-    def _reduce_scatter_add(self, sigma_loc: torch.Tensor):
-        """rows form, step 4: sum over ranks of slot `rank` of the opposite-spin buffers, added to sigma"""
+    def _reduce_scatter_start(self):
+        """rows form, step 4: sum over ranks of slot `rank` of the opposite-spin buffers; asynchronous on
+        NCCL, so that it overlaps the same-spin kernels launched next"""
         if dist.get_backend(self.group) == "nccl":
-            dist.reduce_scatter_tensor(self._rs_out, self._scatter, op=dist.ReduceOp.SUM, group=self.group)
-            sigma_loc += self._rs_out[: self.local_size]
-        else:  # gloo (CPU tests): no reduce-scatter, reduce everything and take the own slot
-            dist.all_reduce(self._scatter, op=dist.ReduceOp.SUM, group=self.group)
-            sigma_loc += self._scatter[self.rank * self._slot: self.rank * self._slot + self.local_size]
+            return dist.reduce_scatter_tensor(self._rs_out, self._scatter, op=dist.ReduceOp.SUM, group=self.group,
+                                              async_op=True)
+        # gloo (CPU tests): no reduce-scatter, reduce everything and take the own slot
+        dist.all_reduce(self._scatter, op=dist.ReduceOp.SUM, group=self.group)
+        self._rs_out[: self._slot].copy_(self._scatter[self.rank * self._slot: (self.rank + 1) * self._slot])
+        return None
+
+    def _reduce_scatter_finish(self, work, sigma_loc: torch.Tensor):
+        if work is not None:
+            work.wait()
+        sigma_loc += self._rs_out[: self.local_size]
 
     def _mark(self, name):
         """phase boundary for profile_phases(): a CUDA event on the current stream"""
@@ -288,10 +295,14 @@ class ShardedSigma:
         if self.form == "rows":
             self._exchange_cols(c_loc)
             self._mark("all-to-all of C (column slab)")
-            self.engine.apply_rows(c_loc, self._xcols, sigma_loc, self._yexch, self._scatter, self.rank, self.world)
-            self._mark("local kernels")
-            self._reduce_scatter_add(sigma_loc)
-            self._mark("reduce-scatter + add")
+            args = (c_loc, self._xcols, sigma_loc, self._yexch, self._scatter, self.rank, self.world)
+            self.engine.apply_rows(*args, phases=1)
+            self._mark("opposite-spin kernel")
+            work = self._reduce_scatter_start()
+            self.engine.apply_rows(*args, phases=2)
+            self._mark("same-spin kernels (reduce-scatter in flight)")
+            self._reduce_scatter_finish(work, sigma_loc)
+            self._mark("reduce-scatter tail + add")
             self._exchange_add(sigma_loc)
             self._mark("all-to-all of the alpha same-spin term + add")
             return

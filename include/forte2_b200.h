@@ -133,10 +133,12 @@ int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4);
  * all-to-all of the row slabs.  On return sigma_local = H0 + beta same-spin term of the owned rows;
  * ycols = alpha same-spin term of [nIa][owned columns] (caller: all-to-all back to the row owners, add);
  * scatter = opposite-spin contributions of the owned INPUT rows to every sigma row in the slot layout
- * above (caller: reduce-scatter over NCCL, add).  Device pointers; stream = cudaStream_t. */
+ * above (caller: reduce-scatter over NCCL, add).  phases: 1 = only the opposite-spin term (launched
+ * first so that the reduce-scatter can overlap the rest), 2 = only H0 and the same-spin terms, 3 = both;
+ * a build is phase 1 followed by phase 2.  Device pointers; stream = cudaStream_t. */
 int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xcols_dev,
                         double* sigma_local_dev, double* ycols_dev, double* scatter_dev, int rank, int world,
-                        void* stream);
+                        int phases, void* stream);
 
 /* <I|H|J> for the n determinants at the given CI-vector addresses, n x n row-major, on the HOST
  * (SlaterRules::slater_rules, forte2/determinant/slater_rules.cc:123-245): the guess Hamiltonian of
