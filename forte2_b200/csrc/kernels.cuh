@@ -957,6 +957,195 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Opposite-spin term, gather form for spaces with several determinant blocks (point-group symmetry,
+// GAS): t3gm_kernel.  Same algebra as t3g_kernel, one CTA per INPUT alpha string Ja; the differences:
+//   * the beta strings come in classes; a chunk of 16 target strings Ib lies inside one class, and the
+//     table entry of (row m, target Ib) names its source as (class, address) -- the value is
+//     C[Ja, that class, that address] when the block (class(Ja), class(Jb)) exists, else zero;
+//   * the B operand is gathered straight from global memory (the rows of C of one alpha string are
+//     L2-resident while its CTA runs; measured on CAS(18,18): staging buys nothing);
+//   * every output row Ia_r has one sigma segment per beta class (or none), looked up in rowoff.
+// Input (Ja, Jb) and output (Ia, Ib) determinants are members of the CI space by construction, so this
+// is P H P without any intermediate outside the space.
+struct T3GMParams {
+    const double* C;
+    double* sigma;
+    const uint32_t* as_ptr;
+    const uint64_t* as_ent;
+    const uint32_t* gsrc;   // [Mpad][gld]: bits 0..19 source address, 20..30 source class, bit 31 sign;
+                            // low 31 bits all ones = no source
+    const uint32_t* chunks; // 2 per chunk: beta class, first address of the 16 targets
+    const uint32_t* gpos;   // [nclsB] first table column of each beta class (multiple of 16)
+    const uint32_t* nB_cls; // [nclsB]
+    const int64_t* crow;    // [nas][nclsB] offset of C[Ja, class, 0], -1 if the block does not exist
+    const int64_t* srow;    // [nas][nclsB] the same for sigma
+    const double* VxT;
+    int64_t gld;
+    int M, Mpad, norb, nclsB, nchunks;
+    int first, astride;
+};
+
+constexpr size_t t3gm_smem_bytes(int rows, int astride, int nclsB) {
+    return size_t(rows) * astride * 8 + size_t(rows) * nclsB * 8 + size_t(nclsB) * 8 + 64;
+}
+
+template <int NM16, bool HAS8, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
+    constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S = p.astride, NC = p.nclsB;
+    double* Asm = reinterpret_cast<double*>(smem_raw);                   // [ROWS][S]
+    long long* rowoff = reinterpret_cast<long long*>(Asm + ROWS * S);    // [ROWS][NC] sigma offset or -1
+    long long* srcbase = rowoff + ROWS * NC;                             // [NC] offset of C[Ja, class, 0] or -1
+    __shared__ int s_kl[ROWS];
+    __shared__ int s_any; // some beta class has a source block for this alpha string
+
+    const uint32_t Ja = p.first + blockIdx.x;
+    if (tid == 0)
+        s_any = 0;
+    const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
+    const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;
+    for (int r = tid; r < ROWS; r += THREADS) {
+        int kl = -1;
+        uint32_t Iar = 0;
+        if (r < Kn) {
+            const uint64_t ent = p.as_ent[e0 + r];
+            Iar = static_cast<uint32_t>(ent);
+            const int klr = static_cast<int>((ent >> 32) & 0xffff);
+            const int k = klr / p.norb, l = klr - k * p.norb;
+            kl = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
+        }
+        s_kl[r] = kl;
+        for (int c = 0; c < NC; ++c)
+            rowoff[r * NC + c] = kl >= 0 ? p.srow[static_cast<size_t>(Iar) * NC + c] : -1;
+    }
+    __syncthreads();
+    for (int c = tid; c < NC; c += THREADS) {
+        const long long b = p.crow[static_cast<size_t>(Ja) * NC + c];
+        srcbase[c] = b;
+        if (b >= 0)
+            s_any = 1;
+    }
+    for (int idx = tid; idx < ROWS * S; idx += THREADS) {
+        const int r = idx / S, m = idx - r * S;
+        double v = 0.0;
+        const int e = s_kl[r];
+        if (e >= 0 && m < p.M) {
+            v = __ldg(p.VxT + static_cast<size_t>(e & 0xffff) * p.M + m);
+            if (e & (1 << 30))
+                v = -v;
+        }
+        Asm[idx] = v;
+    }
+    __syncthreads();
+    if (!s_any)
+        return;
+
+    const int nks = p.Mpad >> 2;
+    for (int chunk = warp; chunk < p.nchunks; chunk += THREADS / 32) {
+        const int cls = static_cast<int>(p.chunks[2 * chunk]);
+        const int loc0 = static_cast<int>(p.chunks[2 * chunk + 1]);
+        const int ncls = static_cast<int>(p.nB_cls[cls]);
+        // does any output row have a sigma segment in this class?  (warp-uniform)
+        bool any = false;
+        for (int r = lane; r < ROWS; r += 32)
+            any = any || rowoff[r * NC + cls] >= 0;
+        if (!__any_sync(0xffffffffu, any))
+            continue;
+        const int n0 = static_cast<int>(p.gpos[cls]) + loc0; // table column of the first target
+        double acc[NM16][2][4];
+        double acc8[2][2];
+#pragma unroll
+        for (int i = 0; i < NM16; ++i)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+                acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
+        acc8[0][0] = acc8[0][1] = acc8[1][0] = acc8[1][1] = 0.0;
+        const uint32_t* gp = p.gsrc + static_cast<size_t>(t) * p.gld + n0 + (g >> 1) + 4 * (g & 1);
+        const size_t gstep = static_cast<size_t>(4) * p.gld;
+        auto table = [&](int ks) {
+            const uint32_t* q = gp + (ks < nks ? ks : 0) * gstep;
+            return make_uint2(__ldg(q), __ldg(q + 8));
+        };
+        auto gather = [&](uint32_t e) {
+            const uint32_t body = e & 0x7fffffffu;
+            double v = 0.0;
+            if (body != 0x7fffffffu) {
+                const long long base = srcbase[body >> 20];
+                if (base >= 0)
+                    v = __ldg(p.C + base + (body & 0xfffffu));
+            }
+            return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
+        };
+        uint2 q0 = table(2), q1 = table(3), q2 = table(4), q3 = table(5);
+        double bn0, bn1, bm0, bm1;
+        {
+            const uint2 x0 = table(0), x1 = table(1);
+            bn0 = gather(x0.x);
+            bn1 = gather(x0.y);
+            bm0 = gather(x1.x);
+            bm1 = gather(x1.y);
+        }
+        const double* ap = Asm + g * S + t;
+#pragma unroll 2
+        for (int ks = 0; ks < nks; ++ks) {
+            const double b0 = bn0, b1 = bn1;
+            bn0 = bm0;
+            bn1 = bm1;
+            bm0 = gather(q0.x);
+            bm1 = gather(q0.y);
+            q0 = q1;
+            q1 = q2;
+            q2 = q3;
+            q3 = table(ks + 6);
+            const double* a = ap + 4 * ks;
+#pragma unroll
+            for (int i = 0; i < NM16; ++i) {
+                const double a0 = a[(16 * i) * S], a1 = a[(16 * i + 8) * S];
+                dmma_16x8x4(acc[i][0], a0, a1, b0);
+                dmma_16x8x4(acc[i][1], a0, a1, b1);
+            }
+            if constexpr (HAS8) {
+                const double a0 = a[(16 * NM16) * S];
+                dmma_8x8x4(acc8[0], a0, b0);
+                dmma_8x8x4(acc8[1], a0, b1);
+            }
+        }
+        // accumulator (row, tile nt, n index 2t + c) is target address loc0 + 8 nt + 4 c + t of the class
+        const int c0 = loc0 + t;
+#pragma unroll
+        for (int i = 0; i < NM16; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long ro = rowoff[(16 * i + g + 8 * h) * NC + cls];
+                if (ro >= 0) {
+                    double* dst = p.sigma + ro + c0;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (c0 + 8 * nt + 4 * c < ncls)
+                                atomicAdd(dst + 8 * nt + 4 * c, acc[i][nt][2 * h + c]);
+                }
+            }
+        if constexpr (HAS8) {
+            const long long ro = rowoff[(16 * NM16 + g) * NC + cls];
+            if (ro >= 0) {
+                double* dst = p.sigma + ro + c0;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (c0 + 8 * nt + 4 * c < ncls)
+                            atomicAdd(dst + 8 * nt + 4 * c, acc8[nt][c]);
+            }
+        }
+    }
+}
+
 struct SSParams {
     const double* X;
     double* Y;

@@ -203,6 +203,13 @@ struct f2_sigma {
     size_t t3g_smem = 0;
     DevBuf<uint32_t> gsrc;
     DevBuf<double> VxT;
+    // gather form over several beta classes (t3gm_kernel): symmetry / GAS blocks, one GPU
+    bool t3gm = false;
+    DevBuf<uint32_t> gm_gsrc, gm_chunks, gm_gpos;
+    DevBuf<int64_t> gm_crow;
+    int gm_nchunks = 0, gm_mpad = 0, gm_nm16 = 0, gm_has8 = 0, gm_astride = 0;
+    int64_t gm_gld = 0;
+    size_t gm_smem = 0;
     bool t3_v4 = false;    // warp-specialised opposite-spin kernel (t3v4_kernel) is applicable
     int t3_v4_ns = 3;
     size_t t3_v4_smem = 0;
@@ -389,6 +396,43 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
             b.t3g_mpad = Mpad;
             b.t3g_gld = static_cast<int64_t>(gld);
         }
+        // the same for several beta classes (t3gm_kernel): table columns are the targets class by class,
+        // every class padded to a multiple of 16; an entry names its source as class << 20 | address
+        b.gm_gsrc.release();
+        b.gm_nchunks = 0;
+        // Opt-in (F2_T3GM=1): without block-aware compaction of its rows and k-steps the kernel multiplies
+        // zeros for every (alpha row, beta class) pair whose block does not exist and loses to the scatter
+        // form on the spaces measured so far (GAS 3x20 twin: 420 ms against 278 ms).
+        if (!b.gsrc.p && nbs > 0 && std::getenv("F2_T3GM") != nullptr) {
+            const int Mpad = (b.M + 3) / 4 * 4;
+            std::vector<uint32_t> gpos(B.nclasses()), chunks;
+            size_t gld = 0;
+            for (size_t c = 0; c < B.nclasses(); ++c) {
+                gpos[c] = static_cast<uint32_t>(gld);
+                for (size_t i0 = 0; i0 < B.strpcls(c); i0 += 16) {
+                    chunks.push_back(static_cast<uint32_t>(c));
+                    chunks.push_back(static_cast<uint32_t>(i0));
+                }
+                gld += (B.strpcls(c) + 15) / 16 * 16;
+            }
+            if (static_cast<size_t>(Mpad) * gld * sizeof(uint32_t) <= (size_t(2) << 30)) {
+                std::vector<uint32_t> Gt(std::max<size_t>(size_t(Mpad) * gld, 1), 0x7fffffffu);
+                for (int m = 0; m < b.M; ++m)
+                    for (size_t gJ = 0; gJ < nbs; ++gJ) {
+                        const uint32_t x = T[size_t(m) * nbs + gJ];
+                        if (x == kNoTarget)
+                            continue;
+                        const size_t pos = gpos[(x >> 20) & 0x7ff] + (x & 0xfffffu);
+                        Gt[size_t(m) * gld + pos] = (L.b_cls[gJ] << 20) | L.b_loc[gJ] | (x & 0x80000000u);
+                    }
+                b.gm_gsrc.upload(Gt);
+                b.gm_chunks.upload(chunks);
+                b.gm_gpos.upload(gpos);
+                b.gm_nchunks = static_cast<int>(chunks.size() / 2);
+                b.gm_mpad = Mpad;
+                b.gm_gld = static_cast<int64_t>(gld);
+            }
+        }
         bool pair = nbs % 2 == 0;
         for (size_t c = 0; c < B.nclasses(); ++c)
             pair = pair && (B.cls_off[c] % 2 == 0) && (B.strpcls(c) % 2 == 0);
@@ -559,6 +603,37 @@ void plan_t3_shape(f2_sigma& b) {
             b.t3g_smem = t3g_smem_bytes(b.t3g_nsm, rows, S);
         }
         b.t3g = shape_ok && b.t3g_smem <= 227 * 1024 - 2048;
+    }
+    // gather form over several beta classes: the A' block and the per-row segment offsets must fit
+    b.t3gm = false;
+    if (!b.t3g && b.gm_gsrc.p && b.gm_nchunks > 0 && b.M >= 16) {
+        const int kn = L.as_max;
+        const int nm16 = kn / 16, rem = kn % 16;
+        b.gm_nm16 = nm16 + (rem > 8 ? 1 : 0);
+        b.gm_has8 = (rem > 0 && rem <= 8) ? 1 : 0;
+        const int rows = b.gm_nm16 * 16 + b.gm_has8 * 8;
+        int S = b.gm_mpad;
+        while (S % 16 != 4)
+            ++S;
+        b.gm_astride = S;
+        b.gm_smem = t3gm_smem_bytes(rows, S, static_cast<int>(nclsB));
+        b.t3gm = b.gm_nm16 >= 1 && b.gm_nm16 <= 8 && !(b.gm_nm16 == 8 && b.gm_has8) &&
+                 b.gm_smem <= 227 * 1024 - 2048;
+        if (b.t3gm && !b.gm_crow.p) {
+            // offset of C[Ja, class c, 0] for every alpha string and beta class (the CI-vector layout)
+            const auto& A = h.space(0, K_STR_N);
+            std::vector<int64_t> crow(static_cast<size_t>(h.nas) * nclsB, -1);
+            for (size_t cA = 0; cA < A.nclasses(); ++cA)
+                for (size_t cB = 0; cB < nclsB; ++cB) {
+                    const int64_t bi = h.block_of[cA * nclsB + cB];
+                    if (bi < 0 || h.blocks[bi].nA * h.blocks[bi].nB == 0)
+                        continue;
+                    const auto& blk = h.blocks[bi];
+                    for (int64_t i = 0; i < blk.nA; ++i)
+                        crow[(A.cls_off[cA] + i) * nclsB + cB] = blk.offset + i * blk.nB;
+                }
+            b.gm_crow.upload(crow);
+        }
     }
     // warp-specialised kernel: 8 MMA warps cover up to 128 rows (+ the 8-row tail strip), even layout
     b.t3_v4 = false;
@@ -998,6 +1073,63 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
     F2_CUDA(cudaGetLastError());
 }
 
+template <int NM16, bool HAS8>
+void launch_t3gm_inst(const f2_sigma& b, const T3GMParams& p, int nrows, cudaStream_t st) {
+    constexpr int THREADS = NM16 >= 6 ? 256 : 384;
+    F2_CUDA(cudaFuncSetAttribute(t3gm_kernel<NM16, HAS8, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(b.gm_smem)));
+    t3gm_kernel<NM16, HAS8, THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
+    b.launches += 1;
+}
+
+// gather-form opposite-spin term for spaces with several determinant blocks (one GPU)
+void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    const DevStrings& D = *b.D;
+    T3GMParams p;
+    p.C = C;
+    p.sigma = sigma;
+    p.as_ptr = D.as_ptr.p;
+    p.as_ent = D.as_ent.p;
+    p.gsrc = b.gm_gsrc.p;
+    p.chunks = b.gm_chunks.p;
+    p.gpos = b.gm_gpos.p;
+    p.nB_cls = D.nB_cls.p;
+    p.crow = b.gm_crow.p;
+    p.srow = b.gm_crow.p;
+    p.VxT = b.VxT.p;
+    p.gld = b.gm_gld;
+    p.M = b.M;
+    p.Mpad = b.gm_mpad;
+    p.norb = h.norb;
+    p.nclsB = static_cast<int>(h.nclsB());
+    p.nchunks = b.gm_nchunks;
+    p.first = 0;
+    p.astride = b.gm_astride;
+    const int nrows = static_cast<int>(h.nas);
+    if (nrows == 0)
+        return;
+    switch (b.gm_nm16 * 2 + b.gm_has8) {
+    case 2: launch_t3gm_inst<1, false>(b, p, nrows, st); break;
+    case 3: launch_t3gm_inst<1, true>(b, p, nrows, st); break;
+    case 4: launch_t3gm_inst<2, false>(b, p, nrows, st); break;
+    case 5: launch_t3gm_inst<2, true>(b, p, nrows, st); break;
+    case 6: launch_t3gm_inst<3, false>(b, p, nrows, st); break;
+    case 7: launch_t3gm_inst<3, true>(b, p, nrows, st); break;
+    case 8: launch_t3gm_inst<4, false>(b, p, nrows, st); break;
+    case 9: launch_t3gm_inst<4, true>(b, p, nrows, st); break;
+    case 10: launch_t3gm_inst<5, false>(b, p, nrows, st); break;
+    case 11: launch_t3gm_inst<5, true>(b, p, nrows, st); break;
+    case 12: launch_t3gm_inst<6, false>(b, p, nrows, st); break;
+    case 13: launch_t3gm_inst<6, true>(b, p, nrows, st); break;
+    case 14: launch_t3gm_inst<7, false>(b, p, nrows, st); break;
+    case 15: launch_t3gm_inst<7, true>(b, p, nrows, st); break;
+    case 16: launch_t3gm_inst<8, false>(b, p, nrows, st); break;
+    default: throw std::runtime_error("CISigmaBuilder: unsupported gather-form shape");
+    }
+    F2_CUDA(cudaGetLastError());
+}
+
 void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma, bool fold,
                cudaStream_t st) {
     if (P.nitems == 0)
@@ -1192,7 +1324,8 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
     }
     F2_CUDA(cudaEventRecord(b.ev[1], st));
     const bool gather = b.t3g && P.world == 1 && P.nitems > 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
-    const bool fold = !gather && b.fold_ok && P.world == 1 && P.nitems > 0;
+    const bool gather_m = !gather && b.t3gm && P.world == 1 && P.nitems > 0;
+    const bool fold = !gather && !gather_m && b.fold_ok && P.world == 1 && P.nitems > 0;
     if (t3_streamed && !gather)
         throw std::logic_error("streamed opposite-spin term without the gather form");
     if (h.na >= 1 && !fold) {
@@ -1217,6 +1350,8 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         ; // done by the caller, piece by piece
     else if (gather)
         launch_t3g(b, C, sigma, st);
+    else if (gather_m)
+        launch_t3gm(b, C, sigma, st);
     else
         launch_t3(b, P, C, sigma, fold, st);
     F2_CUDA(cudaEventRecord(b.ev[4], st));
@@ -1632,7 +1767,7 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
 }
 
 int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
-    out5[5] = h->t3g ? 1 : 0;
+    out5[5] = (h->t3g || h->t3gm) ? 1 : 0;
     out5[0] = h->M;
     if (h->t3g) { // rows of A' actually multiplied, expressed per column of the GEMM K dimension of the list
         const int rows = h->t3g_nm16 * 16 + h->t3g_has8 * 8;

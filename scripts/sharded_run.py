@@ -20,7 +20,15 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {"cas12": (12, 6, 6), "cas14": (14, 7, 7), "cas16": (16, 8, 8), "cas18": (18, 9, 9)}
+def _cas(n):
+    return (n // 2, n // 2, 0, [[0] * n], [], [])
+
+
+# name -> CIStrings arguments.  gas20 is BASELINE.json configs[4] as made concrete in SURVEY.md section 8d
+# (1 865 504 274 determinants, 225 blocks); gas20twin its 1-GPU validation size (22 065 484 determinants).
+WORKLOADS = {"cas12": _cas(12), "cas14": _cas(14), "cas16": _cas(16), "cas18": _cas(18),
+             "gas20": (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [8, 0, 0], [12, 16, 4]),
+             "gas20twin": (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2])}
 
 
 def main():
@@ -48,10 +56,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
 
-    n, na, nb = WORKLOADS[args.workload]
+    space = WORKLOADS[args.workload]
+    na, nb = space[0], space[1]
+    n = sum(len(g) for g in space[3])
     t0 = time.perf_counter()
     E, H, V = synthetic.integrals(n, "D")  # diagonally dominant variant: the Davidson leg converges
-    strings = f2.CIStrings(na, nb, 0, [[0] * n], [], [])
+    strings = f2.CIStrings(*space)
     builder = f2.CISigmaBuilder(strings, E, H, V, 0, device=local_rank)
     builder.set_memory(64 * 1024)
     sh = ShardedSigma(builder, rank, world, form=args.form)
@@ -115,9 +125,10 @@ def main():
     if rank == 0:
         shape = builder.t3_shape()
         ndet = strings.ndet
-        useful = 2.0 * shape["M"] * (na * (n - na) + na) * ndet / world
+        useful = 2.0 * shape["M"] * shape["k_cols"] / world  # k_cols: contracted (k, column) pairs of the full build
         line = {
-            "what": "sharded sigma build", "workload": args.workload, "ndet": ndet, "n_gpus": world,
+            "what": "sharded sigma build", "workload": args.workload, "ndet": ndet, "nblocks": strings.nblocks,
+            "n_gpus": world,
             "form": sh.form, "setup_s": round(setup_s, 2),
             "sigma_ms": float(ms.item()), "sigma_builds_per_s": 1e3 / float(ms.item()),
             "term_ms_rank0": {"H0": last[0], "same_spin_alpha": last[1], "same_spin_beta": last[2],

@@ -216,3 +216,48 @@ def test_gather_form_with_partially_staged_rows(ref, torch_cuda, monkeypatch, ns
     got = np.full_like(c, np.nan)
     gb.Hamiltonian(c, got)
     assert _rel(got, want) <= TOL
+
+
+def test_gas_three_spaces_twenty_orbitals(torch_cuda):
+    """BASELINE.json configs[4] at its 1-GPU validation size: 3 GAS spaces over 20
+    orbitals, 22 065 484 determinants in 36 blocks, against sigma from the reference's own builder
+    (tests/golden/make_golden_gas20.py) at 200 000 sampled positions, plus the norm and <c|sigma>."""
+    import os
+    import forte2_b200 as f2
+    path = os.path.join(os.path.dirname(__file__), "golden", "gas20twin_S.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/gas20twin_S.npz not generated")
+    torch = torch_cuda
+    g = np.load(path)
+    space = (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2])
+    strings = f2.CIStrings(*space)
+    assert strings.ndet == int(g["ndet"]) == 22065484 and strings.nblocks == 36
+    E, H, V = synthetic.integrals(20, "S")
+    b = f2.CISigmaBuilder(strings, E, H, V, 0)
+    b.set_memory(8192)
+    c = torch.from_numpy(synthetic.trial_vector(strings.ndet)).cuda()
+    s = torch.empty_like(c)
+    b.Hamiltonian(c, s)
+    norm = float(g["norm"])
+    got = s[torch.from_numpy(g["idx"]).cuda()].cpu().numpy()
+    assert np.linalg.norm(got - g["sigma_at_idx"]) <= TOL * np.linalg.norm(g["sigma_at_idx"])
+    assert abs(float(s.norm()) - norm) <= 1e-12 * norm
+    assert abs(float(c @ s) - float(g["c_dot_sigma"])) <= 1e-12 * norm
+
+
+@pytest.mark.parametrize("name", ["gas343_54", "gas343_55", "cas66_d2h", "gas2_sym4", "cas66_cs1"])
+def test_gather_form_over_several_beta_classes(ref, torch_cuda, monkeypatch, name):
+    """t3gm_kernel (opt-in, F2_T3GM=1): the gather form of the opposite-spin term for spaces with several
+    determinant blocks (GAS, point-group symmetry) against the reference."""
+    monkeypatch.setenv("F2_T3GM", "1")
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    for ints in (synthetic.integrals(n, "S"), synthetic.four_fold_integrals(n)):
+        rs, rb, gs, gb = _pair(ref, space, ints)
+        c = synthetic.trial_vector(rs.ndet)
+        want = np.zeros_like(c)
+        rb.Hamiltonian(c, want)
+        got = np.full_like(c, np.nan)
+        gb.Hamiltonian(c, got)
+        assert _rel(got, want) <= TOL
+    assert gb.t3_shape()["form"] == "gather"
