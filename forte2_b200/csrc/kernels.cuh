@@ -959,53 +959,63 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
 
 // ---------------------------------------------------------------------------------------------
 // Opposite-spin term, gather form for spaces with several determinant blocks (point-group symmetry,
-// GAS): t3gm_kernel.  Same algebra as t3g_kernel, one CTA per INPUT alpha string Ja; the differences:
-//   * the beta strings come in classes; a chunk of 16 target strings Ib lies inside one class, and the
-//     table entry of (row m, target Ib) names its source as (class, address) -- the value is
-//     C[Ja, that class, that address] when the block (class(Ja), class(Jb)) exists, else zero;
-//   * the B operand is gathered straight from global memory (the rows of C of one alpha string are
-//     L2-resident while its CTA runs; measured on CAS(18,18): staging buys nothing);
-//   * every output row Ia_r has one sigma segment per beta class (or none), looked up in rowoff.
-// Input (Ja, Jb) and output (Ia, Ib) determinants are members of the CI space by construction, so this
-// is P H P without any intermediate outside the space.
+// GAS): t3gm_kernel.  Same algebra as t3g_kernel, one CTA per INPUT alpha string Ja, but block-aware:
+// for a chunk of 16 target beta strings of class cT only
+//   * the output rows r whose block (class(Ia_r), cT) exists are multiplied (compacted per class when
+//     the CTA starts), and
+//   * the integral rows m whose source class srccls(cT, m) has a block with class(Ja) are contracted
+//     (a class-level list made on the host).
+// With point-group symmetry that is one transfer irrep per (Ja, cT): about K/nirrep rows and M/nirrep
+// k-steps instead of K and M.  The B operand is gathered straight from global memory (the rows of C of
+// one alpha string stay L2-resident while its CTA runs); a table entry names its source as
+// class << 20 | address.  Input (Ja, Jb) and output (Ia, Ib) determinants are members of the CI space
+// by construction: P H P without any intermediate outside the space.
 struct T3GMParams {
     const double* C;
     double* sigma;
     const uint32_t* as_ptr;
     const uint64_t* as_ent;
-    const uint32_t* gsrc;   // [Mpad][gld]: bits 0..19 source address, 20..30 source class, bit 31 sign;
-                            // low 31 bits all ones = no source
+    const uint32_t* a_cls;
+    const uint32_t* gsrc;   // [Mpad + 1][gld]: bits 0..19 source address, 20..30 source class, bit 31 sign;
+                            // low 31 bits all ones = no source; row Mpad is all "no source"
     const uint32_t* chunks; // 2 per chunk: beta class, first address of the 16 targets
     const uint32_t* gpos;   // [nclsB] first table column of each beta class (multiple of 16)
     const uint32_t* nB_cls; // [nclsB]
-    const int64_t* crow;    // [nas][nclsB] offset of C[Ja, class, 0], -1 if the block does not exist
-    const int64_t* srow;    // [nas][nclsB] the same for sigma
+    const uint32_t* crow;   // [nas][nclsB] offset of C[Ja, class, 0], 0xffffffff if the block does not exist
+    const uint32_t* srow;   // [nas][nclsB] the same for sigma
+    const uint16_t* ml_ent; // [nclsA][nclsB][Mpad] integral rows to contract for (class(Ja), target class)
+    const int32_t* ml_cnt;  // [nclsA][nclsB]
     const double* VxT;
     int64_t gld;
     int M, Mpad, norb, nclsB, nchunks;
     int first, astride;
 };
 
-constexpr size_t t3gm_smem_bytes(int rows, int astride, int nclsB) {
-    return size_t(rows) * astride * 8 + size_t(rows) * nclsB * 8 + size_t(nclsB) * 8 + 64;
+constexpr uint32_t kNoRow = 0xffffffffu;
+
+constexpr size_t t3gm_smem_bytes(int rows, int astride, int nclsB, int mpad) {
+    return size_t(rows + 1) * astride * 8 + size_t(rows) * nclsB * 4 + size_t(nclsB) * (4 + 4 + 4) +
+           size_t(nclsB) * rows + size_t(nclsB) * mpad * 2 + 64;
 }
 
-template <int NM16, bool HAS8, int THREADS>
+template <int NT16, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
-    constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
+    constexpr int ROWS = NT16 * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int S = p.astride, NC = p.nclsB;
-    double* Asm = reinterpret_cast<double*>(smem_raw);                   // [ROWS][S]
-    long long* rowoff = reinterpret_cast<long long*>(Asm + ROWS * S);    // [ROWS][NC] sigma offset or -1
-    long long* srcbase = rowoff + ROWS * NC;                             // [NC] offset of C[Ja, class, 0] or -1
+    const int S = p.astride, NC = p.nclsB, MP = p.Mpad;
+    double* Asm = reinterpret_cast<double*>(smem_raw);                    // [ROWS + 1][S], last row zero
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(Asm + (ROWS + 1) * S); // [ROWS][NC] sigma offset or kNoRow
+    uint32_t* srcbase = rowoff + ROWS * NC;                               // [NC]
+    int* rcnt = reinterpret_cast<int*>(srcbase + NC);                     // [NC] output rows per target class
+    int* mcnt = rcnt + NC;                                                // [NC] integral rows per target class
+    uint16_t* mlist = reinterpret_cast<uint16_t*>(mcnt + NC);             // [NC][MP]
+    uint8_t* rlist = reinterpret_cast<uint8_t*>(mlist + NC * MP);         // [NC][ROWS]
     __shared__ int s_kl[ROWS];
-    __shared__ int s_any; // some beta class has a source block for this alpha string
 
     const uint32_t Ja = p.first + blockIdx.x;
-    if (tid == 0)
-        s_any = 0;
+    const int cJa = static_cast<int>(p.a_cls[Ja]);
     const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
     const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;
     for (int r = tid; r < ROWS; r += THREADS) {
@@ -1020,19 +1030,20 @@ __global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
         }
         s_kl[r] = kl;
         for (int c = 0; c < NC; ++c)
-            rowoff[r * NC + c] = kl >= 0 ? p.srow[static_cast<size_t>(Iar) * NC + c] : -1;
+            rowoff[r * NC + c] = kl >= 0 ? p.srow[static_cast<size_t>(Iar) * NC + c] : kNoRow;
     }
-    __syncthreads();
     for (int c = tid; c < NC; c += THREADS) {
-        const long long b = p.crow[static_cast<size_t>(Ja) * NC + c];
-        srcbase[c] = b;
-        if (b >= 0)
-            s_any = 1;
+        srcbase[c] = p.crow[static_cast<size_t>(Ja) * NC + c];
+        mcnt[c] = p.ml_cnt[cJa * NC + c];
     }
-    for (int idx = tid; idx < ROWS * S; idx += THREADS) {
+    for (int idx = tid; idx < NC * MP; idx += THREADS)
+        mlist[idx] = p.ml_ent[static_cast<size_t>(cJa) * NC * MP + idx];
+    __syncthreads();
+    // A'[r][m] = s_r VxT[lk_r][m]; columns m >= M, rows r >= Kn and the extra row are zero
+    for (int idx = tid; idx < (ROWS + 1) * S; idx += THREADS) {
         const int r = idx / S, m = idx - r * S;
         double v = 0.0;
-        const int e = s_kl[r];
+        const int e = r < ROWS ? s_kl[r] : -1;
         if (e >= 0 && m < p.M) {
             v = __ldg(p.VxT + static_cast<size_t>(e & 0xffff) * p.M + m);
             if (e & (1 << 30))
@@ -1040,107 +1051,111 @@ __global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
         }
         Asm[idx] = v;
     }
+    // output rows of every target class, compacted in order (one warp per class)
+    for (int c = warp; c < NC; c += THREADS / 32) {
+        int cnt = 0;
+        for (int base = 0; base < ROWS; base += 32) {
+            const int r = base + lane;
+            const bool ok = r < ROWS && rowoff[r * NC + c] != kNoRow;
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok)
+                rlist[c * ROWS + cnt + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint8_t>(r);
+            cnt += __popc(mask);
+        }
+        for (int r = cnt + lane; r < ROWS; r += 32)
+            rlist[c * ROWS + r] = static_cast<uint8_t>(ROWS); // the zero row of A'
+        if (lane == 0)
+            rcnt[c] = cnt;
+    }
     __syncthreads();
-    if (!s_any)
-        return;
 
-    const int nks = p.Mpad >> 2;
     for (int chunk = warp; chunk < p.nchunks; chunk += THREADS / 32) {
         const int cls = static_cast<int>(p.chunks[2 * chunk]);
+        const int nr = rcnt[cls], nm = mcnt[cls];
+        if (nr == 0 || nm == 0)
+            continue;
         const int loc0 = static_cast<int>(p.chunks[2 * chunk + 1]);
         const int ncls = static_cast<int>(p.nB_cls[cls]);
-        // does any output row have a sigma segment in this class?  (warp-uniform)
-        bool any = false;
-        for (int r = lane; r < ROWS; r += 32)
-            any = any || rowoff[r * NC + cls] >= 0;
-        if (!__any_sync(0xffffffffu, any))
-            continue;
+        const int ntile = (nr + 15) >> 4, nks = (nm + 3) >> 2;
         const int n0 = static_cast<int>(p.gpos[cls]) + loc0; // table column of the first target
-        double acc[NM16][2][4];
-        double acc8[2][2];
+        const uint16_t* ml = mlist + cls * MP;
+        const uint8_t* rl = rlist + cls * ROWS;
+        double acc[NT16][2][4];
+        const double* arow[NT16][2];
 #pragma unroll
-        for (int i = 0; i < NM16; ++i)
+        for (int i = 0; i < NT16; ++i) {
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
                 acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
-        acc8[0][0] = acc8[0][1] = acc8[1][0] = acc8[1][1] = 0.0;
-        const uint32_t* gp = p.gsrc + static_cast<size_t>(t) * p.gld + n0 + (g >> 1) + 4 * (g & 1);
-        const size_t gstep = static_cast<size_t>(4) * p.gld;
-        auto table = [&](int ks) {
-            const uint32_t* q = gp + (ks < nks ? ks : 0) * gstep;
+            const int r0 = i < ntile ? rl[16 * i + g] : ROWS, r1 = i < ntile ? rl[16 * i + g + 8] : ROWS;
+            arow[i][0] = Asm + r0 * S;
+            arow[i][1] = Asm + r1 * S;
+        }
+        // lane (g, t) feeds B[k = t][n = g] of both n8 tiles; n index gg of tile nt is the target address
+        // loc0 + 8 nt + (gg >> 1) + 4 (gg & 1): the four lanes of an accumulator row hold consecutive targets
+        const uint32_t* gp = p.gsrc + n0 + (g >> 1) + 4 * (g & 1);
+        auto mrow = [&](int ks) { // integral row of k index 4 ks + t (the all-empty row past the list)
+            const int k = 4 * ks + t;
+            return k < nm ? static_cast<int>(ml[k]) : MP;
+        };
+        auto table = [&](int m) {
+            const uint32_t* q = gp + static_cast<size_t>(m) * p.gld;
             return make_uint2(__ldg(q), __ldg(q + 8));
         };
         auto gather = [&](uint32_t e) {
             const uint32_t body = e & 0x7fffffffu;
             double v = 0.0;
             if (body != 0x7fffffffu) {
-                const long long base = srcbase[body >> 20];
-                if (base >= 0)
-                    v = __ldg(p.C + base + (body & 0xfffffu));
+                const uint32_t base = srcbase[body >> 20];
+                if (base != kNoRow)
+                    v = __ldg(p.C + static_cast<size_t>(base) + (body & 0xfffffu));
             }
             return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
         };
-        uint2 q0 = table(2), q1 = table(3), q2 = table(4), q3 = table(5);
-        double bn0, bn1, bm0, bm1;
+        // table entries two k-steps ahead of the MMAs, gathered operands one ahead
+        int m_cur = mrow(0), m_nxt = mrow(1);
+        uint2 q_nxt = table(m_nxt);
+        double bn0, bn1;
         {
-            const uint2 x0 = table(0), x1 = table(1);
+            const uint2 x0 = table(m_cur);
             bn0 = gather(x0.x);
             bn1 = gather(x0.y);
-            bm0 = gather(x1.x);
-            bm1 = gather(x1.y);
         }
-        const double* ap = Asm + g * S + t;
-#pragma unroll 2
         for (int ks = 0; ks < nks; ++ks) {
             const double b0 = bn0, b1 = bn1;
-            bn0 = bm0;
-            bn1 = bm1;
-            bm0 = gather(q0.x);
-            bm1 = gather(q0.y);
-            q0 = q1;
-            q1 = q2;
-            q2 = q3;
-            q3 = table(ks + 6);
-            const double* a = ap + 4 * ks;
+            const int m = m_cur;
+            bn0 = gather(q_nxt.x);
+            bn1 = gather(q_nxt.y);
+            m_cur = m_nxt;
+            m_nxt = mrow(ks + 2);
+            q_nxt = table(m_nxt);
 #pragma unroll
-            for (int i = 0; i < NM16; ++i) {
-                const double a0 = a[(16 * i) * S], a1 = a[(16 * i + 8) * S];
-                dmma_16x8x4(acc[i][0], a0, a1, b0);
-                dmma_16x8x4(acc[i][1], a0, a1, b1);
-            }
-            if constexpr (HAS8) {
-                const double a0 = a[(16 * NM16) * S];
-                dmma_8x8x4(acc8[0], a0, b0);
-                dmma_8x8x4(acc8[1], a0, b1);
+            for (int i = 0; i < NT16; ++i) {
+                if (i < ntile) {
+                    const double a0 = arow[i][0][m], a1 = arow[i][1][m];
+                    dmma_16x8x4(acc[i][0], a0, a1, b0);
+                    dmma_16x8x4(acc[i][1], a0, a1, b1);
+                }
             }
         }
         // accumulator (row, tile nt, n index 2t + c) is target address loc0 + 8 nt + 4 c + t of the class
         const int c0 = loc0 + t;
 #pragma unroll
-        for (int i = 0; i < NM16; ++i)
+        for (int i = 0; i < NT16; ++i) {
+            if (i < ntile) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const long long ro = rowoff[(16 * i + g + 8 * h) * NC + cls];
-                if (ro >= 0) {
-                    double* dst = p.sigma + ro + c0;
+                for (int h = 0; h < 2; ++h) {
+                    const int r = rl[16 * i + g + 8 * h];
+                    if (r < ROWS) {
+                        double* dst = p.sigma + static_cast<size_t>(rowoff[r * NC + cls]) + c0;
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
+                        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            if (c0 + 8 * nt + 4 * c < ncls)
-                                atomicAdd(dst + 8 * nt + 4 * c, acc[i][nt][2 * h + c]);
+                            for (int c = 0; c < 2; ++c)
+                                if (c0 + 8 * nt + 4 * c < ncls)
+                                    atomicAdd(dst + 8 * nt + 4 * c, acc[i][nt][2 * h + c]);
+                    }
                 }
-            }
-        if constexpr (HAS8) {
-            const long long ro = rowoff[(16 * NM16 + g) * NC + cls];
-            if (ro >= 0) {
-                double* dst = p.sigma + ro + c0;
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if (c0 + 8 * nt + 4 * c < ncls)
-                            atomicAdd(dst + 8 * nt + 4 * c, acc8[nt][c]);
             }
         }
     }
@@ -1261,7 +1276,10 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
         const unsigned* minfo = minfo3 + (j % 3) * ROWS;
         const int m = s_m[j % 3];
         double* A = Abuf + (j & 1) * ROWS * S;
-        for (int idx = tid; idx < ROWS * S; idx += 256) {
+        // only the 16-row tiles that hold parents are multiplied (nothing at all for a string without parents
+        // in this column group, the usual case in GAS and symmetry-blocked spaces), so only they are copied
+        const int rows_used = ((m + 15) >> 4) << 4;
+        for (int idx = tid; idx < (rows_used < ROWS ? rows_used : ROWS) * S; idx += 256) {
             const int a = idx / S, b = idx - a * S;
             const bool in = a < m && b < m;
             const double* src = in ? p.W + static_cast<size_t>(minfo[a] & 0xffff) * p.P + (minfo[b] & 0xffff) : p.W;
@@ -1357,14 +1375,18 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
                         const double* a = ap + 4 * ks;
 #pragma unroll
                         for (int mt = 0; mt < NM16; ++mt) {
-                            const double a0 = a[(16 * mt) * S], a1 = a[(16 * mt + 8) * S];
-                            dmma_16x8x4(acc[mt][0], a0, a1, b0);
-                            dmma_16x8x4(acc[mt][1], a0, a1, b1);
+                            if (16 * mt < m) {
+                                const double a0 = a[(16 * mt) * S], a1 = a[(16 * mt + 8) * S];
+                                dmma_16x8x4(acc[mt][0], a0, a1, b0);
+                                dmma_16x8x4(acc[mt][1], a0, a1, b1);
+                            }
                         }
                         if constexpr (HAS8) {
-                            const double a0 = a[(16 * NM16) * S];
-                            dmma_8x8x4(acc8[0], a0, b0);
-                            dmma_8x8x4(acc8[1], a0, b1);
+                            if (16 * NM16 < m) {
+                                const double a0 = a[(16 * NM16) * S];
+                                dmma_8x8x4(acc8[0], a0, b0);
+                                dmma_8x8x4(acc8[1], a0, b1);
+                            }
                         }
                     }
                 }

@@ -205,9 +205,10 @@ struct f2_sigma {
     DevBuf<double> VxT;
     // gather form over several beta classes (t3gm_kernel): symmetry / GAS blocks, one GPU
     bool t3gm = false;
-    DevBuf<uint32_t> gm_gsrc, gm_chunks, gm_gpos;
-    DevBuf<int64_t> gm_crow;
-    int gm_nchunks = 0, gm_mpad = 0, gm_nm16 = 0, gm_has8 = 0, gm_astride = 0;
+    DevBuf<uint32_t> gm_gsrc, gm_chunks, gm_gpos, gm_crow;
+    DevBuf<uint16_t> gm_ml_ent;
+    DevBuf<int32_t> gm_ml_cnt;
+    int gm_nchunks = 0, gm_mpad = 0, gm_nt16 = 0, gm_astride = 0;
     int64_t gm_gld = 0;
     size_t gm_smem = 0;
     bool t3_v4 = false;    // warp-specialised opposite-spin kernel (t3v4_kernel) is applicable
@@ -397,17 +398,17 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
             b.t3g_gld = static_cast<int64_t>(gld);
         }
         // the same for several beta classes (t3gm_kernel): table columns are the targets class by class,
-        // every class padded to a multiple of 16; an entry names its source as class << 20 | address
+        // every class padded to a multiple of 16; an entry names its source as class << 20 | address.  One
+        // extra all-empty row.  Beside it, for every (alpha class of the input string, target beta class) the
+        // integral rows whose source class has a determinant block with that alpha class.
         b.gm_gsrc.release();
         b.gm_nchunks = 0;
-        // Opt-in (F2_T3GM=1): without block-aware compaction of its rows and k-steps the kernel multiplies
-        // zeros for every (alpha row, beta class) pair whose block does not exist and loses to the scatter
-        // form on the spaces measured so far (GAS 3x20 twin: 420 ms against 278 ms).
-        if (!b.gsrc.p && nbs > 0 && std::getenv("F2_T3GM") != nullptr) {
+        if (!b.gsrc.p && nbs > 0 && h.ndet < (int64_t(1) << 32) - 1 && std::getenv("F2_NO_T3GM") == nullptr) {
             const int Mpad = (b.M + 3) / 4 * 4;
-            std::vector<uint32_t> gpos(B.nclasses()), chunks;
+            const size_t NCb = B.nclasses(), NCa = h.nclsA();
+            std::vector<uint32_t> gpos(NCb), chunks;
             size_t gld = 0;
-            for (size_t c = 0; c < B.nclasses(); ++c) {
+            for (size_t c = 0; c < NCb; ++c) {
                 gpos[c] = static_cast<uint32_t>(gld);
                 for (size_t i0 = 0; i0 < B.strpcls(c); i0 += 16) {
                     chunks.push_back(static_cast<uint32_t>(c));
@@ -415,19 +416,53 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
                 }
                 gld += (B.strpcls(c) + 15) / 16 * 16;
             }
-            if (static_cast<size_t>(Mpad) * gld * sizeof(uint32_t) <= (size_t(2) << 30)) {
-                std::vector<uint32_t> Gt(std::max<size_t>(size_t(Mpad) * gld, 1), 0x7fffffffu);
+            if (static_cast<size_t>(Mpad + 1) * gld * sizeof(uint32_t) <= (size_t(2) << 30) && Mpad < 65535) {
+                std::vector<uint32_t> Gt(std::max<size_t>(size_t(Mpad + 1) * gld, 1), 0x7fffffffu);
+                // [target class][m] -> source classes (a pair-compressed row serves E_ij and E_ji, which can come
+                // from two different classes); -2 in slot 0 = more than two, keep the row unconditionally
+                std::vector<int> srccls(NCb * Mpad * 2, -1);
                 for (int m = 0; m < b.M; ++m)
                     for (size_t gJ = 0; gJ < nbs; ++gJ) {
                         const uint32_t x = T[size_t(m) * nbs + gJ];
                         if (x == kNoTarget)
                             continue;
-                        const size_t pos = gpos[(x >> 20) & 0x7ff] + (x & 0xfffffu);
+                        const uint32_t ct = (x >> 20) & 0x7ff;
+                        const size_t pos = gpos[ct] + (x & 0xfffffu);
                         Gt[size_t(m) * gld + pos] = (L.b_cls[gJ] << 20) | L.b_loc[gJ] | (x & 0x80000000u);
+                        int* sc = &srccls[(ct * Mpad + m) * 2];
+                        const int cj = static_cast<int>(L.b_cls[gJ]);
+                        if (sc[0] == -2 || sc[0] == cj || sc[1] == cj)
+                            ;
+                        else if (sc[0] == -1)
+                            sc[0] = cj;
+                        else if (sc[1] == -1)
+                            sc[1] = cj;
+                        else
+                            sc[0] = -2;
+                    }
+                std::vector<uint16_t> ml(NCa * NCb * Mpad, static_cast<uint16_t>(Mpad));
+                std::vector<int32_t> mc(NCa * NCb, 0);
+                for (size_t ca = 0; ca < NCa; ++ca)
+                    for (size_t ct = 0; ct < NCb; ++ct) {
+                        int n = 0;
+                        for (int m = 0; m < b.M; ++m) {
+                            const int* sc = &srccls[(ct * Mpad + m) * 2];
+                            bool keep = sc[0] == -2;
+                            for (int q = 0; q < 2 && !keep; ++q)
+                                if (sc[q] >= 0) {
+                                    const int64_t bi = h.block_of[ca * NCb + sc[q]];
+                                    keep = bi >= 0 && h.blocks[bi].nA * h.blocks[bi].nB > 0;
+                                }
+                            if (keep)
+                                ml[(ca * NCb + ct) * Mpad + n++] = static_cast<uint16_t>(m);
+                        }
+                        mc[ca * NCb + ct] = n;
                     }
                 b.gm_gsrc.upload(Gt);
                 b.gm_chunks.upload(chunks);
                 b.gm_gpos.upload(gpos);
+                b.gm_ml_ent.upload(ml);
+                b.gm_ml_cnt.upload(mc);
                 b.gm_nchunks = static_cast<int>(chunks.size() / 2);
                 b.gm_mpad = Mpad;
                 b.gm_gld = static_cast<int64_t>(gld);
@@ -604,25 +639,21 @@ void plan_t3_shape(f2_sigma& b) {
         }
         b.t3g = shape_ok && b.t3g_smem <= 227 * 1024 - 2048;
     }
-    // gather form over several beta classes: the A' block and the per-row segment offsets must fit
+    // gather form over several beta classes: the A' block and the per-class row / k lists must fit
     b.t3gm = false;
-    if (!b.t3g && b.gm_gsrc.p && b.gm_nchunks > 0 && b.M >= 16) {
-        const int kn = L.as_max;
-        const int nm16 = kn / 16, rem = kn % 16;
-        b.gm_nm16 = nm16 + (rem > 8 ? 1 : 0);
-        b.gm_has8 = (rem > 0 && rem <= 8) ? 1 : 0;
-        const int rows = b.gm_nm16 * 16 + b.gm_has8 * 8;
-        int S = b.gm_mpad;
+    if (!b.t3g && b.gm_gsrc.p && b.gm_nchunks > 0) {
+        b.gm_nt16 = (L.as_max + 15) / 16;
+        const int rows = b.gm_nt16 * 16;
+        int S = b.gm_mpad + 1;
         while (S % 16 != 4)
             ++S;
         b.gm_astride = S;
-        b.gm_smem = t3gm_smem_bytes(rows, S, static_cast<int>(nclsB));
-        b.t3gm = b.gm_nm16 >= 1 && b.gm_nm16 <= 8 && !(b.gm_nm16 == 8 && b.gm_has8) &&
-                 b.gm_smem <= 227 * 1024 - 2048;
+        b.gm_smem = t3gm_smem_bytes(rows, S, static_cast<int>(nclsB), b.gm_mpad);
+        b.t3gm = b.gm_nt16 >= 1 && b.gm_nt16 <= 8 && b.gm_smem <= 227 * 1024 - 2048;
         if (b.t3gm && !b.gm_crow.p) {
             // offset of C[Ja, class c, 0] for every alpha string and beta class (the CI-vector layout)
             const auto& A = h.space(0, K_STR_N);
-            std::vector<int64_t> crow(static_cast<size_t>(h.nas) * nclsB, -1);
+            std::vector<uint32_t> crow(static_cast<size_t>(h.nas) * nclsB, kNoRow);
             for (size_t cA = 0; cA < A.nclasses(); ++cA)
                 for (size_t cB = 0; cB < nclsB; ++cB) {
                     const int64_t bi = h.block_of[cA * nclsB + cB];
@@ -630,7 +661,7 @@ void plan_t3_shape(f2_sigma& b) {
                         continue;
                     const auto& blk = h.blocks[bi];
                     for (int64_t i = 0; i < blk.nA; ++i)
-                        crow[(A.cls_off[cA] + i) * nclsB + cB] = blk.offset + i * blk.nB;
+                        crow[(A.cls_off[cA] + i) * nclsB + cB] = static_cast<uint32_t>(blk.offset + i * blk.nB);
                 }
             b.gm_crow.upload(crow);
         }
@@ -1073,12 +1104,12 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
     F2_CUDA(cudaGetLastError());
 }
 
-template <int NM16, bool HAS8>
+template <int NT16>
 void launch_t3gm_inst(const f2_sigma& b, const T3GMParams& p, int nrows, cudaStream_t st) {
-    constexpr int THREADS = NM16 >= 6 ? 256 : 384;
-    F2_CUDA(cudaFuncSetAttribute(t3gm_kernel<NM16, HAS8, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    constexpr int THREADS = NT16 >= 6 ? 256 : 384;
+    F2_CUDA(cudaFuncSetAttribute(t3gm_kernel<NT16, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(b.gm_smem)));
-    t3gm_kernel<NM16, HAS8, THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
+    t3gm_kernel<NT16, THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
     b.launches += 1;
 }
 
@@ -1091,12 +1122,15 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     p.sigma = sigma;
     p.as_ptr = D.as_ptr.p;
     p.as_ent = D.as_ent.p;
+    p.a_cls = D.a_cls.p;
     p.gsrc = b.gm_gsrc.p;
     p.chunks = b.gm_chunks.p;
     p.gpos = b.gm_gpos.p;
     p.nB_cls = D.nB_cls.p;
     p.crow = b.gm_crow.p;
     p.srow = b.gm_crow.p;
+    p.ml_ent = b.gm_ml_ent.p;
+    p.ml_cnt = b.gm_ml_cnt.p;
     p.VxT = b.VxT.p;
     p.gld = b.gm_gld;
     p.M = b.M;
@@ -1109,22 +1143,15 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     const int nrows = static_cast<int>(h.nas);
     if (nrows == 0)
         return;
-    switch (b.gm_nm16 * 2 + b.gm_has8) {
-    case 2: launch_t3gm_inst<1, false>(b, p, nrows, st); break;
-    case 3: launch_t3gm_inst<1, true>(b, p, nrows, st); break;
-    case 4: launch_t3gm_inst<2, false>(b, p, nrows, st); break;
-    case 5: launch_t3gm_inst<2, true>(b, p, nrows, st); break;
-    case 6: launch_t3gm_inst<3, false>(b, p, nrows, st); break;
-    case 7: launch_t3gm_inst<3, true>(b, p, nrows, st); break;
-    case 8: launch_t3gm_inst<4, false>(b, p, nrows, st); break;
-    case 9: launch_t3gm_inst<4, true>(b, p, nrows, st); break;
-    case 10: launch_t3gm_inst<5, false>(b, p, nrows, st); break;
-    case 11: launch_t3gm_inst<5, true>(b, p, nrows, st); break;
-    case 12: launch_t3gm_inst<6, false>(b, p, nrows, st); break;
-    case 13: launch_t3gm_inst<6, true>(b, p, nrows, st); break;
-    case 14: launch_t3gm_inst<7, false>(b, p, nrows, st); break;
-    case 15: launch_t3gm_inst<7, true>(b, p, nrows, st); break;
-    case 16: launch_t3gm_inst<8, false>(b, p, nrows, st); break;
+    switch (b.gm_nt16) {
+    case 1: launch_t3gm_inst<1>(b, p, nrows, st); break;
+    case 2: launch_t3gm_inst<2>(b, p, nrows, st); break;
+    case 3: launch_t3gm_inst<3>(b, p, nrows, st); break;
+    case 4: launch_t3gm_inst<4>(b, p, nrows, st); break;
+    case 5: launch_t3gm_inst<5>(b, p, nrows, st); break;
+    case 6: launch_t3gm_inst<6>(b, p, nrows, st); break;
+    case 7: launch_t3gm_inst<7>(b, p, nrows, st); break;
+    case 8: launch_t3gm_inst<8>(b, p, nrows, st); break;
     default: throw std::runtime_error("CISigmaBuilder: unsupported gather-form shape");
     }
     F2_CUDA(cudaGetLastError());

@@ -28,7 +28,11 @@ def _cas(n):
 # (1 865 504 274 determinants, 225 blocks); gas20twin its 1-GPU validation size (22 065 484 determinants).
 WORKLOADS = {"cas12": _cas(12), "cas14": _cas(14), "cas16": _cas(16), "cas18": _cas(18),
              "gas20": (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [8, 0, 0], [12, 16, 4]),
-             "gas20twin": (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2])}
+             "gas20twin": (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2]),
+             # CAS with point-group symmetry: 8 irreps, two orbitals each (the usual forte2 situation)
+             "cas14_d2h": (7, 7, 0, [[i % 8 for i in range(14)]], [], []),
+             "cas16_d2h": (8, 8, 0, [[i % 8 for i in range(16)]], [], []),
+             "cas16_c2v": (8, 8, 0, [[i % 4 for i in range(16)]], [], [])}
 
 
 def main():

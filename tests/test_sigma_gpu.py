@@ -247,9 +247,9 @@ def test_gas_three_spaces_twenty_orbitals(torch_cuda):
 
 @pytest.mark.parametrize("name", ["gas343_54", "gas343_55", "cas66_d2h", "gas2_sym4", "cas66_cs1"])
 def test_gather_form_over_several_beta_classes(ref, torch_cuda, monkeypatch, name):
-    """t3gm_kernel (opt-in, F2_T3GM=1): the gather form of the opposite-spin term for spaces with several
-    determinant blocks (GAS, point-group symmetry) against the reference."""
-    monkeypatch.setenv("F2_T3GM", "1")
+    """t3gm_kernel: the block-aware gather form of the opposite-spin term for spaces with several
+    determinant blocks (GAS, point-group symmetry) against the reference, and against the scatter form
+    (F2_NO_T3GM=1) it replaces on one GPU."""
     space = SMALL_SPACES[name]
     n = sum(len(s) for s in space[3])
     for ints in (synthetic.integrals(n, "S"), synthetic.four_fold_integrals(n)):
@@ -260,4 +260,11 @@ def test_gather_form_over_several_beta_classes(ref, torch_cuda, monkeypatch, nam
         got = np.full_like(c, np.nan)
         gb.Hamiltonian(c, got)
         assert _rel(got, want) <= TOL
-    assert gb.t3_shape()["form"] == "gather"
+        assert gb.t3_shape()["form"] == "gather"
+    monkeypatch.setenv("F2_NO_T3GM", "1")
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    assert gb.t3_shape()["form"] == "scatter"
+    got = np.full_like(c, np.nan)
+    gb.Hamiltonian(c, got)
+    rb.Hamiltonian(c, want)
+    assert _rel(got, want) <= TOL
