@@ -375,12 +375,30 @@ def run_ours(args):
     except Exception:
         hbm_peak = 6650.0
     same_spin_ms = last[1] + last[2]
+    # flops of the same-spin contraction actually executed: per spin sum_K m_K^2 * columns * 2 with
+    # m = C(n - N + 2, 2) parents per (N-2)-electron string (CAS), one-electron part folded in
+    def ss_flops(ne, other_strings):
+        if ne < 2:
+            return 2.0 * n * n * comb(n, ne) * other_strings if ne == 1 else 0.0
+        m = comb(n - ne + 2, 2)
+        return 2.0 * comb(n, ne - 2) * m * m * other_strings
+    ss_fl = (ss_flops(na, comb(n, nb)) + ss_flops(nb, comb(n, na))) * frac_work
+    # FP64 reductions into sigma issued by the two same-spin kernels, against the measured L2 atomic rate
+    ss_red = sum(comb(n, ne - 2) * comb(n - ne + 2, 2) * o for ne, o in ((na, comb(n, nb)), (nb, comb(n, na)))
+                 if ne >= 2) * frac_work
     same_spin = {
         "bound": "hbm", "kernels": "ssg_kernel (alpha) + transposes + ssg_kernel (beta), one-electron folded",
         "algorithmic_bytes": 2 * 24.0 * ndet * frac_work, "ms": same_spin_ms,
         "achieved": (2 * 24.0 * ndet * frac_work) / (same_spin_ms * 1e-3) / 1e9 if same_spin_ms else None,
         "peak": hbm_peak, "unit": "GB/s",
         "frac": ((2 * 24.0 * ndet * frac_work) / (same_spin_ms * 1e-3) / 1e9 / hbm_peak) if same_spin_ms else None,
+        "note": "not HBM-bound at this size (DESIGN.md section 3): the binding resources are the FP64 tensor pipe "
+                "and the L2 atomic units",
+        "tensor_tflops": ss_fl / (same_spin_ms * 1e-3) / 1e12 if same_spin_ms else None,
+        "tensor_frac": ss_fl / (same_spin_ms * 1e-3) / 1e12 / peak if same_spin_ms else None,
+        "reductions_per_s": ss_red / (same_spin_ms * 1e-3) if same_spin_ms else None,
+        "reduction_rate_frac": (ss_red / (same_spin_ms * 1e-3) / 345e9) if same_spin_ms else None,
+        "reduction_rate_peak": "345e9 FP64 red.global.add per s, scripts/micro/red_bench.cu (profiles/r01u_red_bench.log)",
     }
 
     # ---- end to end through the numpy-facing call (host buffers, H2D + D2H inside) ----

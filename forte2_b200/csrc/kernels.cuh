@@ -989,6 +989,7 @@ struct T3GMParams {
     int64_t gld;
     int M, Mpad, norb, nclsB, nchunks;
     int first, astride;
+    const uint32_t* jlist; // sharded build: the owned input alpha strings (NULL: first + blockIdx.x)
 };
 
 constexpr uint32_t kNoRow = 0xffffffffu;
@@ -1014,7 +1015,7 @@ __global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
     uint8_t* rlist = reinterpret_cast<uint8_t*>(mlist + NC * MP);         // [NC][ROWS]
     __shared__ int s_kl[ROWS];
 
-    const uint32_t Ja = p.first + blockIdx.x;
+    const uint32_t Ja = p.jlist ? p.jlist[blockIdx.x] : p.first + blockIdx.x;
     const int cJa = static_cast<int>(p.a_cls[Ja]);
     const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
     const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;

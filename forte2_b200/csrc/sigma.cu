@@ -169,7 +169,12 @@ struct Part {
     // opposite-spin kernel
     SSPlan alpha_cols_plan;
     DevBuf<uint32_t> rowpad;
-    int64_t slot_rows = 0; // rows per reduce-scatter slot (max over ranks of the owned row count)
+    int64_t slot_rows = 0;  // single block: rows per reduce-scatter slot (max over ranks of the owned rows)
+    int64_t slot_elems = 0; // doubles per reduce-scatter slot (max over ranks of the local vector length)
+    // several blocks (t3gm_kernel): owned input strings, their local C offsets per beta class, and the offset
+    // of every (alpha string, beta class) sigma segment in the slot layout
+    DevBuf<uint32_t> jlist, crow_local, srow_slot;
+    int njlist = 0;
     std::vector<std::unique_ptr<BetaPass>> beta_passes;
     bool beta_planned = false;
     DevBuf<CopyPiece> pieces; // owned row slabs: src = full layout, dst = local layout
@@ -644,8 +649,10 @@ void plan_t3_shape(f2_sigma& b) {
     if (!b.t3g && b.gm_gsrc.p && b.gm_nchunks > 0) {
         b.gm_nt16 = (L.as_max + 15) / 16;
         const int rows = b.gm_nt16 * 16;
+        // row stride of A': 4 or 12 (mod 16) doubles puts the rows g = 0..3 of a half-warp's 64-bit loads on
+        // disjoint banks; the finer step keeps 3 GAS spaces x 20 orbitals (M = 210, 25 classes) within 227 KB
         int S = b.gm_mpad + 1;
-        while (S % 16 != 4)
+        while (S % 8 != 4)
             ++S;
         b.gm_astride = S;
         b.gm_smem = t3gm_smem_bytes(rows, S, static_cast<int>(nclsB), b.gm_mpad);
@@ -815,32 +822,83 @@ std::unique_ptr<Part> make_part(f2_sigma& b, int rank, int world) {
         p.tiles.upload(tiles);
         p.al16 = even;
     }
-    // ---- rows form (single determinant block only): column-slab alpha plan and reduce-scatter layout
-    if (world > 1 && nclsA == 1 && nclsB == 1 && h.blocks.size() == 1 && h.ndet > 0) {
-        const uint32_t nc = static_cast<uint32_t>(P->ch[0] - P->cl[0]);
-        std::vector<int64_t> off(1, 0);
-        std::vector<uint32_t> ncols(1, nc), tiles;
+    // ---- rows form: the alpha same-spin plan whose operand is the exchanged column slab (laid out like the
+    // exchange buffer: per block [nIa][owned columns]), and the reduce-scatter layout of the gather-form
+    // opposite-spin kernels: world slots of slot_elems doubles, slot q = the local vector of rank q
+    if (world > 1 && h.ndet > 0) {
+        std::vector<int64_t> xoff(nclsA * nclsB, -1);
+        std::vector<uint32_t> ncols(nclsB), tiles;
+        for (size_t bi = 0; bi < h.blocks.size(); ++bi) {
+            const auto& blk = h.blocks[bi];
+            if (blk.nA * blk.nB > 0)
+                xoff[blk.cA * nclsB + blk.cB] = P->y_off[bi];
+        }
+        for (size_t c = 0; c < nclsB; ++c)
+            ncols[c] = static_cast<uint32_t>(P->ch[c] - P->cl[c]);
         fill_tiles(tiles, ncols);
         SSPlan& p = P->alpha_cols_plan;
-        p.ngroups = 1;
+        p.ngroups = static_cast<int>(nclsB);
         p.ntiles = static_cast<int>(tiles.size() / 2);
-        p.xoff.upload(off);
-        p.yoff.upload(off);
+        p.xoff.upload(xoff);
+        p.yoff.upload(xoff);
         p.g_ncols.upload(ncols);
         p.g_ldx.upload(ncols);
         p.g_ldy.upload(ncols);
         p.tiles.upload(tiles);
         p.al16 = false;
-        const int64_t nA = static_cast<int64_t>(A.strpcls(0));
+        // local layouts of every rank
+        std::vector<std::vector<int64_t>> loc_off(world, std::vector<int64_t>(h.blocks.size(), 0));
         int64_t slot = 0;
-        for (int q = 0; q < world; ++q)
-            slot = std::max(slot, nA * (q + 1) / world - nA * q / world);
-        P->slot_rows = slot;
-        std::vector<uint32_t> rowpad(static_cast<size_t>(nA));
-        for (int q = 0; q < world; ++q)
-            for (int64_t i = nA * q / world; i < nA * (q + 1) / world; ++i)
-                rowpad[static_cast<size_t>(i)] = static_cast<uint32_t>(q * slot + (i - nA * q / world));
-        P->rowpad.upload(rowpad);
+        for (int q = 0; q < world; ++q) {
+            int64_t pos = 0;
+            for (size_t bi = 0; bi < h.blocks.size(); ++bi) {
+                const auto& blk = h.blocks[bi];
+                loc_off[q][bi] = pos;
+                if (blk.nA * blk.nB > 0)
+                    pos += (blk.nA * (q + 1) / world - blk.nA * q / world) * blk.nB;
+            }
+            slot = std::max(slot, pos);
+        }
+        P->slot_elems = slot;
+        if (b.t3g && nclsA == 1 && nclsB == 1 && h.blocks.size() == 1) {
+            const int64_t nA = static_cast<int64_t>(A.strpcls(0));
+            int64_t rows = 0;
+            for (int q = 0; q < world; ++q)
+                rows = std::max(rows, nA * (q + 1) / world - nA * q / world);
+            P->slot_rows = rows;
+            std::vector<uint32_t> rowpad(static_cast<size_t>(nA));
+            for (int q = 0; q < world; ++q)
+                for (int64_t i = nA * q / world; i < nA * (q + 1) / world; ++i)
+                    rowpad[static_cast<size_t>(i)] = static_cast<uint32_t>(q * rows + (i - nA * q / world));
+            P->rowpad.upload(rowpad);
+        } else if (b.t3gm && static_cast<int64_t>(world) * slot < (int64_t(1) << 32) - 1) {
+            std::vector<uint32_t> jl, crow(static_cast<size_t>(h.nas) * nclsB, kNoRow),
+                srow(static_cast<size_t>(h.nas) * nclsB, kNoRow);
+            for (size_t cA = 0; cA < nclsA; ++cA) {
+                const int64_t nA = static_cast<int64_t>(A.strpcls(cA));
+                for (int64_t i = P->lo[cA]; i < P->hi[cA]; ++i)
+                    jl.push_back(A.cls_off[cA] + static_cast<uint32_t>(i));
+                for (size_t cB = 0; cB < nclsB; ++cB) {
+                    const int64_t bi = h.block_of[cA * nclsB + cB];
+                    if (bi < 0 || h.blocks[bi].nA * h.blocks[bi].nB == 0)
+                        continue;
+                    const int64_t nB = h.blocks[bi].nB;
+                    for (int q = 0; q < world; ++q) {
+                        const int64_t lo = nA * q / world, hi = nA * (q + 1) / world;
+                        for (int64_t i = lo; i < hi; ++i) {
+                            const size_t at = (A.cls_off[cA] + i) * nclsB + cB;
+                            srow[at] = static_cast<uint32_t>(q * slot + loc_off[q][bi] + (i - lo) * nB);
+                            if (q == rank)
+                                crow[at] = static_cast<uint32_t>(loc_off[q][bi] + (i - lo) * nB);
+                        }
+                    }
+                }
+            }
+            P->njlist = static_cast<int>(jl.size());
+            P->jlist.upload(jl);
+            P->crow_local.upload(crow);
+            P->srow_slot.upload(srow);
+        }
     }
     return P;
 }
@@ -1113,8 +1171,10 @@ void launch_t3gm_inst(const f2_sigma& b, const T3GMParams& p, int nrows, cudaStr
     b.launches += 1;
 }
 
-// gather-form opposite-spin term for spaces with several determinant blocks (one GPU)
-void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st) {
+// gather-form opposite-spin term for spaces with several determinant blocks.  One GPU: every alpha string,
+// C and sigma in the CI-vector layout.  Sharded (P given): the owned input strings, C = the local vector,
+// sigma = the reduce-scatter buffer in the slot layout.
+void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st, const Part* P = nullptr) {
     const CIStringsHost& h = *b.S->host;
     const DevStrings& D = *b.D;
     T3GMParams p;
@@ -1127,8 +1187,9 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     p.chunks = b.gm_chunks.p;
     p.gpos = b.gm_gpos.p;
     p.nB_cls = D.nB_cls.p;
-    p.crow = b.gm_crow.p;
-    p.srow = b.gm_crow.p;
+    p.crow = P ? P->crow_local.p : b.gm_crow.p;
+    p.srow = P ? P->srow_slot.p : b.gm_crow.p;
+    p.jlist = P ? P->jlist.p : nullptr;
     p.ml_ent = b.gm_ml_ent.p;
     p.ml_cnt = b.gm_ml_cnt.p;
     p.VxT = b.VxT.p;
@@ -1140,7 +1201,7 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     p.nchunks = b.gm_nchunks;
     p.first = 0;
     p.astride = b.gm_astride;
-    const int nrows = static_cast<int>(h.nas);
+    const int nrows = P ? P->njlist : static_cast<int>(h.nas);
     if (nrows == 0)
         return;
     switch (b.gm_nt16) {
@@ -1394,12 +1455,13 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
     apply(b, *b.single, C, sigma, nullptr, st);
 }
 
-// Rows form of the sharded build (single determinant block, gather-form opposite-spin kernel): no
-// rank ever holds the full trial vector.
+// Rows form of the sharded build (gather-form opposite-spin kernels: t3g_kernel for one determinant block,
+// t3gm_kernel for several): no rank ever holds the full trial vector.
 //   sigma_loc  = E C_loc + beta same-spin term of the owned rows                 (complete)
 //   ycols      = alpha same-spin term of [all rows][owned columns], from xcols    (caller: all-to-all, add)
 //   scatter    = opposite-spin contributions of the owned INPUT rows to every sigma row, world slots of
-//                slot_rows x nbs (caller: reduce-scatter, add)
+//                slot_elems doubles, slot q laid out like the local vector of rank q
+//                (caller: reduce-scatter, add)
 // phases: 1 = the opposite-spin term into `scatter` (first, so that the caller can start the
 // reduce-scatter while phase 2 runs), 2 = H0 and the two same-spin terms, 3 = both.
 void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, double* sigma, double* ycols,
@@ -1415,14 +1477,19 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
         plan_beta(b, P);
     if (h.ndet == 0)
         return;
-    const int64_t rows = P.hi[0] - P.lo[0];
     // event order of this form: start, [opposite spin], e1, [H0], e2, [alpha], e3, [beta], e4
     if (phases & 1) {
         F2_CUDA(cudaEventRecord(b.ev[0], st));
-        F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_rows * h.nbs * sizeof(double), st));
-        if (h.na >= 1 && h.nb >= 1 && rows > 0)
-            launch_t3g(b, Cloc - P.lo[0] * h.nbs, scatter, st, static_cast<int>(P.lo[0]), static_cast<int>(rows),
-                       P.rowpad.p);
+        F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_elems * sizeof(double), st));
+        if (h.na >= 1 && h.nb >= 1 && P.local_size > 0) {
+            if (b.t3g) {
+                const int64_t rows = P.hi[0] - P.lo[0];
+                launch_t3g(b, Cloc - P.lo[0] * h.nbs, scatter, st, static_cast<int>(P.lo[0]), static_cast<int>(rows),
+                           P.rowpad.p);
+            } else {
+                launch_t3gm(b, Cloc, scatter, st, &P);
+            }
+        }
         F2_CUDA(cudaEventRecord(b.ev[1], st));
     }
     if (phases & 2) {
@@ -1453,8 +1520,11 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
 // the rows form needs the gather-form kernel and 16-byte aligned row slabs (even nbs)
 bool rows_form_ok(const f2_sigma& b) {
     const CIStringsHost& h = *b.S->host;
-    return b.t3g && h.blocks.size() == 1 && h.nclsA() == 1 && h.nclsB() == 1 && h.nbs % 2 == 0 &&
-           std::getenv("F2_NO_ROWS_FORM") == nullptr;
+    if (std::getenv("F2_NO_ROWS_FORM") != nullptr)
+        return false;
+    if (b.t3g)
+        return h.blocks.size() == 1 && h.nclsA() == 1 && h.nclsB() == 1 && h.nbs % 2 == 0;
+    return b.t3gm; // several blocks: the block-aware gather kernel (the slot layout must fit 32-bit offsets)
 }
 
 Part& shard_of(f2_sigma& b, int rank, int world) {
@@ -1761,10 +1831,12 @@ int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4) {
         out4[0] = out4[1] = out4[2] = out4[3] = 0;
         if (world > 1 && rows_form_ok(*h)) {
             Part& P = shard_of(*h, rank, world);
-            out4[0] = 1;
-            out4[1] = P.slot_rows;
-            out4[2] = h->S->host->nbs;
-            out4[3] = P.y_size;
+            if (h->t3g || P.srow_slot.p) {
+                out4[0] = 1;
+                out4[1] = P.slot_elems;
+                out4[2] = h->S->host->nbs;
+                out4[3] = P.y_size;
+            }
         }
         return F2_OK;
     } catch (const std::exception& e) {
@@ -1777,7 +1849,7 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
     try {
         if (!h || !C_local_dev || !xcols_dev || !sigma_local_dev || !ycols_dev || !scatter_dev)
             throw std::invalid_argument("null argument");
-        if (world <= 1 || !rows_form_ok(*h))
+        if (world <= 1 || !rows_form_ok(*h) || !(h->t3g || shard_of(*h, rank, world).srow_slot.p))
             throw std::runtime_error("CISigmaBuilder: the rows form of the sharded build is not available for "
                                      "this string space (f2_sigma_rows_form)");
         if ((reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)

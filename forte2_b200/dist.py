@@ -14,13 +14,13 @@ Full form (any string space), per sigma build
      rows, for the owned COLUMNS of every row
   3. exchange of the alpha same-spin partial results to the row owners (all-to-all) and add  -- NCCL
 
-Rows form (one determinant block served by the gather-form opposite-spin kernel; no rank ever holds the
-full vector), per sigma build
-  1. all-to-all of C: rank r sends C[rows of r, columns of q] to q and assembles the column slab
-     [all rows][columns of r]                                                                -- NCCL, ndet/world doubles
+Rows form (spaces served by a gather-form opposite-spin kernel: t3g_kernel for one determinant block,
+t3gm_kernel for symmetry / GAS blocks; no rank ever holds the full vector), per sigma build
+  1. all-to-all of C: rank r sends C[rows of r, columns of q] of every block to q and assembles the
+     column slabs [all rows][columns of r]                                                   -- NCCL, ndet/world doubles
   2. local work (f2_sigma_apply_rows): H0 and beta same-spin term of the owned rows from the local
-     slab; alpha same-spin term of the column slab; opposite-spin term of the owned INPUT rows,
-     scattered to every sigma row in a buffer of world equal slots
+     slab; alpha same-spin term of the column slabs; opposite-spin term of the owned INPUT rows,
+     scattered to every sigma row in a buffer of world equal slots (slot q = the local vector of rank q)
   3. all-to-all of the alpha same-spin result back to the row owners, add                      -- NCCL
   4. reduce-scatter of the opposite-spin buffer, add                                          -- NCCL, ndet doubles
 """
@@ -85,10 +85,10 @@ class CudaEngine:
                                                   yexch.data_ptr(), rank, world, stream))
 
     def rows_form(self, rank, world):
-        """(available, slot_rows, nbs) of the rows form (f2_sigma_rows_form)"""
+        """(available, doubles per reduce-scatter slot) of the rows form (f2_sigma_rows_form)"""
         out = np.zeros(4, dtype=np.int64)
         _lib.check(_lib.lib().f2_sigma_rows_form(self.builder._h, rank, world, out.ctypes.data_as(_lib.i64p)))
-        return bool(out[0]), int(out[1]), int(out[2])
+        return bool(out[0]), int(out[1])
 
     def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world, phases=3):
         stream = torch.cuda.current_stream(self.builder.device).cuda_stream
@@ -132,10 +132,11 @@ class ShardedSigma:
         if form not in ("auto", "full", "rows"):
             raise ValueError("form must be 'auto', 'full' or 'rows'")
         if form != "full" and self.world > 1 and hasattr(self.engine, "rows_form"):
-            ok, slot_rows, nbs = self.engine.rows_form(self.rank, self.world)
+            ok, slot = self.engine.rows_form(self.rank, self.world)
             if ok:
+                assert slot == self._max_local
                 self.form = "rows"
-                self._slot = slot_rows * nbs
+                self._slot = slot
                 self._xcols = torch.zeros(max(self.layout.exchange_size, 1), **kw)
                 self._scatter = torch.empty(self.world * self._slot, **kw)
                 self._rs_out = torch.empty(self._slot, **kw)
@@ -234,28 +235,66 @@ class ShardedSigma:
                 blk = sigma_loc[loc:loc + n * nB].view(n, nB)
                 blk[:, cl_q:cl_q + nc_q] += src[pos:pos + n * nc_q].view(n, nc_q)
 
-    def _exchange_cols(self, c_loc: torch.Tensor):
-        """rows form, step 1: column slab [all rows][my columns] of C from the row slabs (one block)"""
+    def _cols_plan(self):
+        """rows form, step 1, per peer q: the pieces C[my rows, columns of q] of every block that go to q
+        (packed into one send buffer) and where the pieces [rows of q][my columns] that arrive belong in the
+        column slab (computed once; the buffers are reused by every build)"""
+        if getattr(self, "_cplan", None) is not None:
+            return self._cplan
         me = self.layout
-        (off, nA, nB), (lo, n, _), (cl, nc, _) = me.blocks[0], me.rows[0], me.cols[0]
-        mine = c_loc.view(n, nB)
-        slab = self._xcols[: nA * nc].view(nA, nc)
-        ops, keep = [], []
+        plan = []
         for q, lay in enumerate(self.layouts):
-            lo_q, n_q, _ = lay.rows[0]
-            cl_q, nc_q, _ = lay.cols[0]
+            sends, recvs = [], []
+            for b, (off, nA, nB) in enumerate(me.blocks):
+                if nA * nB == 0:
+                    continue
+                lo, n, loc = me.rows[b]
+                cl, nc, yoff = me.cols[b]
+                lo_q, n_q, _ = lay.rows[b]
+                cl_q, nc_q, _ = lay.cols[b]
+                if n > 0 and nc_q > 0:
+                    sends.append((loc, n, nB, cl_q, nc_q))
+                if n_q > 0 and nc > 0:
+                    recvs.append((yoff + lo_q * nc, n_q * nc))
+            n_send = sum(n * nc_q for _, n, _, _, nc_q in sends)
+            n_recv = sum(m for _, m in recvs)
+            send_buf = torch.empty(n_send, **self._kw) if q != self.rank else None
+            # one contiguous piece is received in place; several (symmetry / GAS blocks) through a buffer
+            recv_buf = torch.empty(n_recv, **self._kw) if q != self.rank and len(recvs) > 1 else None
+            plan.append((sends, recvs, send_buf, recv_buf))
+        self._cplan = plan
+        return plan
+
+    def _exchange_cols(self, c_loc: torch.Tensor):
+        """rows form, step 1: column slabs [all rows][my columns] of C (per block, laid out like the
+        exchange buffer) from the row slabs"""
+        ops = []
+        plan = self._cols_plan()
+        for q, (sends, recvs, send_buf, recv_buf) in enumerate(plan):
             if q == self.rank:
-                slab[lo:lo + n].copy_(mine[:, cl:cl + nc])
+                for (loc, n, nB, cl_q, nc_q), (start, m) in zip(sends, recvs):
+                    self._xcols[start:start + m].view(n, nc_q).copy_(c_loc[loc:loc + n * nB].view(n, nB)[:, cl_q:cl_q + nc_q])
                 continue
-            if n > 0 and nc_q > 0:
-                piece = mine[:, cl_q:cl_q + nc_q].contiguous()
-                keep.append(piece)
-                ops.append(dist.P2POp(dist.isend, piece, q, group=self.group))
-            if n_q > 0 and nc > 0:
-                ops.append(dist.P2POp(dist.irecv, slab[lo_q:lo_q + n_q], q, group=self.group))
+            pos = 0
+            for loc, n, nB, cl_q, nc_q in sends:
+                send_buf[pos:pos + n * nc_q].view(n, nc_q).copy_(c_loc[loc:loc + n * nB].view(n, nB)[:, cl_q:cl_q + nc_q])
+                pos += n * nc_q
+            if pos:
+                ops.append(dist.P2POp(dist.isend, send_buf, q, group=self.group))
+            if len(recvs) == 1:
+                ops.append(dist.P2POp(dist.irecv, self._xcols[recvs[0][0]:recvs[0][0] + recvs[0][1]], q, group=self.group))
+            elif recvs:
+                ops.append(dist.P2POp(dist.irecv, recv_buf, q, group=self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        for q, (sends, recvs, send_buf, recv_buf) in enumerate(plan):
+            if recv_buf is None:
+                continue
+            pos = 0
+            for start, m in recvs:
+                self._xcols[start:start + m].copy_(recv_buf[pos:pos + m])
+                pos += m
 
     def _reduce_scatter_start(self):
         """rows form, step 4: sum over ranks of slot `rank` of the opposite-spin buffers; asynchronous on

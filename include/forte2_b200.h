@@ -125,12 +125,14 @@ int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_loc
 int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream);
 
 /* Rows form of the sharded build: no rank holds the full trial vector.  Available when the CI space is
- * one determinant block served by the gather-form opposite-spin kernel (f2_sigma_t3_shape out[5]).
- * out4 = {available (0/1), slot_rows, nbs, column-slab length}: the reduce-scatter buffer has world
- * slots of slot_rows*nbs doubles, slot q holding the sigma rows rank q owns. */
+ * served by a gather-form opposite-spin kernel (f2_sigma_t3_shape out[5]): one determinant block, or
+ * symmetry / GAS blocks whose slot layout fits 32-bit offsets.
+ * out4 = {available (0/1), slot, nbs, column-slab length}: the reduce-scatter buffer has world slots of
+ * `slot` doubles (the longest local vector of any rank), slot q laid out like the local vector of rank
+ * q (owned row slabs of every block, in block order). */
 int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4);
-/* C_local: owned rows of C.  xcols: [nIa][owned columns] of C, assembled by the caller with an
- * all-to-all of the row slabs.  On return sigma_local = H0 + beta same-spin term of the owned rows;
+/* C_local: owned rows of C.  xcols: per block [nIa][owned columns] of C (the layout of the exchange
+ * buffer of f2_sigma_apply_part), assembled by the caller with an all-to-all of the row slabs.  On return sigma_local = H0 + beta same-spin term of the owned rows;
  * ycols = alpha same-spin term of [nIa][owned columns] (caller: all-to-all back to the row owners, add);
  * scatter = opposite-spin contributions of the owned INPUT rows to every sigma row in the slot layout
  * above (caller: reduce-scatter over NCCL, add).  phases: 1 = only the opposite-spin term (launched

@@ -46,14 +46,9 @@ class PortEngine:
                 out[loc:loc + n * nB] += alpha_part[off + lo * nB: off + (lo + n) * nB]
 
 
-    # ---- rows form: same contract as f2_sigma_rows_form / f2_sigma_apply_rows (single block) ----
+    # ---- rows form: same contract as f2_sigma_rows_form / f2_sigma_apply_rows ----
     def rows_form(self, rank, world):
-        lay = self.layouts[rank]
-        if len(lay.blocks) != 1:
-            return False, 0, 0
-        _, nA, nB = lay.blocks[0]
-        slot_rows = max(L.rows[0][1] for L in self.layouts)
-        return True, slot_rows, nB
+        return True, max(L.local_size for L in self.layouts)
 
     def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world, phases=3):
         from oracle import checker
@@ -61,22 +56,30 @@ class PortEngine:
             return
         E, H, V = self.ints
         lay = self.layouts[rank]
-        (off, nA, nB), (lo, n, _), (cl, nc, _) = lay.blocks[0], lay.rows[0], lay.cols[0]
-        rows_only = np.zeros(nA * nB)
-        rows_only[lo * nB:(lo + n) * nB] = c_loc.numpy()
-        cols_only = np.zeros((nA, nB))
-        cols_only[:, cl:cl + nc] = xcols.numpy()[: nA * nc].reshape(nA, nc)
+        rows_only = np.zeros(lay.ndet)
+        cols_only = np.zeros(lay.ndet)
+        x = xcols.numpy()
+        for (off, nA, nB), (lo, n, loc), (cl, nc, yoff) in zip(lay.blocks, lay.rows, lay.cols):
+            if nA * nB == 0:
+                continue
+            rows_only[off + lo * nB: off + (lo + n) * nB] = c_loc.numpy()[loc:loc + n * nB]
+            cols_only[off:off + nA * nB].reshape(nA, nB)[:, cl:cl + nc] = x[yoff:yoff + nA * nc].reshape(nA, nc)
         local = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_SCALAR | checker.PART_BETA)
-        sigma_loc.numpy()[:] = local[lo * nB:(lo + n) * nB]
-        alpha = checker.port_sigma(self.dets, E, H, V, cols_only.reshape(-1), checker.PART_ALPHA)
-        ycols.numpy()[: nA * nc] = alpha.reshape(nA, nB)[:, cl:cl + nc].reshape(-1)
-        t3 = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_ALPHA_BETA).reshape(nA, nB)
-        _, slot_rows, _ = self.rows_form(rank, world)
+        alpha = checker.port_sigma(self.dets, E, H, V, cols_only, checker.PART_ALPHA)
+        t3 = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_ALPHA_BETA)
+        y = ycols.numpy()
+        for (off, nA, nB), (lo, n, loc), (cl, nc, yoff) in zip(lay.blocks, lay.rows, lay.cols):
+            if nA * nB == 0:
+                continue
+            sigma_loc.numpy()[loc:loc + n * nB] = local[off + lo * nB: off + (lo + n) * nB]
+            y[yoff:yoff + nA * nc] = alpha[off:off + nA * nB].reshape(nA, nB)[:, cl:cl + nc].reshape(-1)
+        _, slot = self.rows_form(rank, world)
         out = scatter.numpy()
         out[:] = 0.0
         for q, L in enumerate(self.layouts):
-            lo_q, n_q, _ = L.rows[0]
-            out[q * slot_rows * nB: q * slot_rows * nB + n_q * nB] = t3[lo_q:lo_q + n_q].reshape(-1)
+            for (off, nA, nB), (lo_q, n_q, loc_q) in zip(L.blocks, L.rows):
+                if nA * nB > 0:
+                    out[q * slot + loc_q: q * slot + loc_q + n_q * nB] = t3[off + lo_q * nB: off + (lo_q + n_q) * nB]
 
 
 def _worker(rank, world, port, name, form, result_dir):
@@ -122,7 +125,8 @@ def _free_port():
 
 @pytest.mark.parametrize("name,world,form", [("cas66", 2, "full"), ("gas343_54", 2, "full"), ("cas66_d2h", 3, "full"),
                                              ("cas75_odd", 3, "full"), ("cas66", 2, "rows"), ("cas75_odd", 3, "rows"),
-                                             ("cas88", 3, "rows")])
+                                             ("cas88", 3, "rows"), ("gas343_54", 2, "rows"), ("cas66_d2h", 3, "rows"),
+                                             ("gas2_sym4", 2, "rows")])
 def test_sharded_sigma_over_gloo(tmp_path, name, world, form):
     mp.spawn(_worker, args=(world, _free_port(), name, form, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
@@ -162,7 +166,7 @@ def _solver_worker(rank, world, port, name, form, result_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world,form", [("cas66", 2, "rows"), ("cas66_d2h", 3, "full")])
+@pytest.mark.parametrize("name,world,form", [("cas66", 2, "rows"), ("cas66_d2h", 3, "full"), ("cas66_d2h", 2, "rows")])
 def test_sharded_davidson_over_gloo(tmp_path, name, world, form):
     """ShardedCISolver (guess determinants agreed through an all-gather, every Davidson vector a row
     slab, reductions all-reduced) reproduces the two lowest eigenvalues of the dense Hamiltonian."""

@@ -138,39 +138,52 @@ def test_cas_medium(ref, torch_cuda, n):
     assert len(t) == 4 and t[0] > 0
 
 
-@pytest.mark.parametrize("n,world", [(8, 2), (10, 3), (10, 4)])
-def test_rows_form_parts_emulated_on_one_gpu(ref, torch_cuda, n, world):
+@pytest.mark.parametrize("space,world", [((4, 4, 0, [[0] * 8], [], []), 2), ((5, 5, 0, [[0] * 10], [], []), 3),
+                                         ((5, 5, 0, [[0] * 10], [], []), 4), (SMALL_SPACES["gas343_55"], 2),
+                                         (SMALL_SPACES["gas343_54"], 3), (SMALL_SPACES["cas66_d2h"], 2),
+                                         (SMALL_SPACES["gas2_sym4"], 3), ((4, 4, 0, [[0, 1, 2, 3] * 2], [], []), 4)])
+def test_rows_form_parts_emulated_on_one_gpu(ref, torch_cuda, space, world):
     """f2_sigma_apply_rows (the sharded build that never holds the full vector) for every rank of a world,
     run one after the other on this GPU, the three exchanges of forte2_b200/dist.py done by hand:
-    the sum equals the single-GPU sigma and the reference.  The NCCL version is tests/test_dist_gpu.py."""
+    the sum equals the single-GPU sigma and the reference.  One determinant block (t3g_kernel) and
+    symmetry / GAS blocks (t3gm_kernel).  The NCCL version is tests/test_dist_gpu.py."""
     torch = torch_cuda
     from forte2_b200.dist import CudaEngine, Layout
-    space = (n // 2, n // 2, 0, [[0] * n], [], [])
+    n = sum(len(s) for s in space[3])
     rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
     c = synthetic.trial_vector(rs.ndet)
     want = np.zeros_like(c)
     rb.Hamiltonian(c, want)
     eng = CudaEngine(gb)
-    nA, nB = gs.nas, gs.nbs
-    C = torch.from_numpy(c).cuda().view(nA, nB)
+    C = torch.from_numpy(c).cuda()
     lays = [Layout(gs.blocks(), q, world) for q in range(world)]
-    ok, slot_rows, nbs = eng.rows_form(0, world)
-    assert ok and nbs == nB and slot_rows == max(L.rows[0][1] for L in lays)
-    total = torch.zeros(nA, nB, dtype=torch.float64, device="cuda")
+    ok, slot = eng.rows_form(0, world)
+    assert ok and slot == max(L.local_size for L in lays)
+    total = torch.zeros_like(C)
     for q, L in enumerate(lays):
-        (lo, nr, _), (cl, nc, _) = L.rows[0], L.cols[0]
-        c_loc = C[lo:lo + nr].contiguous().view(-1)
-        xcols = C[:, cl:cl + nc].contiguous().view(-1)
+        c_loc = torch.empty(max(L.local_size, 1), dtype=torch.float64, device="cuda")[: L.local_size]
+        xcols = torch.full((max(L.exchange_size, 1),), float("nan"), dtype=torch.float64, device="cuda")
+        for (off, nA, nB), (lo, nr, loc), (cl, nc, yoff) in zip(L.blocks, L.rows, L.cols):
+            if nA * nB == 0:
+                continue
+            blk = C[off:off + nA * nB].view(nA, nB)
+            c_loc[loc:loc + nr * nB] = blk[lo:lo + nr].reshape(-1)
+            xcols[yoff:yoff + nA * nc] = blk[:, cl:cl + nc].reshape(-1)
         sigma_loc = torch.full_like(c_loc, float("nan"))
-        ycols = torch.full((max(nA * nc, 1),), float("nan"), dtype=torch.float64, device="cuda")
-        scatter = torch.full((world * slot_rows * nB,), float("nan"), dtype=torch.float64, device="cuda")
+        ycols = torch.full_like(xcols, float("nan"))
+        scatter = torch.full((world * slot,), float("nan"), dtype=torch.float64, device="cuda")
         eng.apply_rows(c_loc, xcols, sigma_loc, ycols, scatter, q, world)
-        total[lo:lo + nr] += sigma_loc.view(nr, nB)
-        total[:, cl:cl + nc] += ycols[: nA * nc].view(nA, nc)
+        for (off, nA, nB), (lo, nr, loc), (cl, nc, yoff) in zip(L.blocks, L.rows, L.cols):
+            if nA * nB == 0:
+                continue
+            blk = total[off:off + nA * nB].view(nA, nB)
+            blk[lo:lo + nr] += sigma_loc[loc:loc + nr * nB].view(nr, nB)
+            blk[:, cl:cl + nc] += ycols[yoff:yoff + nA * nc].view(nA, nc)
         for r, Lr in enumerate(lays):
-            lo_r, n_r, _ = Lr.rows[0]
-            total[lo_r:lo_r + n_r] += scatter[r * slot_rows * nB: r * slot_rows * nB + n_r * nB].view(n_r, nB)
-    assert _rel(total.view(-1).cpu().numpy(), want) <= TOL
+            for (off, nA, nB), (lo_r, n_r, loc_r) in zip(Lr.blocks, Lr.rows):
+                if nA * nB > 0:
+                    total[off + lo_r * nB: off + (lo_r + n_r) * nB] += scatter[r * slot + loc_r: r * slot + loc_r + n_r * nB]
+    assert _rel(total.cpu().numpy(), want) <= TOL
 
 
 def test_host_path_streams_the_opposite_spin_term(ref, torch_cuda, monkeypatch):
