@@ -1302,7 +1302,7 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
     p.W = W;
     p.P = b.P[spin];
     p.ngroups = plan.ngroups;
-    const bool al16 = plan.al16 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    const bool al16 = plan.al16 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0;
     const int mmax = std::max(L.h2_max[spin], 1);
     const int nm16 = mmax / 16 + (mmax % 16 > 8 ? 1 : 0), has8 = (mmax % 16 > 0 && mmax % 16 <= 8) ? 1 : 0;
     // grid: x = K (fastest: all K of a column panel run together, the panel stays in L2), y = panel
@@ -1852,7 +1852,8 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
         if (world <= 1 || !rows_form_ok(*h) || !(h->t3g || shard_of(*h, rank, world).srow_slot.p))
             throw std::runtime_error("CISigmaBuilder: the rows form of the sharded build is not available for "
                                      "this string space (f2_sigma_rows_form)");
-        if ((reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
+        // t3g_kernel brings its rows of C in with TMA bulk copies; t3gm_kernel gathers and has no such need
+        if (h->t3g && (reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
             throw std::invalid_argument("CISigmaBuilder: the local trial vector must be 16-byte aligned");
         if (phases < 1 || phases > 3)
             throw std::invalid_argument("CISigmaBuilder: phases must be 1, 2 or 3");

@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _die():
+    """a rank that failed leaves at once: tearing the process group down would wait for a peer that is
+    itself waiting in a collective, and the test would only end at its deadline"""
+    import traceback
+    traceback.print_exc()
+    sys.stderr.flush()
+    os._exit(1)
+
+
 def _worker(rank, world, port, spaces, result_dir):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -46,12 +55,15 @@ def _worker(rank, world, port, spaces, result_dir):
                 errs.append(float((got - want).norm() / want.norm()))
             if n >= 8 and len(space[3]) == 1 and strings.nbs % 2 == 0 and strings.nas % 2 == 0:
                 assert "rows" in forms, forms
+            if strings.nblocks > 1:  # symmetry / GAS blocks: the block-aware gather kernel serves the rows form
+                assert "rows" in forms, forms
         np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array(errs))
-    finally:
         dist.destroy_process_group()
+    except BaseException:
+        _die()
 
 
-def _spawn(fn, args, nprocs, timeout=300):
+def _spawn(fn, args, nprocs, timeout=150):
     """mp.spawn with a deadline: a collective mismatch would otherwise hang the GPU box until NCCL's
     watchdog fires"""
     import time
@@ -79,7 +91,8 @@ def test_sharded_sigma_two_gpus(tmp_path):
         pytest.skip("needs 2 GPUs")
     spaces = [(3, 3, 0, [[0] * 6], [], []), (5, 4, 0, [[0] * 3, [0] * 4, [0] * 3], [4, 0, 0], [6, 8, 2]),
               (3, 3, 0, [[0, 5, 2, 3, 6, 7]], [], []), (5, 5, 0, [[0] * 10], [], []), (4, 3, 0, [[0] * 7], [], []),
-              (6, 6, 0, [[0] * 12], [], [])]
+              (6, 6, 0, [[0] * 12], [], []), (5, 5, 0, [[0] * 3, [0] * 4, [0] * 3], [4, 0, 0], [6, 8, 2]),
+              (4, 4, 0, [[0, 1, 2, 3] * 2], [], []), (4, 3, 2, [[0, 1, 2], [3, 0, 1, 2]], [2, 0], [6, 7])]
     _spawn(_worker, (2, _free_port(), spaces, str(tmp_path)), 2)
     for r in range(2):
         errs = np.load(tmp_path / f"err_{r}.npy")
@@ -110,8 +123,9 @@ def _solver_worker(rank, world, port, result_dir):
                                       device=rank, form=form).run()
             out.append(np.concatenate([np.asarray(single.E), np.asarray(sharded.E)]))
         np.save(os.path.join(result_dir, f"roots_{rank}.npy"), np.array(out))
-    finally:
         dist.destroy_process_group()
+    except BaseException:
+        _die()
 
 
 def test_sharded_davidson_roots_two_gpus(tmp_path):
