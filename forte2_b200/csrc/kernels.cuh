@@ -989,6 +989,7 @@ struct T3GMParams {
     int64_t gld;
     int M, Mpad, norb, nclsB, nchunks;
     int first, astride;
+    int rows;              // t3gp_kernel: rows of A' (multiple of 16)
     const uint32_t* jlist; // sharded build: the owned input alpha strings (NULL: first + blockIdx.x)
 };
 
@@ -1158,6 +1159,277 @@ __global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
                     }
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// t3gp_kernel: the same block-aware gather form, organised for latency instead of for register reuse.
+// ncu of t3gm_kernel on symmetry / GAS spaces (profiles/r03e_t3gm_*.md): after the per-class compaction a
+// (Ja, target class) pair has about one 16-row tile and a short k list, so a warp spends its time in the
+// dependent chain  k list -> table entry -> gathered operand -> DMMA  with two warps per scheduler
+// (tensor pipe 15-19 % active, 10 % of the samples waiting for the chunk list).  Here
+//   * work items are (target class, 16 targets, group of T3GP_TG row tiles), enumerated from a per-class
+//     prefix in shared memory (no chunk list in global memory, classes without rows or k entries cost nothing);
+//   * the k loop runs in batches of T3GP_KB k-steps through a three-stage register pipeline that crosses item
+//     boundaries: table entries of batch j+2 and gathered operands of batch j+1 are in flight while batch j
+//     multiplies (8 + 8 independent loads per lane instead of 2 + 2);
+//   * accumulators are T3GP_TG tiles only (wider row sets re-gather the operand per tile group), which leaves
+//     registers for 16 warps per SM.
+constexpr int T3GP_KB = 4;
+constexpr int T3GP_TG = 2;
+constexpr int T3GP_MAXROWS = 128;
+
+constexpr size_t t3gp_smem_bytes(int rows, int astride, int nclsB, int mpad) {
+    return size_t(rows + 1) * astride * 8 + size_t(rows) * nclsB * 4 + size_t(nclsB) * 6 * 4 + 4 +
+           size_t(nclsB) * rows + size_t(nclsB) * mpad * 2 + 64;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) t3gp_kernel(const T3GMParams p) {
+    constexpr int KB = T3GP_KB, TG = T3GP_TG, NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S = p.astride, NC = p.nclsB, MP = p.Mpad, ROWS = p.rows;
+    double* Asm = reinterpret_cast<double*>(smem_raw);                    // [ROWS + 1][S], last row zero
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(Asm + (ROWS + 1) * S); // [ROWS][NC] sigma offset or kNoRow
+    uint32_t* srcbase = rowoff + ROWS * NC;                               // [NC]
+    int* rcnt = reinterpret_cast<int*>(srcbase + NC);                     // [NC] output rows per target class
+    int* mcnt = rcnt + NC;                                                // [NC] integral rows per target class
+    int* nch = mcnt + NC;                                                 // [NC] chunks of 16 targets
+    int* nbc = nch + NC;                                                  // [NC] strings of the class
+    int* istart = nbc + NC;                                               // [NC + 1] first work item of the class
+    uint16_t* mlist = reinterpret_cast<uint16_t*>(istart + NC + 1);       // [NC][MP]
+    uint8_t* rlist = reinterpret_cast<uint8_t*>(mlist + NC * MP);         // [NC][ROWS]
+    __shared__ int s_kl[T3GP_MAXROWS];
+    __shared__ uint32_t s_ia[T3GP_MAXROWS];
+
+    const uint32_t Ja = p.jlist ? p.jlist[blockIdx.x] : p.first + blockIdx.x;
+    const int cJa = static_cast<int>(p.a_cls[Ja]);
+    const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
+    const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;
+    for (int r = tid; r < ROWS; r += THREADS) {
+        int kl = -1;
+        uint32_t Iar = 0;
+        if (r < Kn) {
+            const uint64_t ent = p.as_ent[e0 + r];
+            Iar = static_cast<uint32_t>(ent);
+            const int klr = static_cast<int>((ent >> 32) & 0xffff);
+            const int k = klr / p.norb, l = klr - k * p.norb;
+            kl = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
+        }
+        s_kl[r] = kl;
+        s_ia[r] = Iar;
+    }
+    for (int c = tid; c < NC; c += THREADS) {
+        srcbase[c] = p.crow[static_cast<size_t>(Ja) * NC + c];
+        mcnt[c] = p.ml_cnt[cJa * NC + c];
+        const int nb = static_cast<int>(p.nB_cls[c]);
+        nbc[c] = nb;
+        nch[c] = (nb + 15) >> 4;
+    }
+    for (int idx = tid; idx < NC * MP; idx += THREADS)
+        mlist[idx] = p.ml_ent[static_cast<size_t>(cJa) * NC * MP + idx];
+    __syncthreads();
+    for (int idx = tid; idx < ROWS * NC; idx += THREADS) {
+        const int r = idx / NC, c = idx - r * NC;
+        rowoff[idx] = s_kl[r] >= 0 ? p.srow[static_cast<size_t>(s_ia[r]) * NC + c] : kNoRow;
+    }
+    // A'[r][m] = s_r VxT[lk_r][m]; columns m >= M, rows r >= Kn and the extra row are zero
+    for (int idx = tid; idx < (ROWS + 1) * S; idx += THREADS) {
+        const int r = idx / S, m = idx - r * S;
+        double v = 0.0;
+        const int e = r < ROWS ? s_kl[r] : -1;
+        if (e >= 0 && m < p.M) {
+            v = __ldg(p.VxT + static_cast<size_t>(e & 0xffff) * p.M + m);
+            if (e & (1 << 30))
+                v = -v;
+        }
+        Asm[idx] = v;
+    }
+    __syncthreads();
+    // output rows of every target class, compacted in order (one warp per class)
+    for (int c = warp; c < NC; c += NW) {
+        int cnt = 0;
+        for (int base = 0; base < ROWS; base += 32) {
+            const int r = base + lane;
+            const bool ok = r < ROWS && rowoff[r * NC + c] != kNoRow;
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok)
+                rlist[c * ROWS + cnt + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint8_t>(r);
+            cnt += __popc(mask);
+        }
+        for (int r = cnt + lane; r < ROWS; r += 32)
+            rlist[c * ROWS + r] = static_cast<uint8_t>(ROWS); // the zero row of A'
+        if (lane == 0)
+            rcnt[c] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int at = 0;
+        for (int c = 0; c < NC; ++c) {
+            istart[c] = at;
+            if (rcnt[c] > 0 && mcnt[c] > 0)
+                at += nch[c] * ((((rcnt[c] + 15) >> 4) + TG - 1) / TG);
+        }
+        istart[NC] = at;
+    }
+    __syncthreads();
+    const int total = istart[NC];
+
+    // ---- stage T: k list and table entries of the next batch of the next work item
+    int w = warp, wcls = 0; // cursor of stage T
+    int t_kb = 0, t_nkb = 0, t_nm = 0, t_desc = -1;
+    const uint32_t* t_gp = p.gsrc;
+    const uint16_t* t_ml = mlist;
+    // descriptor: bits 0..10 target class, 11..13 tile group, 14..29 chunk of 16 targets, 30 = last batch
+    auto t_open = [&]() {
+        if (w >= total) {
+            t_desc = -1;
+            return;
+        }
+        while (w >= istart[wcls + 1])
+            ++wcls;
+        const int idx = w - istart[wcls], nc = nch[wcls];
+        const int tg = idx / nc, j = idx - tg * nc;
+        t_nm = mcnt[wcls];
+        t_nkb = (t_nm + 4 * KB - 1) / (4 * KB);
+        t_kb = 0;
+        t_gp = p.gsrc + p.gpos[wcls] + 16 * j + (g >> 1) + 4 * (g & 1);
+        t_ml = mlist + wcls * MP;
+        t_desc = wcls | (tg << 11) | (j << 14);
+    };
+    // lane (g, t) feeds B[k = t][n = g] of both n8 tiles; n index gg of tile nt is the target address
+    // 16 j + 8 nt + (gg >> 1) + 4 (gg & 1): the four lanes of an accumulator row hold consecutive targets
+    auto t_load = [&](uint2(&q)[KB], int(&m)[KB], int& desc) {
+        desc = t_desc;
+        if (t_desc < 0) {
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+                q[u] = make_uint2(0x7fffffffu, 0x7fffffffu);
+                m[u] = MP;
+            }
+            return;
+        }
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+            const int k = 4 * (t_kb * KB + u) + t;
+            m[u] = k < t_nm ? static_cast<int>(t_ml[k]) : MP; // MP: the all-empty table row, zero column of A'
+            const uint32_t* e = t_gp + static_cast<size_t>(m[u]) * p.gld;
+            q[u] = make_uint2(__ldg(e), __ldg(e + 8));
+        }
+        if (++t_kb == t_nkb) {
+            desc |= 1 << 30;
+            w += NW;
+            t_open();
+        }
+    };
+    auto gather = [&](uint32_t e) {
+        const uint32_t body = e & 0x7fffffffu;
+        double v = 0.0;
+        if (body != 0x7fffffffu) {
+            const uint32_t base = srcbase[body >> 20];
+            if (base != kNoRow)
+                v = __ldg(p.C + static_cast<size_t>(base) + (body & 0xfffffu));
+        }
+        return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
+    };
+
+    uint2 tq[KB];
+    int tm[KB], tdesc;
+    double gb0[KB], gb1[KB];
+    int gm[KB], gdesc;
+    t_open();
+    t_load(tq, tm, tdesc);
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+        gb0[u] = gather(tq[u].x);
+        gb1[u] = gather(tq[u].y);
+        gm[u] = tm[u];
+    }
+    gdesc = tdesc;
+    t_load(tq, tm, tdesc);
+
+    double acc[TG][2][4];
+#pragma unroll
+    for (int i = 0; i < TG; ++i)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+            acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
+    bool fresh = true;
+    int tiles = 0;
+    const double* arow[TG][2];
+    const uint8_t* rl = rlist;
+    while (gdesc >= 0) {
+        double b0[KB], b1[KB];
+        int mm[KB];
+        const int desc = gdesc;
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+            b0[u] = gb0[u];
+            b1[u] = gb1[u];
+            mm[u] = gm[u];
+        }
+        // operands of the next batch, table entries of the one after
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+            gb0[u] = gather(tq[u].x);
+            gb1[u] = gather(tq[u].y);
+            gm[u] = tm[u];
+        }
+        gdesc = tdesc;
+        t_load(tq, tm, tdesc);
+
+        const int cls = desc & 0x7ff;
+        if (fresh) {
+            const int tg = (desc >> 11) & 7;
+            rl = rlist + cls * ROWS + tg * TG * 16;
+            tiles = ((rcnt[cls] + 15) >> 4) - tg * TG;
+#pragma unroll
+            for (int i = 0; i < TG; ++i) {
+                const int r0 = i < tiles ? rl[16 * i + g] : ROWS, r1 = i < tiles ? rl[16 * i + g + 8] : ROWS;
+                arow[i][0] = Asm + r0 * S;
+                arow[i][1] = Asm + r1 * S;
+            }
+            fresh = false;
+        }
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+#pragma unroll
+            for (int i = 0; i < TG; ++i) {
+                if (i == 0 || i < tiles) {
+                    const double a0 = arow[i][0][mm[u]], a1 = arow[i][1][mm[u]];
+                    dmma_16x8x4(acc[i][0], a0, a1, b0[u]);
+                    dmma_16x8x4(acc[i][1], a0, a1, b1[u]);
+                }
+            }
+        }
+        if (desc & (1 << 30)) {
+            // accumulator (row, tile nt, n index 2t + c) is target address 16 j + 8 nt + 4 c + t of the class
+            const int c0 = 16 * ((desc >> 14) & 0xffff) + t, ncls = nbc[cls];
+#pragma unroll
+            for (int i = 0; i < TG; ++i) {
+                if (i == 0 || i < tiles) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = rl[16 * i + g + 8 * h];
+                        if (r < ROWS) {
+                            double* dst = p.sigma + static_cast<size_t>(rowoff[r * NC + cls]) + c0;
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+                                    if (c0 + 8 * nt + 4 * c < ncls)
+                                        atomicAdd(dst + 8 * nt + 4 * c, acc[i][nt][2 * h + c]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+                    acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
+            }
+            fresh = true;
         }
     }
 }

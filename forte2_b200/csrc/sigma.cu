@@ -655,7 +655,7 @@ void plan_t3_shape(f2_sigma& b) {
         while (S % 8 != 4)
             ++S;
         b.gm_astride = S;
-        b.gm_smem = t3gm_smem_bytes(rows, S, static_cast<int>(nclsB), b.gm_mpad);
+        b.gm_smem = t3gp_smem_bytes(rows, S, static_cast<int>(nclsB), b.gm_mpad);
         b.t3gm = b.gm_nt16 >= 1 && b.gm_nt16 <= 8 && b.gm_smem <= 227 * 1024 - 2048;
         if (b.t3gm && !b.gm_crow.p) {
             // offset of C[Ja, class c, 0] for every alpha string and beta class (the CI-vector layout)
@@ -1201,9 +1201,19 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     p.nchunks = b.gm_nchunks;
     p.first = 0;
     p.astride = b.gm_astride;
+    p.rows = b.gm_nt16 * 16;
     const int nrows = P ? P->njlist : static_cast<int>(h.nas);
     if (nrows == 0)
         return;
+    if (std::getenv("F2_T3GM_OLD") == nullptr) {
+        constexpr int THREADS = 512;
+        F2_CUDA(cudaFuncSetAttribute(t3gp_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(b.gm_smem)));
+        t3gp_kernel<THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
+        b.launches += 1;
+        F2_CUDA(cudaGetLastError());
+        return;
+    }
     switch (b.gm_nt16) {
     case 1: launch_t3gm_inst<1>(b, p, nrows, st); break;
     case 2: launch_t3gm_inst<2>(b, p, nrows, st); break;
