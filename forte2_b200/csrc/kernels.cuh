@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
 
 // ---------------------------------------------------------------------------------------------
 // Opposite-spin term, gather form for spaces with several determinant blocks (point-group symmetry,
-// GAS): t3gm_kernel.  Same algebra as t3g_kernel, one CTA per INPUT alpha string Ja, but block-aware:
+// GAS): t3gp_kernel.  Same algebra as t3g_kernel, one CTA per INPUT alpha string Ja, but block-aware:
 // for a chunk of 16 target beta strings of class cT only
 //   * the output rows r whose block (class(Ia_r), cT) exists are multiplied (compacted per class when
 //     the CTA starts), and
@@ -978,7 +978,6 @@ struct T3GMParams {
     const uint32_t* a_cls;
     const uint32_t* gsrc;   // [Mpad + 1][gld]: bits 0..19 source address, 20..30 source class, bit 31 sign;
                             // low 31 bits all ones = no source; row Mpad is all "no source"
-    const uint32_t* chunks; // 2 per chunk: beta class, first address of the 16 targets
     const uint32_t* gpos;   // [nclsB] first table column of each beta class (multiple of 16)
     const uint32_t* nB_cls; // [nclsB]
     const uint32_t* crow;   // [nas][nclsB] offset of C[Ja, class, 0], 0xffffffff if the block does not exist
@@ -987,185 +986,18 @@ struct T3GMParams {
     const int32_t* ml_cnt;  // [nclsA][nclsB]
     const double* VxT;
     int64_t gld;
-    int M, Mpad, norb, nclsB, nchunks;
+    int M, Mpad, norb, nclsB;
     int first, astride;
-    int rows;              // t3gp_kernel: rows of A' (multiple of 16)
+    int rows;              // rows of A' (multiple of 16)
     const uint32_t* jlist; // sharded build: the owned input alpha strings (NULL: first + blockIdx.x)
 };
 
 constexpr uint32_t kNoRow = 0xffffffffu;
 
-constexpr size_t t3gm_smem_bytes(int rows, int astride, int nclsB, int mpad) {
-    return size_t(rows + 1) * astride * 8 + size_t(rows) * nclsB * 4 + size_t(nclsB) * (4 + 4 + 4) +
-           size_t(nclsB) * rows + size_t(nclsB) * mpad * 2 + 64;
-}
-
-template <int NT16, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) t3gm_kernel(const T3GMParams p) {
-    constexpr int ROWS = NT16 * 16;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int S = p.astride, NC = p.nclsB, MP = p.Mpad;
-    double* Asm = reinterpret_cast<double*>(smem_raw);                    // [ROWS + 1][S], last row zero
-    uint32_t* rowoff = reinterpret_cast<uint32_t*>(Asm + (ROWS + 1) * S); // [ROWS][NC] sigma offset or kNoRow
-    uint32_t* srcbase = rowoff + ROWS * NC;                               // [NC]
-    int* rcnt = reinterpret_cast<int*>(srcbase + NC);                     // [NC] output rows per target class
-    int* mcnt = rcnt + NC;                                                // [NC] integral rows per target class
-    uint16_t* mlist = reinterpret_cast<uint16_t*>(mcnt + NC);             // [NC][MP]
-    uint8_t* rlist = reinterpret_cast<uint8_t*>(mlist + NC * MP);         // [NC][ROWS]
-    __shared__ int s_kl[ROWS];
-
-    const uint32_t Ja = p.jlist ? p.jlist[blockIdx.x] : p.first + blockIdx.x;
-    const int cJa = static_cast<int>(p.a_cls[Ja]);
-    const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
-    const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;
-    for (int r = tid; r < ROWS; r += THREADS) {
-        int kl = -1;
-        uint32_t Iar = 0;
-        if (r < Kn) {
-            const uint64_t ent = p.as_ent[e0 + r];
-            Iar = static_cast<uint32_t>(ent);
-            const int klr = static_cast<int>((ent >> 32) & 0xffff);
-            const int k = klr / p.norb, l = klr - k * p.norb;
-            kl = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
-        }
-        s_kl[r] = kl;
-        for (int c = 0; c < NC; ++c)
-            rowoff[r * NC + c] = kl >= 0 ? p.srow[static_cast<size_t>(Iar) * NC + c] : kNoRow;
-    }
-    for (int c = tid; c < NC; c += THREADS) {
-        srcbase[c] = p.crow[static_cast<size_t>(Ja) * NC + c];
-        mcnt[c] = p.ml_cnt[cJa * NC + c];
-    }
-    for (int idx = tid; idx < NC * MP; idx += THREADS)
-        mlist[idx] = p.ml_ent[static_cast<size_t>(cJa) * NC * MP + idx];
-    __syncthreads();
-    // A'[r][m] = s_r VxT[lk_r][m]; columns m >= M, rows r >= Kn and the extra row are zero
-    for (int idx = tid; idx < (ROWS + 1) * S; idx += THREADS) {
-        const int r = idx / S, m = idx - r * S;
-        double v = 0.0;
-        const int e = r < ROWS ? s_kl[r] : -1;
-        if (e >= 0 && m < p.M) {
-            v = __ldg(p.VxT + static_cast<size_t>(e & 0xffff) * p.M + m);
-            if (e & (1 << 30))
-                v = -v;
-        }
-        Asm[idx] = v;
-    }
-    // output rows of every target class, compacted in order (one warp per class)
-    for (int c = warp; c < NC; c += THREADS / 32) {
-        int cnt = 0;
-        for (int base = 0; base < ROWS; base += 32) {
-            const int r = base + lane;
-            const bool ok = r < ROWS && rowoff[r * NC + c] != kNoRow;
-            const unsigned mask = __ballot_sync(0xffffffffu, ok);
-            if (ok)
-                rlist[c * ROWS + cnt + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint8_t>(r);
-            cnt += __popc(mask);
-        }
-        for (int r = cnt + lane; r < ROWS; r += 32)
-            rlist[c * ROWS + r] = static_cast<uint8_t>(ROWS); // the zero row of A'
-        if (lane == 0)
-            rcnt[c] = cnt;
-    }
-    __syncthreads();
-
-    for (int chunk = warp; chunk < p.nchunks; chunk += THREADS / 32) {
-        const int cls = static_cast<int>(p.chunks[2 * chunk]);
-        const int nr = rcnt[cls], nm = mcnt[cls];
-        if (nr == 0 || nm == 0)
-            continue;
-        const int loc0 = static_cast<int>(p.chunks[2 * chunk + 1]);
-        const int ncls = static_cast<int>(p.nB_cls[cls]);
-        const int ntile = (nr + 15) >> 4, nks = (nm + 3) >> 2;
-        const int n0 = static_cast<int>(p.gpos[cls]) + loc0; // table column of the first target
-        const uint16_t* ml = mlist + cls * MP;
-        const uint8_t* rl = rlist + cls * ROWS;
-        double acc[NT16][2][4];
-        const double* arow[NT16][2];
-#pragma unroll
-        for (int i = 0; i < NT16; ++i) {
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-                acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
-            const int r0 = i < ntile ? rl[16 * i + g] : ROWS, r1 = i < ntile ? rl[16 * i + g + 8] : ROWS;
-            arow[i][0] = Asm + r0 * S;
-            arow[i][1] = Asm + r1 * S;
-        }
-        // lane (g, t) feeds B[k = t][n = g] of both n8 tiles; n index gg of tile nt is the target address
-        // loc0 + 8 nt + (gg >> 1) + 4 (gg & 1): the four lanes of an accumulator row hold consecutive targets
-        const uint32_t* gp = p.gsrc + n0 + (g >> 1) + 4 * (g & 1);
-        auto mrow = [&](int ks) { // integral row of k index 4 ks + t (the all-empty row past the list)
-            const int k = 4 * ks + t;
-            return k < nm ? static_cast<int>(ml[k]) : MP;
-        };
-        auto table = [&](int m) {
-            const uint32_t* q = gp + static_cast<size_t>(m) * p.gld;
-            return make_uint2(__ldg(q), __ldg(q + 8));
-        };
-        auto gather = [&](uint32_t e) {
-            const uint32_t body = e & 0x7fffffffu;
-            double v = 0.0;
-            if (body != 0x7fffffffu) {
-                const uint32_t base = srcbase[body >> 20];
-                if (base != kNoRow)
-                    v = __ldg(p.C + static_cast<size_t>(base) + (body & 0xfffffu));
-            }
-            return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
-        };
-        // table entries two k-steps ahead of the MMAs, gathered operands one ahead
-        int m_cur = mrow(0), m_nxt = mrow(1);
-        uint2 q_nxt = table(m_nxt);
-        double bn0, bn1;
-        {
-            const uint2 x0 = table(m_cur);
-            bn0 = gather(x0.x);
-            bn1 = gather(x0.y);
-        }
-        for (int ks = 0; ks < nks; ++ks) {
-            const double b0 = bn0, b1 = bn1;
-            const int m = m_cur;
-            bn0 = gather(q_nxt.x);
-            bn1 = gather(q_nxt.y);
-            m_cur = m_nxt;
-            m_nxt = mrow(ks + 2);
-            q_nxt = table(m_nxt);
-#pragma unroll
-            for (int i = 0; i < NT16; ++i) {
-                if (i < ntile) {
-                    const double a0 = arow[i][0][m], a1 = arow[i][1][m];
-                    dmma_16x8x4(acc[i][0], a0, a1, b0);
-                    dmma_16x8x4(acc[i][1], a0, a1, b1);
-                }
-            }
-        }
-        // accumulator (row, tile nt, n index 2t + c) is target address loc0 + 8 nt + 4 c + t of the class
-        const int c0 = loc0 + t;
-#pragma unroll
-        for (int i = 0; i < NT16; ++i) {
-            if (i < ntile) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = rl[16 * i + g + 8 * h];
-                    if (r < ROWS) {
-                        double* dst = p.sigma + static_cast<size_t>(rowoff[r * NC + cls]) + c0;
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                            for (int c = 0; c < 2; ++c)
-                                if (c0 + 8 * nt + 4 * c < ncls)
-                                    atomicAdd(dst + 8 * nt + 4 * c, acc[i][nt][2 * h + c]);
-                    }
-                }
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// t3gp_kernel: the same block-aware gather form, organised for latency instead of for register reuse.
-// ncu of t3gm_kernel on symmetry / GAS spaces (profiles/r03e_t3gm_*.md): after the per-class compaction a
+// t3gp_kernel is organised for latency, not for register reuse.  ncu of its predecessor (one warp per 16
+// targets, all row tiles in registers, k-steps one after the other; profiles/r03e_t3gm_*.md) on symmetry /
+// GAS spaces: after the per-class compaction a
 // (Ja, target class) pair has about one 16-row tile and a short k list, so a warp spends its time in the
 // dependent chain  k list -> table entry -> gathered operand -> DMMA  with two warps per scheduler
 // (tensor pipe 15-19 % active, 10 % of the samples waiting for the chunk list).  Here
@@ -1283,7 +1115,9 @@ __global__ void __launch_bounds__(THREADS, 1) t3gp_kernel(const T3GMParams p) {
     int t_kb = 0, t_nkb = 0, t_nm = 0, t_desc = -1;
     const uint32_t* t_gp = p.gsrc;
     const uint16_t* t_ml = mlist;
-    // descriptor: bits 0..10 target class, 11..13 tile group, 14..29 chunk of 16 targets, 30 = last batch
+    // descriptor: bits 0..10 target class, 11..13 tile group, 14..29 chunk of 16 targets, 30 = last batch.
+    // A short last batch is padded with the all-empty table row (skipping the padded k-steps was measured
+    // and loses: the branch costs more than the DMMAs it saves, profiles/r03h_one_gpu.log)
     auto t_open = [&]() {
         if (w >= total) {
             t_desc = -1;
@@ -1452,6 +1286,12 @@ struct SSParams {
     int ngroups;
     int nk; // number of strings in klist
 };
+// spaces with several determinant blocks: per column group the strings that have a parent in a block of
+// the group (list[ptr[g] .. ptr[g + 1])), instead of SSParams::klist; ptr == NULL: klist serves every group
+struct SSGroupLists {
+    const uint32_t* ptr;
+    const uint32_t* list;
+};
 
 constexpr int SSG_TW = 256; // columns per CTA: a panel of all rows x SSG_TW columns of X and Y stays in L2
 constexpr int SSG_KG = 8;   // (N-2)-electron strings per CTA, software-pipelined
@@ -1480,8 +1320,8 @@ __device__ __forceinline__ double flip_sign(double v, unsigned signbit31) {
 // fastest over the grid so that a column panel of X and Y is reused out of L2 by all K.
 // Reference counterpart: CISigmaBuilder::H2_hz_same_spin and H1_hz
 // (ci_sigma_builder_harrison_zarrabian.cc:14-195).
-template <int NM16, bool HAS8, bool AL16>
-__global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
+template <int NM16, bool HAS8, bool AL16, bool GK>
+__global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p, const SSGroupLists gk) {
     constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
     constexpr int S = ssg_astride(ROWS);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1496,15 +1336,25 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p) {
     const int j0 = p.tiles[2 * blockIdx.y + 1];
     const int ncols = p.g_ncols[grp];
     const long long ldx = p.g_ldx[grp], ldy = p.g_ldy[grp];
+    // GK: per-group string lists (a separate instance: the common-list kernel keeps its register allocation)
     const int k_first = blockIdx.x * SSG_KG;
-    const int k_cnt = p.nk - k_first < SSG_KG ? p.nk - k_first : SSG_KG;
+    const uint32_t* gklist = nullptr;
+    int gnk = 0;
+    if constexpr (GK) {
+        gklist = gk.list + gk.ptr[grp];
+        gnk = static_cast<int>(gk.ptr[grp + 1] - gk.ptr[grp]);
+        if (k_first >= gnk) // the grid is sized for the longest group list
+            return;
+    }
+    const int k_cnt = GK ? (gnk - k_first < SSG_KG ? gnk - k_first : SSG_KG)
+                         : (p.nk - k_first < SSG_KG ? p.nk - k_first : SSG_KG);
 
     auto decode = [&](int j) { // warp 0: parent list of the j-th string of this CTA into slot j % 3
         const int slot = j % 3;
         long long* msrc = msrc3 + slot * ROWS;
         long long* mdst = mdst3 + slot * ROWS;
         unsigned* minfo = minfo3 + slot * ROWS;
-        const uint32_t K = p.klist[k_first + j];
+        const uint32_t K = GK ? gklist[k_first + j] : p.klist[k_first + j];
         const int e0 = p.h2_ptr[K], e1 = p.h2_ptr[K + 1];
         int cnt = 0;
         for (int base = e0; base < e1; base += 32) {

@@ -138,6 +138,9 @@ struct SSPlan {
     DevBuf<int64_t> xoff, yoff;
     DevBuf<uint32_t> g_ncols, g_ldx, g_ldy, tiles;
     bool al16 = false;
+    // several determinant blocks: per column group the (N-2)-electron strings with a parent in the group
+    DevBuf<uint32_t> gk_ptr, gk_list;
+    uint32_t gk_max = 0; // longest group list
 };
 
 struct BetaPass {
@@ -171,7 +174,7 @@ struct Part {
     DevBuf<uint32_t> rowpad;
     int64_t slot_rows = 0;  // single block: rows per reduce-scatter slot (max over ranks of the owned rows)
     int64_t slot_elems = 0; // doubles per reduce-scatter slot (max over ranks of the local vector length)
-    // several blocks (t3gm_kernel): owned input strings, their local C offsets per beta class, and the offset
+    // several blocks (t3gp_kernel): owned input strings, their local C offsets per beta class, and the offset
     // of every (alpha string, beta class) sigma segment in the slot layout
     DevBuf<uint32_t> jlist, crow_local, srow_slot;
     int njlist = 0;
@@ -208,12 +211,12 @@ struct f2_sigma {
     size_t t3g_smem = 0;
     DevBuf<uint32_t> gsrc;
     DevBuf<double> VxT;
-    // gather form over several beta classes (t3gm_kernel): symmetry / GAS blocks, one GPU
+    // gather form over several beta classes (t3gp_kernel): symmetry / GAS blocks, one GPU
     bool t3gm = false;
-    DevBuf<uint32_t> gm_gsrc, gm_chunks, gm_gpos, gm_crow;
+    DevBuf<uint32_t> gm_gsrc, gm_gpos, gm_crow;
     DevBuf<uint16_t> gm_ml_ent;
     DevBuf<int32_t> gm_ml_cnt;
-    int gm_nchunks = 0, gm_mpad = 0, gm_nt16 = 0, gm_astride = 0;
+    int gm_mpad = 0, gm_nt16 = 0, gm_astride = 0;
     int64_t gm_gld = 0;
     size_t gm_smem = 0;
     bool t3_v4 = false;    // warp-specialised opposite-spin kernel (t3v4_kernel) is applicable
@@ -402,23 +405,18 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
             b.t3g_mpad = Mpad;
             b.t3g_gld = static_cast<int64_t>(gld);
         }
-        // the same for several beta classes (t3gm_kernel): table columns are the targets class by class,
+        // the same for several beta classes (t3gp_kernel): table columns are the targets class by class,
         // every class padded to a multiple of 16; an entry names its source as class << 20 | address.  One
         // extra all-empty row.  Beside it, for every (alpha class of the input string, target beta class) the
         // integral rows whose source class has a determinant block with that alpha class.
         b.gm_gsrc.release();
-        b.gm_nchunks = 0;
         if (!b.gsrc.p && nbs > 0 && h.ndet < (int64_t(1) << 32) - 1 && std::getenv("F2_NO_T3GM") == nullptr) {
             const int Mpad = (b.M + 3) / 4 * 4;
             const size_t NCb = B.nclasses(), NCa = h.nclsA();
-            std::vector<uint32_t> gpos(NCb), chunks;
+            std::vector<uint32_t> gpos(NCb);
             size_t gld = 0;
             for (size_t c = 0; c < NCb; ++c) {
                 gpos[c] = static_cast<uint32_t>(gld);
-                for (size_t i0 = 0; i0 < B.strpcls(c); i0 += 16) {
-                    chunks.push_back(static_cast<uint32_t>(c));
-                    chunks.push_back(static_cast<uint32_t>(i0));
-                }
                 gld += (B.strpcls(c) + 15) / 16 * 16;
             }
             if (static_cast<size_t>(Mpad + 1) * gld * sizeof(uint32_t) <= (size_t(2) << 30) && Mpad < 65535) {
@@ -464,11 +462,9 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
                         mc[ca * NCb + ct] = n;
                     }
                 b.gm_gsrc.upload(Gt);
-                b.gm_chunks.upload(chunks);
                 b.gm_gpos.upload(gpos);
                 b.gm_ml_ent.upload(ml);
                 b.gm_ml_cnt.upload(mc);
-                b.gm_nchunks = static_cast<int>(chunks.size() / 2);
                 b.gm_mpad = Mpad;
                 b.gm_gld = static_cast<int64_t>(gld);
             }
@@ -646,7 +642,7 @@ void plan_t3_shape(f2_sigma& b) {
     }
     // gather form over several beta classes: the A' block and the per-class row / k lists must fit
     b.t3gm = false;
-    if (!b.t3g && b.gm_gsrc.p && b.gm_nchunks > 0) {
+    if (!b.t3g && b.gm_gsrc.p) {
         b.gm_nt16 = (L.as_max + 15) / 16;
         const int rows = b.gm_nt16 * 16;
         // row stride of A': 4 or 12 (mod 16) doubles puts the rows g = 0..3 of a half-warp's 64-bit loads on
@@ -695,6 +691,63 @@ void fill_tiles(std::vector<uint32_t>& tiles, const std::vector<uint32_t>& ncols
             tiles.push_back(static_cast<uint32_t>(g));
             tiles.push_back(j0);
         }
+}
+
+// Spaces with several determinant blocks: most (N-2)-electron strings K have no parent in the blocks of a given
+// column group (GAS), and a CTA that finds that out has already paid the latency of decoding eight parent
+// lists.  Per column group, keep the strings that have at least one parent in a block of the group.
+// xoff: [string class][group] offset of the block in the operand, -1 if it does not exist.
+void fill_group_klists(const f2_sigma& b, int spin, SSPlan& p, const std::vector<int64_t>& xoff, int ngroups) {
+    const CIStringsHost& h = *b.S->host;
+    p.gk_ptr.release();
+    p.gk_list.release();
+    p.gk_max = 0;
+    if (h.blocks.size() <= 1 || ngroups <= 0)
+        return;
+    const DeviceLists& L = h.device_lists();
+    const auto& cls = spin == 0 ? L.a_cls : L.b_cls;
+    const auto& klist = L.h2_color_list[spin];
+    const auto& ptr = L.h2_ptr[spin];
+    const auto& ent = L.h2_ent[spin];
+    const size_t ncls = xoff.size() / static_cast<size_t>(ngroups);
+    std::vector<std::vector<int>> groups_of(ncls);
+    for (size_t c = 0; c < ncls; ++c)
+        for (int g = 0; g < ngroups; ++g)
+            if (xoff[c * ngroups + g] >= 0)
+                groups_of[c].push_back(g);
+    std::vector<std::vector<uint32_t>> lists(ngroups);
+    std::vector<int64_t> cls_seen(ncls, -1), grp_seen(ngroups, -1);
+    for (size_t i = 0; i < klist.size(); ++i) {
+        const uint32_t K = klist[i];
+        for (uint32_t e = ptr[K]; e < ptr[K + 1]; ++e) {
+            const uint32_t c = cls[ent[e] & 0xffffffffu];
+            if (cls_seen[c] == static_cast<int64_t>(i))
+                continue;
+            cls_seen[c] = static_cast<int64_t>(i);
+            for (int g : groups_of[c])
+                if (grp_seen[g] != static_cast<int64_t>(i)) {
+                    grp_seen[g] = static_cast<int64_t>(i);
+                    lists[g].push_back(K);
+                }
+        }
+    }
+    std::vector<uint32_t> gptr(ngroups + 1, 0), flat;
+    size_t total = 0;
+    for (int g = 0; g < ngroups; ++g)
+        total += lists[g].size();
+    if (total >= (size_t(1) << 32))
+        return; // keep the common list
+    flat.reserve(total);
+    for (int g = 0; g < ngroups; ++g) {
+        gptr[g] = static_cast<uint32_t>(flat.size());
+        flat.insert(flat.end(), lists[g].begin(), lists[g].end());
+        p.gk_max = std::max<uint32_t>(p.gk_max, static_cast<uint32_t>(lists[g].size()));
+    }
+    gptr[ngroups] = static_cast<uint32_t>(flat.size());
+    if (flat.empty())
+        flat.push_back(0);
+    p.gk_ptr.upload(gptr);
+    p.gk_list.upload(flat);
 }
 
 // ownership: rank r of world owns rows [r nA / world, (r+1) nA / world) of every alpha class and,
@@ -821,6 +874,7 @@ std::unique_ptr<Part> make_part(f2_sigma& b, int rank, int world) {
         p.g_ldy.upload(ldy);
         p.tiles.upload(tiles);
         p.al16 = even;
+        fill_group_klists(b, 0, p, xoff, static_cast<int>(nclsB));
     }
     // ---- rows form: the alpha same-spin plan whose operand is the exchanged column slab (laid out like the
     // exchange buffer: per block [nIa][owned columns]), and the reduce-scatter layout of the gather-form
@@ -846,6 +900,7 @@ std::unique_ptr<Part> make_part(f2_sigma& b, int rank, int world) {
         p.g_ldy.upload(ncols);
         p.tiles.upload(tiles);
         p.al16 = false;
+        fill_group_klists(b, 0, p, xoff, static_cast<int>(nclsB));
         // local layouts of every rank
         std::vector<std::vector<int64_t>> loc_off(world, std::vector<int64_t>(h.blocks.size(), 0));
         int64_t slot = 0;
@@ -1003,6 +1058,7 @@ void plan_beta(f2_sigma& b, Part& P, int64_t cap_elems = 0) {
         bp->plan.g_ldy.upload(ncols);
         bp->plan.tiles.upload(tiles);
         bp->plan.al16 = even;
+        fill_group_klists(b, 1, bp->plan, xoff, ng);
         bp->ntr = static_cast<int>(tr.size());
         bp->ntr_tiles = tile0;
         bp->tr.upload(tr);
@@ -1162,15 +1218,6 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
     F2_CUDA(cudaGetLastError());
 }
 
-template <int NT16>
-void launch_t3gm_inst(const f2_sigma& b, const T3GMParams& p, int nrows, cudaStream_t st) {
-    constexpr int THREADS = NT16 >= 6 ? 256 : 384;
-    F2_CUDA(cudaFuncSetAttribute(t3gm_kernel<NT16, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(b.gm_smem)));
-    t3gm_kernel<NT16, THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
-    b.launches += 1;
-}
-
 // gather-form opposite-spin term for spaces with several determinant blocks.  One GPU: every alpha string,
 // C and sigma in the CI-vector layout.  Sharded (P given): the owned input strings, C = the local vector,
 // sigma = the reduce-scatter buffer in the slot layout.
@@ -1184,7 +1231,6 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     p.as_ent = D.as_ent.p;
     p.a_cls = D.a_cls.p;
     p.gsrc = b.gm_gsrc.p;
-    p.chunks = b.gm_chunks.p;
     p.gpos = b.gm_gpos.p;
     p.nB_cls = D.nB_cls.p;
     p.crow = P ? P->crow_local.p : b.gm_crow.p;
@@ -1198,33 +1244,17 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     p.Mpad = b.gm_mpad;
     p.norb = h.norb;
     p.nclsB = static_cast<int>(h.nclsB());
-    p.nchunks = b.gm_nchunks;
     p.first = 0;
     p.astride = b.gm_astride;
     p.rows = b.gm_nt16 * 16;
     const int nrows = P ? P->njlist : static_cast<int>(h.nas);
     if (nrows == 0)
         return;
-    if (std::getenv("F2_T3GM_OLD") == nullptr) {
-        constexpr int THREADS = 512;
-        F2_CUDA(cudaFuncSetAttribute(t3gp_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(b.gm_smem)));
-        t3gp_kernel<THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
-        b.launches += 1;
-        F2_CUDA(cudaGetLastError());
-        return;
-    }
-    switch (b.gm_nt16) {
-    case 1: launch_t3gm_inst<1>(b, p, nrows, st); break;
-    case 2: launch_t3gm_inst<2>(b, p, nrows, st); break;
-    case 3: launch_t3gm_inst<3>(b, p, nrows, st); break;
-    case 4: launch_t3gm_inst<4>(b, p, nrows, st); break;
-    case 5: launch_t3gm_inst<5>(b, p, nrows, st); break;
-    case 6: launch_t3gm_inst<6>(b, p, nrows, st); break;
-    case 7: launch_t3gm_inst<7>(b, p, nrows, st); break;
-    case 8: launch_t3gm_inst<8>(b, p, nrows, st); break;
-    default: throw std::runtime_error("CISigmaBuilder: unsupported gather-form shape");
-    }
+    constexpr int THREADS = 512;
+    F2_CUDA(cudaFuncSetAttribute(t3gp_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(b.gm_smem)));
+    t3gp_kernel<THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
+    b.launches += 1;
     F2_CUDA(cudaGetLastError());
 }
 
@@ -1272,19 +1302,30 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     F2_CUDA(cudaGetLastError());
 }
 
-template <int NM16, bool HAS8>
-void launch_ssg_inst(const SSParams& p, bool al16, dim3 grid, cudaStream_t st) {
+template <int NM16, bool HAS8, bool AL16, bool GK>
+void launch_ssg_variant(const SSParams& p, const SSGroupLists& gk, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = ssg_smem_bytes(NM16 * 16 + (HAS8 ? 8 : 0));
-    if (al16) {
-        if (smem > 48 * 1024)
-            F2_CUDA(cudaFuncSetAttribute(ssg_kernel<NM16, HAS8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-        ssg_kernel<NM16, HAS8, true><<<grid, 256, smem, st>>>(p);
+    if (smem > 48 * 1024)
+        F2_CUDA(cudaFuncSetAttribute(ssg_kernel<NM16, HAS8, AL16, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    ssg_kernel<NM16, HAS8, AL16, GK><<<grid, 256, smem, st>>>(p, gk);
+}
+
+// GK (per-group string lists) is a separate instance and a separate kernel argument: the common-list kernel
+// keeps the register allocation it was tuned with (114 registers at CAS(16,16); 125 with two more fields in
+// SSParams, measured 4 % slower)
+template <int NM16, bool HAS8>
+void launch_ssg_inst(const SSParams& p, const SSGroupLists& gk, bool al16, dim3 grid, cudaStream_t st) {
+    if (gk.ptr) {
+        if (al16)
+            launch_ssg_variant<NM16, HAS8, true, true>(p, gk, grid, st);
+        else
+            launch_ssg_variant<NM16, HAS8, false, true>(p, gk, grid, st);
     } else {
-        if (smem > 48 * 1024)
-            F2_CUDA(cudaFuncSetAttribute(ssg_kernel<NM16, HAS8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-        ssg_kernel<NM16, HAS8, false><<<grid, 256, smem, st>>>(p);
+        if (al16)
+            launch_ssg_variant<NM16, HAS8, true, false>(p, gk, grid, st);
+        else
+            launch_ssg_variant<NM16, HAS8, false, false>(p, gk, grid, st);
     }
 }
 
@@ -1315,9 +1356,13 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
     const bool al16 = plan.al16 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0;
     const int mmax = std::max(L.h2_max[spin], 1);
     const int nm16 = mmax / 16 + (mmax % 16 > 8 ? 1 : 0), has8 = (mmax % 16 > 0 && mmax % 16 <= 8) ? 1 : 0;
+    const SSGroupLists gk{plan.gk_ptr.p, plan.gk_list.p};
+    if (gk.ptr && plan.gk_max == 0)
+        return; // no string has a parent in any block of this plan
     // grid: x = K (fastest: all K of a column panel run together, the panel stays in L2), y = panel
-    for (size_t k0 = 0; k0 < nk; k0 += size_t(1) << 30) {
-        const uint32_t nkk = static_cast<uint32_t>(std::min<size_t>(size_t(1) << 30, nk - k0));
+    const size_t nk_grid = gk.ptr ? plan.gk_max : nk;
+    for (size_t k0 = 0; k0 < nk_grid; k0 += size_t(1) << 30) {
+        const uint32_t nkk = static_cast<uint32_t>(std::min<size_t>(size_t(1) << 30, nk_grid - k0));
         p.klist = D.h2_clist[spin].p + k0;
         p.nk = static_cast<int>(nkk);
         for (int t0 = 0; t0 < plan.ntiles; t0 += 65535) {
@@ -1326,22 +1371,22 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
             const dim3 grid((nkk + SSG_KG - 1) / SSG_KG, nt);
             b.launches += 1;
             switch (nm16 * 2 + has8) {
-            case 1: launch_ssg_inst<0, true>(p, al16, grid, st); break;
-            case 2: launch_ssg_inst<1, false>(p, al16, grid, st); break;
-            case 3: launch_ssg_inst<1, true>(p, al16, grid, st); break;
-            case 4: launch_ssg_inst<2, false>(p, al16, grid, st); break;
-            case 5: launch_ssg_inst<2, true>(p, al16, grid, st); break;
-            case 6: launch_ssg_inst<3, false>(p, al16, grid, st); break;
-            case 7: launch_ssg_inst<3, true>(p, al16, grid, st); break;
-            case 8: launch_ssg_inst<4, false>(p, al16, grid, st); break;
-            case 9: launch_ssg_inst<4, true>(p, al16, grid, st); break;
-            case 10: launch_ssg_inst<5, false>(p, al16, grid, st); break;
-            case 11: launch_ssg_inst<5, true>(p, al16, grid, st); break;
-            case 12: launch_ssg_inst<6, false>(p, al16, grid, st); break;
-            case 13: launch_ssg_inst<6, true>(p, al16, grid, st); break;
-            case 14: launch_ssg_inst<7, false>(p, al16, grid, st); break;
-            case 15: launch_ssg_inst<7, true>(p, al16, grid, st); break;
-            case 16: launch_ssg_inst<8, false>(p, al16, grid, st); break;
+            case 1: launch_ssg_inst<0, true>(p, gk, al16, grid, st); break;
+            case 2: launch_ssg_inst<1, false>(p, gk, al16, grid, st); break;
+            case 3: launch_ssg_inst<1, true>(p, gk, al16, grid, st); break;
+            case 4: launch_ssg_inst<2, false>(p, gk, al16, grid, st); break;
+            case 5: launch_ssg_inst<2, true>(p, gk, al16, grid, st); break;
+            case 6: launch_ssg_inst<3, false>(p, gk, al16, grid, st); break;
+            case 7: launch_ssg_inst<3, true>(p, gk, al16, grid, st); break;
+            case 8: launch_ssg_inst<4, false>(p, gk, al16, grid, st); break;
+            case 9: launch_ssg_inst<4, true>(p, gk, al16, grid, st); break;
+            case 10: launch_ssg_inst<5, false>(p, gk, al16, grid, st); break;
+            case 11: launch_ssg_inst<5, true>(p, gk, al16, grid, st); break;
+            case 12: launch_ssg_inst<6, false>(p, gk, al16, grid, st); break;
+            case 13: launch_ssg_inst<6, true>(p, gk, al16, grid, st); break;
+            case 14: launch_ssg_inst<7, false>(p, gk, al16, grid, st); break;
+            case 15: launch_ssg_inst<7, true>(p, gk, al16, grid, st); break;
+            case 16: launch_ssg_inst<8, false>(p, gk, al16, grid, st); break;
             default: throw std::runtime_error("CISigmaBuilder: unsupported same-spin block size");
             }
         }
@@ -1466,7 +1511,7 @@ void apply(f2_sigma& b, const double* C, double* sigma, int64_t n, cudaStream_t 
 }
 
 // Rows form of the sharded build (gather-form opposite-spin kernels: t3g_kernel for one determinant block,
-// t3gm_kernel for several): no rank ever holds the full trial vector.
+// t3gp_kernel for several): no rank ever holds the full trial vector.
 //   sigma_loc  = E C_loc + beta same-spin term of the owned rows                 (complete)
 //   ycols      = alpha same-spin term of [all rows][owned columns], from xcols    (caller: all-to-all, add)
 //   scatter    = opposite-spin contributions of the owned INPUT rows to every sigma row, world slots of
@@ -1862,7 +1907,7 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
         if (world <= 1 || !rows_form_ok(*h) || !(h->t3g || shard_of(*h, rank, world).srow_slot.p))
             throw std::runtime_error("CISigmaBuilder: the rows form of the sharded build is not available for "
                                      "this string space (f2_sigma_rows_form)");
-        // t3g_kernel brings its rows of C in with TMA bulk copies; t3gm_kernel gathers and has no such need
+        // t3g_kernel brings its rows of C in with TMA bulk copies; t3gp_kernel gathers and has no such need
         if (h->t3g && (reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
             throw std::invalid_argument("CISigmaBuilder: the local trial vector must be 16-byte aligned");
         if (phases < 1 || phases > 3)

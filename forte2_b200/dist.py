@@ -15,7 +15,7 @@ Full form (any string space), per sigma build
   3. exchange of the alpha same-spin partial results to the row owners (all-to-all) and add  -- NCCL
 
 Rows form (spaces served by a gather-form opposite-spin kernel: t3g_kernel for one determinant block,
-t3gm_kernel for symmetry / GAS blocks; no rank ever holds the full vector), per sigma build
+t3gp_kernel for symmetry / GAS blocks; no rank ever holds the full vector), per sigma build
   1. all-to-all of C: rank r sends C[rows of r, columns of q] of every block to q and assembles the
      column slabs [all rows][columns of r]                                                   -- NCCL, ndet/world doubles
   2. local work (f2_sigma_apply_rows): H0 and beta same-spin term of the owned rows from the local

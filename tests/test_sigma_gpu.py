@@ -146,7 +146,7 @@ def test_rows_form_parts_emulated_on_one_gpu(ref, torch_cuda, space, world):
     """f2_sigma_apply_rows (the sharded build that never holds the full vector) for every rank of a world,
     run one after the other on this GPU, the three exchanges of forte2_b200/dist.py done by hand:
     the sum equals the single-GPU sigma and the reference.  One determinant block (t3g_kernel) and
-    symmetry / GAS blocks (t3gm_kernel).  The NCCL version is tests/test_dist_gpu.py."""
+    symmetry / GAS blocks (t3gp_kernel).  The NCCL version is tests/test_dist_gpu.py."""
     torch = torch_cuda
     from forte2_b200.dist import CudaEngine, Layout
     n = sum(len(s) for s in space[3])
@@ -262,7 +262,7 @@ def test_gas_three_spaces_twenty_orbitals(torch_cuda):
 
 @pytest.mark.parametrize("name", ["gas343_54", "gas343_55", "cas66_d2h", "gas2_sym4", "cas66_cs1"])
 def test_gather_form_over_several_beta_classes(ref, torch_cuda, monkeypatch, name):
-    """t3gm_kernel: the block-aware gather form of the opposite-spin term for spaces with several
+    """t3gp_kernel: the block-aware gather form of the opposite-spin term for spaces with several
     determinant blocks (GAS, point-group symmetry) against the reference, and against the scatter form
     (F2_NO_T3GM=1) it replaces on one GPU."""
     space = SMALL_SPACES[name]
