@@ -40,6 +40,8 @@ class CISigmaBuilder:
         if device is None:
             device = self._current_device()
         self.device = int(device)
+        self._ints = (float(E), H, V)  # the reference keeps handles of H and V too (ci_sigma_builder.h:294-296)
+        self._memory_bytes = 1073741824  # ci_sigma_builder.h:300
         L = _lib.lib()
         self._h = L.f2_sigma_create(lists._h, float(E), H.ctypes.data_as(_lib.f64p),
                                     V.ctypes.data_as(_lib.f64p), int(log_level), self.device)
@@ -71,6 +73,7 @@ class CISigmaBuilder:
             raise RuntimeError("V shape does not match the number of orbitals.")
         _lib.check(_lib.lib().f2_sigma_set_hamiltonian(self._h, float(E), H.ctypes.data_as(_lib.f64p),
                                                        V.ctypes.data_as(_lib.f64p)))
+        self._ints = (float(E), H, V)
 
     def set_algorithm(self, algorithm: str):
         _lib.check(_lib.lib().f2_sigma_set_algorithm(self._h, str(algorithm).encode()))
@@ -80,6 +83,7 @@ class CISigmaBuilder:
 
     def set_memory(self, memory: int):
         _lib.check(_lib.lib().f2_sigma_set_memory(self._h, int(memory)))
+        self._memory_bytes = int(memory) * 1024 * 1024
 
     def set_log_level(self, level: int):
         _lib.check(_lib.lib().f2_sigma_set_log_level(self._h, int(level)))
@@ -148,20 +152,45 @@ class CISigmaBuilder:
     def form_Hdiag_csf(self, dets, spin_adapter, spin_adapt_full_preconditioner: bool = False):
         """Davidson preconditioner in the CSF basis (CISigmaBuilder::form_Hdiag_csf,
         forte2/ci/ci_sigma_builder.cc:317-370) as a CUDA tensor of ncsf doubles.  `dets` is accepted for
-        signature compatibility and not used (the adapter knows its determinants).  Only the default
-        form H_II ~ sum_d c_dI^2 <d|H|d> exists on the device; the exact form (which the reference itself
-        calls too slow to use) is refused."""
+        signature compatibility and not used (the adapter knows its determinants).  The default form
+        H_II ~ sum_d c_dI^2 <d|H|d> is computed on the device; the exact form <I|H|I> (which the reference itself
+        calls too slow to use, ci_sigma_builder.cc:326-332) is computed on the host with Slater rules, as the
+        reference does, and copied to the device."""
         import torch
-        if spin_adapt_full_preconditioner:
-            raise NotImplementedError("spin_adapt_full_preconditioner=True is not available on the device")
         if spin_adapter.ci_strings is not self.ci_strings and spin_adapter.ndet != self.ci_strings.ndet:
             raise ValueError("the spin adapter was prepared for a different determinant space")
+        if spin_adapt_full_preconditioner:
+            return torch.from_numpy(exact_hdiag_csf(self.ci_strings, *self._ints, spin_adapter)).to(
+                f"cuda:{self.device}")
         e_det = self.form_Hdiag_det()
         out = torch.empty(spin_adapter.ncsf, dtype=torch.float64, device=e_det.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().f2_adapter_hdiag_csf(spin_adapter._h, e_det.data_ptr(), out.data_ptr(), self.device,
                                                    stream))
         return out
+
+    # ---- host-side helpers of the callers around sigma (guess vectors, exact diagonalisation of small spaces):
+    # Slater rules over the few determinants involved, f2_slater_matrix; no device work
+    def slater_rules_csf(self, dets, spin_adapter, I: int, J: int) -> float:
+        """<I|H|J> between two CSFs (CISigmaBuilder::slater_rules_csf, forte2/ci/ci_sigma_builder.cc:278-297;
+        the guess Hamiltonian of forte2/ci/ci.py:405-441).  `dets` is accepted for signature compatibility;
+        `spin_adapter` needs csf(i) -> [(determinant address, coefficient)], which both this package's and
+        the reference's adapter offer."""
+        return csf_matrix_element(self.ci_strings, *self._ints, spin_adapter, I, J)
+
+    def energy_csf(self, dets, spin_adapter, I: int) -> float:
+        """<I|H|I> of one CSF (CISigmaBuilder::energy_csf, ci_sigma_builder.cc:299-315)"""
+        return self.slater_rules_csf(dets, spin_adapter, I, I)
+
+    def form_H_csf(self, dets, spin_adapter) -> np.ndarray:
+        """Dense Hamiltonian in the CSF basis, (ncsf, ncsf) numpy array (CISigmaBuilder::form_H_csf,
+        ci_sigma_builder.cc:372-392; the exact-diagonalisation path of forte2/ci/ci.py:305-318), with the
+        reference's memory check and message.  T^t H_det T over the determinants the CSFs use."""
+        ncsf = _ncsf(spin_adapter)
+        if ncsf * ncsf * 8 > self._memory_bytes:
+            raise RuntimeError("Not enough memory to form the full Hamiltonian matrix in the CSF basis. "
+                               "Increase the memory limit or use a different algorithm.")
+        return csf_hamiltonian(self.ci_strings, *self._ints, spin_adapter)
 
     def form_Hdiag_det(self):
         """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""
@@ -170,3 +199,69 @@ class CISigmaBuilder:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().f2_sigma_hdiag(self._h, out.data_ptr(), stream))
         return out
+
+
+def _slater_block(strings: CIStrings, E, H, V, idx) -> np.ndarray:
+    """<d|H|d'> for the determinants at the CI-vector addresses idx (host, f2_slater_matrix:
+    SlaterRules::slater_rules, forte2/determinant/slater_rules.cc:123-245)"""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    block = np.zeros((idx.size, idx.size))
+    _lib.check(_lib.lib().f2_slater_matrix(strings._h, float(E), H.ctypes.data_as(_lib.f64p),
+                                           V.ctypes.data_as(_lib.f64p), idx.ctypes.data_as(_lib.i64p),
+                                           int(idx.size), block.ctypes.data_as(_lib.f64p)))
+    return block
+
+
+def exact_hdiag_csf(strings: CIStrings, E, H, V, spin_adapter) -> np.ndarray:
+    """<I|H|I> = sum_{d d'} c_dI c_d'I <d|H|d'> for every CSF I (CISigmaBuilder::form_Hdiag_csf with
+    spin_adapt_full_preconditioner = true -> energy_csf, forte2/ci/ci_sigma_builder.cc:326-332): host work,
+    O(sum over configurations of ndet_conf^2) Slater-rule matrix elements (f2_slater_matrix; needs no GPU).
+    The CSFs of one configuration share their determinants, so the determinant block is formed once per
+    configuration."""
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    bounds, det, coeff = spin_adapter.table()
+    out = np.zeros(spin_adapter.ncsf)
+    for first, last in spin_adapter.conf_to_csfs_range():
+        if last <= first:
+            continue
+        dets = np.unique(det[bounds[first]:bounds[last]])
+        block = _slater_block(strings, E, H, V, dets)
+        for i in range(first, last):
+            where = np.searchsorted(dets, det[bounds[i]:bounds[i + 1]])
+            c = coeff[bounds[i]:bounds[i + 1]]
+            out[i] = c @ block[np.ix_(where, where)] @ c
+    return out
+
+
+def _ncsf(spin_adapter) -> int:
+    return int(spin_adapter.ncsf() if callable(spin_adapter.ncsf) else spin_adapter.ncsf)
+
+
+def csf_matrix_element(strings: CIStrings, E, H, V, spin_adapter, I: int, J: int) -> float:
+    """<I|H|J> between two CSFs = sum_{d d'} c_dI c_d'J <d|H|d'> (ci_sigma_builder.cc:278-315); host"""
+    row_I, row_J = spin_adapter.csf(int(I)), spin_adapter.csf(int(J))
+    idx = np.array(sorted({int(d) for d, _ in row_I} | {int(d) for d, _ in row_J}), dtype=np.int64)
+    pos = {int(d): k for k, d in enumerate(idx)}
+    c_I, c_J = np.zeros(idx.size), np.zeros(idx.size)
+    for d, c in row_I:
+        c_I[pos[int(d)]] += c
+    for d, c in row_J:
+        c_J[pos[int(d)]] += c
+    return float(c_I @ _slater_block(strings, E, H, V, idx) @ c_J)
+
+
+def csf_hamiltonian(strings: CIStrings, E, H, V, spin_adapter) -> np.ndarray:
+    """T^t H_det T over the determinants the CSFs use (ci_sigma_builder.cc:372-392); host"""
+    ncsf = _ncsf(spin_adapter)
+    rows = [spin_adapter.csf(i) for i in range(ncsf)]
+    idx = np.array(sorted({int(d) for row in rows for d, _ in row}), dtype=np.int64)
+    pos = {int(d): k for k, d in enumerate(idx)}
+    T = np.zeros((idx.size, ncsf))
+    for i, row in enumerate(rows):
+        for d, c in row:
+            T[pos[int(d)], i] += c
+    Hcsf = T.T @ _slater_block(strings, E, H, V, idx) @ T
+    return 0.5 * (Hcsf + Hcsf.T)

@@ -77,6 +77,10 @@ def lib():
         L.ref_adapter_table.restype = i64
         L.ref_adapter_table.argtypes = [vp, i64p, i64p, dp, i64]
         L.ref_hdiag_csf.argtypes = [vp, vp, i, dp]
+        L.ref_form_H_csf.restype = i
+        L.ref_form_H_csf.argtypes = [vp, vp, dp]
+        L.ref_slater_rules_csf.restype = C.c_double
+        L.ref_slater_rules_csf.argtypes = [vp, vp, i64, i64]
         L.ref_set_log_level.argtypes = [i]
         L.ref_set_log_level(0)
         _lib = L
@@ -236,6 +240,17 @@ class RefCISpinAdapter:
         out = np.zeros(self.ncsf)
         lib().ref_hdiag_csf(builder._h, self._h, int(full), _dp(out))
         return out
+
+    def form_H_csf(self, builder: RefCISigmaBuilder):
+        """CISigmaBuilder::form_H_csf (ci_sigma_builder.cc:372-392); RuntimeError as the reference throws"""
+        out = np.zeros((self.ncsf, self.ncsf))
+        if lib().ref_form_H_csf(builder._h, self._h, _dp(out)) != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
+    def slater_rules_csf(self, builder: RefCISigmaBuilder, I, J):
+        """CISigmaBuilder::slater_rules_csf (ci_sigma_builder.cc:278-297)"""
+        return float(lib().ref_slater_rules_csf(builder._h, self._h, int(I), int(J)))
 
 
 def set_threads(n: int | None):

@@ -449,5 +449,24 @@ void ref_hdiag_csf(void* hsig, void* hadapter, int full, double* out) {
     auto v = r->b->form_Hdiag_csf(a->dets, *a->a, full != 0);
     std::memcpy(out, v.data(), v.shape(0) * sizeof(double));
 }
+// dense CSF-basis Hamiltonian and one element of it, forte2/ci/ci_sigma_builder.cc:278-297,372-392
+// returns 0, or 1 when the reference throws (its memory check); the message through ref_last_error
+int ref_form_H_csf(void* hsig, void* hadapter, double* out) {
+    auto* r = static_cast<RefSigma*>(hsig);
+    auto* a = static_cast<RefAdapter*>(hadapter);
+    try {
+        auto m = r->b->form_H_csf(a->dets, *a->a);
+        std::memcpy(out, m.data(), m.shape(0) * m.shape(1) * sizeof(double));
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+double ref_slater_rules_csf(void* hsig, void* hadapter, int64_t I, int64_t J) {
+    auto* r = static_cast<RefSigma*>(hsig);
+    auto* a = static_cast<RefAdapter*>(hadapter);
+    return r->b->slater_rules_csf(a->dets, *a->a, static_cast<size_t>(I), static_cast<size_t>(J));
+}
 
 } // extern "C"

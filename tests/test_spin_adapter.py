@@ -57,6 +57,58 @@ def test_coupling_table_vs_reference_all_spins(ref, name):
         assert np.array_equal(gb, rb) and np.array_equal(gd, rd) and np.array_equal(gc, rc)
 
 
+@pytest.mark.parametrize("name,twoS", [("cas66", 0), ("cas66", 2), ("cas75_odd", 1), ("gas343_54", 1),
+                                       ("cas66_d2h", 0), ("gas2_sym4", 1), ("one_each", 0), ("cas88", 0)])
+def test_exact_csf_preconditioner_vs_reference(ref, name, twoS):
+    """form_Hdiag_csf(..., spin_adapt_full_preconditioner=True): <I|H|I> of every CSF, host Slater rules
+    (forte2/ci/ci_sigma_builder.cc:326-332), against the reference's own energy_csf."""
+    from forte2_b200.ci_sigma_builder import exact_hdiag_csf
+    space = SMALL_SPACES[name]
+    E, H, V = synthetic.integrals(sum(len(s) for s in space[3]), "S")
+    rs = ref.RefCIStrings(*space)
+    rb = ref.RefCISigmaBuilder(rs, E, H, V)
+    ra = ref.RefCISpinAdapter(rs, twoS, space[0] - space[1])
+    want = ra.hdiag_csf(rb, full=True)
+    strings, a = _adapter(name, twoS)
+    got = exact_hdiag_csf(strings, E, H, V, a)
+    assert got.shape == want.shape and a.ncsf > 0
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+    # it differs from the default (diagonal-only) form wherever a CSF has more than one determinant
+    approx = ra.hdiag_csf(rb, full=False)
+    if name == "cas66":
+        assert np.max(np.abs(approx - want)) > 1e-6
+
+
+@pytest.mark.parametrize("name,twoS", [("cas66", 0), ("cas75_odd", 1), ("gas343_54", 1), ("cas66_d2h", 0),
+                                       ("gas2_sym4", 1)])
+def test_csf_hamiltonian_and_elements_vs_reference(ref, name, twoS):
+    """form_H_csf / slater_rules_csf / energy_csf (host helpers of the guess and of exact diagonalisation,
+    forte2/ci/ci_sigma_builder.cc:278-315,372-392) against the reference's own."""
+    from forte2_b200.ci_sigma_builder import csf_hamiltonian, csf_matrix_element
+    space = SMALL_SPACES[name]
+    E, H, V = synthetic.integrals(sum(len(s) for s in space[3]), "S")
+    rs = ref.RefCIStrings(*space)
+    rb = ref.RefCISigmaBuilder(rs, E, H, V)
+    ra = ref.RefCISpinAdapter(rs, twoS, space[0] - space[1])
+    want = ra.form_H_csf(rb)
+    strings, a = _adapter(name, twoS)
+    got = csf_hamiltonian(strings, E, H, V, a)
+    scale = max(1.0, np.max(np.abs(want)))
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= 1e-12 * scale
+    rng = np.random.default_rng(7)
+    for I, J in [(0, 0), (a.ncsf - 1, 0)] + [tuple(rng.integers(0, a.ncsf, 2)) for _ in range(6)]:
+        assert abs(csf_matrix_element(strings, E, H, V, a, I, J) - ra.slater_rules_csf(rb, I, J)) <= 1e-12 * scale
+    # exact diagonalisation (forte2/ci/ci.py:305-318) of that matrix on the Davidson integrals: the committed
+    # golden roots of the reference's CSF solve (tests/golden/make_golden_roots_csf.py)
+    path = os.path.join(GOLD, f"rootscsf_{name}_S{twoS}.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        ED, HD, VD = synthetic.integrals(strings.norb, "D")
+        roots = np.linalg.eigvalsh(csf_hamiltonian(strings, ED, HD, VD, a))[: g["exact"].size]
+        assert np.max(np.abs(roots - g["exact"][: roots.size])) <= 1e-10
+
+
 def test_errors():
     strings = f2.CIStrings(*SMALL_SPACES["cas66"])
     a = f2.CISpinAdapter(0, 2, 6)
@@ -101,6 +153,22 @@ def test_transforms_and_preconditioner_on_gpu(name, twoS):
     b = f2.CISigmaBuilder(strings, E, H, V, 0)
     hd = b.form_Hdiag_csf(None, a).cpu().numpy()
     assert np.max(np.abs(hd - g["hdiag_csf"]), initial=0.0) <= 1e-12 * max(1.0, np.max(np.abs(g["hdiag_csf"]), initial=0.0))
+    # the exact form: host Slater rules (checked against the reference on the CPU), delivered as a device tensor
+    from forte2_b200.ci_sigma_builder import exact_hdiag_csf
+    hx = b.form_Hdiag_csf(None, a, True)
+    assert hx.is_cuda and hx.shape == (a.ncsf,)
+    assert np.array_equal(hx.cpu().numpy(), exact_hdiag_csf(strings, E, H, V, a))
+    # host helpers of the guess / exact diagonalisation through the builder (checked against the reference on the CPU)
+    from forte2_b200.ci_sigma_builder import csf_hamiltonian, csf_matrix_element
+    assert b.slater_rules_csf(None, a, 0, a.ncsf - 1) == csf_matrix_element(strings, E, H, V, a, 0, a.ncsf - 1)
+    assert b.energy_csf(None, a, 0) == csf_matrix_element(strings, E, H, V, a, 0, 0)
+    if a.ncsf <= 400:
+        Hc = b.form_H_csf(None, a)
+        assert np.array_equal(Hc, csf_hamiltonian(strings, E, H, V, a))
+        assert np.max(np.abs(np.diag(Hc) - hx.cpu().numpy())) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
+        b.set_memory(0)
+        with pytest.raises(RuntimeError, match="Not enough memory"):
+            b.form_H_csf(None, a)
     with pytest.raises(ValueError):
         a.csf_C_to_det_C(torch.zeros(a.ncsf + 1, dtype=torch.float64, device="cuda"), d_det)
 
