@@ -401,28 +401,7 @@ __global__ void __launch_bounds__((TAIL ? 256 : (KS <= 24 ? 384 : 320)), 1) t3_k
 }
 
 // ---------------------------------------------------------------------------------------------
-// Opposite-spin term, warp-specialised (v4).  Same algebra and work item as t3_kernel, different
-// schedule: the tensor pipe never waits for address arithmetic.
-//   warps 0..7   MMA: A fragments (signed integral columns of Ia) in registers, B fragments from the
-//                staged C rows, accumulators (16 rows x 32 columns per half tile) stored to a
-//                double-buffered G tile in shared memory.  Nothing else.
-//   warps 8..11  emit: read G row-wise (lane = column), look the replacement target up in the beta
-//                table (coalesced), RED into sigma[Ia, :]; the folded alpha same-spin rows are added
-//                with fully coalesced REDs.  Warp 8 is also the producer: one cp.async.bulk (TMA
-//                1-D bulk copy, mbarrier complete_tx) per gathered C row and tile.
-// Register file: launched with 384 threads, then setmaxnreg gives the MMA warpgroups 216 registers
-// and leaves 72 to the aux warpgroup.
-constexpr int V4_MMA_WARPS = 8;
-constexpr int V4_THREADS = (V4_MMA_WARPS + 4) * 32;
-constexpr int V4_ROWS = V4_MMA_WARPS * 16 + 8; // accumulator rows incl. the tail strip
-constexpr int GS = 40;                         // G row stride in doubles (conflict-free 16-byte stores)
-constexpr int V4_RPW = V4_ROWS / 4;            // rows per emit warp
-
-constexpr size_t t3v4_smem_bytes(int ks, int ns, int nclsB) {
-    return size_t(ns) * ks * 4 * TB * 8 + 2 * size_t(V4_ROWS) * GS * 8 + size_t(ks) * 4 * (8 + 8 + 4) +
-           size_t(nclsB) * 8 + size_t(V4_ROWS) * (8 + 8) + 16 * 8 + 64;
-}
-
+// mbarrier / TMA bulk-copy helpers (t3g_kernel)
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
     return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
@@ -456,303 +435,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 }
 
-template <int KS, bool TAIL>
-__global__ void __launch_bounds__(V4_THREADS, 1) t3v4_kernel(const T3Params p, const int NS) {
-    constexpr int KP = KS * 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    double* Bs = reinterpret_cast<double*>(smem_raw);
-    double* Gs = Bs + NS * KP * TB; // [2][V4_ROWS][GS]
-    long long* ksrc = reinterpret_cast<long long*>(Gs + 2 * V4_ROWS * GS);
-    long long* krow = ksrc + KP;
-    long long* rowbase = krow + KP;
-    long long* frow = rowbase + p.nclsB; // [V4_ROWS] sigma offset of the folded alpha row, -1 if none
-    double* fhalf = reinterpret_cast<double*>(frow + V4_ROWS);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fhalf + V4_ROWS);
-    unsigned long long* full = bars;       // [NS <= 4]  B stage landed
-    unsigned long long* gfull = bars + 4;  // [2]        G buffer written by the 8 MMA warps
-    unsigned long long* gempty = bars + 6; // [2]        G buffer drained by the 4 emit warps
-    unsigned* kinfo = reinterpret_cast<unsigned*>(bars + 16);
-    __shared__ int s_Kn;
-
-    const uint32_t Ia = p.items[2 * blockIdx.x];
-    const int cBp = p.items[2 * blockIdx.x + 1] & 0xffff;
-    const int cA = p.a_cls[Ia];
-    const uint32_t ia = p.a_loc[Ia];
-    const int nBp = p.nB_cls[cBp];
-
-    if (warp == 0) {
-        const int e0 = p.as_ptr[Ia], e1 = p.as_ptr[Ia + 1];
-        int cnt = 0;
-        for (int base = e0; base < e1; base += 32) {
-            const int e = base + lane;
-            bool ok = false;
-            long long src = -1, dst = -1;
-            unsigned info = 0;
-            if (e < e1) {
-                const uint64_t ent = p.as_ent[e];
-                const uint32_t Ja = static_cast<uint32_t>(ent);
-                const int cJ = p.a_cls[Ja];
-                const long long off = p.blk_off[cJ * p.nclsB + cBp];
-                if (off >= 0) {
-                    ok = true;
-                    src = off + static_cast<long long>(p.a_loc[Ja]) * nBp;
-                    const long long so = p.sblk_off[cJ * p.nclsB + cBp];
-                    dst = so >= 0 ? so + (static_cast<long long>(p.a_loc[Ja]) - p.srow0[cJ]) * nBp : -1;
-                    info = static_cast<unsigned>((ent >> 32) & 0xffff) |
-                           (static_cast<unsigned>((ent >> 48) & 1) << 31);
-                }
-            }
-            const unsigned mask = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-                ksrc[pos] = src;
-                krow[pos] = dst;
-                kinfo[pos] = info;
-            }
-            cnt += __popc(mask);
-        }
-        for (int r = cnt + lane; r < KP; r += 32) {
-            ksrc[r] = -1;
-            krow[r] = -1;
-            kinfo[r] = 0;
-        }
-        if (lane == 0)
-            s_Kn = cnt;
-    }
-    for (int c = tid; c < p.nclsB; c += V4_THREADS) {
-        const long long off = p.sblk_off[cA * p.nclsB + c];
-        rowbase[c] = off >= 0 ? off + static_cast<long long>(ia - p.srow0[cA]) * p.nB_cls[c] : -1;
-    }
-    for (int i = tid; i < V4_ROWS; i += V4_THREADS) {
-        frow[i] = -1;
-        fhalf[i] = 0.0;
-    }
-    if (tid == 0) {
-        for (int s = 0; s < 4; ++s)
-            mbar_init(full + s, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(gfull + s, V4_MMA_WARPS);
-            mbar_init(gempty + s, 4);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int Kn = s_Kn;
-    if (Kn == 0)
-        return;
-    // rows of the staged tiles that no copy ever writes multiply zero A fragments: they must be finite
-    for (int i = tid; i < NS * (KP - Kn) * TB; i += V4_THREADS) {
-        const int st = i / ((KP - Kn) * TB), rem = i - st * (KP - Kn) * TB;
-        Bs[(st * KP + Kn) * TB + rem] = 0.0;
-    }
-    if (p.fold) {
-        // <Ia|E_kl|Ja_r> = s_r  <=>  E_lk Ia = s_r Ja_r : row m(l,k) of the accumulators goes to row Ja_r
-        for (int r = tid; r < Kn; r += V4_THREADS) {
-            const int kl = kinfo[r] & 0xffff;
-            const int k = kl / p.norb, l = kl - k * p.norb;
-            const int m = static_cast<int>(p.rowmap[l * p.norb + k]);
-            if (m < V4_ROWS && krow[r] >= 0) {
-                frow[m] = krow[r];
-                fhalf[m] = (kinfo[r] >> 31) ? -0.5 : 0.5;
-            }
-        }
-    }
-    // make the generic-proxy writes above visible to the async proxy (bulk copies land in Bs)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    const int ntiles = (nBp + NT - 1) / NT;
-
-    if (warp < V4_MMA_WARPS) {
-        // ------------------------------------------------------------------ MMA warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        const int m0 = warp * 16;
-        const int mt = V4_MMA_WARPS * 16 + g;
-        const int ldv = p.norb * p.norb;
-        const int nks = (Kn + 3) >> 2;
-        double a[KS][2];
-        double at[TAIL ? KS : 1];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            a[ks][0] = 0.0;
-            a[ks][1] = 0.0;
-            if constexpr (TAIL)
-                at[ks] = 0.0;
-            const int r = 4 * ks + t;
-            if (r < Kn) {
-                const unsigned info = kinfo[r];
-                const double sg = (info >> 31) ? -1.0 : 1.0;
-                const int kl = info & 0xffff;
-                const bool diag = p.fold && (kl / p.norb == kl % p.norb);
-                if (m0 + g < p.M)
-                    a[ks][0] = sg * p.Vx[static_cast<size_t>(m0 + g) * ldv + kl] + (diag ? p.kk2[m0 + g] : 0.0);
-                if (m0 + g + 8 < p.M)
-                    a[ks][1] =
-                        sg * p.Vx[static_cast<size_t>(m0 + g + 8) * ldv + kl] + (diag ? p.kk2[m0 + g + 8] : 0.0);
-                if constexpr (TAIL)
-                    if (mt < p.M)
-                        at[ks] = sg * p.Vx[static_cast<size_t>(mt) * ldv + kl] + (diag ? p.kk2[mt] : 0.0);
-            }
-        }
-        const bool warp_has_rows = m0 < p.M;
-        int stage = 0;
-        unsigned fphase = 0, gph0 = 0, gph1 = 0;
-        int gb = 0;
-        for (int tile = 0; tile < ntiles; ++tile) {
-            mbar_wait(full + stage, fphase);
-            const double* Bst = Bs + stage * KP * TB;
-#pragma unroll 1
-            for (int nh = 0; nh < 2; ++nh) {
-                double acc[NT / 16][4];
-#pragma unroll
-                for (int nt = 0; nt < NT / 16; ++nt)
-                    acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0;
-                const double* bp = Bst + t * TB + nh * (NT / 2) + g;
-                if (warp_has_rows) {
-                    double bc[NT / 16], bn[NT / 16];
-#pragma unroll
-                    for (int nt = 0; nt < NT / 16; ++nt)
-                        bc[nt] = bp[nt * 8];
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        if (ks < nks) {
-                            if (ks + 1 < nks) {
-#pragma unroll
-                                for (int nt = 0; nt < NT / 16; ++nt)
-                                    bn[nt] = bp[(4 * (ks + 1)) * TB + nt * 8];
-                            }
-#pragma unroll
-                            for (int nt = 0; nt < NT / 16; ++nt)
-                                dmma_16x8x4(acc[nt], a[ks][0], a[ks][1], bc[nt]);
-#pragma unroll
-                            for (int nt = 0; nt < NT / 16; ++nt)
-                                bc[nt] = bn[nt];
-                        }
-                    }
-                }
-                double acct[2] = {0.0, 0.0};
-                const int cw = (warp & 3) * 8; // this warp's tail strip inside the half tile
-                if constexpr (TAIL) {
-                    if ((warp >> 2) == nh) {
-#pragma unroll
-                        for (int ks = 0; ks < KS; ++ks)
-                            if (ks < nks)
-                                dmma_8x8x4(acct, at[ks], Bst[(4 * ks + t) * TB + nh * (NT / 2) + cw + g]);
-                    }
-                }
-                // hand the accumulators to the emit warps
-                mbar_wait(gempty + gb, (gb ? gph1 : gph0) ^ 1u);
-                double* G = Gs + gb * V4_ROWS * GS;
-#pragma unroll
-                for (int nt = 0; nt < NT / 16; ++nt) {
-                    *reinterpret_cast<double2*>(G + (m0 + g) * GS + nt * 8 + 2 * t) =
-                        make_double2(acc[nt][0], acc[nt][1]);
-                    *reinterpret_cast<double2*>(G + (m0 + g + 8) * GS + nt * 8 + 2 * t) =
-                        make_double2(acc[nt][2], acc[nt][3]);
-                }
-                if constexpr (TAIL) {
-                    if ((warp >> 2) == nh)
-                        *reinterpret_cast<double2*>(G + mt * GS + cw + 2 * t) = make_double2(acct[0], acct[1]);
-                }
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(gfull + gb);
-                if (gb)
-                    gph1 ^= 1u;
-                else
-                    gph0 ^= 1u;
-                gb ^= 1;
-            }
-            if (++stage == NS) {
-                stage = 0;
-                fphase ^= 1u;
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ emit warps (+ producer)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        const int ew = warp - V4_MMA_WARPS;
-        auto issue_tile = [&](int tile) { // warp-collective, emit warp 0 only
-            if (tile >= ntiles)
-                return;
-            const int st = tile % NS;
-            const int j0 = tile * NT;
-            const int cols = nBp - j0 < NT ? nBp - j0 : NT;
-            const unsigned bytes = static_cast<unsigned>(cols) * 8u;
-            if (lane == 0)
-                mbar_expect_tx(full + st, bytes * static_cast<unsigned>(Kn));
-            __syncwarp();
-            double* dst = Bs + st * KP * TB;
-            for (int r = lane; r < Kn; r += 32)
-                bulk_g2s(dst + r * TB, p.C + ksrc[r] + j0, bytes, full + st);
-        };
-        if (ew == 0)
-            for (int s = 0; s < NS - 1; ++s)
-                issue_tile(s);
-        // rows of this warp: ew, ew + 4, ...; per row the table row and the folded destination
-        const uint32_t* tbase = p.tgt + p.b_off[cBp];
-        const bool oneb = p.nclsB == 1;
-        double* const srow = p.sigma + (rowbase[0] >= 0 ? rowbase[0] : 0);
-        unsigned gph0 = 0, gph1 = 0;
-        int gb = 0;
-        for (int tile = 0; tile < ntiles; ++tile) {
-            const int j0 = tile * NT;
-#pragma unroll 1
-            for (int nh = 0; nh < 2; ++nh) {
-                const int col = j0 + nh * (NT / 2) + lane;
-                const bool cok = col < nBp;
-                // replacement targets of this half tile: independent of G, fetched before the wait
-                uint32_t xs[V4_RPW];
-#pragma unroll
-                for (int i = 0; i < V4_RPW; ++i) {
-                    const int m = ew + 4 * i;
-                    xs[i] = (cok && m < p.M) ? __ldg(tbase + static_cast<size_t>(m) * p.nbs + col) : kNoTarget;
-                }
-                mbar_wait(gfull + gb, gb ? gph1 : gph0);
-                if (ew == 0 && nh == 0)
-                    issue_tile(tile + NS - 1); // every MMA warp has finished tile - 1: its stage is free
-                const double* G = Gs + gb * V4_ROWS * GS;
-#pragma unroll
-                for (int i = 0; i < V4_RPW; ++i) {
-                    const int m = ew + 4 * i;
-                    const double v = G[m * GS + lane];
-                    const uint32_t x = xs[i];
-                    if (oneb) {
-                        asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 u, lo, hi;\n\t.reg .b64 a;\n\t.reg .f64 sv;\n\t"
-                                     "setp.ne.u32 q, %2, 0xffffffff;\n\t"
-                                     "and.b32 u, %2, 0xfffff;\n\t"
-                                     "mad.wide.u32 a, u, 8, %0;\n\t"
-                                     "mov.b64 {lo, hi}, %1;\n\t"
-                                     "and.b32 u, %2, 0x80000000;\n\t"
-                                     "xor.b32 hi, hi, u;\n\t"
-                                     "mov.b64 sv, {lo, hi};\n\t"
-                                     "@q red.global.add.f64 [a], sv;\n\t}" ::"l"(srow),
-                                     "d"(v), "r"(x)
-                                     : "memory");
-                    } else if (x != kNoTarget) {
-                        const long long base = rowbase[(x >> 20) & 0x7ff];
-                        if (base >= 0)
-                            atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -v : v);
-                    }
-                    if (p.fold) {
-                        const long long fr = frow[m];
-                        if (fr >= 0 && cok)
-                            atomicAdd(p.sigma + fr + col, fhalf[m] * v);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(gempty + gb);
-                if (gb)
-                    gph1 ^= 1u;
-                else
-                    gph0 ^= 1u;
-                gb ^= 1;
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Opposite-spin term, gather form (t3g_kernel): one CTA per INPUT alpha string Ja.

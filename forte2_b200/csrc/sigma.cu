@@ -219,9 +219,6 @@ struct f2_sigma {
     int gm_mpad = 0, gm_nt16 = 0, gm_astride = 0;
     int64_t gm_gld = 0;
     size_t gm_smem = 0;
-    bool t3_v4 = false;    // warp-specialised opposite-spin kernel (t3v4_kernel) is applicable
-    int t3_v4_ns = 3;
-    size_t t3_v4_smem = 0;
     bool t3_tail = false;  // last <= 8 integral rows spread over the warps
     bool fold_ok = false;  // alpha same-spin term can ride in the opposite-spin kernel (one GPU)
     DevBuf<double> kk2, Wfold; // 2 kk_ij / na per integral row; beta W with h - 2 kk folded
@@ -667,19 +664,6 @@ void plan_t3_shape(f2_sigma& b) {
                         crow[(A.cls_off[cA] + i) * nclsB + cB] = static_cast<uint32_t>(blk.offset + i * blk.nB);
                 }
             b.gm_crow.upload(crow);
-        }
-    }
-    // warp-specialised kernel: 8 MMA warps cover up to 128 rows (+ the 8-row tail strip), even layout
-    b.t3_v4 = false;
-    if (b.D->al16 && b.M >= 33 && b.M <= V4_ROWS && std::getenv("F2_V4") != nullptr) {
-        for (int ns : {3, 2}) {
-            const size_t need = t3v4_smem_bytes(b.t3_ks, ns, static_cast<int>(nclsB));
-            if (need <= 227 * 1024) {
-                b.t3_v4 = true;
-                b.t3_v4_ns = ns;
-                b.t3_v4_smem = need;
-                break;
-            }
         }
     }
 }
@@ -1133,24 +1117,8 @@ void launch_t3_al(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t
         launch_t3_inst<KS, AL16, 2, false>(b, p, nitems, st);
 }
 
-template <int KS, bool TAIL>
-void launch_t3v4_inst(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
-    F2_CUDA(cudaFuncSetAttribute(t3v4_kernel<KS, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(b.t3_v4_smem)));
-    t3v4_kernel<KS, TAIL><<<nitems, V4_THREADS, b.t3_v4_smem, st>>>(p, b.t3_v4_ns);
-    b.launches += 1;
-}
-
 template <int KS>
 void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t st) {
-    // the bulk copies of the warp-specialised kernel need 16-byte aligned rows of C
-    if (b.t3_v4 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
-        if (b.M > V4_MMA_WARPS * 16)
-            launch_t3v4_inst<KS, true>(b, p, nitems, st);
-        else
-            launch_t3v4_inst<KS, false>(b, p, nitems, st);
-        return;
-    }
     if (b.D->al16 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0)
         launch_t3_al<KS, true>(b, p, nitems, st);
     else
@@ -1934,8 +1902,7 @@ int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
         out5[4] = h->compressed ? 1 : 0;
         return F2_OK;
     }
-    out5[1] = h->t3_v4 ? (h->M > V4_MMA_WARPS * 16 ? V4_ROWS : V4_MMA_WARPS * 16)
-                        : (static_cast<int64_t>(h->t3_warps) * 16 + (h->t3_tail ? 8 : 0)) * h->t3_msplit;
+    out5[1] = (static_cast<int64_t>(h->t3_warps) * 16 + (h->t3_tail ? 8 : 0)) * h->t3_msplit;
     out5[2] = h->S->host->device_lists().as_max;
     out5[3] = h->single ? h->single->t3_kcols : 0;
     out5[4] = h->compressed ? 1 : 0;
