@@ -9,8 +9,9 @@ iterated Gram-Schmidt with the reference's thresholds), but
   reference keeps `(size, max_subspace)` numpy arrays whose columns are strided,
   davidsonliu.py:75-83), so the sigma builder receives contiguous device vectors;
 * every O(size) step is one streaming CUDA kernel of the C ABI (`f2_dl_dots`, `f2_dl_combine`,
-  `f2_dl_residual`, `f2_dl_scale`; forte2_b200/csrc/davidson.cu); only the (<= 16 x 16) subspace
-  problem is solved on the host;
+  `f2_dl_residual`, `f2_dl_scale`; forte2_b200/csrc/davidson.cu); only the small subspace problem is
+  solved on the host.  A kernel call takes at most 16 vectors per side; larger subspaces (many roots, e.g.
+  the reference's own solver tests with 10 roots x 5 vectors) are cut into 16 x 16 pieces by `_ChunkedOps`;
 * with `comm` (a torch.distributed process group) the vectors are the rank's row slab of the CI
   vector and the small reductions are all-reduced.
 
@@ -46,7 +47,80 @@ class DavidsonLiuParams:
                              f"equal to collapse_per_root + 1 ({self.collapse_per_root + 1}).")
 
 
-class _Kernels:
+class _ChunkedOps:
+    """combine / residual for any number of vectors on top of primitives that take at most 16 per side
+    (`_combine16`, `_residual16`: one launch of f2_dl_combine / f2_dl_residual).  With at most 16 subspace
+    vectors -- every large CI space: the subspace is what fills the GPU -- a call is one primitive call; beyond
+    that (many roots on a small space, e.g. the reference's own solver tests with 10 roots x 5 vectors) the
+    work is cut into 16 x 16 pieces, through temporaries where an output row aliases an input row."""
+
+    MAXV = 16
+
+    @staticmethod
+    def _overlap(A, Y):
+        a0, y0 = A.data_ptr(), Y.data_ptr()
+        a1 = a0 + 8 * ((A.shape[0] - 1) * A.stride(0) + A.shape[1])
+        y1 = y0 + 8 * ((Y.shape[0] - 1) * Y.stride(0) + Y.shape[1])
+        return a0 < y1 and y0 < a1
+
+    def combine(self, A, coef, Y, beta=0.0, want_sumsq=False):
+        """Y_j = beta Y_j + sum_i coef[i, j] A_i; rows of Y may alias rows of A. Returns |Y_j|^2 or None."""
+        M = self.MAXV
+        k = Y.shape[0]
+        p = 0 if A is None else A.shape[0]
+        if p <= M and k <= M:
+            return self._combine16(A, coef, Y, beta, want_sumsq)
+        coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(p, k)
+        if k <= M and not self._overlap(A, Y):
+            out = None
+            for i0 in range(0, p, M):
+                i1 = min(p, i0 + M)
+                out = self._combine16(A[i0:i1], coef[i0:i1], Y, beta if i0 == 0 else 1.0,
+                                      want_sumsq and i1 == p)
+            return out
+        T = Y.new_empty((k, Y.shape[1]))
+        sums = []
+        for j0 in range(0, k, M):
+            j1 = min(k, j0 + M)
+            for i0 in range(0, p, M):
+                i1 = min(p, i0 + M)
+                self._combine16(A[i0:i1], coef[i0:i1, j0:j1], T[j0:j1], 0.0 if i0 == 0 else 1.0, False)
+        for j0 in range(0, k, M):  # every input row has been read: the outputs may now be written
+            j1 = min(k, j0 + M)
+            ss = self._combine16(T[j0:j1], np.eye(j1 - j0), Y[j0:j1], beta, want_sumsq)
+            if want_sumsq:
+                sums.append(ss)
+        return np.concatenate(sums) if want_sumsq else None
+
+    def residual(self, B, S, alpha, lam, hdiag, R, thresh):
+        """R_j = preconditioned residual of Ritz pair j = sum_i alpha[i, j] (S_i - lam_j B_i); returns the squared
+        norms of the residuals before preconditioning."""
+        M = self.MAXV
+        m, k = B.shape[0], R.shape[0]
+        if m <= M and k <= M:
+            return self._residual16(B, S, alpha, lam, hdiag, R, thresh)
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(m, k)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(k)
+        out = np.zeros(k)
+        if m <= M:
+            for j0 in range(0, k, M):
+                j1 = min(k, j0 + M)
+                out[j0:j1] = self._residual16(B, S, alpha[:, j0:j1], lam[j0:j1], hdiag, R[j0:j1], thresh)
+            return out
+        # more than 16 basis vectors: Ritz vector and its sigma first, then the one-vector form of the kernel
+        for j0 in range(0, k, M):
+            j1 = min(k, j0 + M)
+            X = R.new_empty((j1 - j0, R.shape[1]))
+            SX = R.new_empty((j1 - j0, R.shape[1]))
+            self.combine(B, alpha[:, j0:j1], X)
+            self.combine(S, alpha[:, j0:j1], SX)
+            for j in range(j0, j1):
+                out[j] = self._residual16(X[j - j0:j - j0 + 1], SX[j - j0:j - j0 + 1], np.ones((1, 1)),
+                                          lam[j:j + 1], hdiag, R[j:j + 1], thresh)[0]
+        return out
+
+
+class _Kernels(_ChunkedOps):
     """Thin typed wrappers over the f2_dl_* entry points for row-major (nvec, size) CUDA tensors."""
 
     def __init__(self, torch, device, comm=None):
@@ -87,8 +161,8 @@ class _Kernels:
                 out[i0:i0 + pc, j0:j0 + qc] = self._reduce(res).reshape(pc, qc)
         return out
 
-    def combine(self, A, coef, Y, beta=0.0, want_sumsq=False):
-        """Y_j = beta Y_j + sum_i coef[i, j] A_i; rows of Y may alias rows of A. Returns |Y_j|^2 or None."""
+    def _combine16(self, A, coef, Y, beta=0.0, want_sumsq=False):
+        """one f2_dl_combine launch (at most 16 input and 16 output rows; outputs may alias inputs)"""
         yp, ldy, k, n = self._rows(Y)
         if A is None or A.shape[0] == 0:
             ap, lda, p = yp, ldy, 0
@@ -105,7 +179,8 @@ class _Kernels:
         self.launches += 2 if want_sumsq else 1
         return self._reduce(ss) if want_sumsq else None
 
-    def residual(self, B, S, alpha, lam, hdiag, R, thresh):
+    def _residual16(self, B, S, alpha, lam, hdiag, R, thresh):
+        """one f2_dl_residual launch (at most 16 basis vectors and 16 roots)"""
         bp, ld, m, n = self._rows(B)
         sp, lds, m2, _ = self._rows(S)
         rp, ldr, k, _ = self._rows(R)
@@ -148,9 +223,6 @@ class DavidsonLiuSolver:
             raise ValueError("Davidson-Liu solver called with zero roots.")
         self.collapse_size = min(self.collapse_per_root * self.nroot, self.global_size)
         self.max_subspace_size = min(self.basis_per_root * self.nroot, self.global_size)
-        if self.max_subspace_size > 16:
-            raise ValueError("the device Davidson-Liu solver holds at most 16 subspace vectors "
-                             f"(basis_per_root * nroot = {self.max_subspace_size})")
         # _kernels: test hook (tests/ inject a host stand-in for the four streaming kernels to exercise the
         # iteration logic without a GPU); the product path below has no CPU fallback
         if _kernels is None:

@@ -43,3 +43,28 @@ class HostKernels:
 
     def scale(self, v, s):
         v.mul_(s)
+
+
+
+from forte2_b200.davidson import _ChunkedOps  # noqa: E402
+
+
+class HostKernels16(_ChunkedOps, HostKernels):
+    """The same stand-in behind the product's chunking layer (forte2_b200.davidson._ChunkedOps): the
+    primitives refuse more than 16 vectors per side, exactly like f2_dl_combine / f2_dl_residual, so a solve with
+    a larger subspace exercises the 16 x 16 decomposition the GPU path uses."""
+
+    def _combine16(self, A, coef, Y, beta=0.0, want_sumsq=False):
+        assert (A is None or A.shape[0] <= 16) and Y.shape[0] <= 16
+        return HostKernels.combine(self, A, coef, Y, beta, want_sumsq)
+
+    def _residual16(self, B, S, alpha, lam, hdiag, R, thresh):
+        assert B.shape[0] <= 16 and R.shape[0] <= 16 and (B.shape[0] == 1 or B.stride(0) == S.stride(0))
+        return HostKernels.residual(self, B, S, alpha, lam, hdiag, R, thresh)
+
+    def dots(self, A, X):
+        out = np.zeros((A.shape[0], X.shape[0]))
+        for i0 in range(0, A.shape[0], 16):
+            for j0 in range(0, X.shape[0], 16):
+                out[i0:i0 + 16, j0:j0 + 16] = HostKernels.dots(self, A[i0:i0 + 16], X[j0:j0 + 16])
+        return out

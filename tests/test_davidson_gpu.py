@@ -70,7 +70,7 @@ def test_streaming_kernels_match_torch(torch_cuda, n):
     assert torch.allclose(v, -2.5 * B[0])
 
 
-@pytest.mark.parametrize("nroot", [1, 3, 4])
+@pytest.mark.parametrize("nroot", [1, 3, 4, 6])  # 6 roots: 24 subspace vectors, the 16 x 16 chunked calls
 def test_solver_matches_eigh_on_dense_matrix(torch_cuda, nroot):
     torch = torch_cuda
     from forte2_b200.davidson import DavidsonLiuSolver
