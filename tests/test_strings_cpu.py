@@ -143,3 +143,60 @@ def test_shard_layout_index_maps():
                 others = np.setdiff1d(np.arange(strings.ndet), glob)
                 assert np.all(lay.local_of_global(others) == -1)
             assert np.all(seen == 1)
+
+
+@pytest.mark.parametrize("name,world", [("gas343_54", 8), ("cas66_d2h", 5), ("gas2_sym4", 8), ("cas66", 7),
+                                        ("one_beta_three_alpha", 4)])
+def test_rows_form_exchange_plans_are_consistent(name, world):
+    """forte2_b200.dist.ShardedSigma._cols_plan / _exchange_plan for many ranks and classes smaller than the
+    world (ranks that own no row or no column of a block): what rank r packs for q is exactly what q expects from
+    r, and replaying the all-to-all in one process assembles the column slabs of a known vector and returns the
+    alpha same-spin partials to the row owners."""
+    import torch
+    from forte2_b200.dist import ShardedSigma
+
+    from forte2_b200.dist import Layout
+
+    strings = f2.CIStrings(*SMALL_SPACES[name])
+    blocks = strings.blocks()
+    slot = max(Layout(blocks, q, world).local_size for q in range(world))
+
+    class NoEngine:  # the plans need the layout only
+        def rows_form(self, rank, world):
+            return True, slot
+
+    full = torch.arange(strings.ndet, dtype=torch.float64) + 1.0
+    ranks = [ShardedSigma(rank=r, world=world, engine=NoEngine(), blocks=blocks, device=torch.device("cpu"),
+                          form="rows") for r in range(world)]
+    assert sum(sh.local_size for sh in ranks) == strings.ndet
+    local = [sh.scatter_full(full) for sh in ranks]
+    # ---- step 1 of the rows form: column slabs
+    for q, shq in enumerate(ranks):
+        shq._xcols.fill_(float("nan"))
+    for r, shr in enumerate(ranks):
+        for q, (sends, _, _, _) in enumerate(shr._cols_plan()):
+            pieces = [local[r][loc:loc + n * nB].view(n, nB)[:, cl:cl + nc].reshape(-1) for loc, n, nB, cl, nc in sends]
+            packed = torch.cat(pieces) if pieces else torch.zeros(0, dtype=torch.float64)
+            recvs = ranks[q]._cols_plan()[r][1]
+            assert packed.numel() == sum(m for _, m in recvs), (r, q)
+            pos = 0
+            for start, m in recvs:
+                ranks[q]._xcols[start:start + m] = packed[pos:pos + m]
+                pos += m
+    for q, shq in enumerate(ranks):
+        for (off, nA, nB), (cl, nc, yoff) in zip(shq.layout.blocks, shq.layout.cols):
+            if nA * nB > 0:
+                want = full[off:off + nA * nB].view(nA, nB)[:, cl:cl + nc].reshape(-1)
+                assert torch.equal(shq._xcols[yoff:yoff + nA * nc], want), (name, q)
+    # ---- step 3: the partials [all rows][my columns] go back to the row owners and are added
+    got = [torch.zeros(sh.local_size, dtype=torch.float64) for sh in ranks]
+    for r, shr in enumerate(ranks):
+        shr._yexch = shr._xcols.clone()  # pretend the alpha same-spin operator is the identity
+        for q, (send_slices, _, _, _) in enumerate(shr._exchange_plan()):
+            packed = torch.cat([shr._yexch[lo:hi] for lo, hi in send_slices]) if send_slices else torch.zeros(0)
+            adds = ranks[q]._exchange_plan()[r][3]
+            assert packed.numel() == sum(n * nc for _, n, _, _, nc, _ in adds), (r, q)
+            for loc, n, nB, cl, nc, pos in adds:
+                got[q][loc:loc + n * nB].view(n, nB)[:, cl:cl + nc] += packed[pos:pos + n * nc].view(n, nc)
+    for q in range(world):
+        assert torch.equal(got[q], local[q]), (name, q)
