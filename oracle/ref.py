@@ -77,6 +77,8 @@ def lib():
         L.ref_adapter_table.restype = i64
         L.ref_adapter_table.argtypes = [vp, i64p, i64p, dp, i64]
         L.ref_hdiag_csf.argtypes = [vp, vp, i, dp]
+        L.ref_rdm.restype = i64
+        L.ref_rdm.argtypes = [vp, i, dp, dp, i64, dp, i64]
         L.ref_form_H_csf.restype = i
         L.ref_form_H_csf.argtypes = [vp, vp, dp]
         L.ref_slater_rules_csf.restype = C.c_double
@@ -180,6 +182,29 @@ class RefCISigmaBuilder:
 
     def get_algorithm(self):
         return lib().ref_sigma_get_algorithm(self._h).decode()
+
+    RDM_KINDS = {"a_1rdm": 0, "b_1rdm": 1, "sf_1rdm": 2, "aa_2rdm": 3, "bb_2rdm": 4, "ab_2rdm": 5, "sf_2rdm": 6,
+                 "sf_2cumulant": 7}
+
+    def rdm(self, kind, c_left, c_right):
+        """CISigmaBuilder::compute_<kind> (ci_sigma_builder_1rdm.cc, ci_sigma_builder_2rdm.cc), shaped as the
+        reference returns it: (n, n), (npairs, npairs) for aa/bb (p > q) or (n, n, n, n)."""
+        k = self.RDM_KINDS[kind]
+        cl = np.ascontiguousarray(c_left, dtype=np.float64)
+        cr = np.ascontiguousarray(c_right, dtype=np.float64)
+        n = lib().ref_rdm(self._h, k, _dp(cl), _dp(cr), cl.shape[0], None, 0)
+        if n < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        out = np.zeros(max(n, 1))
+        lib().ref_rdm(self._h, k, _dp(cl), _dp(cr), cl.shape[0], _dp(out), n)
+        out = out[:n]
+        norb = self.strings.norb
+        if k <= 2:
+            return out.reshape(norb, norb)
+        if k <= 4:
+            m = int(round(np.sqrt(n)))
+            return out.reshape(m, m)
+        return out.reshape(norb, norb, norb, norb)
 
     def set_memory(self, mb):
         _check(lib().ref_sigma_set_memory(self._h, int(mb)))

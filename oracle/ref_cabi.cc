@@ -468,5 +468,34 @@ double ref_slater_rules_csf(void* hsig, void* hadapter, int64_t I, int64_t J) {
     auto* a = static_cast<RefAdapter*>(hadapter);
     return r->b->slater_rules_csf(a->dets, *a->a, static_cast<size_t>(I), static_cast<size_t>(J));
 }
+// Reduced density matrices (forte2/ci/ci_sigma_builder_1rdm.cc:9-84, ci_sigma_builder_2rdm.cc:45-282): the
+// checker of the next widening step.  kind: 0 a_1rdm, 1 b_1rdm, 2 sf_1rdm (n x n);
+// 3 aa_2rdm, 4 bb_2rdm (npairs x npairs, p > q); 5 ab_2rdm, 6 sf_2rdm, 7 sf_2cumulant (n^4).  Returns the number
+// of doubles written (or needed when out is NULL), -1 when the reference throws.
+int64_t ref_rdm(void* hsig, int kind, double* Cl, double* Cr, int64_t n, double* out, int64_t cap) {
+    auto* r = static_cast<RefSigma*>(hsig);
+    try {
+        auto L = wrap_vec(Cl, n), R = wrap_vec(Cr, n);
+        auto put = [&](const double* src, size_t count) -> int64_t {
+            if (out && static_cast<int64_t>(count) <= cap)
+                std::memcpy(out, src, count * sizeof(double));
+            return static_cast<int64_t>(count);
+        };
+        switch (kind) {
+        case 0: { auto m = r->b->compute_a_1rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 1: { auto m = r->b->compute_b_1rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 2: { auto m = r->b->compute_sf_1rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 3: { auto m = r->b->compute_aa_2rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 4: { auto m = r->b->compute_bb_2rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 5: { auto t = r->b->compute_ab_2rdm(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
+        case 6: { auto t = r->b->compute_sf_2rdm(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
+        case 7: { auto t = r->b->compute_sf_2cumulant(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
+        default: g_err = "ref_rdm: unknown kind"; return -1;
+        }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 
 } // extern "C"

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from cases import SMALL_SPACES
+import forte2_b200 as f2
 from forte2_b200 import synthetic
 from oracle import checker, strings_port
 
@@ -63,3 +64,43 @@ def test_reference_hz_kh_dense_agree(ref):
     dense = b.dense_hamiltonian() @ c
     assert np.linalg.norm(out["hz"] - out["kh"]) <= 1e-13 * np.linalg.norm(dense)
     assert np.linalg.norm(out["hz"] - dense) <= 1e-13 * np.linalg.norm(dense)
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas21_4", "one_each", "beta_only"])
+def test_rdm_port_matches_live_reference(ref, name):
+    """oracle/rdm_port.py (RDMs from their definitions over the determinant list) against the reference's own
+    compute_*rdm for a transition pair (left != right): the pinned checker of the next widening step
+    (SURVEY.md section 8f, rank 2)."""
+    from oracle import rdm_port
+    space = SMALL_SPACES[name]
+    norb = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(norb, "S")
+    rs = ref.RefCIStrings(*space)
+    rb = ref.RefCISigmaBuilder(rs, E, H, V)
+    dets = f2.CIStrings(*space).make_determinants()
+    rng = np.random.default_rng(11)
+    left, right = rng.normal(size=rs.ndet), rng.normal(size=rs.ndet)
+    left /= np.linalg.norm(left)
+    right /= np.linalg.norm(right)
+    checks = [("a_1rdm", rdm_port.s_1rdm(dets, norb, left, right, 0)),
+              ("b_1rdm", rdm_port.s_1rdm(dets, norb, left, right, 1)),
+              ("sf_1rdm", rdm_port.sf_1rdm(dets, norb, left, right)),
+              ("ab_2rdm", rdm_port.ab_2rdm(dets, norb, left, right))]
+    if norb >= 2:
+        checks += [("aa_2rdm", rdm_port.ss_2rdm(dets, norb, left, right, 0)),
+                   ("bb_2rdm", rdm_port.ss_2rdm(dets, norb, left, right, 1)),
+                   ("sf_2rdm", rdm_port.sf_2rdm(dets, norb, left, right)),
+                   ("sf_2cumulant", rdm_port.sf_2cumulant(dets, norb, left, right))]
+    for kind, got in checks:
+        want = rb.rdm(kind, left, right)
+        assert got.shape == want.shape, kind
+        assert np.max(np.abs(got - want), initial=0.0) <= 1e-13, kind
+    # the energy functional closes the loop with the sigma oracle: E = E0 + h.g1 + 1/2 V.g2 (forte2/ci/ci.py:356-363)
+    c = right
+    sigma = np.zeros_like(c)
+    rb.set_algorithm("hz")  # the reference's KH path is not P H P with several irreps (SURVEY.md section 7.9)
+    rb.Hamiltonian(c, sigma)
+    g1 = rb.rdm("sf_1rdm", c, c)
+    g2 = rb.rdm("sf_2rdm", c, c)
+    energy = E + np.einsum("pq,pq", H, g1) + 0.5 * np.einsum("pqrs,pqrs", V, g2)
+    assert abs(energy - c @ sigma) <= 1e-11
