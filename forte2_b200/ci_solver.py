@@ -36,7 +36,7 @@ class CISolver:
     """One CI state (nroot lowest roots of one determinant space) on one B200.
 
     Parameters follow forte2/ci/ci.py:30-79 where they exist there: `nroot`, `davidson_liu_params`,
-    `ci_algorithm` ("hz" | "kh" ...), `ci_builder_memory` (MB), `energy_shift`, `log_level`.
+    `ci_algorithm` ("hz" | "kh" | "exact" ...), `ci_builder_memory` (MB), `energy_shift`, `log_level`.
 
     With `spin_adapter` (a prepared forte2_b200.CISpinAdapter) the solve runs in the CSF basis exactly as
     forte2's default path does (forte2/ci/ci.py:147-165, 214-235): the Davidson vectors have ncsf elements,
@@ -145,6 +145,33 @@ class CISolver:
         self.executed = True
         return self
 
+    def _do_exact_diagonalization(self, b):
+        """ci_algorithm = "exact" (forte2/ci/ci.py:193-195,305-322; the reference's cross-check of its sigma
+        algorithms, tests/ci/test_ci_exact_diagonalization.py): the dense Hamiltonian of the variational basis --
+        CSFs with a spin adapter (CISigmaBuilder::form_H_csf), determinants without one (rel_ci.py:125-131) -- from
+        host Slater rules, numpy eigh, energy_shift ordering.  Small spaces only: the builder's memory limit
+        applies as in the reference.  Roots come back as rows of a CUDA tensor like those of the iterative solve."""
+        import torch
+        if self.spin_adapter is not None:
+            Hd = b.form_H_csf(None, self.spin_adapter)
+        else:
+            n = self.ci_strings.ndet
+            if n * n * 8 > self.ci_builder_memory * 1024 * 1024:
+                raise RuntimeError("Not enough memory to form the full Hamiltonian matrix in the determinant "
+                                   "basis. Increase the memory limit or use a different algorithm.")
+            Hd = slater_matrix(self.ci_strings, self.E0, self.H, self.V, np.arange(n, dtype=np.int64))
+            Hd = 0.5 * (Hd + Hd.T)
+        evals, evecs = np.linalg.eigh(Hd)
+        if self.energy_shift is not None:
+            order = np.argsort(np.abs(evals - self.energy_shift))
+            evals, evecs = evals[order], evecs[:, order]
+        self.evals_full, self.evecs_full = evals, evecs
+        k = min(self.nroot, evals.size)
+        self.evals = self.E = evals[:k].copy()
+        self.evecs = torch.from_numpy(np.ascontiguousarray(evecs[:, :k].T)).to(f"cuda:{b.device}")
+        self.converged = self.executed = True
+        return self
+
     def run(self):
         import torch
         s = self.ci_strings
@@ -154,6 +181,8 @@ class CISolver:
             self.ci_sigma_builder = CISigmaBuilder(s, self.E0, self.H, self.V, self.log_level, device=self.device)
             self.ci_sigma_builder.set_memory(self.ci_builder_memory)
         b = self.ci_sigma_builder
+        if self.ci_algorithm.lower() == "exact":
+            return self._do_exact_diagonalization(b)
         b.set_algorithm(self.ci_algorithm.lower())
         if self.spin_adapter is not None:
             return self._run_csf(b)
