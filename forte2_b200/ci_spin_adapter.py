@@ -104,10 +104,15 @@ class CISpinAdapter:
             for v in (src, dst):
                 if v.dtype != np.float64 or v.ndim != 1:
                     raise TypeError("vectors must be one-dimensional float64")
-                if v.size > 1 and v.strides[0] != 8:
-                    raise RuntimeError("np_vector must have stride 1 to convert to std::span.")
-            _lib.check(host_fn(self._h, src.ctypes.data_as(_lib.f64p), src.shape[0], dst.ctypes.data_as(_lib.f64p),
-                               dst.shape[0]))
+            # strided views are accepted like in the reference, which reads and writes through .view()
+            # (ci_spin_adapter.cc:69-97): forte2's Davidson closure passes columns of its C-ordered basis,
+            # Bblock[:, i] and Sblock[:, i] (forte2/ci/ci.py:231-233)
+            s = src if src.size <= 1 or src.strides[0] == 8 else np.ascontiguousarray(src)
+            d = dst if dst.size <= 1 or dst.strides[0] == 8 else np.empty(dst.shape[0])
+            _lib.check(host_fn(self._h, s.ctypes.data_as(_lib.f64p), s.shape[0], d.ctypes.data_as(_lib.f64p),
+                               d.shape[0]))
+            if d is not dst:
+                dst[:] = d
             return
         import torch
         if not _is_torch_tensor(src):

@@ -141,6 +141,15 @@ def test_transforms_and_preconditioner_on_gpu(name, twoS):
     to_csf = np.full(a.ncsf, np.nan)
     a.det_C_to_csf_C(g["c_det"], to_csf)
     assert np.max(np.abs(to_csf - g["to_csf"]), initial=0.0) <= 1e-14
+    # columns of a C-ordered (size, m) basis, as forte2's Davidson closure passes them (ci.py:231-233)
+    basis = np.full((a.ncsf, 3), np.nan)
+    basis[:, 1] = g["c_csf"]
+    to_det2 = np.full(strings.ndet, np.nan)
+    a.csf_C_to_det_C(basis[:, 1], to_det2)
+    assert np.array_equal(to_det2, to_det)
+    out = np.full((a.ncsf, 3), np.nan)
+    a.det_C_to_csf_C(g["c_det"], out[:, 2])
+    assert np.array_equal(out[:, 2], to_csf) and np.all(np.isnan(out[:, :2]))
     # device tensors
     d_det = torch.full((strings.ndet,), float("nan"), dtype=torch.float64, device="cuda")
     a.csf_C_to_det_C(torch.from_numpy(g["c_csf"]).cuda(), d_det)
