@@ -175,6 +175,16 @@ def test_transforms_and_preconditioner_on_gpu(name, twoS):
         Hc = b.form_H_csf(None, a)
         assert np.array_equal(Hc, csf_hamiltonian(strings, E, H, V, a))
         assert np.max(np.abs(np.diag(Hc) - hx.cpu().numpy())) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
+        # forte2's sigma closure, verbatim (forte2/ci/ci.py:221-233): numpy vectors, columns of C-ordered blocks
+        rng = np.random.default_rng(5)
+        Bblock = rng.normal(size=(a.ncsf, 2))
+        Sblock = np.full_like(Bblock, np.nan)
+        b_det, sigma_det = np.zeros(strings.ndet), np.zeros(strings.ndet)
+        for i in range(Bblock.shape[1]):
+            a.csf_C_to_det_C(Bblock[:, i], b_det)
+            b.Hamiltonian(b_det, sigma_det)
+            a.det_C_to_csf_C(sigma_det, Sblock[:, i])
+        assert np.max(np.abs(Sblock - Hc @ Bblock)) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
         b.set_memory(0)
         with pytest.raises(RuntimeError, match="Not enough memory"):
             b.form_H_csf(None, a)
