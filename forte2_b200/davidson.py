@@ -70,6 +70,10 @@ class _ChunkedOps:
         p = 0 if A is None else A.shape[0]
         if p <= M and k <= M:
             return self._combine16(A, coef, Y, beta, want_sumsq)
+        if p == 0:  # Y_j = beta Y_j for more than 16 rows
+            sums = [self._combine16(None, np.zeros((1, min(k, j0 + M) - j0)), Y[j0:j0 + M], beta, want_sumsq)
+                    for j0 in range(0, k, M)]
+            return np.concatenate(sums) if want_sumsq else None
         coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(p, k)
         if k <= M and not self._overlap(A, Y):
             out = None

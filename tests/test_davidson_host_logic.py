@@ -84,3 +84,34 @@ def test_same_roots_as_reference_solver():
     assert np.max(np.abs(lam - want)) < 1e-10
     # the first iterations (before any vector is discarded) follow the reference step by step
     assert s.history[0][4] == 9 and abs(s.history[0][1] - np.mean(np.linalg.eigvalsh(A[:6, :6])[:3])) < 1e-12
+
+
+def test_chunked_ops_equal_the_unchunked_ones():
+    """forte2_b200.davidson._ChunkedOps (the layer that cuts combine / residual into the kernels' 16 x 16 calls)
+    against the same operations done in one piece: pure scaling of more than 16 rows, an in-place collapse whose
+    outputs alias its inputs, accumulation into one vector from 40, residuals with more than 16 basis vectors
+    and / or roots."""
+    from host_dl_kernels import HostKernels16
+    k, one = HostKernels16(), HostKernels()
+    rng = np.random.default_rng(0)
+    t = lambda *shape: torch.from_numpy(rng.normal(size=shape))  # noqa: E731
+    Y = t(20, 7)
+    Y0 = Y.clone()
+    ss = k.combine(None, np.zeros((1, 20)), Y, beta=2.0, want_sumsq=True)
+    assert torch.allclose(Y, 2 * Y0) and np.allclose(ss, (Y * Y).sum(1).numpy())
+    A = t(40, 9)
+    A0, c = A.clone(), rng.normal(size=(40, 20))
+    k.combine(A, c, A[:20])  # outputs are the first 20 input rows
+    assert torch.allclose(A[:20], torch.from_numpy(c).T @ A0)
+    y = t(1, 9)
+    y0, c1 = y.clone(), rng.normal(size=(40, 1))
+    ss = k.combine(A0, c1, y, beta=0.5, want_sumsq=True)
+    want = 0.5 * y0 + torch.from_numpy(c1).T @ A0
+    assert torch.allclose(y, want) and np.allclose(ss, (want * want).sum(1).numpy())
+    B, S, hd = t(40, 9), t(40, 9), t(9)
+    al, lam = rng.normal(size=(40, 20)), rng.normal(size=20)
+    for m in (40, 10):
+        R, R1 = torch.zeros(20, 9, dtype=torch.float64), torch.zeros(20, 9, dtype=torch.float64)
+        rn = k.residual(B[:m], S[:m], al[:m], lam, hd, R, 1e-8)
+        rn1 = one.residual(B[:m], S[:m], al[:m], lam, hd, R1, 1e-8)
+        assert torch.allclose(R, R1) and np.allclose(rn, rn1)
