@@ -192,6 +192,77 @@ class CISigmaBuilder:
                                "Increase the memory limit or use a different algorithm.")
         return csf_hamiltonian(self.ci_strings, *self._ints, spin_adapter)
 
+    # ---- reduced density matrices (forte2/api/ci_helpers_api.cc:110-130): device kernels for the spin blocks
+    # (f2_sigma_rdm, csrc/rdm_kernels.cuh), the spin-free combinations assembled on the host like the reference
+    def _rdm(self, kind, C_left, C_right, shape):
+        import torch
+        dev = torch.device("cuda", self.device)
+        ndet = self.ci_strings.ndet
+
+        def vec(x, name):
+            t = x if _is_torch_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+            if not t.is_cuda or t.dtype != torch.float64 or t.dim() != 1 or (t.numel() > 1 and t.stride(0) != 1):
+                raise TypeError(f"{name} must be a one-dimensional contiguous float64 vector")
+            if t.numel() != ndet:
+                raise RuntimeError("Size of CI vector does not match the number of determinants.")
+            return t
+
+        left, right = vec(C_left, "C_left"), vec(C_right, "C_right")
+        count = int(np.prod(shape))
+        if count == 0 or ndet == 0:
+            return np.zeros(shape)
+        out = torch.empty(count, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_rdm(self._h, kind, left.data_ptr(), right.data_ptr(), out.data_ptr(), stream))
+        return out.cpu().numpy().reshape(shape)
+
+    def a_1rdm(self, C_left, C_right) -> np.ndarray:
+        """<L|a+_p a_q|R> for alpha, (norb, norb) (CISigmaBuilder::compute_a_1rdm, ci_sigma_builder_1rdm.cc:9-65)"""
+        n = self.ci_strings.norb
+        return self._rdm(0, C_left, C_right, (n, n))
+
+    def b_1rdm(self, C_left, C_right) -> np.ndarray:
+        n = self.ci_strings.norb
+        return self._rdm(1, C_left, C_right, (n, n))
+
+    def sf_1rdm(self, C_left, C_right) -> np.ndarray:
+        """spin-free 1-RDM = alpha + beta (ci_sigma_builder_1rdm.cc:71-81)"""
+        return self.a_1rdm(C_left, C_right) + self.b_1rdm(C_left, C_right)
+
+    def _npairs(self):
+        n = self.ci_strings.norb
+        return n * (n - 1) // 2
+
+    def aa_2rdm(self, C_left, C_right) -> np.ndarray:
+        """<L|a+_p a+_q a_s a_r|R>, p > q, r > s, packed (npairs, npairs) (compute_aa_2rdm,
+        ci_sigma_builder_2rdm.cc:45-125); (0, 0) with fewer than two orbitals like the reference"""
+        m = self._npairs() if self.ci_strings.norb >= 2 else 0
+        return self._rdm(3, C_left, C_right, (m, m))
+
+    def bb_2rdm(self, C_left, C_right) -> np.ndarray:
+        m = self._npairs() if self.ci_strings.norb >= 2 else 0
+        return self._rdm(4, C_left, C_right, (m, m))
+
+    def ab_2rdm(self, C_left, C_right) -> np.ndarray:
+        """<L|a+_u(alpha) a+_v(beta) a_y(beta) a_x(alpha)|R>, (norb,) * 4 (compute_ab_2rdm,
+        ci_sigma_builder_2rdm.cc:135-201)"""
+        n = self.ci_strings.norb
+        return self._rdm(5, C_left, C_right, (n, n, n, n))
+
+    def sf_2rdm(self, C_left, C_right) -> np.ndarray:
+        """spin-free 2-RDM (compute_sf_2rdm, ci_sigma_builder_2rdm.cc:203-254)"""
+        n = self.ci_strings.norb
+        ab = self.ab_2rdm(C_left, C_right)
+        if n < 2:
+            return assemble_sf_2rdm(n, ab, None, None)
+        return assemble_sf_2rdm(n, ab, self.aa_2rdm(C_left, C_right), self.bb_2rdm(C_left, C_right))
+
+    def sf_2cumulant(self, C_left, C_right) -> np.ndarray:
+        """L2 = G2 - G1 x G1 + 1/2 exchange (compute_sf_2cumulant, ci_sigma_builder_2rdm.cc:256-279)"""
+        g1 = self.sf_1rdm(C_left, C_right)
+        return (self.sf_2rdm(C_left, C_right) - np.einsum("pr,qs->pqrs", g1, g1)
+                + 0.5 * np.einsum("ps,qr->pqrs", g1, g1))
+
     def form_Hdiag_det(self):
         """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""
         import torch
@@ -265,3 +336,22 @@ def csf_hamiltonian(strings: CIStrings, E, H, V, spin_adapter) -> np.ndarray:
             T[pos[int(d)], i] += c
     Hcsf = T.T @ _slater_block(strings, E, H, V, idx) @ T
     return 0.5 * (Hcsf + Hcsf.T)
+
+
+def assemble_sf_2rdm(norb: int, ab: np.ndarray, aa, bb) -> np.ndarray:
+    """G[p,q,r,s] = ab[p,q,r,s] + ab[q,p,s,r] + the antisymmetric unpacking of the packed same-spin blocks
+    (ci_sigma_builder_2rdm.cc:215-252); aa / bb are (npairs, npairs) over p > q, r > s or None"""
+    out = ab + ab.transpose(1, 0, 3, 2)
+    if norb < 2:
+        return out
+    p, q = np.tril_indices(norb, k=-1)  # p > q in the order of pair_index_gt: p (p - 1) / 2 + q
+    for ss in (aa, bb):
+        if ss is None:
+            continue
+        P, R = p[:, None], p[None, :]
+        Q, S = q[:, None], q[None, :]
+        out[P, Q, R, S] += ss
+        out[Q, P, R, S] -= ss
+        out[P, Q, S, R] -= ss
+        out[Q, P, S, R] += ss
+    return out

@@ -19,6 +19,7 @@
 
 #include "handles.hpp"
 #include "kernels.cuh"
+#include "rdm_kernels.cuh"
 
 namespace f2 {
 
@@ -1917,6 +1918,84 @@ int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream) {
         hdiag_kernel<<<h->hd_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             out_dev, h->hd_blocks.p, h->hd_nblocks, h->ea.p, h->eb.p, h->ja.p, h->D->b_str.p,
             h->norb, h->E);
+        F2_CUDA(cudaGetLastError());
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, void* stream) {
+    try {
+        if (!h || !L_dev || !R_dev || !out_dev)
+            throw std::invalid_argument("null argument");
+        F2_CUDA(cudaSetDevice(h->device));
+        const CIStringsHost& hs = *h->S->host;
+        const DeviceLists& L = hs.device_lists();
+        const DevStrings& D = *h->D;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int64_t n = hs.norb, npairs = n * (n - 1) / 2;
+        int64_t count = 0;
+        switch (kind) {
+        case 0: case 1: count = n * n; break;
+        case 3: case 4: count = npairs * npairs; break;
+        case 5: count = n * n * n * n; break;
+        default: throw std::invalid_argument("f2_sigma_rdm: kind must be 0 (a_1rdm), 1 (b_1rdm), 3 (aa_2rdm), "
+                                             "4 (bb_2rdm) or 5 (ab_2rdm)");
+        }
+        if (count == 0)
+            return F2_OK;
+        F2_CUDA(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(count) * sizeof(double), st));
+        if (hs.ndet == 0)
+            return F2_OK;
+        RdmParams p;
+        p.L = L_dev;
+        p.R = R_dev;
+        p.out = out_dev;
+        p.a_cls = D.a_cls.p;
+        p.a_loc = D.a_loc.p;
+        p.b_cls = D.b_cls.p;
+        p.b_loc = D.b_loc.p;
+        p.nA_cls = D.nA_cls.p;
+        p.nB_cls = D.nB_cls.p;
+        p.blk_off = D.blk_off.p;
+        p.as_ptr = D.as_ptr.p;
+        p.as_ent = D.as_ent.p;
+        p.bs_ent = D.bs_ent.p;
+        p.h2_ptr = nullptr;
+        p.h2_ent = nullptr;
+        p.norb = hs.norb;
+        p.nclsA = static_cast<int>(hs.nclsA());
+        p.nclsB = static_cast<int>(hs.nclsB());
+        p.bs_width = L.bs_width;
+        p.nas = hs.nas;
+        p.nbs = hs.nbs;
+        const size_t tile = static_cast<size_t>(n * n) * sizeof(double);
+        const unsigned rows = static_cast<unsigned>(hs.nas);
+        // the reference returns zeros when the spin has too few electrons (ci_sigma_builder_1rdm.cc:15-17,
+        // ci_sigma_builder_2rdm.cc:64-66,148-151)
+        if (kind == 0 && hs.na >= 1 && rows > 0) {
+            rdm1a_kernel<<<rows, 256, tile, st>>>(p);
+            h->launches += 1;
+        } else if (kind == 1 && hs.nb >= 1 && rows > 0) {
+            rdm1b_kernel<<<rows, 256, tile, st>>>(p);
+            h->launches += 1;
+        } else if (kind == 5 && hs.na >= 1 && hs.nb >= 1 && rows > 0) {
+            rdm2ab_kernel<<<rows, 256, tile, st>>>(p);
+            h->launches += 1;
+        } else if ((kind == 3 && hs.na >= 2) || (kind == 4 && hs.nb >= 2)) {
+            const int spin = kind == 3 ? 0 : 1;
+            const unsigned nk = static_cast<unsigned>(L.h2_ptr[spin].size() > 0 ? L.h2_ptr[spin].size() - 1 : 0);
+            p.h2_ptr = D.h2_ptr[spin].p;
+            p.h2_ent = D.h2_ent[spin].p;
+            if (nk > 0) {
+                if (spin == 0)
+                    rdm2ss_kernel<0><<<nk, 256, 0, st>>>(p, static_cast<int>(npairs));
+                else
+                    rdm2ss_kernel<1><<<nk, 256, 0, st>>>(p, static_cast<int>(npairs));
+                h->launches += 1;
+            }
+        }
         F2_CUDA(cudaGetLastError());
         return F2_OK;
     } catch (const std::exception& e) {

@@ -388,6 +388,40 @@ std::vector<int64_t> CIStringsHost::export_kind(int kind, int spin) const {
                 v.push_back(static_cast<int64_t>(s));
         return v;
     }
+    if (kind >= 20 && kind <= 28) {
+        // device-format tables exactly as the kernels read them (DeviceLists, strings.hpp), for the host models
+        // of the kernels in tests/: 20 as_ptr, 21 as_ent, 22 [width, bs_ent...], 23 h2_ptr[spin], 24 h2_ent[spin],
+        // 25 class of every string of `spin`, 26 its address in the class, 27 block offsets [nclsA][nclsB]
+        // (-1 = no block), 28 strings per class of `spin`
+        const DeviceLists& d = device_lists();
+        auto put = [&](const auto& src) {
+            for (auto x : src)
+                v.push_back(static_cast<int64_t>(x));
+        };
+        switch (kind) {
+        case 20: put(d.as_ptr); break;
+        case 21: put(d.as_ent); break;
+        case 22: v.push_back(d.bs_width); put(d.bs_ent); break;
+        case 23: put(d.h2_ptr[spin]); break;
+        case 24: put(d.h2_ent[spin]); break;
+        case 25: put(spin == 0 ? d.a_cls : d.b_cls); break;
+        case 26: put(spin == 0 ? d.a_loc : d.b_loc); break;
+        case 27: {
+            std::vector<int64_t> off(nclsA() * nclsB(), -1);
+            for (const auto& b : blocks)
+                off[b.cA * nclsB() + b.cB] = b.offset;
+            put(off);
+            break;
+        }
+        case 28: {
+            const auto& sp = space(spin, K_STR_N);
+            for (size_t c = 0; c < sp.nclasses(); ++c)
+                v.push_back(static_cast<int64_t>(sp.strpcls(c)));
+            break;
+        }
+        }
+        return v;
+    }
     const auto& N = space(spin, K_STR_N);
     if (kind == K_VO || kind == K_VO2) {
         // J = sign a+_p a_q I, (p,q) outer loops, strings inner (ci_strings_makers.cc:75-161)

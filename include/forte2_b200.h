@@ -58,7 +58,9 @@ int64_t f2_strings_occupations(const f2_strings* h, int which, int64_t* out, int
  *   1H   rows: class_K add_K class_I sign p I        a_p I = sign K
  *   1H2  rows: class_K class_I K sign p I
  *   2H   rows: class_K add_K class_I sign p q I      a_p a_q I = sign K, p > q
- *   3H   rows: class_K add_K class_I sign p q r I */
+ *   3H   rows: class_K add_K class_I sign p q r I
+ * kinds 20..28: the device-format tables as the kernels read them (csrc/strings.hpp DeviceLists; packed
+ * entries reinterpreted as int64), for host models of the kernels in tests/ */
 int64_t f2_strings_export(const f2_strings* h, int kind, int spin, int64_t* out, int64_t cap);
 /* CIStrings::make_determinants / determinant / determinant_index (ci_strings.cc:186-230):
  * occupation words (alpha, beta) */
@@ -120,6 +122,17 @@ int f2_sigma_part_layout(f2_sigma* h, int rank, int world, int64_t* sizes2, int6
  * send to the row owners (all-to-all) and add.  Device pointers; stream = cudaStream_t. */
 int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_local_dev, double* exch_dev,
                         int rank, int world, void* stream);
+
+/* Reduced density matrices <L| ... |R> of two device CI vectors (ndet doubles each), one GPU; out_dev is
+ * overwritten.  kind 0 a_1rdm, 1 b_1rdm: norb^2 doubles, [p][q] = <L|a+_p a_q|R>
+ * (CISigmaBuilder::compute_a_1rdm / compute_b_1rdm, forte2/ci/ci_sigma_builder_1rdm.cc:9-69);
+ * kind 3 aa_2rdm, 4 bb_2rdm: npairs^2 doubles, npairs = norb (norb - 1) / 2, [pq][rs] = <L|a+_p a+_q a_s a_r|R>
+ * with p > q, r > s and pair index p (p - 1) / 2 + q (compute_aa_2rdm / compute_bb_2rdm,
+ * ci_sigma_builder_2rdm.cc:45-133); kind 5 ab_2rdm: norb^4 doubles, [u][v][x][y] =
+ * <L|a+_u(alpha) a+_v(beta) a_y(beta) a_x(alpha)|R> (compute_ab_2rdm, ci_sigma_builder_2rdm.cc:135-201).
+ * The spin-free combinations (sf_1rdm, sf_2rdm, sf_2cumulant; ci_sigma_builder_1rdm.cc:71-81,
+ * ci_sigma_builder_2rdm.cc:203-279) are assembled from these by the Python mirror. */
+int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, void* stream);
 
 /* determinant energies of the owned rows, in the local (row slab) layout; synchronises the stream */
 int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream);

@@ -104,3 +104,47 @@ def test_rdm_port_matches_live_reference(ref, name):
     g2 = rb.rdm("sf_2rdm", c, c)
     energy = E + np.einsum("pq,pq", H, g1) + 0.5 * np.einsum("pqrs,pqrs", V, g2)
     assert abs(energy - c @ sigma) <= 1e-11
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas21_4", "one_each", "cas75_odd",
+                                  "one_beta_three_alpha", "beta_only", "sym2_11"])
+def test_rdm_kernel_models_match_the_definitions(name):
+    """tests/rdm_kernel_model.py (the RDM kernels of csrc/rdm_kernels.cuh restated statement by statement on the
+    host, reading the device-format tables) against oracle/rdm_port.py, itself pinned to the reference: list
+    semantics, unpacking and offset arithmetic of the kernels are right before they ever run on a GPU."""
+    from oracle import rdm_port
+    import rdm_kernel_model as km
+    space = SMALL_SPACES[name]
+    strings = f2.CIStrings(*space)
+    norb = strings.norb
+    dets = strings.make_determinants()
+    rng = np.random.default_rng(3)
+    left, right = rng.normal(size=strings.ndet), rng.normal(size=strings.ndet)
+    t = km.Tables(strings)
+    tol = 1e-13
+    if space[0] >= 1:
+        assert np.max(np.abs(km.rdm1a(t, left, right) - rdm_port.s_1rdm(dets, norb, left, right, 0))) <= tol
+    if space[1] >= 1:
+        assert np.max(np.abs(km.rdm1b(t, left, right) - rdm_port.s_1rdm(dets, norb, left, right, 1))) <= tol
+    if space[0] >= 1 and space[1] >= 1:
+        assert np.max(np.abs(km.rdm2ab(t, left, right) - rdm_port.ab_2rdm(dets, norb, left, right))) <= tol
+    if space[0] >= 2:
+        assert np.max(np.abs(km.rdm2ss(t, left, right, 0) - rdm_port.ss_2rdm(dets, norb, left, right, 0))) <= tol
+    if space[1] >= 2:
+        assert np.max(np.abs(km.rdm2ss(t, left, right, 1) - rdm_port.ss_2rdm(dets, norb, left, right, 1))) <= tol
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas21_4"])
+def test_sf_2rdm_assembly_matches_the_definitions(name):
+    """forte2_b200.ci_sigma_builder.assemble_sf_2rdm (host assembly of the spin-free 2-RDM from the spin blocks the
+    kernels produce) against oracle/rdm_port.sf_2rdm"""
+    from oracle import rdm_port
+    from forte2_b200.ci_sigma_builder import assemble_sf_2rdm
+    space = SMALL_SPACES[name]
+    strings = f2.CIStrings(*space)
+    norb, dets = strings.norb, strings.make_determinants()
+    rng = np.random.default_rng(8)
+    left, right = rng.normal(size=strings.ndet), rng.normal(size=strings.ndet)
+    got = assemble_sf_2rdm(norb, rdm_port.ab_2rdm(dets, norb, left, right),
+                           rdm_port.ss_2rdm(dets, norb, left, right, 0), rdm_port.ss_2rdm(dets, norb, left, right, 1))
+    assert np.max(np.abs(got - rdm_port.sf_2rdm(dets, norb, left, right))) <= 1e-13
