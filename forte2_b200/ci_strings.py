@@ -11,7 +11,9 @@ from . import _lib
 KINDS = {
     "strings": 0, "strings_1h": 1, "strings_2h": 2, "strings_3h": 3, "strings_1h1p": 4,
     "vo": 10, "vo2": 11, "1h": 12, "1h2": 13, "2h": 14, "3h": 15,
-    # device-format tables as the kernels read them (csrc/strings.hpp DeviceLists)
+}
+# device-format tables as the kernels read them (csrc/strings.hpp DeviceLists), for host models of kernels in tests/
+DEV_KINDS = {
     "dev_as_ptr": 20, "dev_as_ent": 21, "dev_bs_ent": 22, "dev_h2_ptr": 23, "dev_h2_ent": 24, "dev_cls": 25,
     "dev_loc": 26, "dev_blk_off": 27, "dev_ncls": 28,
 }
@@ -109,7 +111,7 @@ class CIStrings:
 
     def export(self, kind, spin):
         L = _lib.lib()
-        k = KINDS[kind]
+        k = KINDS[kind] if kind in KINDS else DEV_KINDS[kind]
         n = L.f2_strings_export(self._h, k, spin, None, 0)
         if n < 0:
             raise RuntimeError(_lib.last_error())
