@@ -17,7 +17,9 @@ The JSON line carries, beside the driver contract's keys:
   davidson     (N = 1) time of one Davidson-Liu iteration of a 3-root solve on the same workload: 3 sigma
                builds + the device solver's streaming passes (forte2_b200/davidson.py)
   cpu_baseline the reference's own C++ CISigmaBuilder::Hamiltonian (oracle/_ref) timed on the host cores
-               on a bounded sample, scaled to the workload by the reference's own GEMM flop count
+               on a bounded sample, scaled to the workload by the reference's own GEMM flop count; the sigma of
+               that sample build (CAS(14,14), 11 778 624 determinants: BASELINE.json configs[1]) is compared with
+               this package's sigma of the same vector on the GPU: cpu_baseline.parity_rel_l2_vs_gpu
   e2e          the same metric through the numpy-facing call (host buffers in, host buffers out)
 --impl reference times that CPU implementation alone, in the same units.
 """
@@ -130,9 +132,10 @@ def measure_fp64_peak(torch, n=8192, reps=5):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def reference_sample(workload, budget_s, steps, warmup, threads=None):
+def reference_sample(workload, budget_s, steps, warmup, threads=None, check=None):
     """Time the reference's own CPU builder (oracle/_ref, else the port) on a bounded sample and scale
-    to the workload.  Returns (builds_per_s_scaled, info dict)."""
+    to the workload.  Returns (builds_per_s_scaled, info dict).  check(space, E, H, V, c, sigma_ref), if given,
+    is called with the sample's last build and its return value is reported as info["parity_rel_l2_vs_gpu"]."""
     import numpy as np
 
     from forte2_b200 import synthetic
@@ -178,18 +181,30 @@ def reference_sample(workload, budget_s, steps, warmup, threads=None):
             b.Hamiltonian(c, sg)
             if i >= reps_warm:
                 times.append(time.perf_counter() - t)
+        parity.clear()
+        if check is not None and reps > 0:
+            try:
+                parity.append(check((sa, sb, 0, [[0] * sn], [], []), E, H, V, c, sg))
+            except Exception as e:  # the parity figure must never cost the bench line
+                parity.append(f"not computed: {e}"[:200])
         return sum(times) / len(times), s.ndet
 
+    parity = []
     probe, _ = run(12, 0, 1)
     est14 = probe * hz_gemm_flops(14, 7, 7) / hz_gemm_flops(12, 6, 6)
     sn = 14 if (n >= 14 and est14 * (steps + warmup) <= budget_s) else min(12, n)
     per, ndet = run(sn, warmup, steps)
     scale = hz_gemm_flops(n, na, nb) / hz_gemm_flops(sn, sn // 2, sn // 2)
-    return 1.0 / (per * scale), {
+    info = {
         "kind": "reference", "cores": cores, "seconds_per_sample_build": per,
         "sample": f"reference CISigmaBuilder::Hamiltonian (hz, oracle/_ref, FORTE_NUM_THREADS_OVERRIDE={cores}, "
                   f"OPENBLAS_NUM_THREADS={os.environ['OPENBLAS_NUM_THREADS']}) on CAS({sn},{sn}) ({ndet} dets), "
                   f"{steps} build(s); scaled x{scale:.4g} by its HZ GEMM flop count 2 n^4 K1a K1b to {workload}"}
+    if parity:
+        info["parity_rel_l2_vs_gpu"] = parity[0]
+        info["parity_note"] = (f"sigma of this package on the GPU against the reference's sigma of the sample build, "
+                               f"CAS({sn},{sn}), same integrals and trial vector; the bar is 1e-12")
+    return 1.0 / (per * scale), info
 
 
 def run_reference(args):
@@ -434,8 +449,16 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        def gpu_parity(space, Es, Hs, Vs, cs, sigma_ref):
+            # BASELINE.json configs[1] when the sample is CAS(14,14): the reference's own sigma vs ours, full size
+            st = f2.CIStrings(*space)
+            bs = f2.CISigmaBuilder(st, Es, Hs, Vs, 0, device=local_rank)
+            got = np.empty_like(cs)
+            bs.Hamiltonian(cs, got)
+            return float(np.linalg.norm(got - sigma_ref) / np.linalg.norm(sigma_ref))
+
         with quiet_stdout():
-            v, info = reference_sample(args.workload, budget_s=30.0, steps=1, warmup=0)
+            v, info = reference_sample(args.workload, budget_s=30.0, steps=1, warmup=0, check=gpu_parity)
         cpu = {"value": v, "unit": "sigma builds/s", **info}
 
     line = {
