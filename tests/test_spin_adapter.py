@@ -141,15 +141,6 @@ def test_transforms_and_preconditioner_on_gpu(name, twoS):
     to_csf = np.full(a.ncsf, np.nan)
     a.det_C_to_csf_C(g["c_det"], to_csf)
     assert np.max(np.abs(to_csf - g["to_csf"]), initial=0.0) <= 1e-14
-    # columns of a C-ordered (size, m) basis, as forte2's Davidson closure passes them (ci.py:231-233)
-    basis = np.full((a.ncsf, 3), np.nan)
-    basis[:, 1] = g["c_csf"]
-    to_det2 = np.full(strings.ndet, np.nan)
-    a.csf_C_to_det_C(basis[:, 1], to_det2)
-    assert np.max(np.abs(to_det2 - to_det), initial=0.0) <= 1e-14
-    out = np.full((a.ncsf, 3), np.nan)
-    a.det_C_to_csf_C(g["c_det"], out[:, 2])
-    assert np.max(np.abs(out[:, 2] - to_csf), initial=0.0) <= 1e-14 and np.all(np.isnan(out[:, :2]))
     # device tensors
     d_det = torch.full((strings.ndet,), float("nan"), dtype=torch.float64, device="cuda")
     a.csf_C_to_det_C(torch.from_numpy(g["c_csf"]).cuda(), d_det)
@@ -162,32 +153,6 @@ def test_transforms_and_preconditioner_on_gpu(name, twoS):
     b = f2.CISigmaBuilder(strings, E, H, V, 0)
     hd = b.form_Hdiag_csf(None, a).cpu().numpy()
     assert np.max(np.abs(hd - g["hdiag_csf"]), initial=0.0) <= 1e-12 * max(1.0, np.max(np.abs(g["hdiag_csf"]), initial=0.0))
-    # the exact form: host Slater rules (checked against the reference on the CPU), delivered as a device tensor
-    from forte2_b200.ci_sigma_builder import exact_hdiag_csf
-    hx = b.form_Hdiag_csf(None, a, True)
-    assert hx.is_cuda and hx.shape == (a.ncsf,)
-    assert np.array_equal(hx.cpu().numpy(), exact_hdiag_csf(strings, E, H, V, a))
-    # host helpers of the guess / exact diagonalisation through the builder (checked against the reference on the CPU)
-    from forte2_b200.ci_sigma_builder import csf_hamiltonian, csf_matrix_element
-    assert b.slater_rules_csf(None, a, 0, a.ncsf - 1) == csf_matrix_element(strings, E, H, V, a, 0, a.ncsf - 1)
-    assert b.energy_csf(None, a, 0) == csf_matrix_element(strings, E, H, V, a, 0, 0)
-    if a.ncsf <= 400:
-        Hc = b.form_H_csf(None, a)
-        assert np.array_equal(Hc, csf_hamiltonian(strings, E, H, V, a))
-        assert np.max(np.abs(np.diag(Hc) - hx.cpu().numpy())) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
-        # forte2's sigma closure, verbatim (forte2/ci/ci.py:221-233): numpy vectors, columns of C-ordered blocks
-        rng = np.random.default_rng(5)
-        Bblock = rng.normal(size=(a.ncsf, 2))
-        Sblock = np.full_like(Bblock, np.nan)
-        b_det, sigma_det = np.zeros(strings.ndet), np.zeros(strings.ndet)
-        for i in range(Bblock.shape[1]):
-            a.csf_C_to_det_C(Bblock[:, i], b_det)
-            b.Hamiltonian(b_det, sigma_det)
-            a.det_C_to_csf_C(sigma_det, Sblock[:, i])
-        assert np.max(np.abs(Sblock - Hc @ Bblock)) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
-        b.set_memory(0)
-        with pytest.raises(RuntimeError, match="Not enough memory"):
-            b.form_H_csf(None, a)
     with pytest.raises(ValueError):
         a.csf_C_to_det_C(torch.zeros(a.ncsf + 1, dtype=torch.float64, device="cuda"), d_det)
 
