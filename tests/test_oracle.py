@@ -148,3 +148,66 @@ def test_sf_2rdm_assembly_matches_the_definitions(name):
     got = assemble_sf_2rdm(norb, rdm_port.ab_2rdm(dets, norb, left, right),
                            rdm_port.ss_2rdm(dets, norb, left, right, 0), rdm_port.ss_2rdm(dets, norb, left, right, 1))
     assert np.max(np.abs(got - rdm_port.sf_2rdm(dets, norb, left, right))) <= 1e-13
+
+
+@pytest.fixture(scope="module")
+def rdm_emu(tmp_path_factory):
+    """the RDM kernels' own source (csrc/rdm_kernels.cuh) compiled for the host under the SIMT emulator of
+    tests/simt_emu (one std::thread per CUDA thread, barriers for __syncthreads and the shuffles)"""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    out = tmp_path_factory.mktemp("simt")
+    script = os.path.join(os.path.dirname(__file__), "simt_emu", "build.sh")
+    r = subprocess.run(["bash", script, str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return ctypes.CDLL(os.path.join(str(out), "librdm_emu.so"))
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas21_4", "beta_only"])
+def test_rdm_kernel_source_under_the_simt_emulator(rdm_emu, name):
+    """The CUDA text of rdm1a / rdm1b / rdm2ab / rdm2ss<0,1> executed thread by thread on the host (64 threads per
+    block: two warps, so the cross-warp reduction, the shuffles, the shared-memory atomics and every barrier are
+    exercised) against oracle/rdm_port.py.  Together with the host models this checks everything about these
+    kernels that does not need the hardware."""
+    import ctypes
+    from oracle import rdm_port
+    import rdm_kernel_model as km
+    space = SMALL_SPACES[name]
+    strings = f2.CIStrings(*space)
+    norb, dets = strings.norb, strings.make_determinants()
+    t = km.Tables(strings)
+    rng = np.random.default_rng(4)
+    left, right = rng.normal(size=strings.ndet), rng.normal(size=strings.ndet)
+    u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)  # noqa: E731
+    u64 = lambda a: np.ascontiguousarray(a).astype(np.uint64) if a.dtype != np.uint64 else np.ascontiguousarray(a)  # noqa: E731
+    keep = dict(a_cls=u32(t.a_cls), a_loc=u32(t.a_loc), b_cls=u32(t.b_cls), b_loc=u32(t.b_loc), nA=u32(t.nA_cls),
+                nB=u32(t.nB_cls), blk=np.ascontiguousarray(t.blk_off, dtype=np.int64), as_ptr=u32(t.as_ptr),
+                as_ent=u64(t.as_ent), bs_ent=u64(t.bs_ent) if t.bs_ent.size else np.zeros(1, dtype=np.uint64))
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+    def run(kind, count, spin=0):
+        out = np.zeros(max(count, 1))
+        h2p, h2e = u32(t.h2_ptr[spin]), u64(t.h2_ent[spin]) if t.h2_ent[spin].size else np.zeros(1, dtype=np.uint64)
+        rc = rdm_emu.emu_rdm(kind, 64, ptr(left), ptr(right), ptr(out), ptr(keep["a_cls"]), ptr(keep["a_loc"]),
+                             ptr(keep["b_cls"]), ptr(keep["b_loc"]), ptr(keep["nA"]), ptr(keep["nB"]), ptr(keep["blk"]),
+                             ptr(keep["as_ptr"]), ptr(keep["as_ent"]), ptr(keep["bs_ent"]), ptr(h2p), ptr(h2e),
+                             max(len(h2p) - 1, 0), norb, t.nclsA, t.nclsB, t.bs_width,
+                             ctypes.c_int64(t.nas), ctypes.c_int64(t.nbs))
+        assert rc == 0
+        return out[:count]
+
+    n2, npairs = norb * norb, norb * (norb - 1) // 2
+    tol = 1e-12
+    if space[0] >= 1:
+        assert np.max(np.abs(run(0, n2) - rdm_port.s_1rdm(dets, norb, left, right, 0).reshape(-1))) <= tol
+    if space[1] >= 1:
+        assert np.max(np.abs(run(1, n2) - rdm_port.s_1rdm(dets, norb, left, right, 1).reshape(-1))) <= tol
+    if space[0] >= 1 and space[1] >= 1:
+        assert np.max(np.abs(run(5, n2 * n2) - rdm_port.ab_2rdm(dets, norb, left, right).reshape(-1))) <= tol
+    if space[0] >= 2:
+        assert np.max(np.abs(run(3, npairs * npairs, 0) - rdm_port.ss_2rdm(dets, norb, left, right, 0).reshape(-1))) <= tol
+    if space[1] >= 2:
+        assert np.max(np.abs(run(4, npairs * npairs, 1) - rdm_port.ss_2rdm(dets, norb, left, right, 1).reshape(-1))) <= tol

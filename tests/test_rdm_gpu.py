@@ -4,8 +4,8 @@ where oracle/_ref is present, the reference itself; transition pairs (left != ri
 and the energy functional E0 + h.g1 + 1/2 V.g2 against <c|sigma> of the device sigma build.
 
 These kernels were written after the round's GPU budget was spent: their list handling and index arithmetic are
-checked on the CPU through statement-by-statement host models (tests/rdm_kernel_model.py), the CUDA mechanics have
-not run on hardware yet.  Hence every case runs in its own process (a faulting kernel cannot poison the CUDA context
+checked on the CPU through statement-by-statement host models (tests/rdm_kernel_model.py) and by executing the
+kernel source itself under a SIMT emulator (tests/simt_emu, tests/test_oracle.py); they have not run on hardware yet.  Hence every case runs in its own process (a faulting kernel cannot poison the CUDA context
 of the suite) and is marked xfail(strict=False): the outcome is recorded either way without gating the suite."""
 import os
 import subprocess
