@@ -1796,6 +1796,11 @@ int f2_sigma_times(f2_sigma* h, double* out4) {
         collect_times(*h);
         for (int i = 0; i < 4; ++i)
             out4[i] = h->builds ? h->t_acc[i] / static_cast<double>(h->builds) : 0.0;
+        if (h->algorithm == "Knowles-Handy") {
+            // the reference's KH path has one two-electron stage: [total, H2_kh, 0, 0] (ci_sigma_builder.cc:194-199)
+            out4[1] += out4[2] + out4[3];
+            out4[2] = out4[3] = 0.0;
+        }
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);

@@ -191,3 +191,93 @@ void port_energies(int64_t ndet, const uint64_t* dets, int n, double E, const do
     for (int64_t I = 0; I < ndet; ++I)
         out[I] = port_energy(n, E, H, V, dets[2 * I], dets[2 * I + 1]);
 }
+
+/* ---------------------------------------------------------------------------------------------------
+ * Sampled checker (sizes no full oracle sigma can reach: CAS(16,16), CAS(18,18), 3 GAS / 20 orbitals).
+ * For nsamp determinants I = (a[s], b[s]) list every determinant J of the FULL Fock sector (same na, nb)
+ * that H connects to I -- I itself, the single replacements of either spin, the same-spin and the
+ * opposite-spin double replacements -- together with <I|H|J> (SlaterRules::slater_rules,
+ * forte2/determinant/slater_rules.cc:154-245; phases: bitarray.hpp:575-583).  The caller (oracle/sampled.py)
+ * maps (alpha word, beta word) to CI-vector addresses, drops the J outside the CI space (P H P, what
+ * the reference's sigma computes) and sums <I|H|J> C[J].
+ * Every sample produces the same count: 1 + Sa + Sb + Daa + Dbb + Sa Sb with S = N (n - N),
+ * D = C(N,2) C(n-N,2).  Returns that count (out_* may be NULL to size the buffers). */
+static int64_t connections_one(int n, double E, const double* H, const double* V, uint64_t wa, uint64_t wb,
+                               uint64_t* oa, uint64_t* ob, double* oh) {
+    int64_t k = 0;
+#define EMIT(xa, xb, val)                                                                                    \
+    do {                                                                                                     \
+        if (oa) {                                                                                            \
+            oa[k] = (xa);                                                                                    \
+            ob[k] = (xb);                                                                                    \
+            oh[k] = (val);                                                                                   \
+        }                                                                                                    \
+        ++k;                                                                                                 \
+    } while (0)
+    EMIT(wa, wb, port_energy(n, E, H, V, wa, wb));
+    for (int spin = 0; spin < 2; ++spin) {
+        const uint64_t w = spin == 0 ? wa : wb, o = spin == 0 ? wb : wa;
+        for (int i = 0; i < n; ++i) {
+            if (!((w >> i) & 1))
+                continue;
+            const uint64_t w1 = w & ~(1ull << i);
+            const double si = sign_below(w, i);
+            for (int x = 0; x < n; ++x) {
+                if ((w >> x) & 1)
+                    continue;
+                const uint64_t w2 = w1 | (1ull << x);
+                const double sg = si * sign_below(w1, x);
+                const double h1 = sg * single_coupling(n, H, V, i, x, w, o, 1, 1);
+                if (spin == 0)
+                    EMIT(w2, wb, h1);
+                else
+                    EMIT(wa, w2, h1);
+                /* same-spin doubles (i < j) -> (x < y) */
+                for (int j = i + 1; j < n; ++j) {
+                    if (!((w >> j) & 1))
+                        continue;
+                    const uint64_t w3 = w2 & ~(1ull << j);
+                    const double sj = sign_below(w2, j);
+                    for (int y = x + 1; y < n; ++y) {
+                        if ((w >> y) & 1)
+                            continue;
+                        const uint64_t w4 = w3 | (1ull << y);
+                        const double h2 = sg * sj * sign_below(w3, y) * (V4(i, j, x, y) - V4(i, j, y, x));
+                        if (spin == 0)
+                            EMIT(w4, wb, h2);
+                        else
+                            EMIT(wa, w4, h2);
+                    }
+                }
+                /* opposite-spin doubles, once, from the alpha side */
+                if (spin == 0)
+                    for (int j = 0; j < n; ++j) {
+                        if (!((wb >> j) & 1))
+                            continue;
+                        const uint64_t b1 = wb & ~(1ull << j);
+                        const double sbj = sign_below(wb, j);
+                        for (int y = 0; y < n; ++y) {
+                            if ((wb >> y) & 1)
+                                continue;
+                            EMIT(w2, b1 | (1ull << y), sg * sbj * sign_below(b1, y) * V4(i, j, x, y));
+                        }
+                    }
+            }
+        }
+    }
+#undef EMIT
+    return k;
+}
+
+int64_t port_connections(int n, double E, const double* H, const double* V, int64_t nsamp, const uint64_t* a,
+                         const uint64_t* b, uint64_t* out_a, uint64_t* out_b, double* out_h) {
+    if (nsamp <= 0)
+        return 0;
+    const int64_t per = connections_one(n, E, H, V, a[0], b[0], NULL, NULL, NULL);
+    if (!out_a)
+        return per;
+    for (int64_t s = 0; s < nsamp; ++s)
+        if (connections_one(n, E, H, V, a[s], b[s], out_a + s * per, out_b + s * per, out_h + s * per) != per)
+            return -1; /* samples with different electron counts */
+    return per;
+}

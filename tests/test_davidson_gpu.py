@@ -171,3 +171,58 @@ def test_ci_roots_match_reference(torch_cuda, fixture, nroot):
     sg = torch.empty_like(v[0])
     solver.ci_sigma_builder.Hamiltonian(v[0].contiguous(), sg)
     assert float((sg - solver.evals[0] * v[0]).norm()) < 1e-5
+
+
+def test_solver_with_24_subspace_vectors(torch_cuda):
+    """6 roots x basis_per_root 4: combine / residual go through the 16 x 16 chunked calls (davidson._ChunkedOps)"""
+    torch = torch_cuda
+    from forte2_b200.davidson import DavidsonLiuSolver
+    n, nroot = 600, 6
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(n, n))
+    A = 0.02 * (A + A.T) + np.diag(np.linspace(0.0, 20.0, n))
+    Ad = torch.from_numpy(A).cuda()
+    s = DavidsonLiuSolver(size=n, nroot=nroot)
+    s.add_h_diag(np.diag(A).copy())
+    s.add_sigma_builder(lambda Bb, Sb: Sb.copy_(Bb @ Ad))
+    g = np.zeros((n, 2 * nroot))
+    g[np.arange(2 * nroot), np.arange(2 * nroot)] = 1.0
+    s.add_guesses(g)
+    lam, ev = s.solve()
+    assert s.converged
+    want = np.linalg.eigvalsh(A)[:nroot]
+    assert np.max(np.abs(lam - want)) < 1e-11
+    evh = ev.cpu().numpy()
+    assert np.allclose(evh @ evh.T, np.eye(nroot), atol=1e-10)
+    assert np.max(np.abs(evh @ A - lam[:, None] * evh)) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["cas66", "cas66_d2h"])
+def test_exact_diagonalization_equals_the_iterative_solve(torch_cuda, name):
+    """ci_algorithm="exact" (forte2/ci/ci.py:305-322; tests/ci/test_ci_exact_diagonalization.py pins HZ == exact):
+    dense Hamiltonian from host Slater rules, in the determinant basis and in the CSF basis, against the committed
+    exact eigenvalues, and its eigenvector against one sigma build."""
+    import forte2_b200 as f2
+    from forte2_b200.ci_solver import CISolver
+    torch = torch_cuda
+    space = SPACES[name]
+    n = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(n, "D")
+    strings = f2.CIStrings(*space)
+    g = np.load(os.path.join(GOLD, f"roots_{name}_D.npz"))
+    solver = CISolver(strings, E, H, V, nroot=3, ci_algorithm="exact", log_level=0).run()
+    assert solver.converged and solver.evecs.is_cuda and solver.evecs.shape == (3, strings.ndet)
+    assert np.max(np.abs(solver.E - g["exact"][:3])) <= ROOT_TOL
+    sg = torch.empty_like(solver.evecs[0])
+    solver.ci_sigma_builder.Hamiltonian(solver.evecs[0].contiguous(), sg)
+    assert float((sg - solver.E[0] * solver.evecs[0]).norm()) < 1e-9
+    # CSF basis (singlets): the lowest singlet of the dense CSF Hamiltonian is a root of the determinant problem
+    gc = np.load(os.path.join(GOLD, f"rootscsf_{name}_S0.npz"))
+    adapter = f2.CISpinAdapter(0, space[0] - space[1], n)
+    adapter.prepare_couplings(strings)
+    csf = CISolver(strings, E, H, V, nroot=2, ci_algorithm="exact", log_level=0, spin_adapter=adapter).run()
+    assert csf.evecs.shape == (2, adapter.ncsf)
+    assert np.max(np.abs(csf.E - gc["exact"][:2])) <= ROOT_TOL
+    shifted = CISolver(strings, E, H, V, nroot=1, ci_algorithm="exact", log_level=0, spin_adapter=adapter,
+                       energy_shift=float(gc["exact"][1]) + 1e-6).run()
+    assert abs(shifted.E[0] - gc["exact"][1]) <= ROOT_TOL

@@ -110,6 +110,13 @@ def _worker(rank, world, port, name, form, result_dir):
         want = checker.port_sigma(dets, *ints, c_full.numpy())
         err = np.linalg.norm(got - want) / np.linalg.norm(want)
         assert sum(lay.local_size for lay in sh.layouts) == strings.ndet
+        # the sampled checker in its sharded form (oracle/sampled.py: what bench.py runs at CAS(18,18) on 8 GPUs)
+        from oracle import sampled
+        serr, ns = sampled.sharded_rel_error(space, *ints, sh.layouts, rank, c_loc, sigma_loc, nsamp_per_rank=48)
+        assert ns > 0 and serr <= 1e-13, (serr, ns)
+        bad = sigma_loc.clone()
+        bad[: max(1, bad.numel() // 2)] *= 1.0 + 1e-8
+        assert sampled.sharded_rel_error(space, *ints, sh.layouts, rank, c_loc, bad, nsamp_per_rank=48)[0] > 1e-10
         np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array([err]))
     finally:
         dist.destroy_process_group()

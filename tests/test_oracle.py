@@ -211,3 +211,55 @@ def test_rdm_kernel_source_under_the_simt_emulator(rdm_emu, name):
         assert np.max(np.abs(run(3, npairs * npairs, 0) - rdm_port.ss_2rdm(dets, norb, left, right, 0).reshape(-1))) <= tol
     if space[1] >= 2:
         assert np.max(np.abs(run(4, npairs * npairs, 1) - rdm_port.ss_2rdm(dets, norb, left, right, 1).reshape(-1))) <= tol
+
+
+# ---- the sampled Slater-rules checker (oracle/sampled.py): what the parity tests at 10^8 - 10^9 determinants rest on
+@pytest.mark.parametrize("fixture", SIGMA_FIXTURES)
+def test_sampled_checker_matches_golden_sigma(fixture):
+    """every sampled sigma_I rebuilt from Slater rules + the restated string layout equals the reference's sigma
+    (committed goldens: CAS, GAS, point-group symmetry, na != nb; 8-fold and 4-fold symmetric integrals)"""
+    from oracle import sampled
+    name, variant = fixture.rsplit("_", 1) if not fixture.endswith("four_fold") else (fixture[:-10], "four_fold")
+    space = SMALL_SPACES[name]
+    g = np.load(os.path.join(GOLD, f"sigma_{fixture}.npz"))
+    lay = sampled.layout(space)
+    assert lay.ndet == len(g["c"])
+    assert np.array_equal(lay.address(g["dets"][:, 0], g["dets"][:, 1]), np.arange(lay.ndet))
+    wa, wb = lay.determinant(np.arange(lay.ndet))
+    assert np.array_equal(wa, g["dets"][:, 0]) and np.array_equal(wb, g["dets"][:, 1])
+    n = sum(len(s) for s in space[3])
+    E, H, V = _ints(n, variant)
+    err, ns = sampled.sampled_rel_error(space, E, H, V, g["c"], g["sigma_hz"], nsamp=400)
+    assert ns > 0 and err <= 1e-13
+    if lay.ndet > 20:  # and it is not vacuous
+        bad = g["sigma_hz"].copy()
+        bad[sampled.sample_addresses(lay.ndet, 400)[0]] += 1e-9 * np.linalg.norm(bad)
+        assert sampled.sampled_rel_error(space, E, H, V, g["c"], bad, nsamp=400)[0] > 1e-10
+
+
+@pytest.mark.parametrize("name", ["gas343_55", "cas66_d2h", "gas2_sym4", "cas88"])
+def test_sampled_checker_matches_live_reference(ref, name):
+    from oracle import sampled
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    E, H, V = _ints(n, "D")
+    c = synthetic.trial_vector(ref.RefCIStrings(*space).ndet, seed=11)
+    want, kind = checker.sigma(space, E, H, V, c)
+    assert kind == "reference"
+    err, _ = sampled.sampled_rel_error(space, E, H, V, c, want, nsamp=500)
+    assert err <= 1e-13
+
+
+def test_layout_of_large_spaces_without_enumerating_determinants():
+    """sizes and block counts of BASELINE configs 3-5 from the restated layout alone"""
+    from oracle import sampled
+    assert sampled.layout((9, 9, 0, [[0] * 18], [], [])).ndet == 2363904400
+    lay = sampled.layout((10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [8, 0, 0], [12, 16, 4]))
+    assert lay.ndet == 1865504274 and sum(1 for b in lay.blocks if b[3] * b[4] > 0) == 225
+    lay = sampled.layout((10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2]))
+    assert lay.ndet == 22065484 and len(lay.blocks) == 36
+    strings = f2.CIStrings(10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2])
+    adr = sampled.sample_addresses(lay.ndet, 300)
+    wa, wb = lay.determinant(adr)
+    for k in range(0, len(adr), 37):  # the product's own addressing agrees
+        assert strings.determinant(int(adr[k])) == (int(wa[k]), int(wb[k]))

@@ -58,6 +58,37 @@ def test_sigma_matches_reference(ref, torch_cuda, name, variant):
     assert _rel(sd.cpu().numpy(), want) <= TOL
 
 
+# the reference's KH sigma is not a valid oracle with several irreps nor when one spin has no
+# electrons (probe: beta_only, gas2_20, one_alpha differ from its own HZ / Slater rules by 2-19 %)
+ONE_IRREP = sorted(k for k, sp in SMALL_SPACES.items()
+                   if max(x for s in sp[3] for x in s) == 0 and sp[0] > 0 and sp[1] > 0)
+
+
+@pytest.mark.parametrize("name", ONE_IRREP)
+@pytest.mark.parametrize("variant", ["S", "D"])
+def test_sigma_matches_reference_knowles_handy(ref, torch_cuda, name, variant):
+    """second oracle: the reference's Knowles-Handy sigma (ci_sigma_builder_knowles_handy.cc:88-171), valid with one
+    irrep and 8-fold symmetric integrals, against set_algorithm("kh") of this builder; and the
+    KH form of avg_build_time(): [total, H2_kh, 0, 0] (ci_sigma_builder.cc:194-199)"""
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, variant))
+    rb.set_algorithm("kh")
+    gb.set_algorithm("kh")
+    assert gb.get_algorithm() == rb.get_algorithm() == "Knowles-Handy"
+    c = synthetic.trial_vector(max(rs.ndet, 1))[: rs.ndet].copy()
+    want = np.zeros_like(c)
+    rb.Hamiltonian(c, want)
+    got = np.full_like(c, np.nan)
+    gb.Hamiltonian(c, got)
+    assert _rel(got, want) <= TOL
+    t = gb.avg_build_time()
+    assert len(t) == 4 and t[2] == 0.0 and t[3] == 0.0 and t[0] >= t[1] >= 0.0
+    gb.set_algorithm("hz")
+    t = gb.avg_build_time()
+    assert t[1] + t[2] + t[3] <= t[0] * (1 + 1e-9) + 1e-9
+
+
 @pytest.mark.parametrize("name", ["cas66", "cas66_d2h", "gas343_54", "cas75_odd"])
 def test_hdiag_matches_slater_rules(ref, torch_cuda, name):
     space = SMALL_SPACES[name]
@@ -148,43 +179,13 @@ def test_rows_form_parts_emulated_on_one_gpu(ref, torch_cuda, space, world):
     the sum equals the single-GPU sigma and the reference.  One determinant block (t3g_kernel) and
     symmetry / GAS blocks (t3gp_kernel).  The NCCL version is tests/test_dist_gpu.py."""
     torch = torch_cuda
-    from forte2_b200.dist import CudaEngine, Layout
+    from rows_emulation import rows_form_sigma
     n = sum(len(s) for s in space[3])
     rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
     c = synthetic.trial_vector(rs.ndet)
     want = np.zeros_like(c)
     rb.Hamiltonian(c, want)
-    eng = CudaEngine(gb)
-    C = torch.from_numpy(c).cuda()
-    lays = [Layout(gs.blocks(), q, world) for q in range(world)]
-    ok, slot = eng.rows_form(0, world)
-    assert ok and slot == max(L.local_size for L in lays)
-    total = torch.zeros_like(C)
-    for q, L in enumerate(lays):
-        # several blocks: the vectors need no 16-byte alignment (rows of a Davidson basis with an odd length)
-        skew = 1 if gs.nblocks > 1 else 0
-        c_loc = torch.empty(L.local_size + 1, dtype=torch.float64, device="cuda")[skew: skew + L.local_size]
-        xcols = torch.full((max(L.exchange_size, 1),), float("nan"), dtype=torch.float64, device="cuda")
-        for (off, nA, nB), (lo, nr, loc), (cl, nc, yoff) in zip(L.blocks, L.rows, L.cols):
-            if nA * nB == 0:
-                continue
-            blk = C[off:off + nA * nB].view(nA, nB)
-            c_loc[loc:loc + nr * nB] = blk[lo:lo + nr].reshape(-1)
-            xcols[yoff:yoff + nA * nc] = blk[:, cl:cl + nc].reshape(-1)
-        sigma_loc = torch.full((L.local_size + 1,), float("nan"), dtype=torch.float64, device="cuda")[skew: skew + L.local_size]
-        ycols = torch.full_like(xcols, float("nan"))
-        scatter = torch.full((world * slot,), float("nan"), dtype=torch.float64, device="cuda")
-        eng.apply_rows(c_loc, xcols, sigma_loc, ycols, scatter, q, world)
-        for (off, nA, nB), (lo, nr, loc), (cl, nc, yoff) in zip(L.blocks, L.rows, L.cols):
-            if nA * nB == 0:
-                continue
-            blk = total[off:off + nA * nB].view(nA, nB)
-            blk[lo:lo + nr] += sigma_loc[loc:loc + nr * nB].view(nr, nB)
-            blk[:, cl:cl + nc] += ycols[yoff:yoff + nA * nc].view(nA, nc)
-        for r, Lr in enumerate(lays):
-            for (off, nA, nB), (lo_r, n_r, loc_r) in zip(Lr.blocks, Lr.rows):
-                if nA * nB > 0:
-                    total[off + lo_r * nB: off + (lo_r + n_r) * nB] += scatter[r * slot + loc_r: r * slot + loc_r + n_r * nB]
+    total = rows_form_sigma(torch, gs, gb, torch.from_numpy(c).cuda(), world)
     assert _rel(total.cpu().numpy(), want) <= TOL
 
 

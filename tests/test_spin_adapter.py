@@ -187,3 +187,66 @@ def test_spin_adapted_roots_match_reference(name, twoS, nroot):
     hv = torch.empty_like(v[0])
     solver.ci_sigma_builder.Hamiltonian(v[0].contiguous(), hv)
     assert float((hv - float(solver.E[0]) * v[0]).norm()) <= 1e-5
+
+
+@pytest.fixture
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,twoS", CASES)
+def test_adapter_accepts_strided_numpy_views(torch_cuda, name, twoS):
+    g = np.load(os.path.join(GOLD, f"csf_{name}_S{twoS}.npz"))
+    strings, a = _adapter(name, twoS)
+    to_det = np.full(strings.ndet, np.nan)
+    a.csf_C_to_det_C(g["c_csf"], to_det)
+    to_csf = np.full(a.ncsf, np.nan)
+    a.det_C_to_csf_C(g["c_det"], to_csf)
+    # columns of a C-ordered (size, m) basis, as forte2's Davidson closure passes them (ci.py:231-233)
+    basis = np.full((a.ncsf, 3), np.nan)
+    basis[:, 1] = g["c_csf"]
+    to_det2 = np.full(strings.ndet, np.nan)
+    a.csf_C_to_det_C(basis[:, 1], to_det2)
+    assert np.max(np.abs(to_det2 - to_det), initial=0.0) <= 1e-14
+    out = np.full((a.ncsf, 3), np.nan)
+    a.det_C_to_csf_C(g["c_det"], out[:, 2])
+    assert np.max(np.abs(out[:, 2] - to_csf), initial=0.0) <= 1e-14 and np.all(np.isnan(out[:, :2]))
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,twoS", CASES)
+def test_builder_csf_helpers_and_forte2_closure(torch_cuda, name, twoS):
+    strings, a = _adapter(name, twoS)
+    E, H, V = synthetic.integrals(strings.norb, "S")
+    b = f2.CISigmaBuilder(strings, E, H, V, 0)
+    # the exact form: host Slater rules (checked against the reference on the CPU), delivered as a device tensor
+    from forte2_b200.ci_sigma_builder import exact_hdiag_csf
+    hx = b.form_Hdiag_csf(None, a, True)
+    assert hx.is_cuda and hx.shape == (a.ncsf,)
+    assert np.array_equal(hx.cpu().numpy(), exact_hdiag_csf(strings, E, H, V, a))
+    # host helpers of the guess / exact diagonalisation through the builder (checked against the reference on the CPU)
+    from forte2_b200.ci_sigma_builder import csf_hamiltonian, csf_matrix_element
+    assert b.slater_rules_csf(None, a, 0, a.ncsf - 1) == csf_matrix_element(strings, E, H, V, a, 0, a.ncsf - 1)
+    assert b.energy_csf(None, a, 0) == csf_matrix_element(strings, E, H, V, a, 0, 0)
+    if a.ncsf <= 400:
+        Hc = b.form_H_csf(None, a)
+        assert np.array_equal(Hc, csf_hamiltonian(strings, E, H, V, a))
+        assert np.max(np.abs(np.diag(Hc) - hx.cpu().numpy())) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
+        # forte2's sigma closure, verbatim (forte2/ci/ci.py:221-233): numpy vectors, columns of C-ordered blocks
+        rng = np.random.default_rng(5)
+        Bblock = rng.normal(size=(a.ncsf, 2))
+        Sblock = np.full_like(Bblock, np.nan)
+        b_det, sigma_det = np.zeros(strings.ndet), np.zeros(strings.ndet)
+        for i in range(Bblock.shape[1]):
+            a.csf_C_to_det_C(Bblock[:, i], b_det)
+            b.Hamiltonian(b_det, sigma_det)
+            a.det_C_to_csf_C(sigma_det, Sblock[:, i])
+        assert np.max(np.abs(Sblock - Hc @ Bblock)) <= 1e-12 * max(1.0, np.max(np.abs(Hc)))
+        b.set_memory(0)
+        with pytest.raises(RuntimeError, match="Not enough memory"):
+            b.form_H_csf(None, a)
