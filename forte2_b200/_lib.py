@@ -53,6 +53,9 @@ SIGNATURES = {
     "f2_sigma_apply_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p]),
     "f2_sigma_hdiag_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "f2_sigma_hdiag_spin_averaged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "f2_sigma_apply_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "f2_spin2_matrix": (C.c_int, [C.c_void_p, i64p, C.c_int, f64p]),
     "f2_sigma_rows_form": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p]),
     "f2_sigma_apply_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -76,6 +79,11 @@ SIGNATURES = {
                                  C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "f2_dl_scale": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, C.c_void_p]),
+    "f2_dl_residual_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, f64p, f64p, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "f2_dl_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, f64p, f64p,
+                                C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

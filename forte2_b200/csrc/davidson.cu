@@ -202,6 +202,147 @@ __global__ void __launch_bounds__(DL_THREADS) dl_scale_kernel(double* __restrict
         v[e] *= s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused passes of one Davidson-Liu iteration (at most 4 roots, 16 basis vectors).  The candidate block is
+// orthonormalised as a block instead of vector by vector (davidsonliu.py:415-484 does modified Gram-Schmidt
+// with one pass over the basis per candidate and cycle): every pass below reads the basis once, writes the k
+// candidates once and returns, from the same registers, the overlaps the NEXT pass needs.
+//
+//   RESID:  z_j = precondition( sum_i alpha[i,j] (S_i - lam_j B_i) )      residual kernel
+//   else :  z_j = sum_l T[l,j] ( Y_l - sum_i c[i,l] B_i )                 projection + in-block transform
+//   both :  out = [ |r_j|^2 before preconditioning (RESID only) ; d[i,j] = <B_i|z_j> ; g[j,j'] = <z_j|z_j'> ]
+//
+// HBM-bound: 8 (2m + k) or 8 (m + 2k) bytes per element for a few hundred flops.
+constexpr int DLF_MAXK = 4;
+constexpr int DLF_THREADS = 128;
+constexpr int DLF_CTAS = 148 * 4;
+
+struct DlfCoef {
+    double c[DL_MAXV * DLF_MAXK]; // [i * k + j]
+};
+struct DlfSmall {
+    double t[DLF_MAXK * DLF_MAXK];
+};
+
+template <int KT, int MT, bool RESID>
+__global__ void __launch_bounds__(DLF_THREADS)
+    dl_fused_kernel(const double* __restrict__ B, const double* __restrict__ S, int64_t ld, int m, const double* Yin,
+                    int64_t ldin, int kin, const DlfCoef coef, const DlfSmall T, const double* __restrict__ hdiag,
+                    double thresh, double* Zout, int64_t ldout, int kout, int64_t n, double* __restrict__ part) {
+    constexpr int NV = (RESID ? KT : 0) + MT * KT + KT * KT;
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+        acc[v] = 0.0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * DLF_THREADS;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * DLF_THREADS + threadIdx.x; e < n; e += stride) {
+        double b[MT], z[KT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+            b[i] = i < m ? __ldg(B + i * ld + e) : 0.0;
+        if constexpr (RESID) {
+            double s[MT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+                s[i] = i < m ? __ldg(S + i * ld + e) : 0.0;
+            const double h = hdiag ? __ldg(hdiag + e) : 0.0;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                double sb = 0.0, sv = 0.0;
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    const double a = coef.c[i * kout + (j < kout ? j : 0)];
+                    sb = fma(a, b[i], sb);
+                    sv = fma(a, s[i], sv);
+                }
+                double r = j < kout ? sv - T.t[j] * sb : 0.0; // T.t[j] = lam_j
+                acc[j] = fma(r, r, acc[j]);
+                if (hdiag) {
+                    const double d = T.t[j] - h;
+                    r = fabs(d) > thresh ? r / d : 0.0;
+                }
+                z[j] = j < kout ? r : 0.0;
+            }
+        } else {
+            double y[KT];
+#pragma unroll
+            for (int l = 0; l < KT; ++l)
+                y[l] = l < kin ? Yin[l * ldin + e] : 0.0;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int l = 0; l < KT; ++l)
+                    y[l] = fma(-coef.c[i * kin + (l < kin ? l : 0)], b[i], y[l]);
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                double x = 0.0;
+#pragma unroll
+                for (int l = 0; l < KT; ++l)
+                    x = fma(T.t[l * DLF_MAXK + j], y[l], x); // zero outside kin x kout
+                z[j] = x;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+            if (j < kout)
+                Zout[j * ldout + e] = z[j];
+        constexpr int D0 = RESID ? KT : 0;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                acc[D0 + i * KT + j] = fma(b[i], z[j], acc[D0 + i * KT + j]);
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+#pragma unroll
+            for (int jj = 0; jj < KT; ++jj)
+                acc[D0 + MT * KT + j * KT + jj] = fma(z[j], z[jj], acc[D0 + MT * KT + j * KT + jj]);
+    }
+    __shared__ double red[DLF_THREADS / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double x = acc[v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0)
+            red[warp][v] = x;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < NV; v += DLF_THREADS) {
+        double x = 0.0;
+#pragma unroll
+        for (int w = 0; w < DLF_THREADS / 32; ++w)
+            x += red[w][v];
+        part[static_cast<size_t>(blockIdx.x) * NV + v] = x;
+    }
+}
+
+// out[(rn2: k) ; d: m x kout ; g: kout x kout] from the padded per-CTA partials [ (KT) ; MT x KT ; KT x KT ]
+__global__ void dl_fused_finish_kernel(const double* __restrict__ part, int nctas, int nv, int KT, int MT, bool resid,
+                                       int m, int kout, double* __restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_r = resid ? kout : 0;
+    const int total = n_r + m * kout + kout * kout;
+    if (o >= total)
+        return;
+    int src;
+    if (o < n_r)
+        src = o;
+    else if (o < n_r + m * kout) {
+        const int q = o - n_r;
+        src = (resid ? KT : 0) + (q / kout) * KT + q % kout;
+    } else {
+        const int q = o - n_r - m * kout;
+        src = (resid ? KT : 0) + MT * KT + (q / kout) * KT + q % kout;
+    }
+    double x = 0.0;
+    for (int c = 0; c < nctas; ++c)
+        x += part[static_cast<size_t>(c) * nv + src];
+    out[o] = x;
+}
+
 namespace {
 
 void check_launch() {
@@ -349,6 +490,103 @@ int f2_dl_scale(double* v, double s, int64_t n, void* stream) {
     try {
         dl_scale_kernel<<<grid_for(n), DL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(v, s, n);
         check_launch();
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+} // extern "C"
+
+namespace {
+template <int KT, int MT, bool RESID>
+void launch_fused(int grid, cudaStream_t st, const double* B, const double* S, int64_t ld, int m, const double* Yin,
+                  int64_t ldin, int kin, const DlfCoef& coef, const DlfSmall& T, const double* hdiag, double thresh,
+                  double* Zout, int64_t ldout, int kout, int64_t n, double* work, double* out) {
+    constexpr int NV = (RESID ? KT : 0) + MT * KT + KT * KT;
+    dl_fused_kernel<KT, MT, RESID><<<grid, DLF_THREADS, 0, st>>>(B, S, ld, m, Yin, ldin, kin, coef, T, hdiag, thresh,
+                                                                 Zout, ldout, kout, n, work);
+    check_launch();
+    const int total = (RESID ? kout : 0) + m * kout + kout * kout;
+    dl_fused_finish_kernel<<<(total + 63) / 64, 64, 0, st>>>(work, grid, NV, KT, MT, RESID, m, kout, out);
+    check_launch();
+}
+
+template <bool RESID>
+void dispatch_fused(int grid, cudaStream_t st, const double* B, const double* S, int64_t ld, int m, const double* Yin,
+                    int64_t ldin, int kin, const DlfCoef& coef, const DlfSmall& T, const double* hdiag, double thresh,
+                    double* Zout, int64_t ldout, int kout, int64_t n, double* work, double* out) {
+    const int kt = (kin > kout ? kin : kout) <= 1 ? 1 : ((kin > kout ? kin : kout) <= 2 ? 2 : 4);
+    const int mt = m <= 4 ? 4 : (m <= 8 ? 8 : (m <= 12 ? 12 : 16));
+#define F2_FUSED(KT, MT)                                                                                            \
+    launch_fused<KT, MT, RESID>(grid, st, B, S, ld, m, Yin, ldin, kin, coef, T, hdiag, thresh, Zout, ldout, kout, n, \
+                                work, out)
+#define F2_FUSED_M(KT)                                                                                              \
+    do {                                                                                                            \
+        if (mt == 4)                                                                                                \
+            F2_FUSED(KT, 4);                                                                                        \
+        else if (mt == 8)                                                                                           \
+            F2_FUSED(KT, 8);                                                                                        \
+        else if (mt == 12)                                                                                          \
+            F2_FUSED(KT, 12);                                                                                       \
+        else                                                                                                        \
+            F2_FUSED(KT, 16);                                                                                       \
+    } while (0)
+    if (kt == 1)
+        F2_FUSED_M(1);
+    else if (kt == 2)
+        F2_FUSED_M(2);
+    else
+        F2_FUSED_M(4);
+#undef F2_FUSED_M
+#undef F2_FUSED
+}
+
+int fused_grid(int64_t n) {
+    const int64_t need = (n + DLF_THREADS - 1) / DLF_THREADS;
+    return static_cast<int>(need < 1 ? 1 : (need < DLF_CTAS ? need : DLF_CTAS));
+}
+} // namespace
+
+extern "C" {
+
+int f2_dl_residual_fused(const double* B, const double* S, int64_t ld, int m, const double* alpha_host,
+                         const double* lam_host, const double* hdiag, double* R, int64_t ldr, int k,
+                         double denom_threshold, int64_t n, double* out_dev, double* work_dev, void* stream) {
+    try {
+        if (m < 1 || m > DL_MAXV || k < 1 || k > DLF_MAXK || n < 0)
+            throw std::invalid_argument("f2_dl_residual_fused: need 1 <= m <= 16, 1 <= k <= 4 and n >= 0");
+        DlfCoef a;
+        DlfSmall l;
+        std::memset(&a, 0, sizeof(a));
+        std::memset(&l, 0, sizeof(l));
+        std::memcpy(a.c, alpha_host, sizeof(double) * m * k);
+        std::memcpy(l.t, lam_host, sizeof(double) * k);
+        dispatch_fused<true>(fused_grid(n), static_cast<cudaStream_t>(stream), B, S, ld, m, nullptr, 0, k, a, l, hdiag,
+                             denom_threshold, R, ldr, k, n, work_dev, out_dev);
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_dl_project(const double* B, int64_t ld, int m, const double* Yin, int64_t ldin, int kin, const double* c_host,
+                  const double* T_host, double* Zout, int64_t ldout, int kout, int64_t n, double* out_dev,
+                  double* work_dev, void* stream) {
+    try {
+        if (m < 0 || m > DL_MAXV || kin < 1 || kin > DLF_MAXK || kout < 1 || kout > DLF_MAXK || n < 0)
+            throw std::invalid_argument("f2_dl_project: need 0 <= m <= 16, 1 <= kin, kout <= 4 and n >= 0");
+        DlfCoef c;
+        DlfSmall T;
+        std::memset(&c, 0, sizeof(c));
+        std::memset(&T, 0, sizeof(T));
+        if (m > 0)
+            std::memcpy(c.c, c_host, sizeof(double) * m * kin);
+        for (int l = 0; l < kin; ++l)
+            for (int j = 0; j < kout; ++j)
+                T.t[l * DLF_MAXK + j] = T_host[l * kout + j];
+        dispatch_fused<false>(fused_grid(n), static_cast<cudaStream_t>(stream), B, nullptr, ld, m, Yin, ldin, kin, c, T,
+                              nullptr, 0.0, Zout, ldout, kout, n, work_dev, out_dev);
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);

@@ -1,6 +1,8 @@
 // Opaque handle types behind include/forte2_b200.h.
 #pragma once
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -31,9 +33,12 @@ struct f2_strings {
     } mutable export_cache;
     // the replacement lists live on the GPU with the strings object, not with the builder, because
     // forte2 rebuilds the builder on every CI run but keeps CIStrings (forte2/ci/ci.py:171-192)
-    f2::DevStrings* dev = nullptr;
+    // One copy per device, created on first use and kept until the strings object dies: builders on different
+    // devices share one CIStrings and hold raw pointers into this map, so an entry is never replaced or freed early.
+    std::map<int, f2::DevStrings*> dev;
+    std::mutex dev_mutex;
     ~f2_strings() {
-        if (dev)
-            f2::destroy_dev_strings(dev);
+        for (auto& kv : dev)
+            f2::destroy_dev_strings(kv.second);
     }
 };

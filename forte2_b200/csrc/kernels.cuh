@@ -1341,11 +1341,39 @@ struct HdiagBlock {
     uint32_t tile0;
 };
 
+// Spin-symmetric diagonal for determinant-basis solves without a CSF adapter: the determinant energies averaged
+// over the determinants of the same orbital configuration (same doubly / singly occupied orbitals, same Ms).  Only
+// the exchange between singly occupied orbitals depends on how the spins are distributed:
+//   E_avg = E_det + sum_{p<q open, same spin in this determinant} K_pq - P_same(N_open) sum_{p<q open} K_pq
+// with K_pq = <pq|qp> and P_same the fraction of spin distributions that give p and q the same spin.  A
+// preconditioner built from it commutes with S^2, so spin-pure trial vectors stay spin-pure.
+struct SpinAvg {
+    const double* kx;    // [norb * norb] exchange integrals
+    const double* psame; // [65] P_same by number of open shells
+};
+
+__device__ __forceinline__ double open_shell_exchange(uint64_t w, const double* __restrict__ kx, int norb) {
+    double s = 0.0;
+    uint64_t u = w;
+    while (u) {
+        const int p = __ffsll(static_cast<long long>(u)) - 1;
+        u &= u - 1;
+        uint64_t v = u;
+        while (v) {
+            const int q = __ffsll(static_cast<long long>(v)) - 1;
+            v &= v - 1;
+            s += kx[p * norb + q];
+        }
+    }
+    return s;
+}
+
 // E_det = E + ea[Ia] + eb[Ib] + sum_{q in Ib} ja[Ia][q]   (SlaterRules::energy)
 __global__ void hdiag_kernel(double* __restrict__ out, const HdiagBlock* __restrict__ blocks,
                              int nblocks, const double* __restrict__ ea,
                              const double* __restrict__ eb, const double* __restrict__ ja,
-                             const uint64_t* __restrict__ bstr, int norb, double E) {
+                             const uint64_t* __restrict__ bstr, int norb, double E,
+                             const uint64_t* __restrict__ astr = nullptr, SpinAvg avg = SpinAvg{nullptr, nullptr}) {
     int lo = 0, hi = nblocks - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -1358,13 +1386,20 @@ __global__ void hdiag_kernel(double* __restrict__ out, const HdiagBlock* __restr
     const int i = blockIdx.x - b.tile0; // one alpha row per CTA
     const double* jrow = ja + static_cast<size_t>(b.a0 + i) * norb;
     const double e0 = E + ea[b.a0 + i];
+    const uint64_t wa = avg.kx ? astr[b.a0 + i] : 0ull;
     for (int j = threadIdx.x; j < b.nB; j += blockDim.x) {
-        uint64_t w = bstr[b.b0 + j];
+        const uint64_t wb = bstr[b.b0 + j];
+        uint64_t w = wb;
         double e = e0 + eb[b.b0 + j];
         while (w) {
             const int q = __ffsll(static_cast<long long>(w)) - 1;
             e += jrow[q];
             w &= w - 1;
+        }
+        if (avg.kx) {
+            const uint64_t open = wa ^ wb;
+            e += open_shell_exchange(wa & open, avg.kx, norb) + open_shell_exchange(wb & open, avg.kx, norb) -
+                 avg.psame[__popcll(open)] * open_shell_exchange(open, avg.kx, norb);
         }
         out[b.off + static_cast<int64_t>(i) * b.nB + j] = e;
     }

@@ -71,15 +71,23 @@ struct DevStrings {
     bool al16 = false;        // every block offset and leading dimension is even
 };
 
-void destroy_dev_strings(DevStrings* d) { delete d; }
+void destroy_dev_strings(DevStrings* d) {
+    if (!d)
+        return;
+    int cur = 0;
+    const bool have = cudaGetDevice(&cur) == cudaSuccess;
+    cudaSetDevice(d->device); // the buffers are freed on the device that owns them
+    delete d;
+    if (have)
+        cudaSetDevice(cur);
+}
 
+// the device copy of the lists for `device` (the caller has made it current); created once per device
 static DevStrings* device_strings(f2_strings* S, int device) {
-    if (S->dev && S->dev->device == device)
-        return S->dev;
-    if (S->dev) {
-        delete S->dev;
-        S->dev = nullptr;
-    }
+    std::lock_guard<std::mutex> lock(S->dev_mutex);
+    auto it = S->dev.find(device);
+    if (it != S->dev.end())
+        return it->second;
     const CIStringsHost& h = *S->host;
     const DeviceLists& L = h.device_lists();
     auto d = std::make_unique<DevStrings>();
@@ -129,8 +137,9 @@ static DevStrings* device_strings(f2_strings* S, int device) {
     d->blk_off.upload(off);
     d->blk_offT.upload(offT);
     d->al16 = even;
-    S->dev = d.release();
-    return S->dev;
+    DevStrings* out = d.release();
+    S->dev[device] = out;
+    return out;
 }
 
 // one same-spin launch plan: which column groups exist, where each (row class, group) sits
@@ -199,6 +208,7 @@ struct f2_sigma {
     size_t memory_size = size_t(1) << 30;    // bytes; reference default 1 GiB
     // integral tables
     DevBuf<double> Vx, W[2], ea, eb, ja;
+    DevBuf<double> kx, psame; // exchange integrals <pq|qp> and P_same(N_open): the spin-averaged diagonal
     DevBuf<uint16_t> rowmap;
     DevBuf<uint32_t> tgt; // [M][nbs] beta replacement table
     int tgt_pair = 0;
@@ -563,6 +573,30 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
                 e[g++] = x;
             }
     };
+    {
+        // P_same(No): of the C(No, nao) ways to give nao of the No singly occupied orbitals an alpha electron
+        // (nao - nbo = na - nb), the fraction in which two given ones carry the same spin
+        std::vector<double> ps(65, 0.0);
+        auto binom = [](int n, int k) {
+            if (k < 0 || k > n)
+                return 0.0;
+            double x = 1.0;
+            for (int i = 1; i <= k; ++i)
+                x = x * (n - k + i) / i;
+            return x;
+        };
+        for (int no = 2; no <= 64; ++no) {
+            const int twoms = h.na - h.nb;
+            if ((no + twoms) % 2 != 0 || no + twoms < 0 || no - twoms < 0)
+                continue;
+            const int nao = (no + twoms) / 2;
+            const double all = binom(no, nao);
+            if (all > 0.0)
+                ps[no] = (binom(no - 2, nao - 2) + binom(no - 2, nao)) / all;
+        }
+        b.kx.upload(K);
+        b.psame.upload(ps);
+    }
     std::vector<double> ea, eb, ja;
     string_energy(h.space(0, K_STR_N), ea, &ja);
     string_energy(h.space(1, K_STR_N), eb, nullptr);
@@ -1672,6 +1706,20 @@ int f2_sigma_apply(f2_sigma* h, const double* C_dev, double* sigma_dev, int64_t 
     }
 }
 
+int f2_sigma_apply_batch(f2_sigma* h, const double* C_dev, double* sigma_dev, int64_t n, int nvec, int64_t ld,
+                         void* stream) {
+    try {
+        if (nvec < 0 || (nvec > 1 && ld < n))
+            throw std::invalid_argument("CISigmaBuilder.Hamiltonian: need nvec >= 0 and ld >= ndet");
+        for (int v = 0; v < nvec; ++v)
+            apply(*h, C_dev + static_cast<int64_t>(v) * ld, sigma_dev + static_cast<int64_t>(v) * ld, n,
+                  static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
 int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, int64_t n) {
     try {
         const CIStringsHost& s = *h->S->host;
@@ -2008,7 +2056,17 @@ int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev
     }
 }
 
+static int hdiag_part_impl(f2_sigma* h, double* out_local_dev, int rank, int world, bool spin_averaged, void* stream);
+
 int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream) {
+    return hdiag_part_impl(h, out_local_dev, rank, world, false, stream);
+}
+
+int f2_sigma_hdiag_spin_averaged(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream) {
+    return hdiag_part_impl(h, out_local_dev, rank, world, true, stream);
+}
+
+static int hdiag_part_impl(f2_sigma* h, double* out_local_dev, int rank, int world, bool spin_averaged, void* stream) {
     try {
         if (!h || !out_local_dev)
             throw std::invalid_argument("null argument");
@@ -2038,7 +2096,8 @@ int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world,
         dev.upload(hb);
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         hdiag_kernel<<<tile0, 256, 0, st>>>(out_local_dev, dev.p, static_cast<int>(hb.size()), h->ea.p, h->eb.p,
-                                            h->ja.p, h->D->b_str.p, h->norb, h->E);
+                                            h->ja.p, h->D->b_str.p, h->norb, h->E, h->D->a_str.p,
+                                            spin_averaged ? SpinAvg{h->kx.p, h->psame.p} : SpinAvg{nullptr, nullptr});
         F2_CUDA(cudaGetLastError());
         F2_CUDA(cudaStreamSynchronize(st)); // the block table is freed on return
         return F2_OK;

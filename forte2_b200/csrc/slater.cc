@@ -124,3 +124,42 @@ extern "C" int f2_slater_matrix(const f2_strings* h, double E, const double* H, 
         return status_of(e);
     }
 }
+
+// <I|S^2|J> between determinants of the CI space, on the host: the spin control of determinant-basis solves
+// (forte2/sci/sci.py:405-455 builds the same matrix over its guess determinants with det.spin2,
+// forte2/determinant/determinant_helpers.cc:154-203).  S^2 = S- S+ + Sz (Sz + 1):
+//   diagonal      Ms (Ms + 1) + (number of singly occupied orbitals that carry a beta electron)
+//   off-diagonal  -phase when J is I with the spins of two singly occupied orbitals exchanged, 0 otherwise;
+//                 phase = product of the four same-spin string phases (no cross-spin phase, as everywhere here)
+extern "C" int f2_spin2_matrix(const f2_strings* h, const int64_t* addresses, int n, double* out) {
+    try {
+        const CIStringsHost& S = *h->host;
+        std::vector<uint64_t> a(n), b(n);
+        for (int k = 0; k < n; ++k) {
+            if (addresses[k] < 0 || addresses[k] >= S.ndet)
+                throw std::out_of_range("f2_spin2_matrix: determinant address out of range");
+            S.determinant(addresses[k], a[k], b[k]);
+        }
+        const double ms = 0.5 * (S.na - S.nb);
+        auto below = [](uint64_t w, int p) { return __builtin_popcountll(w & ((1ull << p) - 1ull)); };
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c <= r; ++c) {
+                double x = 0.0;
+                const uint64_t da = a[r] ^ a[c], db = b[r] ^ b[c];
+                if (da == 0 && db == 0) {
+                    x = ms * (ms + 1.0) + __builtin_popcountll(b[r] & ~a[r]);
+                } else if (da == db && __builtin_popcountll(da) == 2 && (a[r] & da) == (b[c] & db) &&
+                           (a[c] & da) == (b[r] & db) && __builtin_popcountll(a[r] & da) == 1) {
+                    const int j = __builtin_ctzll(a[r] & da); // alpha in r, beta in c
+                    const int i = __builtin_ctzll(a[c] & da); // alpha in c, beta in r
+                    const int par = below(a[c], i) + below(b[c], j) + below(a[r], j) + below(b[r], i);
+                    x = (par & 1) ? 1.0 : -1.0;
+                }
+                out[static_cast<size_t>(r) * n + c] = x;
+                out[static_cast<size_t>(c) * n + r] = x;
+            }
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}

@@ -324,6 +324,9 @@ void to_device(f2_adapter& A, int device) {
     A.d_det_ptr.upload(A.det_ptr);
     A.d_det_csf.upload(A.det_csf);
     A.d_det_coef.upload(A.det_coef);
+    // cudaMemcpy from pageable memory returns once the data is staged: the DMA tail must have landed before a
+    // kernel on the caller's (possibly non-blocking) stream reads the tables
+    F2A_CUDA(cudaDeviceSynchronize());
     A.device = device;
 }
 

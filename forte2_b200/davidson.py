@@ -133,6 +133,7 @@ class _Kernels(_ChunkedOps):
         self.work = torch.empty(int(self.L.f2_dl_workspace_doubles()), dtype=torch.float64, device=device)
         self.small = torch.empty(256, dtype=torch.float64, device=device)
         self.launches = 0
+        self.bytes = 0  # 8 x (vector rows read + written) x length, call by call: the HBM traffic of the passes
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -162,6 +163,7 @@ class _Kernels(_ChunkedOps):
                 _lib.check(self.L.f2_dl_dots(ap + 8 * lda * i0, lda, pc, xp + 8 * ldx * j0, ldx, qc, n,
                                              res.data_ptr(), self.work.data_ptr(), self._stream()))
                 self.launches += 2 * ((qc + 3) // 4)
+                self.bytes += 8 * n * (pc * ((qc + 3) // 4) + qc)
                 out[i0:i0 + pc, j0:j0 + qc] = self._reduce(res).reshape(pc, qc)
         return out
 
@@ -181,6 +183,7 @@ class _Kernels(_ChunkedOps):
                                         ss.data_ptr() if want_sumsq else None, self.work.data_ptr(),
                                         self._stream()))
         self.launches += 2 if want_sumsq else 1
+        self.bytes += 8 * n * (p + k + (k if beta != 0.0 else 0))
         return self._reduce(ss) if want_sumsq else None
 
     def _residual16(self, B, S, alpha, lam, hdiag, R, thresh):
@@ -197,12 +200,60 @@ class _Kernels(_ChunkedOps):
                                          hdiag.data_ptr() if hdiag is not None else None, rp, ldr, k,
                                          float(thresh), n, out.data_ptr(), self.work.data_ptr(), self._stream()))
         self.launches += 2
+        self.bytes += 8 * n * (2 * m + k + 1)
         return self._reduce(out)
 
     def scale(self, v, s):
         assert v.dim() == 1 and v.stride(0) == 1
         _lib.check(self.L.f2_dl_scale(v.data_ptr(), float(s), v.shape[0], self._stream()))
         self.launches += 1
+        self.bytes += 16 * v.shape[0]
+
+    # ---- fused passes (at most 4 roots, 16 basis vectors): f2_dl_residual_fused / f2_dl_project
+    FUSED_MAXK, FUSED_MAXM = 4, 16
+
+    def residual_fused(self, B, S, alpha, lam, hdiag, R, thresh):
+        """R_j = preconditioned residual of Ritz pair j; returns (|r_j|^2 before preconditioning (k),
+        <B_i|R_j> (m, k), <R_j|R_j'> (k, k)), summed over ranks"""
+        bp, ld, m, n = self._rows(B)
+        sp, lds, m2, _ = self._rows(S)
+        rp, ldr, k, _ = self._rows(R)
+        assert m == m2 and (ld == lds or m == 1) and m <= self.FUSED_MAXM and k <= self.FUSED_MAXK
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(m, k)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(k)
+        nout = k + m * k + k * k
+        out = self.small[:nout]
+        _lib.check(self.L.f2_dl_residual_fused(bp, sp, ld, m, alpha.ctypes.data_as(_lib.f64p),
+                                               lam.ctypes.data_as(_lib.f64p),
+                                               hdiag.data_ptr() if hdiag is not None else None, rp, ldr, k,
+                                               float(thresh), n, out.data_ptr(), self.work.data_ptr(), self._stream()))
+        self.launches += 2
+        self.bytes += 8 * n * (2 * m + k + 1)
+        o = self._reduce(out)
+        return o[:k], o[k:k + m * k].reshape(m, k), o[k + m * k:].reshape(k, k)
+
+    def project(self, B, Y, c, T, Z):
+        """Z_j = sum_l T[l, j] (Y_l - sum_i c[i, l] B_i); Z may alias Y.  Returns (<B_i|Z_j> (m, kout),
+        <Z_j|Z_j'> (kout, kout)), summed over ranks"""
+        yp, ldy, kin, n = self._rows(Y)
+        zp, ldz, kout, _ = self._rows(Z)
+        if B is None or B.shape[0] == 0:
+            bp, ld, m = yp, ldy, 0
+            c = np.zeros((1, kin))
+        else:
+            bp, ld, m, _ = self._rows(B)
+        assert m <= self.FUSED_MAXM and kin <= self.FUSED_MAXK and kout <= self.FUSED_MAXK
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(max(m, 1), kin)
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(kin, kout)
+        nout = m * kout + kout * kout
+        out = self.small[:nout]
+        _lib.check(self.L.f2_dl_project(bp, ld, m, yp, ldy, kin, c.ctypes.data_as(_lib.f64p),
+                                        T.ctypes.data_as(_lib.f64p), zp, ldz, kout, n, out.data_ptr(),
+                                        self.work.data_ptr(), self._stream()))
+        self.launches += 2
+        self.bytes += 8 * n * (m + kin + kout)
+        o = self._reduce(out)
+        return o[:m * kout].reshape(m, kout), o[m * kout:].reshape(kout, kout)
 
 
 class DavidsonLiuSolver:
@@ -364,6 +415,87 @@ class DavidsonLiuSolver:
                 self._accepted[j] = True
         return added
 
+    def _fused_ok(self, m, k):
+        return (self._proj_out is None and hasattr(self.k, "project") and 0 < k <= self.k.FUSED_MAXK
+                and m <= self.k.FUSED_MAXM)
+
+    @staticmethod
+    def _gram_schmidt_coefficients(g, alive, room, discard):
+        """Sequential Gram-Schmidt of the columns y_j (Gram matrix g) in coefficient form: returns T (k, nacc) with
+        z = y T orthonormal, skipping columns whose remainder is shorter than `discard` (davidsonliu.py:460-463)
+        and stopping at `room` accepted columns, and the list of accepted columns."""
+        k = g.shape[0]
+        cols, acc = [], []
+        for j in range(k):
+            if not alive[j] or len(cols) >= room:
+                continue
+            t = np.zeros(k)
+            t[j] = 1.0
+            for _ in range(2):
+                for ta in cols:
+                    t = t - (ta @ g @ t) * ta
+            nrm2 = float(t @ g @ t)
+            if not np.isfinite(nrm2) or nrm2 < discard * discard:
+                continue
+            cols.append(t / np.sqrt(nrm2))
+            acc.append(j)
+        T = np.stack(cols, axis=1) if cols else np.zeros((k, 0))
+        return T, acc
+
+    def _add_block_orthonormalized(self, cand, c):
+        """Block form of _add_and_orthonormalize for at most 4 candidates and 16 basis vectors (the usual CI
+        solve): cand (k, size) is projected against b[:basis_size] with the overlaps c = <b_i|cand_j> already
+        known from the pass that produced it (None: computed here), re-projected until the overlaps of the
+        normalised remainders are below the reference's threshold, then orthonormalised among themselves and
+        written to the next basis slots.  Every pass reads the basis once for all candidates and returns the
+        overlaps of its own result.  Returns the number of vectors added, or -1 if the block did not reach the
+        thresholds (the caller then takes the vector-by-vector path)."""
+        k, cur = cand.shape[0], self.basis_size
+        room = self.max_subspace_size - cur
+        self._accepted = [False] * k
+        if room <= 0:
+            return 0
+        B = self.b[:cur] if cur > 0 else None
+        eye = np.eye(k)
+        if c is None:
+            c = self.k.dots(B, cand) if cur > 0 else np.zeros((0, k))
+        tiny = self.schmidt_orthogonality_threshold
+        d = g = None
+        for cycle in range(10):
+            d, g = self.k.project(B, cand, c, eye, cand)
+            norms = np.sqrt(np.maximum(np.diag(g), 0.0))
+            alive = np.isfinite(norms) & (norms >= self.schmidt_discard_threshold)
+            if not alive.any():
+                return 0
+            rel = max((np.abs(d[:, j]).max() / norms[j] for j in range(k) if alive[j] and cur > 0), default=0.0)
+            if rel < tiny:
+                break
+            c = d
+        else:
+            return -1
+        # remainder after one more (tiny) projection has the Gram matrix g - d^T d to first order
+        g2 = g - d.T @ d if cur > 0 else g
+        T, acc = self._gram_schmidt_coefficients(g2, alive, room, self.schmidt_discard_threshold)
+        if not acc:
+            return 0
+        slots = self.b[cur:cur + len(acc)]
+        dz, gz = self.k.project(B, cand, d if cur > 0 else np.zeros((0, k)), T, slots)
+        for refine in range(3):
+            off = max(np.abs(dz).max() if cur > 0 else 0.0, np.abs(gz - np.eye(len(acc))).max())
+            if off < tiny:
+                break
+            # nearly dependent candidates: the Gram form loses digits; one more pass on the result restores them
+            T2, acc2 = self._gram_schmidt_coefficients(gz - (dz.T @ dz if cur > 0 else 0.0), np.ones(len(acc), bool),
+                                                       len(acc), self.schmidt_discard_threshold)
+            if len(acc2) != len(acc):
+                return -1
+            dz, gz = self.k.project(B, slots, dz if cur > 0 else np.zeros((0, len(acc))), T2, slots)
+        else:
+            return -1
+        for j in acc:
+            self._accepted[j] = True
+        return len(acc)
+
     def _events(self):
         if self.device.type == "cuda":
             return self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
@@ -406,11 +538,13 @@ class DavidsonLiuSolver:
         self.iter = 0
         self.converged = False
         self.iter_times = []
+        self.iter_bytes = []  # bytes moved by the solver's own passes in each iteration (sigma builds excluded)
         self.history = []
         g_valid = self.sigma_size  # rows/columns of self.G that are up to date
 
         for self.iter in range(self.maxiter):
             t0 = time.perf_counter()
+            bytes0 = getattr(self.k, "bytes", 0)
             ev0, ev1 = self._events()
             ev0.record()
             # 2. sigma for the new basis vectors
@@ -440,8 +574,14 @@ class DavidsonLiuSolver:
             ar, lamr = alpha[:, :kr], lam[:kr]
 
             # 4. residuals, their norms and the preconditioned corrections in one pass
-            rn2 = self.k.residual(Bblk, Sblk, ar, lamr, self.h_diag, self.r[:kr],
-                                  self.preconditioner_denom_threshold)
+            fused = self._fused_ok(m, kr)
+            c_res = None
+            if fused:
+                rn2, c_res, _ = self.k.residual_fused(Bblk, Sblk, ar, lamr, self.h_diag, self.r[:kr],
+                                                      self.preconditioner_denom_threshold)
+            else:
+                rn2 = self.k.residual(Bblk, Sblk, ar, lamr, self.h_diag, self.r[:kr],
+                                      self.preconditioner_denom_threshold)
             rnorms = np.sqrt(rn2)
             avg_e = float(lamr.mean())
             max_de = float(np.max(np.abs(lamr - self.lam_old[:kr])))
@@ -452,6 +592,7 @@ class DavidsonLiuSolver:
                 ev1.record()
                 ev1.synchronize()
                 self.iter_times.append(ev0.elapsed_time(ev1) * 1e-3)
+                self.iter_bytes.append(getattr(self.k, "bytes", 0) - bytes0)
                 self.history.append((self.iter, avg_e, max_de, max_r, m, m_new))
                 break
             # Root locking (a deliberate difference from davidsonliu.py:306-366): the reference adds a
@@ -475,6 +616,8 @@ class DavidsonLiuSolver:
                 self.G[:k, :k] = Gk
                 self.basis_size = self.sigma_size = g_valid = k
                 m = k
+                if c_res is not None:  # overlaps with the collapsed basis b_new = B alpha_k
+                    c_res = ak.T @ c_res
 
             # 6. corrections: project out, orthonormalise against the basis, append
             to_add = min(len(active), self.max_subspace_size - self.basis_size)
@@ -487,7 +630,11 @@ class DavidsonLiuSolver:
                         self.r[dst].copy_(self.r[src])
             R0 = self.r[:to_add]
             self.do_project_out(R0)
-            added = self._add_and_orthonormalize(R0)
+            added = -1
+            if fused and c_res is not None:
+                added = self._add_block_orthonormalized(R0, c_res[:, active[:to_add]])
+            if added < 0:
+                added = self._add_and_orthonormalize(R0)
             self.basis_size += added
             msg = ""
             missing = to_add - added
@@ -500,6 +647,7 @@ class DavidsonLiuSolver:
             ev1.record()
             ev1.synchronize()
             self.iter_times.append(ev0.elapsed_time(ev1) * 1e-3)
+            self.iter_bytes.append(getattr(self.k, "bytes", 0) - bytes0)
             self.history.append((self.iter, avg_e, max_de, max_r, self.basis_size, m_new))
             self._say(f"{self.iter:4d} {avg_e:20.12f} {max_de:+12.4e} {max_r:+12.4e} {self.basis_size:4d} "
                       f"{time.perf_counter() - t0:10.4f} {msg}")

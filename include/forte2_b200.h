@@ -86,6 +86,10 @@ int f2_sigma_set_log_level(f2_sigma* h, int level);
 /* CISigmaBuilder::Hamiltonian (ci_sigma_builder.cc:187-218) on DEVICE buffers of ndet doubles,
  * sigma overwritten; stream = cudaStream_t (NULL = default stream). */
 int f2_sigma_apply(f2_sigma* h, const double* C_dev, double* sigma_dev, int64_t n, void* stream);
+/* the same for nvec trial vectors, vector v at C_dev + v * ld (ld >= n): what the Davidson-Liu closure of
+ * forte2/ci/ci.py:228-233 does column by column, as one call */
+int f2_sigma_apply_batch(f2_sigma* h, const double* C_dev, double* sigma_dev, int64_t n, int nvec, int64_t ld,
+                         void* stream);
 /* same call on HOST buffers (what the reference's numpy-facing method receives): H2D copy, device
  * build, D2H copy, synchronous. */
 int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, int64_t n);
@@ -136,6 +140,10 @@ int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev
 
 /* determinant energies of the owned rows, in the local (row slab) layout; synchronises the stream */
 int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream);
+/* the same averaged over the determinants of each orbital configuration (same doubly / singly occupied orbitals):
+ * a diagonal that commutes with S^2, the preconditioner of determinant-basis solves with spin control where the
+ * reference would use form_Hdiag_csf (ci_sigma_builder.cc:317-370) through its CSF adapter */
+int f2_sigma_hdiag_spin_averaged(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream);
 
 /* Rows form of the sharded build: no rank holds the full trial vector.  Available when the CI space is
  * served by a gather-form opposite-spin kernel (f2_sigma_t3_shape out[5]): one determinant block, or
@@ -160,6 +168,9 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
  * forte2/ci/ci.py:411-452.  H, V as in f2_sigma_create.  Needs no GPU. */
 int f2_slater_matrix(const f2_strings* h, double E, const double* H, const double* V,
                      const int64_t* addresses, int n, double* out);
+/* <I|S^2|J> for the determinants at the given CI-vector addresses, n x n row-major on the host (det.spin2,
+ * forte2/determinant/determinant_helpers.cc:154-203; used as forte2/sci/sci.py:405-455 uses it) */
+int f2_spin2_matrix(const f2_strings* h, const int64_t* addresses, int n, double* out);
 
 /* ---- CISpinAdapter: forte2/determinant/ci_spin_adapter.h:48, forte2/api/ci_helpers_api.cc:190-201 ----
  * CSF <-> determinant transform of the CI vector, executed before and after every sigma build of a
@@ -212,6 +223,20 @@ int f2_dl_residual(const double* B, const double* S, int64_t ld, int m, const do
                    const double* lam_host, const double* hdiag, double* R, int64_t ldr, int k,
                    double denom_threshold, int64_t n, double* rnorm2_dev, double* work_dev, void* stream);
 int f2_dl_scale(double* v, double s, int64_t n, void* stream);
+
+/* Fused passes of one iteration for at most 4 roots (k) and 16 basis vectors (m): the candidate block is
+ * orthonormalised as a block (the reference does it vector by vector, davidsonliu.py:415-484).  Each pass reads
+ * the basis once and returns the overlaps the next pass needs.
+ *   f2_dl_residual_fused  R_j = preconditioned residual as f2_dl_residual;
+ *                         out_dev = [ |r_j|^2 (k) ; <B_i|R_j> (m x k) ; <R_j|R_j'> (k x k) ]
+ *   f2_dl_project         Z_j = sum_l T[l, j] (Y_l - sum_i c[i, l] B_i), l < kin, j < kout (Z may alias Y; m = 0: no basis)
+ *                         out_dev = [ <B_i|Z_j> (m x kout) ; <Z_j|Z_j'> (kout x kout) ] */
+int f2_dl_residual_fused(const double* B, const double* S, int64_t ld, int m, const double* alpha_host,
+                         const double* lam_host, const double* hdiag, double* R, int64_t ldr, int k,
+                         double denom_threshold, int64_t n, double* out_dev, double* work_dev, void* stream);
+int f2_dl_project(const double* B, int64_t ld, int m, const double* Yin, int64_t ldin, int kin, const double* c_host,
+                  const double* T_host, double* Zout, int64_t ldout, int kout, int64_t n, double* out_dev,
+                  double* work_dev, void* stream);
 
 #ifdef __cplusplus
 }

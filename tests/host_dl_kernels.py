@@ -44,6 +44,34 @@ class HostKernels:
     def scale(self, v, s):
         v.mul_(s)
 
+    FUSED_MAXK, FUSED_MAXM = 4, 16
+    bytes = 0
+
+    def residual_fused(self, B, S, alpha, lam, hdiag, R, thresh):
+        assert B.shape[0] <= 16 and R.shape[0] <= 4
+        a = torch.from_numpy(np.ascontiguousarray(alpha, dtype=np.float64).reshape(B.shape[0], R.shape[0]))
+        l = torch.from_numpy(np.ascontiguousarray(lam, dtype=np.float64))
+        r = a.T @ S - l[:, None] * (a.T @ B)
+        rn2 = (r * r).sum(dim=1).numpy()
+        if hdiag is not None:
+            d = l[:, None] - hdiag[None, :]
+            r = torch.where(d.abs() > thresh, r / d, torch.zeros_like(r))
+        R.copy_(r)
+        return self._reduce(rn2), self._reduce((B @ R.T).numpy()), self._reduce((R @ R.T).numpy())
+
+    def project(self, B, Y, c, T, Z):
+        kin, kout = Y.shape[0], Z.shape[0]
+        assert kin <= 4 and kout <= 4 and (B is None or B.shape[0] <= 16)
+        y = Y.clone()
+        m = 0 if B is None else B.shape[0]
+        if m:
+            cc = torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64).reshape(m, kin))
+            y = y - cc.T @ B
+        TT = torch.from_numpy(np.ascontiguousarray(T, dtype=np.float64).reshape(kin, kout))
+        Z.copy_(TT.T @ y)
+        d = (B @ Z.T).numpy() if m else np.zeros((0, kout))
+        return self._reduce(d).reshape(m, kout), self._reduce((Z @ Z.T).numpy())
+
 
 
 from forte2_b200.davidson import _ChunkedOps  # noqa: E402

@@ -70,6 +70,53 @@ def test_streaming_kernels_match_torch(torch_cuda, n):
     assert torch.allclose(v, -2.5 * B[0])
 
 
+@pytest.mark.parametrize("n", [1, 1000, 65537, (1 << 20) + 3])
+def test_fused_passes_match_torch(torch_cuda, n):
+    """f2_dl_residual_fused / f2_dl_project (block orthonormalisation of the candidates, csrc/davidson.cu) against
+    plain fp64 torch: vectors written, and the overlaps returned from the same pass"""
+    torch = torch_cuda
+    from forte2_b200.davidson import _Kernels
+    k = _Kernels(torch, torch.device("cuda", 0))
+    g = torch.Generator(device="cuda").manual_seed(n + 1)
+    tol = dict(rtol=1e-11, atol=1e-11 * np.sqrt(n))
+    for m, kr in [(1, 1), (3, 2), (6, 3), (12, 3), (9, 4), (16, 4)]:
+        B = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
+        S = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
+        h = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+        lam = np.linspace(-0.3, 0.7, kr)
+        h[:: 5] = lam[0] + 1e-9
+        alpha = np.random.default_rng(m * 7 + kr).normal(size=(m, kr))
+        R = torch.full((kr, n), float("nan"), dtype=torch.float64, device="cuda")
+        rn2, c, gg = k.residual_fused(B, S, alpha, lam, h, R, 1e-8)
+        a = torch.from_numpy(alpha).cuda()
+        Rw = a.T @ S - torch.from_numpy(lam).cuda()[:, None] * (a.T @ B)
+        den = torch.from_numpy(lam).cuda()[:, None] - h[None, :]
+        Rp = torch.where(den.abs() > 1e-8, Rw / den, torch.zeros_like(Rw))
+        assert np.allclose(rn2, (Rw * Rw).sum(dim=1).cpu().numpy(), rtol=1e-12)
+        assert torch.allclose(R, Rp, rtol=1e-12, atol=1e-12)
+        scale = max(1.0, float(Rp.abs().max()))
+        assert np.allclose(c, (B @ Rp.T).cpu().numpy(), rtol=1e-11, atol=1e-11 * np.sqrt(n) * scale)
+        assert np.allclose(gg, (Rp @ Rp.T).cpu().numpy(), rtol=1e-11, atol=1e-11 * np.sqrt(n) * scale ** 2)
+        # projection + in-block transform, fewer outputs than inputs, out of place and in place
+        for kout in sorted({1, kr}):
+            Y = torch.randn((kr, n), dtype=torch.float64, device="cuda", generator=g)
+            cc = np.random.default_rng(kout).normal(size=(m, kr))
+            T = np.random.default_rng(kout + 9).normal(size=(kr, kout))
+            want = torch.from_numpy(T).cuda().T @ (Y - torch.from_numpy(cc).cuda().T @ B)
+            Z = torch.full((kout, n), float("nan"), dtype=torch.float64, device="cuda")
+            d, g2 = k.project(B, Y, cc, T, Z)
+            assert torch.allclose(Z, want, rtol=1e-12, atol=1e-12)
+            assert np.allclose(d, (B @ want.T).cpu().numpy(), **tol) and np.allclose(g2, (want @ want.T).cpu().numpy(), **tol)
+            Y2 = Y.clone()
+            d, g2 = k.project(B, Y2, cc, T, Y2[:kout])
+            assert torch.allclose(Y2[:kout], want, rtol=1e-12, atol=1e-12) and torch.equal(Y2[kout:], Y[kout:])
+        # no basis at all (first guess block)
+        Y = torch.randn((kr, n), dtype=torch.float64, device="cuda", generator=g)
+        T = np.triu(np.random.default_rng(3).normal(size=(kr, kr)))
+        d, g2 = k.project(None, Y, np.zeros((0, kr)), T, Y)
+        assert d.shape == (0, kr) and np.allclose(g2, (Y @ Y.T).cpu().numpy(), **tol)
+
+
 @pytest.mark.parametrize("nroot", [1, 3, 4])
 def test_solver_matches_eigh_on_dense_matrix(torch_cuda, nroot):
     torch = torch_cuda

@@ -115,3 +115,41 @@ def test_chunked_ops_equal_the_unchunked_ones():
         rn = k.residual(B[:m], S[:m], al[:m], lam, hd, R, 1e-8)
         rn1 = one.residual(B[:m], S[:m], al[:m], lam, hd, R1, 1e-8)
         assert torch.allclose(R, R1) and np.allclose(rn, rn1)
+
+
+def test_block_orthonormalisation_is_the_path_taken_and_handles_dependent_candidates():
+    """at most 4 roots and 16 basis vectors: the corrections are orthonormalised as a block (two passes over the
+    basis per iteration instead of 3 per candidate); candidates that are nearly dependent on the basis or on each
+    other go through the re-projection / refinement cycles and still give an orthonormal basis"""
+    calls = {"project": 0, "residual_fused": 0}
+
+    class Counting(HostKernels):
+        def project(self, *a):
+            calls["project"] += 1
+            return HostKernels.project(self, *a)
+
+        def residual_fused(self, *a):
+            calls["residual_fused"] += 1
+            return HostKernels.residual_fused(self, *a)
+
+    A = _matrix(500, 21, coupling=0.05)
+    At = torch.from_numpy(A)
+    s = DavidsonLiuSolver(size=500, nroot=3, _kernels=Counting())
+    s.add_h_diag(np.diag(A).copy())
+    s.add_sigma_builder(lambda B, S: S.copy_(B @ At))
+    lam, ev = s.solve()
+    assert s.converged and np.max(np.abs(lam - np.linalg.eigvalsh(A)[:3])) < 1e-10
+    assert calls["residual_fused"] == len(s.iter_times) and calls["project"] >= 2 * (len(s.iter_times) - 1)
+    assert len(s.iter_bytes) == len(s.iter_times)
+    # direct: a block with one candidate inside the span of the basis, one nearly parallel to another
+    rng = np.random.default_rng(4)
+    s2 = DavidsonLiuSolver(size=300, nroot=3, _kernels=HostKernels())
+    Q, _ = np.linalg.qr(rng.normal(size=(300, 5)))
+    s2.b[:5] = torch.from_numpy(Q.T.copy())
+    s2.basis_size = 5
+    v = rng.normal(size=300)
+    cand = torch.from_numpy(np.stack([Q[:, 0] * 2.0 + 1e-12 * v, v, v * (1 + 1e-9) + 1e-7 * rng.normal(size=300)]))
+    added = s2._add_block_orthonormalized(cand, None)
+    assert added == 2 and s2._accepted == [False, True, True]
+    Bn = s2.b[:7].numpy()
+    assert np.max(np.abs(Bn @ Bn.T - np.eye(7))) < 1e-12
