@@ -47,6 +47,8 @@ SIGNATURES = {
     "f2_sigma_last_ms": (C.c_int, [C.c_void_p, f64p]),
     "f2_sigma_hdiag": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_sigma_rdm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f2_sigma_rdm_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f2_sigma_trdm1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_sigma_launch_count": (C.c_int64, [C.c_void_p]),
     "f2_sigma_t3_shape": (C.c_int, [C.c_void_p, i64p]),
     "f2_sigma_part_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p, i64p]),

@@ -107,6 +107,24 @@ class CISigmaBuilder:
             basis = torch.from_dlpack(basis)
         if not _is_torch_tensor(sigma):
             sigma = torch.from_dlpack(sigma)
+        if basis.dim() == 2 and sigma.dim() == 2:
+            # a block of trial vectors, row v = vector v (the Davidson-Liu basis block): one call for all of them
+            for name, t in (("basis", basis), ("sigma", sigma)):
+                if not t.is_cuda or t.dtype != torch.float64:
+                    raise TypeError(f"{name} must be a float64 CUDA tensor")
+                if t.shape[1] > 1 and t.stride(1) != 1:
+                    raise RuntimeError("np_vector must have stride 1 to convert to std::span.")
+                if t.device.index != self.device:
+                    raise ValueError(f"{name} lives on cuda:{t.device.index}, the builder on cuda:{self.device}")
+            if basis.shape != sigma.shape:
+                raise ValueError("basis and sigma must have the same shape")
+            nvec, n = basis.shape
+            ld = basis.stride(0) if nvec > 1 else n
+            if nvec > 1 and sigma.stride(0) != ld:
+                raise ValueError("basis and sigma blocks must have the same row stride")
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(L.f2_sigma_apply_batch(self._h, basis.data_ptr(), sigma.data_ptr(), n, nvec, ld, stream))
+            return
         for name, t in (("basis", basis), ("sigma", sigma)):
             if not t.is_cuda or t.dtype != torch.float64 or t.dim() != 1:
                 raise TypeError(f"{name} must be a one-dimensional float64 CUDA tensor")
@@ -140,13 +158,14 @@ class CISigmaBuilder:
         return {"M": int(out[0]), "M_pad": int(out[1]), "K_max": int(out[2]), "k_cols": int(out[3]),
                 "pair_compressed": bool(out[4]), "form": "gather" if out[5] else "scatter"}
 
-    def form_Hdiag_det_part(self, rank: int, world: int, local_size: int):
+    def form_Hdiag_det_part(self, rank: int, world: int, local_size: int, spin_averaged: bool = False):
         """determinant energies of the alpha rows rank `rank` of `world` owns, in the local layout of
-        forte2_b200/dist.py (f2_sigma_hdiag_part)"""
+        forte2_b200/dist.py (f2_sigma_hdiag_part / f2_sigma_hdiag_spin_averaged)"""
         import torch
         out = torch.empty(local_size, dtype=torch.float64, device=f"cuda:{self.device}")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(_lib.lib().f2_sigma_hdiag_part(self._h, out.data_ptr(), rank, world, stream))
+        fn = _lib.lib().f2_sigma_hdiag_spin_averaged if spin_averaged else _lib.lib().f2_sigma_hdiag_part
+        _lib.check(fn(self._h, out.data_ptr(), rank, world, stream))
         return out
 
     def form_Hdiag_csf(self, dets, spin_adapter, spin_adapt_full_preconditioner: bool = False):
@@ -263,12 +282,120 @@ class CISigmaBuilder:
         return (self.sf_2rdm(C_left, C_right) - np.einsum("pr,qs->pqrs", g1, g1)
                 + 0.5 * np.einsum("ps,qr->pqrs", g1, g1))
 
-    def form_Hdiag_det(self):
-        """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor."""
+    # ---- three-body blocks, cumulant, transition 1-RDMs (forte2/api/ci_helpers_api.cc:131-145)
+    def _ntriplets(self):
+        n = self.ci_strings.norb
+        return n * (n - 1) * (n - 2) // 6
+
+    def aaa_3rdm(self, C_left, C_right) -> np.ndarray:
+        """<L|a+_p a+_q a+_r a_u a_t a_s|R>, p > q > r, s > t > u, packed (ntriplets, ntriplets) (compute_aaa_3rdm,
+        ci_sigma_builder_3rdm.cc:84-162); (0, 0) with fewer than three orbitals like the reference"""
+        m = self._ntriplets() if self.ci_strings.norb >= 3 else 0
+        return self._rdm(8, C_left, C_right, (m, m))
+
+    def bbb_3rdm(self, C_left, C_right) -> np.ndarray:
+        m = self._ntriplets() if self.ci_strings.norb >= 3 else 0
+        return self._rdm(11, C_left, C_right, (m, m))
+
+    def aab_3rdm(self, C_left, C_right) -> np.ndarray:
+        """<L|a+_p a+_q b+_r b_u a_t a_s|R>, [(p > q), r, (s > t), u] (compute_aab_3rdm,
+        ci_sigma_builder_3rdm.cc:172-262)"""
+        n = self.ci_strings.norb
+        if n < 2:
+            return np.zeros((0, 0, 0, 0))
+        return self._rdm(9, C_left, C_right, (self._npairs(), n, self._npairs(), n))
+
+    def abb_3rdm(self, C_left, C_right) -> np.ndarray:
+        """<L|a+_p b+_q b+_r b_u b_t a_s|R>, [p, (q > r), s, (t > u)] (compute_abb_3rdm,
+        ci_sigma_builder_3rdm.cc:264-318)"""
+        n = self.ci_strings.norb
+        if n < 2:
+            return np.zeros((0, 0, 0, 0))
+        return self._rdm(10, C_left, C_right, (n, self._npairs(), n, self._npairs()))
+
+    def sf_3rdm(self, C_left, C_right) -> np.ndarray:
+        """spin-free 3-RDM, (norb,) * 6 (compute_sf_3rdm, ci_sigma_builder_3rdm.cc:320-495): the four spin blocks from
+        the device, unpacked and summed on the host"""
+        n = self.ci_strings.norb
+        if n < 2:
+            return np.zeros((n,) * 6)
+        sss = None
+        if n >= 3:
+            sss = self.aaa_3rdm(C_left, C_right) + self.bbb_3rdm(C_left, C_right)
+        return assemble_sf_3rdm(n, self.aab_3rdm(C_left, C_right), self.abb_3rdm(C_left, C_right), sss)
+
+    def sf_3cumulant(self, C_left, C_right) -> np.ndarray:
+        """L3 = G3 - sum G1 G2 + sum G1 G1 G1 with the spin-free prefactors of compute_sf_3cumulant
+        (ci_sigma_builder_3rdm.cc:497-540)"""
+        g1 = self.sf_1rdm(C_left, C_right)
+        g2 = self.sf_2rdm(C_left, C_right)
+        return sf_3cumulant_from(g1, g2, self.sf_3rdm(C_left, C_right))
+
+    def _trdm(self, spin, right, C_left, C_right):
+        import torch
+        if not isinstance(right, CISigmaBuilder):
+            raise TypeError("sigmabuilder_right must be a CISigmaBuilder")
+        dev = torch.device("cuda", self.device)
+
+        def vec(x, ndet, name):
+            t = x if _is_torch_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+            if not t.is_cuda or t.dtype != torch.float64 or t.dim() != 1 or (t.numel() > 1 and t.stride(0) != 1):
+                raise TypeError(f"{name} must be a one-dimensional contiguous float64 vector")
+            if t.numel() != ndet:
+                raise RuntimeError("Size of CI vector does not match the number of determinants.")
+            return t
+
+        left = vec(C_left, self.ci_strings.ndet, "C_left")
+        rvec = vec(C_right, right.ci_strings.ndet, "C_right")
+        n = self.ci_strings.norb
+        out = torch.zeros(max(n * n, 1), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_trdm1(self._h, right._h, spin, left.data_ptr(), rvec.data_ptr(), out.data_ptr(),
+                                            stream))
+        return out[: n * n].cpu().numpy().reshape(n, n)
+
+    def a_1trdm(self, sigmabuilder_right, C_left, C_right) -> np.ndarray:
+        """<L|a+_p a_q|R> (alpha) between this builder's CI space (left) and another builder's (right): same orbitals and
+        electron numbers, different symmetry / GAS restrictions (compute_a_1trdm, ci_sigma_builder_1trdm.cc:11-113)"""
+        return self._trdm(0, sigmabuilder_right, C_left, C_right)
+
+    def b_1trdm(self, sigmabuilder_right, C_left, C_right) -> np.ndarray:
+        return self._trdm(1, sigmabuilder_right, C_left, C_right)
+
+    def sf_1trdm(self, sigmabuilder_right, C_left, C_right) -> np.ndarray:
+        """alpha + beta (compute_sf_1trdm, ci_sigma_builder_1trdm.cc:121-133)"""
+        return (self._trdm(0, sigmabuilder_right, C_left, C_right)
+                + self._trdm(1, sigmabuilder_right, C_left, C_right))
+
+    def make_sparse_state(self, C, threshold: float = 1e-12):
+        """{determinant (alpha word, beta word): coefficient} of the entries with |c| > threshold
+        (CISigmaBuilder::make_sparse_state, ci_sigma_builder.cc; the reference returns its SparseState type, which is
+        outside this path: a plain dict keyed by the two occupation words stands in)"""
+        c = C.detach().cpu().numpy() if _is_torch_tensor(C) else np.asarray(C, dtype=np.float64)
+        if c.shape != (self.ci_strings.ndet,):
+            raise RuntimeError("Size of CI vector does not match the number of determinants.")
+        dets = self.ci_strings.make_determinants()
+        keep = np.nonzero(np.abs(c) > threshold)[0]
+        return {(int(dets[k][0]), int(dets[k][1])): float(c[k]) for k in keep}
+
+    def _debug_rdm(self, *args, **kwargs):
+        raise NotImplementedError("the *_debug RDM builders of the reference (sparse-operator based cross-checks, "
+                                  "api/ci_helpers_api.cc:148-190) are not part of the device path")
+
+    a_1rdm_debug = aa_2rdm_debug = ab_2rdm_debug = aaa_3rdm_debug = aab_3rdm_debug = abb_3rdm_debug = _debug_rdm
+    aaaa_4rdm_debug = aaab_4rdm_debug = aabb_4rdm_debug = abbb_4rdm_debug = _debug_rdm
+
+    def form_Hdiag_det(self, spin_averaged: bool = False):
+        """<I|H|I> for every determinant (forte2/determinant/slater_rules.cc:86-121) as a CUDA tensor.
+        spin_averaged: the average over the determinants of each orbital configuration instead (a diagonal that
+        commutes with S^2; the preconditioner of determinant-basis solves with spin control)."""
         import torch
         out = torch.empty(self.ci_strings.ndet, dtype=torch.float64, device=f"cuda:{self.device}")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(_lib.lib().f2_sigma_hdiag(self._h, out.data_ptr(), stream))
+        if spin_averaged:
+            _lib.check(_lib.lib().f2_sigma_hdiag_spin_averaged(self._h, out.data_ptr(), 0, 1, stream))
+        else:
+            _lib.check(_lib.lib().f2_sigma_hdiag(self._h, out.data_ptr(), stream))
         return out
 
 
@@ -336,6 +463,63 @@ def csf_hamiltonian(strings: CIStrings, E, H, V, spin_adapter) -> np.ndarray:
             T[pos[int(d)], i] += c
     Hcsf = T.T @ _slater_block(strings, E, H, V, idx) @ T
     return 0.5 * (Hcsf + Hcsf.T)
+
+
+def _pair_expansion(n):
+    """E[pq, p, q] = +1, E[pq, q, p] = -1 for p > q, pq = p (p - 1) / 2 + q"""
+    m = n * (n - 1) // 2
+    E = np.zeros((m, n, n))
+    p, q = np.tril_indices(n, -1)
+    k = p * (p - 1) // 2 + q
+    E[k, p, q] = 1.0
+    E[k, q, p] = -1.0
+    return E
+
+
+def _triplet_expansion(n):
+    """E[pqr, a, b, c] = sign of the permutation (a, b, c) of p > q > r, pqr = p (p-1) (p-2) / 6 + q (q-1) / 2 + r"""
+    from itertools import combinations
+    m = n * (n - 1) * (n - 2) // 6
+    E = np.zeros((m, n, n, n))
+    for r, q, p in combinations(range(n), 3):
+        k = p * (p - 1) * (p - 2) // 6 + q * (q - 1) // 2 + r
+        E[k, p, q, r] = E[k, r, p, q] = E[k, q, r, p] = 1.0
+        E[k, p, r, q] = E[k, r, q, p] = E[k, q, p, r] = -1.0
+    return E
+
+
+def assemble_sf_3rdm(n, aab, abb, sss) -> np.ndarray:
+    """spin-free 3-RDM from the packed spin blocks (the scatter loops of compute_sf_3rdm,
+    ci_sigma_builder_3rdm.cc:337-493): aab [(p>q), r, (s>t), u], abb [p, (q>r), s, (t>u)], sss = aaa + bbb
+    [(p>q>r), (s>t>u)] (None with fewer than three orbitals)"""
+    P = _pair_expansion(n)
+    m = P.shape[0]
+    # X[p,q,r,s,t,u] = <a+_p a+_q b+_r b_u a_t a_s>, antisymmetric in (p,q) and (s,t)
+    X = np.tensordot(P.reshape(m, n * n).T, aab.reshape(m, n * m * n), axes=1).reshape(n, n, n, m, n)
+    X = np.tensordot(X, P, axes=([3], [0])).transpose(0, 1, 2, 4, 5, 3)  # p q r u s t -> p q r s t u
+    # Y[p,q,r,s,t,u] = <a+_p b+_q b+_r b_u b_t a_s>, antisymmetric in (q,r) and (t,u)
+    Y = np.tensordot(abb.reshape(n, m, n, m), P, axes=([3], [0]))  # p, qr, s, t, u
+    Y = np.tensordot(P, Y, axes=([0], [1])).transpose(2, 0, 1, 3, 4, 5)  # q r p s t u -> p q r s t u
+    out = (X + X.transpose(0, 2, 1, 3, 5, 4) + X.transpose(2, 0, 1, 5, 3, 4)
+           + Y + Y.transpose(1, 0, 2, 4, 3, 5) + Y.transpose(1, 2, 0, 4, 5, 3))
+    if sss is not None and n >= 3:
+        T = _triplet_expansion(n)
+        k = T.shape[0]
+        Tm = T.reshape(k, n ** 3)
+        out = out + (Tm.T @ sss @ Tm).reshape((n,) * 6)
+    return np.ascontiguousarray(out)
+
+
+def sf_3cumulant_from(g1, g2, g3) -> np.ndarray:
+    """compute_sf_3cumulant (ci_sigma_builder_3rdm.cc:497-540) from the spin-free 1-, 2- and 3-RDM"""
+    e = np.einsum
+    return (g3 - e("ps,qrtu->pqrstu", g1, g2) - e("qt,prsu->pqrstu", g1, g2) - e("ru,pqst->pqrstu", g1, g2)
+            + 0.5 * e("pt,qrsu->pqrstu", g1, g2) + 0.5 * e("pu,qrts->pqrstu", g1, g2)
+            + 0.5 * e("qs,prtu->pqrstu", g1, g2) + 0.5 * e("qu,prst->pqrstu", g1, g2)
+            + 0.5 * e("rs,pqut->pqrstu", g1, g2) + 0.5 * e("rt,pqsu->pqrstu", g1, g2)
+            + 2.0 * e("ps,qt,ru->pqrstu", g1, g1, g1) - e("ps,qu,rt->pqrstu", g1, g1, g1)
+            - e("pu,qt,rs->pqrstu", g1, g1, g1) - e("pt,qs,ru->pqrstu", g1, g1, g1)
+            + 0.5 * e("pt,qu,rs->pqrstu", g1, g1, g1) + 0.5 * e("pu,qs,rt->pqrstu", g1, g1, g1))
 
 
 def assemble_sf_2rdm(norb: int, ab: np.ndarray, aa, bb) -> np.ndarray:

@@ -32,6 +32,62 @@ def slater_matrix(strings: CIStrings, E, H, V, addresses) -> np.ndarray:
     return out
 
 
+def spin2_matrix(strings: CIStrings, addresses) -> np.ndarray:
+    """<I|S^2|J> for the determinants at `addresses` (host; det.spin2,
+    forte2/determinant/determinant_helpers.cc:154-203)."""
+    idx = np.ascontiguousarray(addresses, dtype=np.int64)
+    out = np.zeros((idx.size, idx.size))
+    _lib.check(_lib.lib().f2_spin2_matrix(strings._h, idx.ctypes.data_as(_lib.i64p), int(idx.size),
+                                          out.ctypes.data_as(_lib.f64p)))
+    return out
+
+
+def spin_complete(strings: CIStrings, addresses) -> np.ndarray:
+    """The given determinants plus every determinant with the same doubly / singly occupied orbitals and the same
+    Ms (forte2/sci/sci.py:543-565, _generate_spin_complement_pairs): S^2 is block diagonal over such sets.  Keeps
+    the given order, complements appended in first-seen order."""
+    from itertools import combinations
+    out, seen = [], set()
+    for adr in np.asarray(addresses, dtype=np.int64):
+        a, b = strings.determinant(int(adr))
+        docc, socc = a & b, a ^ b
+        open_orbs = [p for p in range(strings.norb) if (socc >> p) & 1]
+        nao = bin(a & socc).count("1")
+        first = [int(adr)]
+        for alpha in combinations(open_orbs, nao):
+            wa = docc
+            for p in alpha:
+                wa |= 1 << p
+            wb = docc | (socc & ~wa)
+            if (wa, wb) != (a, b):
+                first.append(strings.determinant_index((wa, wb)))
+        for x in first:
+            if x not in seen:
+                seen.add(x)
+                out.append(x)
+    return np.array(out, dtype=np.int64)
+
+
+def spin_adapted_guess(strings: CIStrings, E, H, V, addresses, multiplicity, nstates):
+    """Spin-pure guess vectors in the space of the given determinants, as forte2's determinant-basis driver makes them
+    (forte2/sci/sci.py:405-455): the determinant set is made spin complete, S^2 is diagonalised in it, the guess
+    Hamiltonian is diagonalised inside the eigenspace of S(S+1), and the other S^2 eigenvectors are returned to be
+    projected out of every trial vector.  Returns (addresses, guess (n, nstates'), wrong_spin (n, nwrong))."""
+    idx = spin_complete(strings, addresses)
+    S2 = spin2_matrix(strings, idx)
+    svals, svecs = np.linalg.eigh(S2)
+    S = 0.5 * (multiplicity - 1)
+    close = np.isclose(svals, S * (S + 1.0), atol=1e-8)
+    if not close.any():
+        raise ValueError(f"no guess determinant combination with S(S+1) = {S * (S + 1.0)}: the multiplicity "
+                         f"{multiplicity} is not compatible with na - nb = {strings.na - strings.nb}")
+    sub = svecs[:, close]
+    Hg = slater_matrix(strings, E, H, V, idx)
+    Hs = sub.T @ Hg @ sub
+    _, ev = np.linalg.eigh(0.5 * (Hs + Hs.T))
+    return idx, sub @ ev[:, :min(nstates, sub.shape[1])], svecs[:, ~close]
+
+
 class CISolver:
     """One CI state (nroot lowest roots of one determinant space) on one B200.
 
@@ -43,12 +99,20 @@ class CISolver:
     the preconditioner is form_Hdiag_csf, and every sigma build is csf_C_to_det_C -> Hamiltonian ->
     det_C_to_csf_C, all on device vectors.  Without it the solve runs in the determinant basis
     (forte2/ci/rel_ci.py:96-114), which is the only option once the coupling table no longer fits.
+
+    Determinant-basis spin control (`multiplicity` given, no spin adapter): what keeps the roots of a large solve
+    in the wanted spin sector.  As forte2's own determinant-basis driver does (forte2/sci/sci.py:405-455,543-565)
+    the guess determinants are made spin complete, the guesses are eigenvectors of S^2 with eigenvalue S(S+1) and
+    the other S^2 eigenvectors of the guess space are projected out of every sigma and correction vector; in addition
+    the Davidson preconditioner is the configuration-averaged diagonal (f2_sigma_hdiag_spin_averaged), which commutes
+    with S^2, so the corrections do not leave the spin sector.
     """
 
     def __init__(self, strings: CIStrings, E, H, V, nroot=1, davidson_liu_params=None, ci_algorithm="hz",
                  ci_builder_memory=1024, energy_shift=None, log_level=3, device=None, log=None, builder=None,
-                 spin_adapter=None):
+                 spin_adapter=None, multiplicity=None):
         self.spin_adapter = spin_adapter
+        self.multiplicity = None if multiplicity is None else int(multiplicity)
         self.ci_strings = strings
         self.E0, self.H, self.V = float(E), np.asarray(H, dtype=np.float64), np.asarray(V, dtype=np.float64)
         self.nroot = int(nroot)
@@ -69,6 +133,18 @@ class CISolver:
         key = hdiag if self.energy_shift is None else (hdiag - self.energy_shift).abs()
         indices = torch.topk(key, nguess_dets, largest=False, sorted=True).indices
         idx = indices.cpu().numpy().astype(np.int64)
+        if self.multiplicity is not None:
+            idx, coeff, wrong = spin_adapted_guess(self.ci_strings, self.E0, self.H, self.V, idx, self.multiplicity,
+                                                   self.num_guess_states)
+            if coeff.shape[1] < min(self.nroot, self.num_guess_states):
+                raise ValueError(f"only {coeff.shape[1]} guess vectors of multiplicity {self.multiplicity} in the "
+                                 f"space of the {idx.size} guess determinants; increase ndets_per_guess")
+            self.num_guess_states = coeff.shape[1]
+            self._guess_addresses, self._wrong_spin = idx, wrong
+            indices = torch.from_numpy(idx).to(hdiag.device)
+            guess = torch.zeros((self.num_guess_states, ndet), dtype=torch.float64, device=hdiag.device)
+            guess[:, indices] = torch.from_numpy(np.ascontiguousarray(coeff.T)).to(hdiag.device)
+            return guess
         Hguess = slater_matrix(self.ci_strings, self.E0, self.H, self.V, idx)
         _, evecs = np.linalg.eigh(Hguess)
         guess = torch.zeros((self.num_guess_states, ndet), dtype=torch.float64, device=hdiag.device)
@@ -186,7 +262,7 @@ class CISolver:
         b.set_algorithm(self.ci_algorithm.lower())
         if self.spin_adapter is not None:
             return self._run_csf(b)
-        hdiag = b.form_Hdiag_det()
+        hdiag = b.form_Hdiag_det(spin_averaged=self.multiplicity is not None)
         if s.ndet == 1:
             self.evals = hdiag[:1].cpu().numpy()
             self.evecs = torch.ones((1, 1), dtype=torch.float64, device=hdiag.device)
@@ -198,11 +274,12 @@ class CISolver:
                 size=s.ndet, nroot=self.nroot, davidson_liu_params=self.davidson_liu_params,
                 energy_shift=self.energy_shift, log_level=self.log_level, device=b.device, log=self._log)
             self.eigensolver.add_guesses(self._build_guess_vectors(hdiag))
+            if self.multiplicity is not None and self._wrong_spin.shape[1] > 0:
+                self.eigensolver.add_project_out_sparse(self._guess_addresses, self._wrong_spin.T)
         self.eigensolver.add_h_diag(hdiag)
 
         def sigma_builder(Bblock, Sblock):
-            for i in range(Bblock.shape[0]):
-                b.Hamiltonian(Bblock[i], Sblock[i])
+            b.Hamiltonian(Bblock, Sblock)  # every new trial vector in one call (f2_sigma_apply_batch)
 
         self.eigensolver.add_sigma_builder(sigma_builder)
         self.evals, self.evecs = self.eigensolver.solve()
@@ -223,7 +300,7 @@ class ShardedCISolver:
 
     def __init__(self, strings: CIStrings, E, H, V, nroot=1, davidson_liu_params=None, ci_algorithm="hz",
                  ci_builder_memory=1024, log_level=3, device=None, log=None, builder=None, group=None,
-                 form="auto", _sharded=None, _hdiag=None, _kernels=None):
+                 form="auto", multiplicity=None, _sharded=None, _hdiag=None, _kernels=None):
         # _sharded / _hdiag / _kernels: test hooks (tests/ run the host logic over gloo with CPU stand-ins
         # for the GPU work); the product path below has no CPU fallback
         import torch.distributed as dist
@@ -239,6 +316,8 @@ class ShardedCISolver:
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.eigensolver = None
         self.sharded = _sharded
+        self.multiplicity = None if multiplicity is None else int(multiplicity)  # spin control as in CISolver
+        self._wrong_spin = None
         self._hdiag, self._kernels = _hdiag, _kernels
         self.executed = False
 
@@ -269,8 +348,20 @@ class ShardedCISolver:
         v, a = v[keep], a[keep]
         order = np.lexsort((a, v))[:nguess_dets]  # by energy, ties by address: identical on every rank
         idx = a[order].astype(np.int64)
-        Hguess = slater_matrix(self.ci_strings, self.E0, self.H, self.V, idx)
-        _, evecs = np.linalg.eigh(Hguess)
+        if self.multiplicity is not None:
+            idx, evecs, wrong = spin_adapted_guess(self.ci_strings, self.E0, self.H, self.V, idx, self.multiplicity,
+                                                   self.num_guess_states)
+            if evecs.shape[1] < min(self.nroot, self.num_guess_states):
+                raise ValueError(f"only {evecs.shape[1]} guess vectors of multiplicity {self.multiplicity} in the "
+                                 f"space of the {idx.size} guess determinants; increase ndets_per_guess")
+            self.num_guess_states = evecs.shape[1]
+            if wrong.shape[1] > 0:  # globally orthonormal (eigenvectors of S^2); every rank keeps its components
+                loc = lay.local_of_global(idx)
+                own = np.nonzero(loc >= 0)[0]
+                self._wrong_spin = (loc[own], np.ascontiguousarray(wrong[own].T))
+        else:
+            Hguess = slater_matrix(self.ci_strings, self.E0, self.H, self.V, idx)
+            _, evecs = np.linalg.eigh(Hguess)
         guess = torch.zeros((self.num_guess_states, lay.local_size), dtype=torch.float64, device=hdiag_loc.device)
         local = lay.local_of_global(idx)
         mine = np.nonzero(local >= 0)[0]
@@ -294,14 +385,16 @@ class ShardedCISolver:
         if self.sharded is None:
             self.sharded = ShardedSigma(b, self.rank, self.world, group=self.group, form=self.form)
         sh = self.sharded
-        hdiag = self._hdiag if self._hdiag is not None else b.form_Hdiag_det_part(self.rank, self.world,
-                                                                                  sh.local_size)
+        hdiag = self._hdiag if self._hdiag is not None else b.form_Hdiag_det_part(
+            self.rank, self.world, sh.local_size, spin_averaged=self.multiplicity is not None)
         if self.eigensolver is None:
             self.eigensolver = DavidsonLiuSolver(
                 size=sh.local_size, nroot=self.nroot, davidson_liu_params=self.davidson_liu_params,
                 log_level=self.log_level, device=hdiag.device, comm=self.group, global_size=s.ndet, log=self._log,
                 _kernels=self._kernels)
             self.eigensolver.add_guesses(self._build_guess_vectors(hdiag))
+            if self._wrong_spin is not None:
+                self.eigensolver.add_project_out_sparse(*self._wrong_spin)
         self.eigensolver.add_h_diag(hdiag)
 
         def sigma_builder(Bblock, Sblock):

@@ -16,6 +16,9 @@ KINDS = {
 DEV_KINDS = {
     "dev_as_ptr": 20, "dev_as_ent": 21, "dev_bs_ent": 22, "dev_h2_ptr": 23, "dev_h2_ent": 24, "dev_cls": 25,
     "dev_loc": 26, "dev_blk_off": 27, "dev_ncls": 28,
+    # hole lists of the RDM path (csrc/strings.hpp HoleLists), level 0..3: CSR pointer and packed entries
+    "hole_ptr0": 30, "hole_ptr1": 31, "hole_ptr2": 32, "hole_ptr3": 33,
+    "hole_ent0": 34, "hole_ent1": 35, "hole_ent2": 36, "hole_ent3": 37,
 }
 ROW_WIDTH = {"vo": 7, "vo2": 6, "1h": 6, "1h2": 6, "2h": 7, "3h": 8}
 

@@ -73,6 +73,8 @@ __global__ void dl_finish_kernel(const double* __restrict__ part, int nctas, int
     out[v] = x;
 }
 
+constexpr int DL_TILE = 4096; // elements a CTA reads contiguously from every row before moving on
+
 template <int PT, int QT>
 __global__ void __launch_bounds__(DL_THREADS)
     dl_dots_kernel(const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ X,
@@ -81,20 +83,23 @@ __global__ void __launch_bounds__(DL_THREADS)
 #pragma unroll
     for (int i = 0; i < PT * QT; ++i)
         acc[i] = 0.0;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * DL_THREADS;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * DL_THREADS + threadIdx.x; e < n; e += stride) {
-        double x[QT];
+    const int64_t ntiles = (n + DL_TILE - 1) / DL_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t t0 = tile * DL_TILE;
+        const int64_t t1 = t0 + DL_TILE < n ? t0 + DL_TILE : n;
+        for (int64_t e = t0 + threadIdx.x; e < t1; e += DL_THREADS) {
+            double x[QT], a[PT];
 #pragma unroll
-        for (int j = 0; j < QT; ++j)
-            x[j] = j < q ? __ldg(X + j * ldx + e) : 0.0;
+            for (int j = 0; j < QT; ++j)
+                x[j] = j < q ? __ldg(X + j * ldx + e) : 0.0;
 #pragma unroll
-        for (int i = 0; i < PT; ++i) {
-            if (i < p) {
-                const double a = __ldg(A + i * lda + e);
+            for (int i = 0; i < PT; ++i)
+                a[i] = i < p ? __ldg(A + i * lda + e) : 0.0;
+#pragma unroll
+            for (int i = 0; i < PT; ++i)
 #pragma unroll
                 for (int j = 0; j < QT; ++j)
-                    acc[i * QT + j] = fma(a, x[j], acc[i * QT + j]);
-            }
+                    acc[i * QT + j] = fma(a[i], x[j], acc[i * QT + j]);
         }
     }
     __shared__ double red[DL_THREADS / 32][PT * QT];
@@ -119,9 +124,11 @@ __global__ void __launch_bounds__(DL_THREADS)
     }
 }
 
-// Y_j = beta * Y_j + sum_i coef[i * k + j] * A_i for j < k.  Safe when rows of Y alias rows of A:
+// Y_j = beta * Y_j + sum_i coef[i, j] * A_i for j < k.  Safe when rows of Y alias rows of A:
 // a thread reads every A_i[e] before it writes any Y_j[e].  WANT_SS: per-CTA partials of |Y_j|^2.
-template <int KT, bool WANT_SS>
+// coef.c[i * DL_MAXV + j]: compile-time strides, so that the unrolled FMAs take their coefficient straight from
+// the constant bank; PT = p rounded up to a multiple of 4 (zero coefficients, no loads, for the padding rows).
+template <int KT, int PT, bool WANT_SS>
 __global__ void __launch_bounds__(DL_THREADS)
     dl_combine_kernel(const double* A, int64_t lda, int p, const DlCoef coef, double* Y, int64_t ldy,
                       int k, double beta, int64_t n, double* __restrict__ part) {
@@ -129,25 +136,31 @@ __global__ void __launch_bounds__(DL_THREADS)
 #pragma unroll
     for (int j = 0; j < KT; ++j)
         ss[j] = 0.0;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * DL_THREADS;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * DL_THREADS + threadIdx.x; e < n; e += stride) {
-        double y[KT];
+    const int64_t ntiles = (n + DL_TILE - 1) / DL_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t t0 = tile * DL_TILE;
+        const int64_t t1 = t0 + DL_TILE < n ? t0 + DL_TILE : n;
+        for (int64_t e = t0 + threadIdx.x; e < t1; e += DL_THREADS) {
+            double y[KT], a[PT > 0 ? PT : 1];
 #pragma unroll
-        for (int j = 0; j < KT; ++j)
-            y[j] = (beta != 0.0 && j < k) ? beta * Y[j * ldy + e] : 0.0;
-        for (int i = 0; i < p; ++i) {
-            const double a = A[i * lda + e];
+            for (int i = 0; i < PT; ++i)
+                a[i] = i < p ? A[i * lda + e] : 0.0;
 #pragma unroll
             for (int j = 0; j < KT; ++j)
-                y[j] = fma(coef.c[i * k + (j < k ? j : 0)], a, y[j]);
-        }
+                y[j] = (beta != 0.0 && j < k) ? beta * Y[j * ldy + e] : 0.0;
 #pragma unroll
-        for (int j = 0; j < KT; ++j)
-            if (j < k) {
-                Y[j * ldy + e] = y[j];
-                if (WANT_SS)
-                    ss[j] = fma(y[j], y[j], ss[j]);
-            }
+            for (int i = 0; i < PT; ++i)
+#pragma unroll
+                for (int j = 0; j < KT; ++j)
+                    y[j] = fma(coef.c[i * DL_MAXV + j], a[i], y[j]);
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < k) {
+                    Y[j * ldy + e] = y[j];
+                    if (WANT_SS)
+                        ss[j] = fma(y[j], y[j], ss[j]);
+                }
+        }
     }
     if (WANT_SS)
         cta_partials<KT>(ss, k, part);
@@ -224,79 +237,92 @@ struct DlfSmall {
     double t[DLF_MAXK * DLF_MAXK];
 };
 
+// Coefficients sit in the kernel parameters with COMPILE-TIME strides (coef.c[i * DLF_MAXK + j], T.t[l * DLF_MAXK + j],
+// zero outside the live m x k part): after unrolling every coefficient is a constant-bank operand of its DFMA.  (The
+// first version indexed them with the runtime k: an address computation and a load per FMA, 666 instructions per
+// element and issue-bound at 2.2 TB/s, profiles/r2c_dl_fused.md.)  A CTA walks contiguous tiles of DLF_TILE
+// elements, so that each of the up to 28 row streams it reads stays inside one DRAM page for a while.
+constexpr int DLF_TILE = 2048;
+
 template <int KT, int MT, bool RESID>
 __global__ void __launch_bounds__(DLF_THREADS)
     dl_fused_kernel(const double* __restrict__ B, const double* __restrict__ S, int64_t ld, int m, const double* Yin,
                     int64_t ldin, int kin, const DlfCoef coef, const DlfSmall T, const double* __restrict__ hdiag,
                     double thresh, double* Zout, int64_t ldout, int kout, int64_t n, double* __restrict__ part) {
     constexpr int NV = (RESID ? KT : 0) + MT * KT + KT * KT;
+    constexpr int D0 = RESID ? KT : 0;
     double acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v)
         acc[v] = 0.0;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * DLF_THREADS;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * DLF_THREADS + threadIdx.x; e < n; e += stride) {
-        double b[MT], z[KT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-            b[i] = i < m ? __ldg(B + i * ld + e) : 0.0;
-        if constexpr (RESID) {
-            double s[MT];
+    const int64_t ntiles = (n + DLF_TILE - 1) / DLF_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t t0 = tile * DLF_TILE;
+        const int64_t t1 = t0 + DLF_TILE < n ? t0 + DLF_TILE : n;
+        for (int64_t e = t0 + threadIdx.x; e < t1; e += DLF_THREADS) {
+            double b[MT], z[KT];
 #pragma unroll
             for (int i = 0; i < MT; ++i)
-                s[i] = i < m ? __ldg(S + i * ld + e) : 0.0;
-            const double h = hdiag ? __ldg(hdiag + e) : 0.0;
+                b[i] = i < m ? __ldg(B + i * ld + e) : 0.0;
+            if constexpr (RESID) {
+                double sb[KT], sv[KT];
 #pragma unroll
-            for (int j = 0; j < KT; ++j) {
-                double sb = 0.0, sv = 0.0;
+                for (int j = 0; j < KT; ++j)
+                    sb[j] = sv[j] = 0.0;
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                    const double a = coef.c[i * kout + (j < kout ? j : 0)];
-                    sb = fma(a, b[i], sb);
-                    sv = fma(a, s[i], sv);
-                }
-                double r = j < kout ? sv - T.t[j] * sb : 0.0; // T.t[j] = lam_j
-                acc[j] = fma(r, r, acc[j]);
-                if (hdiag) {
-                    const double d = T.t[j] - h;
-                    r = fabs(d) > thresh ? r / d : 0.0;
-                }
-                z[j] = j < kout ? r : 0.0;
-            }
-        } else {
-            double y[KT];
+                    const double s = i < m ? __ldg(S + i * ld + e) : 0.0;
 #pragma unroll
-            for (int l = 0; l < KT; ++l)
-                y[l] = l < kin ? Yin[l * ldin + e] : 0.0;
+                    for (int j = 0; j < KT; ++j) {
+                        sb[j] = fma(coef.c[i * DLF_MAXK + j], b[i], sb[j]);
+                        sv[j] = fma(coef.c[i * DLF_MAXK + j], s, sv[j]);
+                    }
+                }
+                const double h = hdiag ? __ldg(hdiag + e) : 0.0;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    double r = sv[j] - T.t[j] * sb[j]; // T.t[j] = lam_j; zero coefficients give r = 0 for j >= k
+                    acc[j] = fma(r, r, acc[j]);
+                    if (hdiag) {
+                        const double d = T.t[j] - h;
+                        r = fabs(d) > thresh ? r / d : 0.0;
+                    }
+                    z[j] = r;
+                }
+            } else {
+                double y[KT];
+#pragma unroll
+                for (int l = 0; l < KT; ++l)
+                    y[l] = l < kin ? Yin[l * ldin + e] : 0.0;
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int l = 0; l < KT; ++l)
+                        y[l] = fma(-coef.c[i * DLF_MAXK + l], b[i], y[l]);
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int l = 0; l < KT; ++l)
+                        x = fma(T.t[l * DLF_MAXK + j], y[l], x); // zero outside kin x kout
+                    z[j] = x;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (j < kout)
+                    Zout[j * ldout + e] = z[j];
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
-                for (int l = 0; l < KT; ++l)
-                    y[l] = fma(-coef.c[i * kin + (l < kin ? l : 0)], b[i], y[l]);
-#pragma unroll
-            for (int j = 0; j < KT; ++j) {
-                double x = 0.0;
-#pragma unroll
-                for (int l = 0; l < KT; ++l)
-                    x = fma(T.t[l * DLF_MAXK + j], y[l], x); // zero outside kin x kout
-                z[j] = x;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < KT; ++j)
-            if (j < kout)
-                Zout[j * ldout + e] = z[j];
-        constexpr int D0 = RESID ? KT : 0;
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
+                for (int j = 0; j < KT; ++j)
+                    acc[D0 + i * KT + j] = fma(b[i], z[j], acc[D0 + i * KT + j]);
 #pragma unroll
             for (int j = 0; j < KT; ++j)
-                acc[D0 + i * KT + j] = fma(b[i], z[j], acc[D0 + i * KT + j]);
 #pragma unroll
-        for (int j = 0; j < KT; ++j)
-#pragma unroll
-            for (int jj = 0; jj < KT; ++jj)
-                acc[D0 + MT * KT + j * KT + jj] = fma(z[j], z[jj], acc[D0 + MT * KT + j * KT + jj]);
+                for (int jj = j; jj < KT; ++jj) // upper triangle; the finish kernel mirrors it
+                    acc[D0 + MT * KT + j * KT + jj] = fma(z[j], z[jj], acc[D0 + MT * KT + j * KT + jj]);
+        }
     }
     __shared__ double red[DLF_THREADS / 32][NV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -335,7 +361,8 @@ __global__ void dl_fused_finish_kernel(const double* __restrict__ part, int ncta
         src = (resid ? KT : 0) + (q / kout) * KT + q % kout;
     } else {
         const int q = o - n_r - m * kout;
-        src = (resid ? KT : 0) + MT * KT + (q / kout) * KT + q % kout;
+        const int a = q / kout, b = q % kout;
+        src = (resid ? KT : 0) + MT * KT + (a < b ? a : b) * KT + (a < b ? b : a);
     }
     double x = 0.0;
     for (int c = 0; c < nctas; ++c)
@@ -382,7 +409,8 @@ int f2_dl_dots(const double* A, int64_t lda, int p, const double* X, int64_t ldx
         if (p < 1 || p > DL_MAXV || q < 1 || q > DL_MAXV || n < 0)
             throw std::invalid_argument("f2_dl_dots: need 1 <= p, q <= 16 and n >= 0");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const int grid = grid_for(n);
+        const int64_t tiles = (n + DL_TILE - 1) / DL_TILE;
+        const int grid = static_cast<int>(tiles < 1 ? 1 : (tiles < DL_CTAS ? tiles : DL_CTAS));
         for (int j0 = 0; j0 < q; j0 += 4) {
             const int qc = q - j0 < 4 ? q - j0 : 4;
             // partials of this column chunk: [grid][p*qc]; finished into a p x qc scratch, then placed
@@ -391,6 +419,8 @@ int f2_dl_dots(const double* A, int64_t lda, int p, const double* X, int64_t ldx
                 dots_q<4>(qc, grid, st, A, lda, p, X + j0 * ldx, ldx, n, part);
             else if (p <= 8)
                 dots_q<8>(qc, grid, st, A, lda, p, X + j0 * ldx, ldx, n, part);
+            else if (p <= 12)
+                dots_q<12>(qc, grid, st, A, lda, p, X + j0 * ldx, ldx, n, part);
             else
                 dots_q<16>(qc, grid, st, A, lda, p, X + j0 * ldx, ldx, n, part);
             check_launch();
@@ -417,16 +447,32 @@ int f2_dl_combine(const double* A, int64_t lda, int p, const double* coef_host, 
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         DlCoef c;
         std::memset(&c, 0, sizeof(c));
-        if (p > 0)
-            std::memcpy(c.c, coef_host, sizeof(double) * p * k);
-        const int grid = grid_for(n);
+        for (int i = 0; i < p; ++i)
+            for (int jj = 0; jj < k; ++jj)
+                c.c[i * DL_MAXV + jj] = coef_host[i * k + jj];
+        const int64_t tiles = (n + DL_TILE - 1) / DL_TILE;
+        const int grid = static_cast<int>(tiles < 1 ? 1 : (tiles < DL_CTAS ? tiles : DL_CTAS));
         const bool ss = sumsq_dev != nullptr;
-#define F2_COMBINE(KT)                                                                                     \
-    do {                                                                                                   \
-        if (ss)                                                                                            \
-            dl_combine_kernel<KT, true><<<grid, DL_THREADS, 0, st>>>(A, lda, p, c, Y, ldy, k, beta, n, work_dev); \
-        else                                                                                               \
-            dl_combine_kernel<KT, false><<<grid, DL_THREADS, 0, st>>>(A, lda, p, c, Y, ldy, k, beta, n, work_dev); \
+        const int pt = (p + 3) / 4 * 4;
+#define F2_COMBINE_P(KT, PT)                                                                                \
+    do {                                                                                                    \
+        if (ss)                                                                                             \
+            dl_combine_kernel<KT, PT, true><<<grid, DL_THREADS, 0, st>>>(A, lda, p, c, Y, ldy, k, beta, n, work_dev); \
+        else                                                                                                \
+            dl_combine_kernel<KT, PT, false><<<grid, DL_THREADS, 0, st>>>(A, lda, p, c, Y, ldy, k, beta, n, work_dev); \
+    } while (0)
+#define F2_COMBINE(KT)                                                                                      \
+    do {                                                                                                    \
+        if (pt == 0)                                                                                        \
+            F2_COMBINE_P(KT, 0);                                                                            \
+        else if (pt == 4)                                                                                   \
+            F2_COMBINE_P(KT, 4);                                                                            \
+        else if (pt == 8)                                                                                   \
+            F2_COMBINE_P(KT, 8);                                                                            \
+        else if (pt == 12)                                                                                  \
+            F2_COMBINE_P(KT, 12);                                                                           \
+        else                                                                                                \
+            F2_COMBINE_P(KT, 16);                                                                           \
     } while (0)
         if (k <= 1)
             F2_COMBINE(1);
@@ -439,6 +485,7 @@ int f2_dl_combine(const double* A, int64_t lda, int p, const double* coef_host, 
         else
             F2_COMBINE(16);
 #undef F2_COMBINE
+#undef F2_COMBINE_P
         check_launch();
         if (ss) {
             dl_finish_kernel<<<1, 64, 0, st>>>(work_dev, grid, k, sumsq_dev);
@@ -516,7 +563,7 @@ template <bool RESID>
 void dispatch_fused(int grid, cudaStream_t st, const double* B, const double* S, int64_t ld, int m, const double* Yin,
                     int64_t ldin, int kin, const DlfCoef& coef, const DlfSmall& T, const double* hdiag, double thresh,
                     double* Zout, int64_t ldout, int kout, int64_t n, double* work, double* out) {
-    const int kt = (kin > kout ? kin : kout) <= 1 ? 1 : ((kin > kout ? kin : kout) <= 2 ? 2 : 4);
+    const int kt = kin > kout ? kin : kout;
     const int mt = m <= 4 ? 4 : (m <= 8 ? 8 : (m <= 12 ? 12 : 16));
 #define F2_FUSED(KT, MT)                                                                                            \
     launch_fused<KT, MT, RESID>(grid, st, B, S, ld, m, Yin, ldin, kin, coef, T, hdiag, thresh, Zout, ldout, kout, n, \
@@ -536,6 +583,8 @@ void dispatch_fused(int grid, cudaStream_t st, const double* B, const double* S,
         F2_FUSED_M(1);
     else if (kt == 2)
         F2_FUSED_M(2);
+    else if (kt == 3)
+        F2_FUSED_M(3);
     else
         F2_FUSED_M(4);
 #undef F2_FUSED_M
@@ -543,7 +592,7 @@ void dispatch_fused(int grid, cudaStream_t st, const double* B, const double* S,
 }
 
 int fused_grid(int64_t n) {
-    const int64_t need = (n + DLF_THREADS - 1) / DLF_THREADS;
+    const int64_t need = (n + DLF_TILE - 1) / DLF_TILE;
     return static_cast<int>(need < 1 ? 1 : (need < DLF_CTAS ? need : DLF_CTAS));
 }
 } // namespace
@@ -560,7 +609,9 @@ int f2_dl_residual_fused(const double* B, const double* S, int64_t ld, int m, co
         DlfSmall l;
         std::memset(&a, 0, sizeof(a));
         std::memset(&l, 0, sizeof(l));
-        std::memcpy(a.c, alpha_host, sizeof(double) * m * k);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < k; ++j)
+                a.c[i * DLF_MAXK + j] = alpha_host[i * k + j];
         std::memcpy(l.t, lam_host, sizeof(double) * k);
         dispatch_fused<true>(fused_grid(n), static_cast<cudaStream_t>(stream), B, S, ld, m, nullptr, 0, k, a, l, hdiag,
                              denom_threshold, R, ldr, k, n, work_dev, out_dev);
@@ -580,8 +631,9 @@ int f2_dl_project(const double* B, int64_t ld, int m, const double* Yin, int64_t
         DlfSmall T;
         std::memset(&c, 0, sizeof(c));
         std::memset(&T, 0, sizeof(T));
-        if (m > 0)
-            std::memcpy(c.c, c_host, sizeof(double) * m * kin);
+        for (int i = 0; i < m; ++i)
+            for (int l = 0; l < kin; ++l)
+                c.c[i * DLF_MAXK + l] = c_host[i * kin + l];
         for (int l = 0; l < kin; ++l)
             for (int j = 0; j < kout; ++j)
                 T.t[l * DLF_MAXK + j] = T_host[l * kout + j];

@@ -262,6 +262,14 @@ struct f2_sigma {
     double last_ms[5] = {0, 0, 0, 0, 0};
     long builds = 0;
     mutable int64_t launches = 0; // kernels launched by the last build
+    // reduced density matrices: hole lists of (spin, level) on the device (uploaded on first use) and the two
+    // D buffers of the gather + GEMM formulation (csrc/rdm_kernels.cuh)
+    struct RdmLists {
+        DevBuf<uint32_t> ptr;
+        DevBuf<uint64_t> ent;
+        bool up = false;
+    } rdm_lists[2][4];
+    DevBuf<double> rdmD[2];
     // host staging for f2_sigma_apply_host
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
@@ -1978,78 +1986,258 @@ int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream) {
     }
 }
 
-int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, void* stream) {
+namespace {
+
+int64_t binom64(int n, int k) {
+    if (k < 0 || k > n)
+        return 0;
+    int64_t x = 1;
+    for (int i = 1; i <= k; ++i)
+        x = x * (n - k + i) / i;
+    return x;
+}
+
+f2_sigma::RdmLists& rdm_device_lists(f2_sigma& b, int spin, int level) {
+    auto& d = b.rdm_lists[spin][level];
+    if (!d.up) {
+        const HoleLists& hl = b.S->host->hole_lists(spin, level);
+        d.ptr.upload(hl.ptr);
+        d.ent.upload(hl.ent);
+        d.up = true;
+    }
+    return d;
+}
+
+// one spin block <L| (la alpha creators)(lb beta creators)(lb beta annihilators)(la alpha annihilators) |R> as the
+// M x M matrix over rows opA * Pb + opB, M = C(norb, la) C(norb, lb)
+void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, double* out, cudaStream_t st) {
+    const CIStringsHost& hs = *b.S->host;
+    const DevStrings& D = *b.D;
+    if (la < 0 || lb < 0 || la + lb < 1 || la + lb > 3)
+        throw std::invalid_argument("f2_sigma_rdm_block: need 1 <= la + lb <= 3");
+    const int n = hs.norb;
+    const int64_t Pa = binom64(n, la), Pb = binom64(n, lb), M = Pa * Pb;
+    if (M == 0)
+        return;
+    if (M > (int64_t(1) << 15))
+        throw std::overflow_error("f2_sigma_rdm_block: more than 32768 operator tuples per side");
+    F2_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(M * M) * sizeof(double), st));
+    // the reference returns zeros when a spin has too few electrons (ci_sigma_builder_1rdm.cc:15-17,
+    // ci_sigma_builder_2rdm.cc:64-66,148-151, ci_sigma_builder_3rdm.cc:101-103,189-191)
+    if (hs.ndet == 0 || hs.na < la || hs.nb < lb)
+        return;
+    const HoleLists& HA = hs.hole_lists(0, la);
+    const HoleLists& HB = hs.hole_lists(1, lb);
+    const int64_t nKa = static_cast<int64_t>(HA.nK()), nKb = static_cast<int64_t>(HB.nK());
+    if (nKa == 0 || nKb == 0)
+        return;
+    auto& LA = rdm_device_lists(b, 0, la);
+    auto& LB = rdm_device_lists(b, 1, lb);
+    const bool same = L == R;
+    // the K-block budget of the reference (acquire_local_Kblock_buffers, ci_sigma_builder.cc:70-78,
+    // knowles_handy.cc:15-32): two buffers of M rows inside set_memory; at least one column each
+    const int64_t cap = static_cast<int64_t>(b.memory_size / ((same ? 1 : 2) * sizeof(double)));
+    int64_t kc_max = cap / M;
+    kc_max -= kc_max % 2;
+    if (kc_max < 2)
+        throw std::runtime_error("The CI builder memory limit (" + std::to_string(b.memory_size) +
+                                 " bytes) is too small for one K-block column of " + std::to_string(M) +
+                                 " elements per buffer.");
+    kc_max = std::min<int64_t>(kc_max, int64_t(1) << 30);
+    if (const char* e = std::getenv("F2_RDM_CHUNK_COLS")) // test hook: columns per chunk (several chunks on small spaces)
+        kc_max = std::max<int64_t>(2, std::min<int64_t>(kc_max, std::atoll(e) & ~int64_t(1)));
+    int64_t cka, ckb; // chunk extents
+    if (nKb <= kc_max) {
+        ckb = nKb;
+        cka = std::min<int64_t>(nKa, kc_max / nKb);
+    } else {
+        cka = 1;
+        ckb = kc_max;
+    }
+    ckb = std::min<int64_t>(ckb, int64_t(65535) * RDM_GATHER_THREADS);
+    const int64_t ld_max = (cka * ckb + 1) / 2 * 2;
+    for (int v = 0; v < (same ? 1 : 2); ++v)
+        if (b.rdmD[v].n < static_cast<size_t>(M * ld_max))
+            b.rdmD[v].alloc(static_cast<size_t>(M * ld_max));
+    F2_CUDA(cudaFuncSetAttribute(rdm_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(rdm_gemm_smem_bytes())));
+    RdmGatherParams g;
+    g.ptrA = LA.ptr.p;
+    g.entA = LA.ent.p;
+    g.ptrB = LB.ptr.p;
+    g.entB = LB.ent.p;
+    g.a_cls = D.a_cls.p;
+    g.a_loc = D.a_loc.p;
+    g.b_cls = D.b_cls.p;
+    g.b_loc = D.b_loc.p;
+    g.nB_cls = D.nB_cls.p;
+    g.blk_off = D.blk_off.p;
+    g.nclsB = static_cast<int>(hs.nclsB());
+    g.Pb = static_cast<int>(Pb);
+    const int tiles = static_cast<int>((M + RG_BM - 1) / RG_BM);
+    for (int64_t ka0 = 0; ka0 < nKa; ka0 += cka)
+        for (int64_t kb0 = 0; kb0 < nKb; kb0 += ckb) {
+            g.ka0 = static_cast<uint32_t>(ka0);
+            g.kb0 = static_cast<uint32_t>(kb0);
+            g.nka = static_cast<uint32_t>(std::min(cka, nKa - ka0));
+            g.nkb = static_cast<uint32_t>(std::min(ckb, nKb - kb0));
+            const int64_t K = static_cast<int64_t>(g.nka) * g.nkb;
+            g.ldd = (K + 1) / 2 * 2;
+            const dim3 grid(g.nka, (g.nkb + RDM_GATHER_THREADS - 1) / RDM_GATHER_THREADS);
+            for (int v = 0; v < (same ? 1 : 2); ++v) {
+                g.X = v == 0 ? L : R;
+                g.D = b.rdmD[v].p;
+                F2_CUDA(cudaMemsetAsync(g.D, 0, static_cast<size_t>(M * g.ldd) * sizeof(double), st));
+                rdm_gather_kernel<<<grid, RDM_GATHER_THREADS, 0, st>>>(g);
+                b.launches += 1;
+            }
+            RdmGemmParams q;
+            q.A = b.rdmD[0].p;
+            q.B = same ? b.rdmD[0].p : b.rdmD[1].p;
+            q.C = out;
+            q.M = static_cast<int>(M);
+            q.K = K;
+            q.ld = g.ldd;
+            const int64_t nsteps = (K + RG_BK - 1) / RG_BK;
+            q.ksplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsteps, (2 * 148 + tiles * tiles - 1) / (tiles * tiles))));
+            rdm_gemm_kernel<<<tiles * tiles * q.ksplit, RG_THREADS, rdm_gemm_smem_bytes(), st>>>(q);
+            b.launches += 1;
+        }
+    F2_CUDA(cudaGetLastError());
+}
+
+// segments of consecutive strings of right class c that are consecutive strings of one left class
+struct ClassSegment {
+    uint32_t r0, cl, l0, len;
+};
+
+std::vector<std::vector<ClassSegment>> match_classes(const StringSpace& Rs, const StringSpace& Ls) {
+    std::vector<std::vector<ClassSegment>> out(Rs.nclasses());
+    for (size_t c = 0; c < Rs.nclasses(); ++c) {
+        auto& segs = out[c];
+        for (uint32_t j = 0; j < Rs.cls[c].size(); ++j) {
+            uint32_t add, cl;
+            if (!Ls.find(Rs.cls[c][j], add, cl))
+                continue;
+            if (!segs.empty() && segs.back().cl == cl && segs.back().r0 + segs.back().len == j &&
+                segs.back().l0 + segs.back().len == add)
+                segs.back().len += 1;
+            else
+                segs.push_back({j, cl, add, 1});
+        }
+    }
+    return out;
+}
+
+} // namespace
+
+int f2_sigma_rdm_block(f2_sigma* h, int la, int lb, const double* L_dev, const double* R_dev, double* out_dev,
+                       void* stream) {
     try {
         if (!h || !L_dev || !R_dev || !out_dev)
             throw std::invalid_argument("null argument");
         F2_CUDA(cudaSetDevice(h->device));
-        const CIStringsHost& hs = *h->S->host;
-        const DeviceLists& L = hs.device_lists();
-        const DevStrings& D = *h->D;
+        rdm_block(*h, la, lb, L_dev, R_dev, out_dev, static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, void* stream) {
+    static const int levels[][2] = {{1, 0}, {0, 1}, {-1, -1}, {2, 0}, {0, 2}, {1, 1}, {-1, -1}, {-1, -1},
+                                    {3, 0}, {2, 1}, {1, 2}, {0, 3}};
+    if (kind < 0 || kind > 11 || levels[kind][0] < 0) {
+        g_last_error = "f2_sigma_rdm: kind must be 0 (a_1rdm), 1 (b_1rdm), 3 (aa_2rdm), 4 (bb_2rdm), 5 (ab_2rdm), "
+                       "8 (aaa_3rdm), 9 (aab_3rdm), 10 (abb_3rdm) or 11 (bbb_3rdm)";
+        return F2_EINVAL;
+    }
+    return f2_sigma_rdm_block(h, levels[kind][0], levels[kind][1], L_dev, R_dev, out_dev, stream);
+}
+
+int f2_sigma_trdm1(f2_sigma* hl, f2_sigma* hr, int spin, const double* L_dev, const double* R_dev, double* out_dev,
+                   void* stream) {
+    try {
+        if (!hl || !hr || !L_dev || !R_dev || !out_dev || spin < 0 || spin > 1)
+            throw std::invalid_argument("f2_sigma_trdm1: null argument or spin outside {0, 1}");
+        const CIStringsHost& SL = *hl->S->host;
+        const CIStringsHost& SR = *hr->S->host;
+        // the reference's checks and messages (ci_sigma_builder_1trdm.cc:24-34)
+        if (SL.norb != SR.norb)
+            throw std::runtime_error("FCI transition RDMs: The number of MOs must be the same in the two wave functions.");
+        if (SL.na != SR.na || SL.nb != SR.nb)
+            throw std::runtime_error("FCI transition RDMs: The number of alpha and beta electrons must be the same in the "
+                                     "two wave functions.");
+        if (hl->device != hr->device)
+            throw std::invalid_argument("f2_sigma_trdm1: both builders must live on the same device");
+        F2_CUDA(cudaSetDevice(hl->device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const int64_t n = hs.norb, npairs = n * (n - 1) / 2;
-        int64_t count = 0;
-        switch (kind) {
-        case 0: case 1: count = n * n; break;
-        case 3: case 4: count = npairs * npairs; break;
-        case 5: count = n * n * n * n; break;
-        default: throw std::invalid_argument("f2_sigma_rdm: kind must be 0 (a_1rdm), 1 (b_1rdm), 3 (aa_2rdm), "
-                                             "4 (bb_2rdm) or 5 (ab_2rdm)");
-        }
-        if (count == 0)
+        const int n = SL.norb;
+        F2_CUDA(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(n) * n * sizeof(double), st));
+        if ((spin == 0 ? SL.na : SL.nb) < 1 || SL.ndet == 0 || SR.ndet == 0)
             return F2_OK;
-        F2_CUDA(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(count) * sizeof(double), st));
-        if (hs.ndet == 0)
-            return F2_OK;
-        RdmParams p;
-        p.L = L_dev;
-        p.R = R_dev;
-        p.out = out_dev;
-        p.a_cls = D.a_cls.p;
-        p.a_loc = D.a_loc.p;
-        p.b_cls = D.b_cls.p;
-        p.b_loc = D.b_loc.p;
-        p.nA_cls = D.nA_cls.p;
-        p.nB_cls = D.nB_cls.p;
-        p.blk_off = D.blk_off.p;
-        p.as_ptr = D.as_ptr.p;
-        p.as_ent = D.as_ent.p;
-        p.bs_ent = D.bs_ent.p;
-        p.h2_ptr = nullptr;
-        p.h2_ent = nullptr;
-        p.norb = hs.norb;
-        p.nclsA = static_cast<int>(hs.nclsA());
-        p.nclsB = static_cast<int>(hs.nclsB());
-        p.bs_width = L.bs_width;
-        p.nas = hs.nas;
-        p.nbs = hs.nbs;
-        const size_t tile = static_cast<size_t>(n * n) * sizeof(double);
-        const unsigned rows = static_cast<unsigned>(hs.nas);
-        // the reference returns zeros when the spin has too few electrons (ci_sigma_builder_1rdm.cc:15-17,
-        // ci_sigma_builder_2rdm.cc:64-66,148-151)
-        if (kind == 0 && hs.na >= 1 && rows > 0) {
-            rdm1a_kernel<<<rows, 256, tile, st>>>(p);
-            h->launches += 1;
-        } else if (kind == 1 && hs.nb >= 1 && rows > 0) {
-            rdm1b_kernel<<<rows, 256, tile, st>>>(p);
-            h->launches += 1;
-        } else if (kind == 5 && hs.na >= 1 && hs.nb >= 1 && rows > 0) {
-            rdm2ab_kernel<<<rows, 256, tile, st>>>(p);
-            h->launches += 1;
-        } else if ((kind == 3 && hs.na >= 2) || (kind == 4 && hs.nb >= 2)) {
-            const int spin = kind == 3 ? 0 : 1;
-            const unsigned nk = static_cast<unsigned>(L.h2_ptr[spin].size() > 0 ? L.h2_ptr[spin].size() - 1 : 0);
-            p.h2_ptr = D.h2_ptr[spin].p;
-            p.h2_ent = D.h2_ent[spin].p;
-            if (nk > 0) {
-                if (spin == 0)
-                    rdm2ss_kernel<0><<<nk, 256, 0, st>>>(p, static_cast<int>(npairs));
-                else
-                    rdm2ss_kernel<1><<<nk, 256, 0, st>>>(p, static_cast<int>(npairs));
-                h->launches += 1;
+        // acted-on spin: strings of the right space and their single replacements found in the left space;
+        // untouched spin: class-to-class segments of identical strings
+        const StringSpace& Ract = SR.space(spin, K_STR_N);
+        const StringSpace& Lact = SL.space(spin, K_STR_N);
+        const auto segs = match_classes(SR.space(1 - spin, K_STR_N), SL.space(1 - spin, K_STR_N));
+        const size_t nclsB_L = SL.nclsB(), nclsB_R = SR.nclsB();
+        std::vector<TrdmEntry> ent;
+        for (const auto& blkR : SR.blocks) {
+            if (blkR.nA * blkR.nB == 0)
+                continue;
+            const int cActR = spin == 0 ? blkR.cA : blkR.cB;  // class of the acted-on strings in this block
+            const int cOthR = spin == 0 ? blkR.cB : blkR.cA;
+            for (uint32_t x = 0; x < Ract.cls[cActR].size(); ++x) {
+                const uint64_t w = Ract.cls[cActR][x];
+                for (int q = 0; q < n; ++q) {
+                    if (!((w >> q) & 1))
+                        continue;
+                    const int sq = slater_sign(w, q);
+                    const uint64_t w1 = w & ~(1ull << q);
+                    for (int pp = 0; pp < n; ++pp) {
+                        if ((w1 >> pp) & 1)
+                            continue;
+                        uint32_t addL, clsL;
+                        if (!Lact.find(w1 | (1ull << pp), addL, clsL))
+                            continue;
+                        const int sign = sq * slater_sign(w1, pp);
+                        for (const ClassSegment& sg : segs[cOthR]) {
+                            const int64_t bi = spin == 0 ? SL.block_of[clsL * nclsB_L + sg.cl]
+                                                         : SL.block_of[sg.cl * nclsB_L + clsL];
+                            if (bi < 0 || SL.blocks[bi].nA * SL.blocks[bi].nB == 0)
+                                continue;
+                            const auto& blkL = SL.blocks[bi];
+                            TrdmEntry e;
+                            if (spin == 0) { // rows are the acted-on strings, the dot runs along a row
+                                e.offL = blkL.offset + static_cast<int64_t>(addL) * blkL.nB + sg.l0;
+                                e.offR = blkR.offset + static_cast<int64_t>(x) * blkR.nB + sg.r0;
+                                e.strideL = e.strideR = 1;
+                            } else { // columns are the acted-on strings, the dot runs down a column
+                                e.offL = blkL.offset + static_cast<int64_t>(sg.l0) * blkL.nB + addL;
+                                e.offR = blkR.offset + static_cast<int64_t>(sg.r0) * blkR.nB + x;
+                                e.strideL = static_cast<int32_t>(blkL.nB);
+                                e.strideR = static_cast<int32_t>(blkR.nB);
+                            }
+                            e.len = static_cast<int32_t>(sg.len);
+                            e.out = (pp * n + q) | (sign < 0 ? static_cast<int32_t>(0x80000000u) : 0);
+                            ent.push_back(e);
+                        }
+                    }
+                }
             }
         }
+        (void)nclsB_R;
+        if (ent.empty())
+            return F2_OK;
+        DevBuf<TrdmEntry> dev;
+        dev.upload(ent);
+        const int64_t nent = static_cast<int64_t>(ent.size());
+        const int64_t ctas = (nent * 32 + 255) / 256;
+        trdm_kernel<<<static_cast<unsigned>(ctas), 256, 0, st>>>(L_dev, R_dev, dev.p, nent, out_dev);
+        hl->launches += 1;
         F2_CUDA(cudaGetLastError());
+        F2_CUDA(cudaStreamSynchronize(st)); // the entry table is freed on return
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);

@@ -422,6 +422,17 @@ std::vector<int64_t> CIStringsHost::export_kind(int kind, int spin) const {
         }
         return v;
     }
+    if (kind >= 30 && kind <= 37) {
+        // hole lists of the reduced density matrices (HoleLists, strings.hpp): 30 + level = ptr, 34 + level = entries
+        const HoleLists& h = hole_lists(spin, (kind - 30) & 3);
+        if (kind < 34)
+            for (auto x : h.ptr)
+                v.push_back(static_cast<int64_t>(x));
+        else
+            for (auto x : h.ent)
+                v.push_back(static_cast<int64_t>(x));
+        return v;
+    }
     const auto& N = space(spin, K_STR_N);
     if (kind == K_VO || kind == K_VO2) {
         // J = sign a+_p a_q I, (p,q) outer loops, strings inner (ci_strings_makers.cc:75-161)
@@ -538,6 +549,86 @@ const DeviceLists& CIStringsHost::device_lists() const {
     if (!dl_built_)
         build_device_lists();
     return dl_;
+}
+
+const HoleLists& CIStringsHost::hole_lists(int spin, int level) const {
+    if (spin < 0 || spin > 1 || level < 0 || level > 3)
+        throw std::invalid_argument("hole_lists: spin in {0, 1}, level in 0..3");
+    HoleLists& h = holes_[spin][level];
+    if (h.built)
+        return h;
+    const StringSpace& S = space(spin, K_STR_N);
+    const int ne = spin == 0 ? na : nb;
+    h.ptr.assign(1, 0);
+    h.ent.clear();
+    h.max_parents = 0;
+    if (level == 0) {
+        for (size_t g = 0; g < S.nstr(); ++g) {
+            h.ent.push_back(static_cast<uint64_t>(g));
+            h.ptr.push_back(static_cast<uint32_t>(h.ent.size()));
+        }
+        h.max_parents = S.nstr() ? 1 : 0;
+        h.built = true;
+        return h;
+    }
+    if (ne >= level) {
+        struct Item {
+            uint64_t k, ent;
+        };
+        std::vector<Item> items;
+        for (size_t c = 0; c < S.nclasses(); ++c)
+            for (size_t x = 0; x < S.cls[c].size(); ++x) {
+                const uint64_t w = S.cls[c][x];
+                const uint64_t g = S.cls_off[c] + x;
+                int occ[64], nocc = 0;
+                for (int p = 0; p < norb; ++p)
+                    if ((w >> p) & 1)
+                        occ[nocc++] = p;
+                // every increasing tuple o1 < o2 < o3 of occupied orbitals, removed in that order
+                for (int i1 = 0; i1 < nocc; ++i1) {
+                    const int o1 = occ[i1];
+                    const int s1 = slater_sign(w, o1);
+                    const uint64_t w1 = w & ~(1ull << o1);
+                    if (level == 1) {
+                        items.push_back({w1, g | (uint64_t(o1) << 32) | (uint64_t(s1 < 0) << 48)});
+                        continue;
+                    }
+                    for (int i2 = i1 + 1; i2 < nocc; ++i2) {
+                        const int o2 = occ[i2];
+                        const int s2 = s1 * slater_sign(w1, o2);
+                        const uint64_t w2 = w1 & ~(1ull << o2);
+                        if (level == 2) {
+                            const uint64_t op = uint64_t(o2) * (o2 - 1) / 2 + o1;
+                            items.push_back({w2, g | (op << 32) | (uint64_t(s2 < 0) << 48)});
+                            continue;
+                        }
+                        for (int i3 = i2 + 1; i3 < nocc; ++i3) {
+                            const int o3 = occ[i3];
+                            const int s3 = s2 * slater_sign(w2, o3);
+                            const uint64_t w3 = w2 & ~(1ull << o3);
+                            const uint64_t op = uint64_t(o3) * (o3 - 1) * (o3 - 2) / 6 + uint64_t(o2) * (o2 - 1) / 2 + o1;
+                            if (op > 0xffff)
+                                throw std::overflow_error("hole_lists: orbital triple index exceeds 16 bits");
+                            items.push_back({w3, g | (op << 32) | (uint64_t(s3 < 0) << 48)});
+                        }
+                    }
+                }
+            }
+        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.k < b.k; });
+        if (items.size() >= (size_t(1) << 32))
+            throw std::overflow_error("hole_lists: more than 2^32 entries");
+        for (size_t i = 0; i < items.size(); ++i) {
+            if (i > 0 && items[i].k != items[i - 1].k)
+                h.ptr.push_back(static_cast<uint32_t>(h.ent.size()));
+            h.ent.push_back(items[i].ent);
+        }
+        if (!items.empty())
+            h.ptr.push_back(static_cast<uint32_t>(h.ent.size()));
+        for (size_t k = 0; k + 1 < h.ptr.size(); ++k)
+            h.max_parents = std::max<int>(h.max_parents, h.ptr[k + 1] - h.ptr[k]);
+    }
+    h.built = true;
+    return h;
 }
 
 void CIStringsHost::build_device_lists() const {

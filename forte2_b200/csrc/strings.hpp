@@ -93,6 +93,20 @@ struct DeviceLists {
     std::vector<uint32_t> a_cls, a_loc, b_cls, b_loc;
 };
 
+/// Hole lists for the reduced density matrices: every (N - level)-electron string K that is a sub-string of some
+/// N-electron string of one spin, CSR over K (K indexed by increasing occupation word), entry = one parent:
+///   bits 0..31 I (global index of the N-electron string), 32..47 index of the decreasing tuple of the removed
+///   orbitals (p; p (p-1)/2 + q; p (p-1) (p-2)/6 + q (q-1)/2 + r), bit 48 sign of removing them smallest first.
+/// Level 0 is the identity (K = I).  Reference counterparts: the 1h / 2h / 3h lists of
+/// forte2/ci/ci_strings_makers.cc:215-322 as the RDM code uses them (ci_sigma_builder_{1,2,3}rdm.cc).
+struct HoleLists {
+    std::vector<uint32_t> ptr;
+    std::vector<uint64_t> ent;
+    int max_parents = 0;
+    bool built = false;
+    size_t nK() const { return ptr.empty() ? 0 : ptr.size() - 1; }
+};
+
 class CIStringsHost {
   public:
     CIStringsHost(int64_t na, int64_t nb, int symmetry,
@@ -124,9 +138,13 @@ class CIStringsHost {
 
     int symmetry_of(uint64_t s) const;
 
+    /// level in 0..3
+    const HoleLists& hole_lists(int spin, int level) const;
+
   private:
     mutable StringSpace sp_[2][5];
     mutable DeviceLists dl_;
+    mutable HoleLists holes_[2][4];
     mutable bool dl_built_ = false;
     void build_space(int spin, int kind) const;
     std::vector<occ_t> occs_of(int spin, int kind) const;

@@ -353,7 +353,35 @@ class DavidsonLiuSolver:
         Q, _ = np.linalg.qr(np.stack(arrs, axis=1), mode="reduced")
         self._proj_out = self.torch.from_numpy(np.ascontiguousarray(Q.T)).to(self.device)
 
+    def add_project_out_sparse(self, indices, vectors):
+        """Vectors to project out that live on a few components only: vectors[j] holds the components of vector j on
+        the (local) vector indices `indices`, zero elsewhere (the wrong-spin combinations of the guess determinants,
+        forte2/sci/sci.py:437-441).  On one GPU they are orthonormalised here (QR, like add_project_out); with
+        sharded vectors the caller passes every rank its components of globally orthonormal vectors."""
+        torch = self.torch
+        V = np.asarray(vectors, dtype=np.float64)
+        if V.ndim != 2 or V.shape[1] != len(indices):
+            raise ValueError("vectors must be shape (n_vectors, len(indices))")
+        if V.shape[0] == 0:
+            return
+        if self.comm is None:
+            Q, _ = np.linalg.qr(V.T, mode="reduced")
+            V = np.ascontiguousarray(Q.T)
+        self._proj_sparse = (torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(self.device),
+                             torch.from_numpy(np.ascontiguousarray(V)).to(self.device))
+
+    def _do_project_out_sparse(self, rows):
+        idx, Q = self._proj_sparse
+        sub = rows[:, idx]                    # (k, nidx)
+        v = sub @ Q.T                         # overlaps (k, nproj)
+        if self.comm is not None:
+            import torch.distributed as dist
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.comm)
+        rows[:, idx] = sub - v @ Q
+
     def do_project_out(self, rows):
+        if rows.shape[0] > 0 and getattr(self, "_proj_sparse", None) is not None:
+            self._do_project_out_sparse(rows)
         if self._proj_out is None or rows.shape[0] == 0:
             return
         psize = self._proj_out.shape[1]
@@ -416,8 +444,10 @@ class DavidsonLiuSolver:
         return added
 
     def _fused_ok(self, m, k):
-        return (self._proj_out is None and hasattr(self.k, "project") and 0 < k <= self.k.FUSED_MAXK
-                and m <= self.k.FUSED_MAXM)
+        return hasattr(self.k, "project") and 0 < k <= self.k.FUSED_MAXK and m <= self.k.FUSED_MAXM
+
+    def _projecting(self):
+        return self._proj_out is not None or getattr(self, "_proj_sparse", None) is not None
 
     @staticmethod
     def _gram_schmidt_coefficients(g, alive, room, discard):
@@ -632,7 +662,8 @@ class DavidsonLiuSolver:
             self.do_project_out(R0)
             added = -1
             if fused and c_res is not None:
-                added = self._add_block_orthonormalized(R0, c_res[:, active[:to_add]])
+                # after a project-out the overlaps returned by the residual pass are stale: recomputed inside
+                added = self._add_block_orthonormalized(R0, None if self._projecting() else c_res[:, active[:to_add]])
             if added < 0:
                 added = self._add_and_orthonormalize(R0)
             self.basis_size += added

@@ -60,7 +60,8 @@ int64_t f2_strings_occupations(const f2_strings* h, int which, int64_t* out, int
  *   2H   rows: class_K add_K class_I sign p q I      a_p a_q I = sign K, p > q
  *   3H   rows: class_K add_K class_I sign p q r I
  * kinds 20..28: the device-format tables as the kernels read them (csrc/strings.hpp DeviceLists; packed
- * entries reinterpreted as int64), for host models of the kernels in tests/ */
+ * entries reinterpreted as int64), for host models of the kernels in tests/; kinds 30 + level / 34 + level (level 0..3): CSR
+ * pointer / packed entries of the hole lists of the RDM path (csrc/strings.hpp HoleLists) */
 int64_t f2_strings_export(const f2_strings* h, int kind, int spin, int64_t* out, int64_t cap);
 /* CIStrings::make_determinants / determinant / determinant_index (ci_strings.cc:186-230):
  * occupation words (alpha, beta) */
@@ -137,6 +138,20 @@ int f2_sigma_apply_part(f2_sigma* h, const double* C_full_dev, double* sigma_loc
  * The spin-free combinations (sf_1rdm, sf_2rdm, sf_2cumulant; ci_sigma_builder_1rdm.cc:71-81,
  * ci_sigma_builder_2rdm.cc:203-279) are assembled from these by the Python mirror. */
 int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, void* stream);
+/* The general form behind it, every spin block up to three-body: the matrix
+ *   out[opA * Pb + opB][opA' * Pb + opB'] = <L| (la alpha creators A)(lb beta creators B)(B' annihilators)(A' annihilators) |R>
+ * over decreasing orbital tuples (index p; p (p-1)/2 + q; p (p-1) (p-2)/6 + q (q-1)/2 + r), Pb = C(norb, lb), 1 <= la + lb <= 3.
+ * (1,0) a_1rdm, (0,1) b_1rdm, (2,0) aa_2rdm, (1,1) ab_2rdm [u][v][x][y], (0,2) bb_2rdm, (3,0) aaa_3rdm, (2,1) aab_3rdm
+ * [(uv)][w][(xy)][z], (1,2) abb_3rdm, (0,3) bbb_3rdm (compute_*_3rdm, forte2/ci/ci_sigma_builder_3rdm.cc:86-318; f2_sigma_rdm
+ * kinds 8..11).  Gather + FP64 tensor-core GEMM over chunks of the hole index sized by f2_sigma_set_memory, as the reference's
+ * K blocks are (ci_sigma_builder_3rdm.cc:235-258); the same "too small for one K-block column" error. */
+int f2_sigma_rdm_block(f2_sigma* h, int la, int lb, const double* L_dev, const double* R_dev, double* out_dev,
+                       void* stream);
+/* transition 1-RDM <L| a+_p a_q |R> of spin 0 (alpha) / 1 (beta) between the CI spaces of two builders with the same orbitals
+ * and electron numbers (different symmetry or GAS restrictions): norb x norb doubles (CISigmaBuilder::compute_a_1trdm /
+ * compute_b_1trdm, forte2/ci/ci_sigma_builder_1trdm.cc:11-118; same error messages).  Synchronises the stream. */
+int f2_sigma_trdm1(f2_sigma* h_left, f2_sigma* h_right, int spin, const double* L_dev, const double* R_dev,
+                   double* out_dev, void* stream);
 
 /* determinant energies of the owned rows, in the local (row slab) layout; synchronises the stream */
 int f2_sigma_hdiag_part(f2_sigma* h, double* out_local_dev, int rank, int world, void* stream);

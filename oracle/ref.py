@@ -79,6 +79,8 @@ def lib():
         L.ref_hdiag_csf.argtypes = [vp, vp, i, dp]
         L.ref_rdm.restype = i64
         L.ref_rdm.argtypes = [vp, i, dp, dp, i64, dp, i64]
+        L.ref_trdm.restype = i64
+        L.ref_trdm.argtypes = [vp, vp, i, dp, i64, dp, i64, dp, i64]
         L.ref_form_H_csf.restype = i
         L.ref_form_H_csf.argtypes = [vp, vp, dp]
         L.ref_slater_rules_csf.restype = C.c_double
@@ -184,11 +186,13 @@ class RefCISigmaBuilder:
         return lib().ref_sigma_get_algorithm(self._h).decode()
 
     RDM_KINDS = {"a_1rdm": 0, "b_1rdm": 1, "sf_1rdm": 2, "aa_2rdm": 3, "bb_2rdm": 4, "ab_2rdm": 5, "sf_2rdm": 6,
-                 "sf_2cumulant": 7}
+                 "sf_2cumulant": 7, "aaa_3rdm": 8, "aab_3rdm": 9, "abb_3rdm": 10, "bbb_3rdm": 11, "sf_3rdm": 12,
+                 "sf_3cumulant": 13}
 
     def rdm(self, kind, c_left, c_right):
         """CISigmaBuilder::compute_<kind> (ci_sigma_builder_1rdm.cc, ci_sigma_builder_2rdm.cc), shaped as the
-        reference returns it: (n, n), (npairs, npairs) for aa/bb (p > q) or (n, n, n, n)."""
+        reference returns it: (n, n), (npairs, npairs) for aa/bb (p > q), (n, n, n, n); the 3-RDM blocks
+        (ci_sigma_builder_3rdm.cc) as (ntriplets, ntriplets), (npairs, n, npairs, n), (n, npairs, n, npairs), (n,) * 6."""
         k = self.RDM_KINDS[kind]
         cl = np.ascontiguousarray(c_left, dtype=np.float64)
         cr = np.ascontiguousarray(c_right, dtype=np.float64)
@@ -201,10 +205,30 @@ class RefCISigmaBuilder:
         norb = self.strings.norb
         if k <= 2:
             return out.reshape(norb, norb)
-        if k <= 4:
+        if k <= 4 or k in (8, 11):
             m = int(round(np.sqrt(n)))
             return out.reshape(m, m)
+        npairs = norb * (norb - 1) // 2
+        if k == 9:
+            return out.reshape((npairs, norb, npairs, norb) if n else (0, 0, 0, 0))
+        if k == 10:
+            return out.reshape((norb, npairs, norb, npairs) if n else (0, 0, 0, 0))
+        if k >= 12:
+            return out.reshape((norb,) * 6)
         return out.reshape(norb, norb, norb, norb)
+
+    def trdm(self, kind, right_builder, c_left, c_right):
+        """CISigmaBuilder::compute_{a,b,sf}_1trdm(sigmabuilder_right, C_left, C_right) (ci_sigma_builder_1trdm.cc:11-133);
+        self is the left wave function's builder"""
+        k = {"a_1trdm": 0, "b_1trdm": 1, "sf_1trdm": 2}[kind]
+        cl = np.ascontiguousarray(c_left, dtype=np.float64)
+        cr = np.ascontiguousarray(c_right, dtype=np.float64)
+        norb = self.strings.norb
+        out = np.zeros(max(norb * norb, 1))
+        n = lib().ref_trdm(self._h, right_builder._h, k, _dp(cl), cl.shape[0], _dp(cr), cr.shape[0], _dp(out), out.size)
+        if n < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out[:n].reshape(norb, norb)
 
     def set_memory(self, mb):
         _check(lib().ref_sigma_set_memory(self._h, int(mb)))

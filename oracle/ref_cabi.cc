@@ -490,8 +490,36 @@ int64_t ref_rdm(void* hsig, int kind, double* Cl, double* Cr, int64_t n, double*
         case 5: { auto t = r->b->compute_ab_2rdm(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
         case 6: { auto t = r->b->compute_sf_2rdm(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
         case 7: { auto t = r->b->compute_sf_2cumulant(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
+        case 8: { auto m = r->b->compute_aaa_3rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 9: { auto t = r->b->compute_aab_3rdm(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
+        case 10: { auto t = r->b->compute_abb_3rdm(L, R); return put(t.data(), t.shape(0) * t.shape(1) * t.shape(2) * t.shape(3)); }
+        case 11: { auto m = r->b->compute_bbb_3rdm(L, R); return put(m.data(), m.shape(0) * m.shape(1)); }
+        case 12: { auto t = r->b->compute_sf_3rdm(L, R);
+                   size_t c = 1; for (int d = 0; d < 6; ++d) c *= t.shape(d); return put(t.data(), c); }
+        case 13: { auto t = r->b->compute_sf_3cumulant(L, R);
+                   size_t c = 1; for (int d = 0; d < 6; ++d) c *= t.shape(d); return put(t.data(), c); }
         default: g_err = "ref_rdm: unknown kind"; return -1;
         }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// transition 1-RDMs between two CI spaces with the same orbitals and electron numbers (CISigmaBuilder::compute_*_1trdm,
+// ci_sigma_builder_1trdm.cc:11-133): kind 0 alpha, 1 beta, 2 spin-free; left vector of the left builder's space
+int64_t ref_trdm(void* hleft, void* hright, int kind, double* Cl, int64_t nl, double* Cr, int64_t nr, double* out,
+                 int64_t cap) {
+    auto* l = static_cast<RefSigma*>(hleft);
+    auto* r = static_cast<RefSigma*>(hright);
+    try {
+        auto L = wrap_vec(Cl, nl), R = wrap_vec(Cr, nr);
+        auto m = kind == 0 ? l->b->compute_a_1trdm(*r->b, L, R)
+                           : (kind == 1 ? l->b->compute_b_1trdm(*r->b, L, R) : l->b->compute_sf_1trdm(*r->b, L, R));
+        const int64_t count = static_cast<int64_t>(m.shape(0) * m.shape(1));
+        if (out && count <= cap)
+            std::memcpy(out, m.data(), count * sizeof(double));
+        return count;
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1;

@@ -273,3 +273,65 @@ def test_exact_diagonalization_equals_the_iterative_solve(torch_cuda, name):
     shifted = CISolver(strings, E, H, V, nroot=1, ci_algorithm="exact", log_level=0, spin_adapter=adapter,
                        energy_shift=float(gc["exact"][1]) + 1e-6).run()
     assert abs(shifted.E[0] - gc["exact"][1]) <= ROOT_TOL
+
+
+@pytest.mark.parametrize("name", ["cas66", "cas75_odd", "gas343_54", "cas66_d2h"])
+def test_spin_averaged_diagonal_and_batched_hamiltonian(torch_cuda, name):
+    """f2_sigma_hdiag_spin_averaged = determinant energies averaged over each orbital configuration (the S^2-invariant
+    preconditioner of determinant-basis solves); f2_sigma_apply_batch = the vector-by-vector builds"""
+    import forte2_b200 as f2
+    torch = torch_cuda
+    space = SPACES[name]
+    n = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(n, "S")
+    strings = f2.CIStrings(*space)
+    b = f2.CISigmaBuilder(strings, E, H, V, 0)
+    e = b.form_Hdiag_det().cpu().numpy()
+    got = b.form_Hdiag_det(spin_averaged=True).cpu().numpy()
+    conf = {}
+    for k, (wa, wb) in enumerate(strings.make_determinants()):
+        conf.setdefault((int(wa & wb), int(wa ^ wb)), []).append(k)
+    want = e.copy()
+    for members in conf.values():
+        want[members] = e[members].mean()
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+    C = torch.from_numpy(np.random.default_rng(2).normal(size=(3, strings.ndet))).cuda()
+    pad = torch.full((3, strings.ndet + 5), float("nan"), dtype=torch.float64, device="cuda")
+    Cp, Sp = pad[:, :strings.ndet], torch.full_like(pad, float("nan"))[:, :strings.ndet]
+    Cp.copy_(C)
+    S1 = torch.empty_like(C)
+    for i in range(3):
+        b.Hamiltonian(C[i], S1[i])
+    S2 = torch.full_like(C, float("nan"))
+    b.Hamiltonian(C, S2)
+    b.Hamiltonian(Cp, Sp)  # rows with a stride longer than ndet
+    scale = float(S1.abs().max())
+    assert float((S1 - S2).abs().max()) <= 1e-13 * scale and float((S1 - Sp).abs().max()) <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("n,multiplicity,nroot", [(8, 1, 3), (8, 3, 2), (12, 1, 3)])
+def test_spin_controlled_determinant_roots_match_the_csf_path(torch_cuda, n, multiplicity, nroot):
+    """Determinant-basis solve with spin control (spin-pure guesses from S^2 in the spin-complete guess space,
+    wrong-spin guess combinations projected out, configuration-averaged preconditioner: forte2/sci/sci.py:405-455 and
+    SURVEY.md 7.4) against the spin-adapted solve forte2 itself would run (CSF basis, forte2/ci/ci.py:214-235): same
+    roots to 1e-10 Eh, and the determinant vectors lie in the CSF space of that multiplicity."""
+    import forte2_b200 as f2
+    from forte2_b200.ci_solver import CISolver
+    torch = torch_cuda
+    space = (n // 2, n // 2, 0, [[0] * n], [], [])
+    E, H, V = synthetic.integrals(n, "D")
+    strings = f2.CIStrings(*space)
+    adapter = f2.CISpinAdapter(multiplicity - 1, 0, n)
+    adapter.prepare_couplings(strings)
+    csf = CISolver(strings, E, H, V, nroot=nroot, log_level=0, spin_adapter=adapter).run()
+    det = CISolver(strings, E, H, V, nroot=nroot, log_level=0, multiplicity=multiplicity).run()
+    assert csf.converged and det.converged
+    assert np.max(np.abs(np.asarray(det.E) - np.asarray(csf.E))) <= ROOT_TOL
+    back = torch.empty(adapter.ncsf, dtype=torch.float64, device="cuda")
+    for i in range(nroot):
+        v = det.evecs[i].contiguous()
+        adapter.det_C_to_csf_C(v, back)
+        assert abs(float(back.norm()) - 1.0) <= 1e-9  # nothing of the vector lies outside the spin sector
+    # without spin control the same solve finds the lowest roots of ANY spin
+    free = CISolver(strings, E, H, V, nroot=nroot, log_level=0).run()
+    assert np.all(np.asarray(free.E) <= np.asarray(csf.E) + 1e-9)

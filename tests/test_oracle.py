@@ -106,32 +106,128 @@ def test_rdm_port_matches_live_reference(ref, name):
     assert abs(energy - c @ sigma) <= 1e-11
 
 
+def _hole_tables(strings, spin, level):
+    ptr = strings.export(f"hole_ptr{level}", spin)
+    ent = strings.export(f"hole_ent{level}", spin).astype(np.uint64)
+    return ptr, ent
+
+
+def _gather_model(strings, x, la, lb):
+    """rdm_gather_kernel of csrc/rdm_kernels.cuh restated with numpy over the exported tables: the dense D matrix
+    D[(opA Pb + opB), (Ka, Kb)] = s_A s_B x[Ka + A, Kb + B] (all columns at once)"""
+    from math import comb
+    n = strings.norb
+    Pa, Pb = comb(n, la), comb(n, lb)
+    ptrA, entA = _hole_tables(strings, 0, la)
+    ptrB, entB = _hole_tables(strings, 1, lb)
+    a_cls, a_loc = strings.export("dev_cls", 0), strings.export("dev_loc", 0)
+    b_cls, b_loc = strings.export("dev_cls", 1), strings.export("dev_loc", 1)
+    nB = strings.export("dev_ncls", 1)
+    off = strings.export("dev_blk_off", 0).reshape(len(strings.export("dev_ncls", 0)), len(nB))
+    nKa, nKb = len(ptrA) - 1, len(ptrB) - 1
+    D = np.zeros((Pa * Pb, max(nKa, 0) * max(nKb, 0)))
+    for Ka in range(nKa):
+        for ea in entA[ptrA[Ka]:ptrA[Ka + 1]]:
+            I, opA, negA = int(ea & 0xffffffff), int((ea >> 32) & 0xffff), int((ea >> 48) & 1)
+            for Kb in range(nKb):
+                for eb in entB[ptrB[Kb]:ptrB[Kb + 1]]:
+                    J, opB, negB = int(eb & 0xffffffff), int((eb >> 32) & 0xffff), int((eb >> 48) & 1)
+                    o = off[a_cls[I], b_cls[J]]
+                    if o < 0:
+                        continue
+                    v = x[o + a_loc[I] * nB[b_cls[J]] + b_loc[J]]
+                    D[opA * Pb + opB, Ka * nKb + Kb] = -v if negA ^ negB else v
+    return D
+
+
 @pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas21_4", "one_each", "cas75_odd",
                                   "one_beta_three_alpha", "beta_only", "sym2_11"])
-def test_rdm_kernel_models_match_the_definitions(name):
-    """tests/rdm_kernel_model.py (the RDM kernels of csrc/rdm_kernels.cuh restated statement by statement on the
-    host, reading the device-format tables) against oracle/rdm_port.py, itself pinned to the reference: list
-    semantics, unpacking and offset arithmetic of the kernels are right before they ever run on a GPU."""
+def test_rdm_gather_gemm_formulation_matches_the_definitions(name):
+    """Gamma = D_L D_R^T with D gathered through the hole lists (csrc/strings.hpp HoleLists; the formulation of
+    csrc/rdm_kernels.cuh, restated over the tables the kernels read) against oracle/rdm_port.general_rdm for every
+    spin block up to three-body: list contents, packing, phases and offsets are right before the kernels run"""
     from oracle import rdm_port
-    import rdm_kernel_model as km
     space = SMALL_SPACES[name]
     strings = f2.CIStrings(*space)
-    norb = strings.norb
-    dets = strings.make_determinants()
+    norb, dets = strings.norb, strings.make_determinants()
     rng = np.random.default_rng(3)
     left, right = rng.normal(size=strings.ndet), rng.normal(size=strings.ndet)
-    t = km.Tables(strings)
-    tol = 1e-13
-    if space[0] >= 1:
-        assert np.max(np.abs(km.rdm1a(t, left, right) - rdm_port.s_1rdm(dets, norb, left, right, 0))) <= tol
-    if space[1] >= 1:
-        assert np.max(np.abs(km.rdm1b(t, left, right) - rdm_port.s_1rdm(dets, norb, left, right, 1))) <= tol
-    if space[0] >= 1 and space[1] >= 1:
-        assert np.max(np.abs(km.rdm2ab(t, left, right) - rdm_port.ab_2rdm(dets, norb, left, right))) <= tol
-    if space[0] >= 2:
-        assert np.max(np.abs(km.rdm2ss(t, left, right, 0) - rdm_port.ss_2rdm(dets, norb, left, right, 0))) <= tol
-    if space[1] >= 2:
-        assert np.max(np.abs(km.rdm2ss(t, left, right, 1) - rdm_port.ss_2rdm(dets, norb, left, right, 1))) <= tol
+    levels = [(1, 0), (0, 1), (2, 0), (1, 1), (0, 2)]
+    if strings.ndet <= 400:
+        levels += [(3, 0), (2, 1), (1, 2), (0, 3)]
+    for la, lb in levels:
+        if space[0] < la or space[1] < lb:
+            continue
+        got = _gather_model(strings, left, la, lb) @ _gather_model(strings, right, la, lb).T
+        want = rdm_port.general_rdm(dets, norb, left, right, la, lb)
+        assert got.shape == want.shape and np.max(np.abs(got - want), initial=0.0) <= 1e-12, (la, lb)
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas21_4", "cas75_odd", "one_each", "beta_only"])
+def test_general_rdm_port_and_3rdm_assembly_match_live_reference(ref, name):
+    """oracle/rdm_port.general_rdm (any spin block from the definition) against the reference's compute_*_3rdm
+    (ci_sigma_builder_3rdm.cc) and its 1-/2-body blocks; the host assembly of the spin-free 3-RDM and 3-cumulant
+    (forte2_b200.ci_sigma_builder.assemble_sf_3rdm / sf_3cumulant_from) against compute_sf_3rdm / compute_sf_3cumulant"""
+    from oracle import rdm_port
+    from forte2_b200.ci_sigma_builder import assemble_sf_3rdm, sf_3cumulant_from
+    space = SMALL_SPACES[name]
+    norb = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(norb, "S")
+    rs = ref.RefCIStrings(*space)
+    rb = ref.RefCISigmaBuilder(rs, E, H, V)
+    dets = f2.CIStrings(*space).make_determinants()
+    rng = np.random.default_rng(12)
+    left, right = rng.normal(size=rs.ndet), rng.normal(size=rs.ndet)
+    left /= np.linalg.norm(left)
+    right /= np.linalg.norm(right)
+    blocks = {}
+    for kind, (la, lb) in {"a_1rdm": (1, 0), "b_1rdm": (0, 1), "aa_2rdm": (2, 0), "bb_2rdm": (0, 2), "ab_2rdm": (1, 1),
+                           "aaa_3rdm": (3, 0), "aab_3rdm": (2, 1), "abb_3rdm": (1, 2), "bbb_3rdm": (0, 3)}.items():
+        if norb < max(la, lb) or (la and lb and norb < 2):
+            continue
+        want = rb.rdm(kind, left, right)
+        got = rdm_port.general_rdm(dets, norb, left, right, la, lb)
+        assert got.size == want.size, kind
+        assert np.max(np.abs(got.reshape(want.shape) - want), initial=0.0) <= 1e-13, kind
+        blocks[kind] = got.reshape(want.shape)
+    if norb >= 2:
+        sss = blocks["aaa_3rdm"] + blocks["bbb_3rdm"] if norb >= 3 else None
+        g3 = assemble_sf_3rdm(norb, blocks["aab_3rdm"], blocks["abb_3rdm"], sss)
+        want3 = rb.rdm("sf_3rdm", left, right)
+        assert np.max(np.abs(g3 - want3), initial=0.0) <= 1e-13
+        l3 = sf_3cumulant_from(rb.rdm("sf_1rdm", left, right), rb.rdm("sf_2rdm", left, right), want3)
+        assert np.max(np.abs(l3 - rb.rdm("sf_3cumulant", left, right)), initial=0.0) <= 1e-12
+    if norb <= 4 and norb >= 2:
+        assert np.max(np.abs(rdm_port.sf_3rdm(dets, norb, left, right) - rb.rdm("sf_3rdm", left, right))) <= 1e-13
+
+
+TRDM_PAIRS = {
+    # (left space, right space): same orbitals and electron numbers, different symmetry / GAS restrictions
+    "sym_0_3": ((3, 3, 0, [[0, 1, 2, 3, 0, 1]], [], []), (3, 3, 3, [[0, 1, 2, 3, 0, 1]], [], [])),
+    "sym_1_2_odd": ((3, 2, 1, [[0, 1, 0, 1, 1]], [], []), (3, 2, 0, [[0, 1, 0, 1, 1]], [], [])),
+    "gas_vs_cas": ((3, 3, 0, [[0] * 3, [0] * 3], [2, 0], [6, 4]), (3, 3, 0, [[0] * 3, [0] * 3], [], [])),
+    "gas_vs_gas": ((3, 2, 0, [[0] * 2, [0] * 4], [2, 0], [3, 3]), (3, 2, 0, [[0] * 2, [0] * 4], [3, 0], [4, 2])),
+    "same": ((3, 3, 0, [[0] * 6], [], []), (3, 3, 0, [[0] * 6], [], [])),
+}
+
+
+@pytest.mark.parametrize("pair", sorted(TRDM_PAIRS))
+def test_trdm_port_matches_live_reference(ref, pair):
+    """oracle/rdm_port.trdm1 against the reference's compute_{a,b,sf}_1trdm (ci_sigma_builder_1trdm.cc)"""
+    from oracle import rdm_port
+    sl, sr = TRDM_PAIRS[pair]
+    norb = sum(len(s) for s in sl[3])
+    E, H, V = synthetic.integrals(norb, "S")
+    bl = ref.RefCISigmaBuilder(ref.RefCIStrings(*sl), E, H, V)
+    br = ref.RefCISigmaBuilder(ref.RefCIStrings(*sr), E, H, V)
+    dl, dr = f2.CIStrings(*sl).make_determinants(), f2.CIStrings(*sr).make_determinants()
+    rng = np.random.default_rng(5)
+    left, right = rng.normal(size=len(dl)), rng.normal(size=len(dr))
+    a = rdm_port.trdm1(dl, dr, norb, left, right, 0)
+    b = rdm_port.trdm1(dl, dr, norb, left, right, 1)
+    assert np.max(np.abs(a - bl.trdm("a_1trdm", br, left, right))) <= 1e-13
+    assert np.max(np.abs(b - bl.trdm("b_1trdm", br, left, right))) <= 1e-13
+    assert np.max(np.abs(a + b - bl.trdm("sf_1trdm", br, left, right))) <= 1e-13
 
 
 @pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas21_4"])
@@ -148,69 +244,6 @@ def test_sf_2rdm_assembly_matches_the_definitions(name):
     got = assemble_sf_2rdm(norb, rdm_port.ab_2rdm(dets, norb, left, right),
                            rdm_port.ss_2rdm(dets, norb, left, right, 0), rdm_port.ss_2rdm(dets, norb, left, right, 1))
     assert np.max(np.abs(got - rdm_port.sf_2rdm(dets, norb, left, right))) <= 1e-13
-
-
-@pytest.fixture(scope="module")
-def rdm_emu(tmp_path_factory):
-    """the RDM kernels' own source (csrc/rdm_kernels.cuh) compiled for the host under the SIMT emulator of
-    tests/simt_emu (one std::thread per CUDA thread, barriers for __syncthreads and the shuffles)"""
-    import ctypes
-    import shutil
-    import subprocess
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    out = tmp_path_factory.mktemp("simt")
-    script = os.path.join(os.path.dirname(__file__), "simt_emu", "build.sh")
-    r = subprocess.run(["bash", script, str(out)], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    return ctypes.CDLL(os.path.join(str(out), "librdm_emu.so"))
-
-
-@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas21_4", "beta_only"])
-def test_rdm_kernel_source_under_the_simt_emulator(rdm_emu, name):
-    """The CUDA text of rdm1a / rdm1b / rdm2ab / rdm2ss<0,1> executed thread by thread on the host (64 threads per
-    block: two warps, so the cross-warp reduction, the shuffles, the shared-memory atomics and every barrier are
-    exercised) against oracle/rdm_port.py.  Together with the host models this checks everything about these
-    kernels that does not need the hardware."""
-    import ctypes
-    from oracle import rdm_port
-    import rdm_kernel_model as km
-    space = SMALL_SPACES[name]
-    strings = f2.CIStrings(*space)
-    norb, dets = strings.norb, strings.make_determinants()
-    t = km.Tables(strings)
-    rng = np.random.default_rng(4)
-    left, right = rng.normal(size=strings.ndet), rng.normal(size=strings.ndet)
-    u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)  # noqa: E731
-    u64 = lambda a: np.ascontiguousarray(a).astype(np.uint64) if a.dtype != np.uint64 else np.ascontiguousarray(a)  # noqa: E731
-    keep = dict(a_cls=u32(t.a_cls), a_loc=u32(t.a_loc), b_cls=u32(t.b_cls), b_loc=u32(t.b_loc), nA=u32(t.nA_cls),
-                nB=u32(t.nB_cls), blk=np.ascontiguousarray(t.blk_off, dtype=np.int64), as_ptr=u32(t.as_ptr),
-                as_ent=u64(t.as_ent), bs_ent=u64(t.bs_ent) if t.bs_ent.size else np.zeros(1, dtype=np.uint64))
-    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-
-    def run(kind, count, spin=0):
-        out = np.zeros(max(count, 1))
-        h2p, h2e = u32(t.h2_ptr[spin]), u64(t.h2_ent[spin]) if t.h2_ent[spin].size else np.zeros(1, dtype=np.uint64)
-        rc = rdm_emu.emu_rdm(kind, 64, ptr(left), ptr(right), ptr(out), ptr(keep["a_cls"]), ptr(keep["a_loc"]),
-                             ptr(keep["b_cls"]), ptr(keep["b_loc"]), ptr(keep["nA"]), ptr(keep["nB"]), ptr(keep["blk"]),
-                             ptr(keep["as_ptr"]), ptr(keep["as_ent"]), ptr(keep["bs_ent"]), ptr(h2p), ptr(h2e),
-                             max(len(h2p) - 1, 0), norb, t.nclsA, t.nclsB, t.bs_width,
-                             ctypes.c_int64(t.nas), ctypes.c_int64(t.nbs))
-        assert rc == 0
-        return out[:count]
-
-    n2, npairs = norb * norb, norb * (norb - 1) // 2
-    tol = 1e-12
-    if space[0] >= 1:
-        assert np.max(np.abs(run(0, n2) - rdm_port.s_1rdm(dets, norb, left, right, 0).reshape(-1))) <= tol
-    if space[1] >= 1:
-        assert np.max(np.abs(run(1, n2) - rdm_port.s_1rdm(dets, norb, left, right, 1).reshape(-1))) <= tol
-    if space[0] >= 1 and space[1] >= 1:
-        assert np.max(np.abs(run(5, n2 * n2) - rdm_port.ab_2rdm(dets, norb, left, right).reshape(-1))) <= tol
-    if space[0] >= 2:
-        assert np.max(np.abs(run(3, npairs * npairs, 0) - rdm_port.ss_2rdm(dets, norb, left, right, 0).reshape(-1))) <= tol
-    if space[1] >= 2:
-        assert np.max(np.abs(run(4, npairs * npairs, 1) - rdm_port.ss_2rdm(dets, norb, left, right, 1).reshape(-1))) <= tol
 
 
 # ---- the sampled Slater-rules checker (oracle/sampled.py): what the parity tests at 10^8 - 10^9 determinants rest on

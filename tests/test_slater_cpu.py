@@ -48,3 +48,31 @@ def test_address_out_of_range():
     s = f2.CIStrings(2, 2, 0, [[0] * 4], [], [])
     with pytest.raises(IndexError):
         slater_matrix(s, 0.0, np.zeros((4, 4)), np.zeros((4,) * 4), [s.ndet])
+
+
+@pytest.mark.parametrize("name", ["cas66", "cas75_odd", "one_beta_three_alpha", "gas343_54", "cas66_d2h", "gas2_sym4"])
+def test_spin2_matrix_and_spin_adapted_guess(name):
+    """f2_spin2_matrix (det.spin2 of the reference, determinant_helpers.cc:154-203): over a whole space its eigenvalues
+    are S(S+1) with S = |Ms|, |Ms|+1, ..., it commutes with the Slater-rules Hamiltonian (which fixes every phase), and
+    the guess made from it (ci_solver.spin_adapted_guess, forte2/sci/sci.py:405-455) is spin pure."""
+    from forte2_b200.ci_solver import spin2_matrix, spin_adapted_guess, spin_complete
+    space = SMALL_SPACES[name]
+    s = f2.CIStrings(*space)
+    E, H, V = synthetic.integrals(s.norb, "D")
+    idx = np.arange(s.ndet, dtype=np.int64)
+    S2, Hd = spin2_matrix(s, idx), slater_matrix(s, E, H, V, idx)
+    assert np.allclose(S2, S2.T)
+    assert np.abs(S2 @ Hd - Hd @ S2).max() < 1e-12 * max(1.0, np.abs(Hd).max())
+    w = np.linalg.eigvalsh(S2)
+    S = 0.5 * (-1.0 + np.sqrt(1.0 + 4.0 * np.maximum(w, 0.0)))
+    ms = 0.5 * abs(space[0] - space[1])
+    assert np.allclose(S - ms, np.round(S - ms), atol=1e-9) and S.min() > ms - 1e-9
+    # guesses from a few determinants: spin-complete set, eigenvectors of S^2, wrong-spin vectors orthogonal to them
+    mult = int(round(2 * ms)) + 1
+    start = idx[:: max(1, s.ndet // 7)][:6]
+    gidx, guess, wrong = spin_adapted_guess(s, E, H, V, start, mult, 4)
+    assert set(start) <= set(gidx) and set(spin_complete(s, gidx)) == set(gidx)
+    S2g = spin2_matrix(s, gidx)
+    assert np.allclose(S2g @ guess, ms * (ms + 1) * guess, atol=1e-10)
+    assert np.allclose(guess.T @ guess, np.eye(guess.shape[1]), atol=1e-10)
+    assert np.abs(wrong.T @ guess).max(initial=0.0) < 1e-10
