@@ -31,6 +31,7 @@ SIGNATURES = {
     "f2_strings_blocks": (C.c_int, [C.c_void_p, i64p]),
     "f2_strings_occupations": (C.c_int64, [C.c_void_p, C.c_int, i64p, C.c_int64]),
     "f2_strings_export": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, i64p, C.c_int64]),
+    "f2_strings_build_lists": (C.c_int, [C.c_void_p, C.c_int]),
     "f2_strings_determinants": (C.c_int, [C.c_void_p, u64p]),
     "f2_strings_determinant": (C.c_int, [C.c_void_p, C.c_int64, u64p]),
     "f2_strings_determinant_index": (C.c_int64, [C.c_void_p, C.c_uint64, C.c_uint64]),

@@ -112,6 +112,11 @@ class CIStrings:
     def occupations(self, which):
         return self._occ(which).reshape(-1, 6 if which < 2 else 2)
 
+    def build_lists(self, device=None):
+        """build the replacement lists now: on GPU `device` (CUDA kernels, csrc/lists_device.cu) or, with None, on the
+        host; CISigmaBuilder does the former on its own when the lists do not exist yet"""
+        _lib.check(_lib.lib().f2_strings_build_lists(self._h, -1 if device is None else int(device)))
+
     def export(self, kind, spin):
         L = _lib.lib()
         k = KINDS[kind] if kind in KINDS else DEV_KINDS[kind]

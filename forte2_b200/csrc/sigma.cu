@@ -19,6 +19,7 @@
 
 #include "handles.hpp"
 #include "kernels.cuh"
+#include "lists_device.hpp"
 #include "rdm_kernels.cuh"
 
 namespace f2 {
@@ -89,6 +90,9 @@ static DevStrings* device_strings(f2_strings* S, int device) {
     if (it != S->dev.end())
         return it->second;
     const CIStringsHost& h = *S->host;
+    // the lists are made on this GPU unless the host has made them already (F2_HOST_LISTS: the host builder always)
+    if (!h.lists_built() && std::getenv("F2_HOST_LISTS") == nullptr)
+        build_lists_on_device(h);
     const DeviceLists& L = h.device_lists();
     auto d = std::make_unique<DevStrings>();
     d->device = device;
@@ -1679,6 +1683,29 @@ int f2_sigma_set_algorithm(f2_sigma* h, const char* name) {
 }
 
 const char* f2_sigma_get_algorithm(const f2_sigma* h) { return h->algorithm.c_str(); }
+
+int f2_strings_build_lists(f2_strings* S, int device) {
+    try {
+        if (!S)
+            throw std::invalid_argument("null argument");
+        std::lock_guard<std::mutex> lock(S->dev_mutex);
+        const CIStringsHost& h = *S->host;
+        if (h.lists_built())
+            return F2_OK;
+        if (device < 0) {
+            h.device_lists();
+            return F2_OK;
+        }
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count)
+            throw std::runtime_error("f2_strings_build_lists: no CUDA device " + std::to_string(device));
+        F2_CUDA(cudaSetDevice(device));
+        build_lists_on_device(h);
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
 
 int f2_sigma_set_memory(f2_sigma* h, int64_t mb) {
     if (mb < 0) {

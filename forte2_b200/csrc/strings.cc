@@ -2,6 +2,9 @@
 #include "strings.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -631,7 +634,7 @@ const HoleLists& CIStringsHost::hole_lists(int spin, int level) const {
     return h;
 }
 
-void CIStringsHost::build_device_lists() const {
+void CIStringsHost::lists_prologue() const {
     DeviceLists& d = dl_;
     const auto& A = space(0, K_STR_N);
     const auto& B = space(1, K_STR_N);
@@ -648,6 +651,59 @@ void CIStringsHost::build_device_lists() const {
     fill_cls(B, d.b_cls, d.b_loc);
     if (B.nclasses() > 4096 || norb * norb > 65535)
         throw std::overflow_error("CIStrings: class or orbital-pair index exceeds the packed list format");
+}
+
+// one electron of this spin: the only same-spin operator is h_pq a+_p a_q; treat the vacuum as the single "hole"
+// string whose parents are all one-electron strings and let the pair index carry the occupied orbital
+void CIStringsHost::lists_one_electron(int spin) const {
+    DeviceLists& d = dl_;
+    const auto& S = space(spin, K_STR_N);
+    auto& ptr = d.h2_ptr[spin];
+    auto& ent = d.h2_ent[spin];
+    ptr.assign(2, 0);
+    ent.clear();
+    for (size_t c = 0; c < S.nclasses(); ++c)
+        for (size_t x = 0; x < S.cls[c].size(); ++x)
+            ent.push_back(uint64_t(S.cls_off[c] + x) | (uint64_t(__builtin_ctzll(S.cls[c][x])) << 32));
+    ptr[1] = static_cast<uint32_t>(ent.size());
+}
+
+// after h2_ptr / h2_ent of `spin` are in place: the longest parent list and the launch order of the (N-2)-electron
+// strings that have parents.  Neighbouring strings share most of their parents, so strings that run at the same time
+// (consecutive entries of the list) are taken far apart: a stride permutation (golden-ratio stride made coprime with
+// the count) -- the reductions of concurrent CTAs then hit different rows of sigma.
+void CIStringsHost::lists_epilogue(int spin) const {
+    DeviceLists& d = dl_;
+    const auto& ptr = d.h2_ptr[spin];
+    auto& order = d.h2_color_list[spin];
+    auto& cptr = d.h2_color_ptr[spin];
+    order.clear();
+    cptr.assign(1, 0);
+    d.h2_max[spin] = 0;
+    std::vector<uint32_t> live;
+    for (size_t K = 0; K + 1 < ptr.size(); ++K) {
+        const int m = static_cast<int>(ptr[K + 1] - ptr[K]);
+        if (m > 0)
+            live.push_back(static_cast<uint32_t>(K));
+        d.h2_max[spin] = std::max(d.h2_max[spin], m);
+    }
+    const uint64_t n = live.size();
+    if (n == 0)
+        return;
+    uint64_t stride = static_cast<uint64_t>(0.6180339887498949 * static_cast<double>(n)) | 1ull;
+    while (std::gcd(stride, n) != 1)
+        stride += 2;
+    order.resize(n);
+    for (uint64_t i = 0; i < n; ++i)
+        order[i] = live[(i * stride) % n];
+    cptr.push_back(static_cast<uint32_t>(n));
+}
+
+void CIStringsHost::build_device_lists() const {
+    DeviceLists& d = dl_;
+    lists_prologue();
+    const auto& A = space(0, K_STR_N);
+    const auto& B = space(1, K_STR_N);
 
     // alpha singles from the output row: Ja = sign a+_l a_k Ia  <=>  <Ia|E_kl|Ja> = sign
     d.as_ptr.assign(A.nstr() + 1, 0);
@@ -712,96 +768,46 @@ void CIStringsHost::build_device_lists() const {
                 d.bs_ent[t * B.nstr() + g] = per[g][t];
     }
 
-    // two-hole members and colouring
+    // two-hole members
     for (int spin = 0; spin < 2; ++spin) {
         const auto& S = spin == 0 ? A : B;
         const int ne = spin == 0 ? na : nb;
         auto& ptr = d.h2_ptr[spin];
         auto& ent = d.h2_ent[spin];
-        auto& cptr = d.h2_color_ptr[spin];
-        auto& clist = d.h2_color_list[spin];
         ptr.assign(1, 0);
         ent.clear();
-        cptr.assign(1, 0);
-        clist.clear();
-        d.h2_max[spin] = 0;
-        if (ne == 1) {
-            // one electron of this spin: the only same-spin operator is h_pq a+_p a_q; treat the
-            // vacuum as the single "hole" string whose parents are all one-electron strings and
-            // let the pair index carry the occupied orbital
-            ptr.assign(2, 0);
+        if (ne == 1)
+            lists_one_electron(spin);
+        if (ne >= 2) {
+            const auto& H = space(spin, K_STR_2H);
+            const size_t nK = H.nstr();
+            std::vector<std::vector<uint64_t>> per(nK);
             for (size_t c = 0; c < S.nclasses(); ++c)
-                for (size_t x = 0; x < S.cls[c].size(); ++x)
-                    ent.push_back(uint64_t(S.cls_off[c] + x) |
-                                  (uint64_t(__builtin_ctzll(S.cls[c][x])) << 32));
-            ptr[1] = static_cast<uint32_t>(ent.size());
-            d.h2_max[spin] = static_cast<int>(ent.size());
-            if (!ent.empty()) {
-                clist.push_back(0);
-                cptr.push_back(1);
+                for (size_t x = 0; x < S.cls[c].size(); ++x) {
+                    const uint64_t s = S.cls[c][x];
+                    const size_t g = S.cls_off[c] + x;
+                    for (int q = 0; q < norb; ++q)
+                        for (int p = q + 1; p < norb; ++p) {
+                            if (!((s >> p) & 1) || !((s >> q) & 1))
+                                continue;
+                            const uint64_t s1 = s & ~(1ull << q);
+                            const uint64_t s2 = s1 & ~(1ull << p);
+                            uint32_t ak, ck;
+                            if (!H.find(s2, ak, ck))
+                                continue;
+                            const int sign = slater_sign(s1, q) * slater_sign(s2, p);
+                            const uint32_t K = H.cls_off[ck] + ak;
+                            per[K].push_back(uint64_t(g) | (uint64_t(p * (p - 1) / 2 + q) << 32) |
+                                             (uint64_t(sign < 0) << 48));
+                        }
+                }
+            ptr.assign(nK + 1, 0);
+            for (size_t K = 0; K < nK; ++K) {
+                ent.insert(ent.end(), per[K].begin(), per[K].end());
+                ptr[K + 1] = static_cast<uint32_t>(ent.size());
             }
-            continue;
         }
-        if (ne < 2)
-            continue;
-        const auto& H = space(spin, K_STR_2H);
-        const size_t nK = H.nstr();
-        std::vector<std::vector<uint64_t>> per(nK);
-        // parents of every N string: the 2h strings it belongs to (for the colouring)
-        std::vector<std::vector<uint32_t>> parents_of(S.nstr());
-        for (size_t c = 0; c < S.nclasses(); ++c)
-            for (size_t x = 0; x < S.cls[c].size(); ++x) {
-                const uint64_t s = S.cls[c][x];
-                const size_t g = S.cls_off[c] + x;
-                for (int q = 0; q < norb; ++q)
-                    for (int p = q + 1; p < norb; ++p) {
-                        if (!((s >> p) & 1) || !((s >> q) & 1))
-                            continue;
-                        const uint64_t s1 = s & ~(1ull << q);
-                        const uint64_t s2 = s1 & ~(1ull << p);
-                        uint32_t ak, ck;
-                        if (!H.find(s2, ak, ck))
-                            continue;
-                        const int sign = slater_sign(s1, q) * slater_sign(s2, p);
-                        const uint32_t K = H.cls_off[ck] + ak;
-                        per[K].push_back(uint64_t(g) | (uint64_t(p * (p - 1) / 2 + q) << 32) |
-                                         (uint64_t(sign < 0) << 48));
-                        parents_of[g].push_back(K);
-                    }
-            }
-        ptr.assign(nK + 1, 0);
-        for (size_t K = 0; K < nK; ++K) {
-            ent.insert(ent.end(), per[K].begin(), per[K].end());
-            ptr[K + 1] = static_cast<uint32_t>(ent.size());
-            d.h2_max[spin] = std::max<int>(d.h2_max[spin], static_cast<int>(per[K].size()));
-        }
-        // greedy colouring: K and K' conflict when some N string contains both
-        std::vector<int> color(nK, -1);
-        std::vector<uint32_t> stamp;
-        int ncolors = 0;
-        for (size_t K = 0; K < nK; ++K) {
-            if (per[K].empty())
-                continue;
-            stamp.assign(static_cast<size_t>(ncolors) + 1, 0);
-            for (uint64_t e : per[K])
-                for (uint32_t K2 : parents_of[e & 0xffffffffu])
-                    if (color[K2] >= 0)
-                        stamp[color[K2]] = 1;
-            int cfree = 0;
-            while (cfree < ncolors && stamp[cfree])
-                ++cfree;
-            color[K] = cfree;
-            ncolors = std::max(ncolors, cfree + 1);
-        }
-        std::vector<std::vector<uint32_t>> by_color(ncolors);
-        for (size_t K = 0; K < nK; ++K)
-            if (color[K] >= 0)
-                by_color[color[K]].push_back(static_cast<uint32_t>(K));
-        cptr.assign(1, 0);
-        for (auto& v : by_color) {
-            clist.insert(clist.end(), v.begin(), v.end());
-            cptr.push_back(static_cast<uint32_t>(clist.size()));
-        }
+        lists_epilogue(spin);
     }
     dl_built_ = true;
 }

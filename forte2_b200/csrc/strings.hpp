@@ -82,12 +82,12 @@ struct DeviceLists {
     // beta scatter, ELL: entry t of string Jb at [t * nbs + Jb]
     std::vector<uint64_t> bs_ent;
     int bs_width = 0;
-    // two-hole members per spin, CSR over global 2h string index, plus a colouring of the 2h
-    // strings such that two strings of one colour never share a parent N-electron string
+    // two-hole members per spin, CSR over global 2h string index, plus the launch order of the 2h strings that
+    // have parents (a stride permutation: strings that run concurrently share few parents)
     std::vector<uint32_t> h2_ptr[2];
     std::vector<uint64_t> h2_ent[2];
-    std::vector<uint32_t> h2_color_ptr[2];  // colour -> range in h2_color_list
-    std::vector<uint32_t> h2_color_list[2]; // 2h string ids grouped by colour
+    std::vector<uint32_t> h2_color_ptr[2];  // {0, count}
+    std::vector<uint32_t> h2_color_list[2]; // 2h string ids in launch order
     int h2_max[2] = {0, 0};
     // per global string: class and address in class
     std::vector<uint32_t> a_cls, a_loc, b_cls, b_loc;
@@ -140,6 +140,16 @@ class CIStringsHost {
 
     /// level in 0..3
     const HoleLists& hole_lists(int spin, int level) const;
+
+    /// pieces of the list construction, for the device builder (csrc/lists_device.cu): it runs the prologue (class and
+    /// address of every string), fills as_* / bs_* / h2_ptr / h2_ent of lists_storage() from the GPU, then the epilogue
+    /// per spin, and marks the lists as built
+    bool lists_built() const { return dl_built_; }
+    DeviceLists& lists_storage() const { return dl_; }
+    void lists_prologue() const;
+    void lists_one_electron(int spin) const;
+    void lists_epilogue(int spin) const;
+    void lists_adopt() const { dl_built_ = true; }
 
   private:
     mutable StringSpace sp_[2][5];

@@ -63,6 +63,10 @@ int64_t f2_strings_occupations(const f2_strings* h, int which, int64_t* out, int
  * entries reinterpreted as int64), for host models of the kernels in tests/; kinds 30 + level / 34 + level (level 0..3): CSR
  * pointer / packed entries of the hole lists of the RDM path (csrc/strings.hpp HoleLists) */
 int64_t f2_strings_export(const f2_strings* h, int kind, int spin, int64_t* out, int64_t cap);
+/* Build the replacement lists now instead of on first use: device >= 0 with CUDA kernels on that GPU
+ * (csrc/lists_device.cu; what f2_sigma_create does on its own), device < 0 with the host builder.  Both give the same
+ * arrays (forte2/ci/ci_strings_makers.cc:75-322 is the reference counterpart).  No effect once the lists exist. */
+int f2_strings_build_lists(f2_strings* h, int device);
 /* CIStrings::make_determinants / determinant / determinant_index (ci_strings.cc:186-230):
  * occupation words (alpha, beta) */
 int f2_strings_determinants(const f2_strings* h, uint64_t* out /* 2*ndet */);
