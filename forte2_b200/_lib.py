@@ -7,6 +7,7 @@ forte2_b200/csrc).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libforte2_b200.so"
@@ -98,7 +99,8 @@ def lib():
                 f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import "
                 "__graft_entry__ as g; g.build()' or make -C forte2_b200/csrc). forte2_b200 has no "
                 "CPU fallback.")
-        L = C.CDLL(str(LIB_PATH))
+        # F2_LIB_PATH: another build of the same library (kernel tuning variants, scripts/tune_ssg.sh)
+        L = C.CDLL(os.environ.get("F2_LIB_PATH") or str(LIB_PATH))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -186,6 +186,51 @@ class CISolver:
             self.spin_adapter.csf_C_to_det_C(self.evecs[i].contiguous(), out[i])
         return out
 
+    # ---- reduced density matrices of the converged roots (forte2/ci/ci.py:476-760: make_1rdm ... make_sf_3cumulant);
+    # the roots stay on the device, every spin block comes from the builder's kernels
+    def _root_pair(self, left_root: int, right_root):
+        if not self.executed:
+            raise RuntimeError("CI solver has not been executed yet; call run() first")
+        ev = self.evecs_det()
+        left = ev[int(left_root)].contiguous()
+        return left, (left if right_root is None else ev[int(right_root)].contiguous())
+
+    def make_sd_1rdm(self, left_root: int, right_root=None):
+        """spin-dependent 1-RDMs (a, b)"""
+        l, r = self._root_pair(left_root, right_root)
+        return self.ci_sigma_builder.a_1rdm(l, r), self.ci_sigma_builder.b_1rdm(l, r)
+
+    def make_sd_2rdm(self, left_root: int, right_root=None):
+        """spin-dependent 2-RDMs (aa, ab, bb)"""
+        l, r = self._root_pair(left_root, right_root)
+        b = self.ci_sigma_builder
+        return b.aa_2rdm(l, r), b.ab_2rdm(l, r), b.bb_2rdm(l, r)
+
+    def make_sd_3rdm(self, left_root: int, right_root=None):
+        """spin-dependent 3-RDMs (aaa, aab, abb, bbb)"""
+        l, r = self._root_pair(left_root, right_root)
+        b = self.ci_sigma_builder
+        return b.aaa_3rdm(l, r), b.aab_3rdm(l, r), b.abb_3rdm(l, r), b.bbb_3rdm(l, r)
+
+    def make_sf_1rdm(self, left_root: int, right_root=None):
+        return self.ci_sigma_builder.sf_1rdm(*self._root_pair(left_root, right_root))
+
+    def make_sf_2rdm(self, left_root: int, right_root=None):
+        return self.ci_sigma_builder.sf_2rdm(*self._root_pair(left_root, right_root))
+
+    def make_sf_3rdm(self, left_root: int, right_root=None):
+        return self.ci_sigma_builder.sf_3rdm(*self._root_pair(left_root, right_root))
+
+    def make_sf_2cumulant(self, left_root: int, right_root=None):
+        return self.ci_sigma_builder.sf_2cumulant(*self._root_pair(left_root, right_root))
+
+    def make_sf_3cumulant(self, left_root: int, right_root=None):
+        return self.ci_sigma_builder.sf_3cumulant(*self._root_pair(left_root, right_root))
+
+    # the non-relativistic solver's make_1rdm ... make_3cumulant are the spin-free ones (forte2/ci/ci.py:476-574)
+    make_1rdm, make_2rdm, make_3rdm = make_sf_1rdm, make_sf_2rdm, make_sf_3rdm
+    make_2cumulant, make_3cumulant = make_sf_2cumulant, make_sf_3cumulant
+
     def _run_csf(self, b):
         import torch
         s, sa = self.ci_strings, self.spin_adapter
@@ -407,3 +452,21 @@ class ShardedCISolver:
         self.converged = self.eigensolver.converged
         self.executed = True
         return self
+
+
+def make_average_rdms(sub_solvers, weights, max_body: int = 2):
+    """State-averaged spin-free RDMs over the roots of one or several solved CISolver objects
+    (forte2/base_classes/ci_base.py:104-149: make_average_1rdm / make_average_2rdm / make_average_3rdm):
+    weights[i][j] is the weight of root j of sub_solvers[i].  Returns (G1, G2) or, with max_body = 3, (G1, G2, G3)."""
+    out = None
+    for solver, ws in zip(sub_solvers, weights):
+        for j, w in enumerate(ws):
+            if w == 0.0:
+                continue
+            parts = [solver.make_sf_1rdm(j), solver.make_sf_2rdm(j)]
+            if max_body >= 3:
+                parts.append(solver.make_sf_3rdm(j))
+            out = [w * x for x in parts] if out is None else [o + w * x for o, x in zip(out, parts)]
+    if out is None:
+        raise ValueError("make_average_rdms: no root with a non-zero weight")
+    return tuple(out)

@@ -474,11 +474,13 @@ constexpr size_t t3g_smem_bytes(int64_t nsm, int rows, int astride) {
     return size_t(nsm + 2) * 8 + size_t(rows) * astride * 8 + size_t(rows) * 8 + 64;
 }
 
-// LONG = false: the whole row is staged (nsm == nbs).  THREADS: 384 (12 warps) up to 88 output rows,
-// 256 above (the accumulators of 96 rows need more than 170 registers per thread).
-template <int NM16, bool HAS8, bool LONG, int THREADS>
+// LONG = false: the whole row is staged (nsm == nbs).  NT = n8 tiles (8 target columns each) per warp work item:
+// 2 up to 88 output rows; 1 above (CAS(18,18): 90 rows = 6 row tiles), which halves the accumulators so that the
+// kernel keeps 12 warps per SM -- the gathers of a long row mostly go to L2 and need the extra warps to hide it.
+template <int NM16, bool HAS8, bool LONG, int THREADS, int NT>
 __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
     constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
+    constexpr int CW = 8 * NT; // target columns per work item
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -505,32 +507,79 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
         row[nsm] = 0.0;
         row[nsm + 1] = 0.0;
     }
-    // the single replacements of Ja, read as <Ia_r| E_{lk} |Ja> = s_r from the list of Ja as an output row
+    // the single replacements of Ja, read as <Ia_r| E_{lk} |Ja> = s_r from the list of Ja as an output row.  The
+    // diagonal ones (k = l, one per electron) all have Ia_r = Ja and phase +1: they share ONE row of A', the sum of
+    // their integral rows, placed behind the others (CAS(18,18): 82 rows = 5 tiles + 8 instead of 90 = 6 tiles)
+    __shared__ int s_diag[64]; // k norb + k of the occupied orbitals
+    __shared__ int s_cnt[2];   // rows (merged one included), diagonal entries
     const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
-    const int Kn = (e1 - e0) < ROWS ? (e1 - e0) : ROWS;
-    for (int r = tid; r < ROWS; r += THREADS) {
-        if (r < Kn) {
-            const uint64_t ent = p.as_ent[e0 + r];
-            const uint32_t Iar = static_cast<uint32_t>(ent);
-            const int kl = static_cast<int>((ent >> 32) & 0xffff);
-            const int k = kl / p.norb, l = kl - k * p.norb;
-            s_kl[r] = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
-            rowoff[r] = static_cast<long long>(p.rowpad ? p.rowpad[Iar] : Iar) * p.nbs;
-        } else {
+    if (warp == 0) {
+        int nrow = 0, ndiag = 0;
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            bool off = false, dia = false;
+            uint64_t ent = 0;
+            int k = 0, l = 0;
+            if (e < e1) {
+                ent = p.as_ent[e];
+                const int kl = static_cast<int>((ent >> 32) & 0xffff);
+                k = kl / p.norb;
+                l = kl - k * p.norb;
+                dia = k == l;
+                off = !dia;
+            }
+            const unsigned moff = __ballot_sync(0xffffffffu, off), mdia = __ballot_sync(0xffffffffu, dia);
+            const unsigned below = (1u << lane) - 1u;
+            if (off) {
+                const int r = nrow + __popc(moff & below);
+                if (r < ROWS - 1) {
+                    const uint32_t Iar = static_cast<uint32_t>(ent);
+                    s_kl[r] = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
+                    rowoff[r] = static_cast<long long>(p.rowpad ? p.rowpad[Iar] : Iar) * p.nbs;
+                }
+            }
+            if (dia) {
+                const int d = ndiag + __popc(mdia & below);
+                if (d < 64)
+                    s_diag[d] = k * p.norb + k;
+            }
+            nrow += __popc(moff);
+            ndiag += __popc(mdia);
+        }
+        nrow = nrow < ROWS - 1 ? nrow : ROWS - 1;
+        ndiag = ndiag < 64 ? ndiag : 64;
+        if (ndiag > 0) {
+            if (lane == 0) {
+                s_kl[nrow] = -2; // the merged diagonal row
+                rowoff[nrow] = static_cast<long long>(p.rowpad ? p.rowpad[Ja] : Ja) * p.nbs;
+            }
+            nrow += 1;
+        }
+        for (int r = nrow + lane; r < ROWS; r += 32) {
             s_kl[r] = -1;
             rowoff[r] = -1;
         }
+        if (lane == 0) {
+            s_cnt[0] = nrow;
+            s_cnt[1] = ndiag;
+        }
     }
     __syncthreads();
-    // A'[r][m] = s_r VxT[lk_r][m]; columns m >= M and rows r >= Kn are zero
+    // A'[r][m] = s_r VxT[lk_r][m]; columns m >= M and rows past the list are zero
+    const int ndiag = s_cnt[1];
     for (int idx = tid; idx < ROWS * S; idx += THREADS) {
         const int r = idx / S, m = idx - r * S;
         double v = 0.0;
         const int e = s_kl[r];
-        if (e >= 0 && m < p.M) {
-            v = __ldg(p.VxT + static_cast<size_t>(e & 0xffff) * p.M + m);
-            if (e & (1 << 30))
-                v = -v;
+        if (m < p.M) {
+            if (e >= 0) {
+                v = __ldg(p.VxT + static_cast<size_t>(e & 0xffff) * p.M + m);
+                if (e & (1 << 30))
+                    v = -v;
+            } else if (e == -2) {
+                for (int d = 0; d < ndiag; ++d)
+                    v += __ldg(p.VxT + static_cast<size_t>(s_diag[d]) * p.M + m);
+            }
         }
         Asm[idx] = v;
     }
@@ -538,26 +587,35 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
     mbar_wait(bar, 0);
 
     const int nks = p.Mpad >> 2;
-    const int nchunks = static_cast<int>((p.nbs + 15) >> 4);
+    const int nchunks = static_cast<int>((p.nbs + CW - 1) / CW);
     const uint32_t nbs32 = static_cast<uint32_t>(p.nbs);
     for (int chunk = warp; chunk < nchunks; chunk += THREADS / 32) {
-        const int n0 = chunk << 4;
-        double acc[NM16][2][4];
-        double acc8[2][2];
+        const int n0 = chunk * CW;
+        double acc[NM16][NT][4];
+        double acc8[NT][2];
 #pragma unroll
         for (int i = 0; i < NM16; ++i)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
                 acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.0;
-        acc8[0][0] = acc8[0][1] = acc8[1][0] = acc8[1][1] = 0.0;
-        // lane (g, t) feeds B[k = t][n = g] of both n8 tiles; n index gg of tile nt is the actual column
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+            acc8[nt][0] = acc8[nt][1] = 0.0;
+        // lane (g, t) feeds B[k = t][n = g] of every n8 tile; n index gg of tile nt is the actual column
         // n0 + 8 nt + (gg >> 1) + 4 (gg & 1), so that the four lanes of an accumulator row hold four
         // consecutive columns (one full 32-byte sector per reduction instruction and row)
         const uint32_t* gp = p.gsrc + static_cast<size_t>(t) * p.gld + n0 + (g >> 1) + 4 * (g & 1);
         const size_t gstep = static_cast<size_t>(4) * p.gld;
+        struct Q {
+            uint32_t e[NT];
+        };
         auto table = [&](int ks) { // entries of k-step ks (clamped: never used past the end)
             const uint32_t* q = gp + (ks < nks ? ks : 0) * gstep;
-            return make_uint2(__ldg(q), __ldg(q + 8));
+            Q r;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                r.e[nt] = __ldg(q + 8 * nt);
+            return r;
         };
         auto gather = [&](uint32_t e) {
             const uint32_t idx = e & 0xfffffu;
@@ -573,23 +631,26 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
             return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
         };
         // table entries run five k-steps ahead of the MMAs, gathered operands one (LONG: two) ahead
-        uint2 q0 = table(2), q1 = table(3), q2 = table(4), q3 = table(5);
-        double bn0, bn1, bm0, bm1;
+        Q q0 = table(2), q1 = table(3), q2 = table(4), q3 = table(5);
+        double bn[NT], bm[NT];
         {
-            const uint2 x0 = table(0), x1 = table(1);
-            bn0 = gather(x0.x);
-            bn1 = gather(x0.y);
-            bm0 = gather(x1.x);
-            bm1 = gather(x1.y);
+            const Q x0 = table(0), x1 = table(1);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                bn[nt] = gather(x0.e[nt]);
+                bm[nt] = gather(x1.e[nt]);
+            }
         }
         const double* ap = Asm + g * S + t;
 #pragma unroll 4
         for (int ks = 0; ks < nks; ++ks) {
-            const double b0 = bn0, b1 = bn1;
-            bn0 = bm0;
-            bn1 = bm1;
-            bm0 = gather(q0.x);
-            bm1 = gather(q0.y);
+            double b[NT];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                b[nt] = bn[nt];
+                bn[nt] = bm[nt];
+                bm[nt] = gather(q0.e[nt]);
+            }
             q0 = q1;
             q1 = q2;
             q2 = q3;
@@ -598,13 +659,15 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
 #pragma unroll
             for (int i = 0; i < NM16; ++i) {
                 const double a0 = a[(16 * i) * S], a1 = a[(16 * i + 8) * S];
-                dmma_16x8x4(acc[i][0], a0, a1, b0);
-                dmma_16x8x4(acc[i][1], a0, a1, b1);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    dmma_16x8x4(acc[i][nt], a0, a1, b[nt]);
             }
             if constexpr (HAS8) {
                 const double a0 = a[(16 * NM16) * S];
-                dmma_8x8x4(acc8[0], a0, b0);
-                dmma_8x8x4(acc8[1], a0, b1);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    dmma_8x8x4(acc8[nt], a0, b[nt]);
             }
         }
         // accumulator (row, tile nt, n index 2t + c) is column n0 + 8 nt + 4 c + t
@@ -617,7 +680,7 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
                 if (ro >= 0) {
                     double* dst = p.sigma + ro + c0;
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
+                    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
                             if (c0 + 8 * nt + 4 * c < p.nbs)
@@ -629,7 +692,7 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
             if (ro >= 0) {
                 double* dst = p.sigma + ro + c0;
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
                         if (c0 + 8 * nt + 4 * c < p.nbs)
@@ -975,8 +1038,18 @@ struct SSGroupLists {
     const uint32_t* list;
 };
 
-constexpr int SSG_TW = 256; // columns per CTA: a panel of all rows x SSG_TW columns of X and Y stays in L2
-constexpr int SSG_KG = 8;   // (N-2)-electron strings per CTA, software-pipelined
+// (the F2_SSG_* macros are tuning hooks for scripts/tune_ssg.sh; the defaults are the measured best)
+#ifndef F2_SSG_TW
+#define F2_SSG_TW 256
+#endif
+#ifndef F2_SSG_KG
+#define F2_SSG_KG 8
+#endif
+#ifndef F2_SSG_PFB
+#define F2_SSG_PFB 2
+#endif
+constexpr int SSG_TW = F2_SSG_TW; // columns per CTA: a panel of all rows x SSG_TW columns of X and Y stays in L2
+constexpr int SSG_KG = F2_SSG_KG; // (N-2)-electron strings per CTA, software-pipelined
 __host__ __device__ constexpr int ssg_astride(int rows) { // smallest stride >= rows, == 4 (mod 16)
     int s = rows;
     while (s % 16 != 4)
@@ -1105,7 +1178,7 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p, const SSG
 
     const int jend = j0 + SSG_TW < ncols ? j0 + SSG_TW : ncols;
     const int nchunks = (jend - j0 + 15) >> 4;
-    constexpr int PFB = 2; // k-steps per register batch; the next batch loads while this one multiplies
+    constexpr int PFB = F2_SSG_PFB; // k-steps per register batch; the next batch loads while this one multiplies
     double cur[PFB][2], nxt[PFB][2];
     unsigned scur[PFB], snxt[PFB];
     // parent row 4ks + t of the string in slot `slot`, columns cb and cb + 8 (zeros past the end)
@@ -1236,6 +1309,191 @@ __global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p, const SSG
             }
         }
         cp_async_wait<0>();
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shape-generic kernels (FP64 FMA pipe, no tensor tiles): the sigma terms for spaces whose parent lists or
+// single-replacement lists are longer than the tensor-core kernels hold in shared memory and registers (more than 112
+// parents per (N-2)-electron string, e.g. 4 electrons of one spin in 20 orbitals; more than 128 single replacements per
+// alpha string, e.g. 8 alpha electrons in 24 orbitals).  Same operands, lists, plans and launch grids as ssg_kernel /
+// t3_kernel; the panel of columns a CTA works on is cut into strips of `tw` columns (a power of two, at most the
+// number of threads) so that the staged rows fit in shared memory whatever the list length.
+constexpr int GEN_THREADS = 256;
+
+constexpr size_t gen_smem_bytes(int rows, int tw, int extra8 = 0) {
+    return size_t(rows) * tw * 8 + size_t(rows) * (8 + 8 + 4) + size_t(extra8) * 8 + 64;
+}
+
+// same-spin term: one CTA per ((N-2)-electron string K, column panel); Y[I_a, col] += s_a sum_b W[pair_a, pair_b] s_b X[I_b, col]
+template <bool GK>
+__global__ void __launch_bounds__(GEN_THREADS) ss_generic_kernel(const SSParams p, const SSGroupLists gk, const int rows,
+                                                                 const int tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Xs = reinterpret_cast<double*>(smem_raw);               // [rows][tw], phase applied
+    long long* msrc = reinterpret_cast<long long*>(Xs + rows * tw); // [rows]
+    long long* mdst = msrc + rows;
+    unsigned* minfo = reinterpret_cast<unsigned*>(mdst + rows);
+    __shared__ int s_m;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int grp = p.tiles[2 * blockIdx.y];
+    const int j0 = p.tiles[2 * blockIdx.y + 1];
+    const int ncols = p.g_ncols[grp];
+    const long long ldx = p.g_ldx[grp], ldy = p.g_ldy[grp];
+    uint32_t K;
+    if constexpr (GK) {
+        const int gnk = static_cast<int>(gk.ptr[grp + 1] - gk.ptr[grp]);
+        if (static_cast<int>(blockIdx.x) >= gnk)
+            return;
+        K = gk.list[gk.ptr[grp] + blockIdx.x];
+    } else {
+        K = p.klist[blockIdx.x];
+    }
+    if (tid < 32) { // parents of K that have a block in this column group, compacted in list order
+        const int e0 = p.h2_ptr[K], e1 = p.h2_ptr[K + 1];
+        int cnt = 0;
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            bool ok = false;
+            long long src = -1, dst = -1;
+            unsigned info = 0;
+            if (e < e1) {
+                const uint64_t ent = p.h2_ent[e];
+                const uint32_t I = static_cast<uint32_t>(ent);
+                const int c = p.s_cls[I];
+                const long long xo = p.xoff[c * p.ngroups + grp];
+                if (xo >= 0) {
+                    ok = true;
+                    src = xo + static_cast<long long>(p.s_loc[I]) * ldx;
+                    dst = p.yoff[c * p.ngroups + grp] + static_cast<long long>(p.s_loc[I]) * ldy;
+                    info = static_cast<unsigned>((ent >> 32) & 0xffff) | (static_cast<unsigned>((ent >> 48) & 1) << 31);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+                if (pos < rows) {
+                    msrc[pos] = src;
+                    mdst[pos] = dst;
+                    minfo[pos] = info;
+                }
+            }
+            cnt += __popc(mask);
+        }
+        if (lane == 0)
+            s_m = cnt < rows ? cnt : rows;
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (m == 0)
+        return;
+    const int jend = j0 + SSG_TW < ncols ? j0 + SSG_TW : ncols;
+    const int c = tid & (tw - 1), a_first = tid / tw, a_step = GEN_THREADS / tw;
+    for (int s0 = j0; s0 < jend; s0 += tw) {
+        for (int idx = tid; idx < m * tw; idx += GEN_THREADS) {
+            const int r = idx / tw, cc = idx - r * tw;
+            double v = 0.0;
+            if (s0 + cc < jend)
+                v = flip_sign(__ldg(p.X + msrc[r] + s0 + cc), minfo[r]);
+            Xs[idx] = v;
+        }
+        __syncthreads();
+        if (s0 + c < jend) {
+            for (int a = a_first; a < m; a += a_step) {
+                const double* w = p.W + static_cast<size_t>(minfo[a] & 0xffff) * p.P;
+                double acc = 0.0;
+                for (int b = 0; b < m; ++b)
+                    acc += __ldg(w + (minfo[b] & 0xffff)) * Xs[b * tw + c];
+                atomicAdd(p.Y + mdst[a] + s0 + c, flip_sign(acc, minfo[a]));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// opposite-spin term, scatter form: one CTA per (output alpha string Ia, beta class of the intermediate column);
+// G[m, Jb] = sum_r s_r Vx[m, kl_r] C[Ja_r, Jb], then sigma[Ia, Ib] += s' G[m, Jb] through the beta replacement table
+__global__ void __launch_bounds__(GEN_THREADS) t3_generic_kernel(const T3Params p, const int rows, const int tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Cs = reinterpret_cast<double*>(smem_raw);               // [rows][tw], phase applied
+    long long* ksrc = reinterpret_cast<long long*>(Cs + rows * tw); // [rows]
+    long long* unused = ksrc + rows;                                // (keeps the layout of gen_smem_bytes)
+    unsigned* kinfo = reinterpret_cast<unsigned*>(unused + rows);   // [rows]
+    long long* rowbase = reinterpret_cast<long long*>(kinfo + rows + (rows & 1)); // [nclsB]
+    __shared__ int s_Kn;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t Ia = p.items[2 * blockIdx.x];
+    const int cBp = p.items[2 * blockIdx.x + 1] & 0xffff;
+    const int cA = p.a_cls[Ia];
+    const uint32_t ia = p.a_loc[Ia];
+    const int nBp = p.nB_cls[cBp];
+    if (tid < 32) {
+        const int e0 = p.as_ptr[Ia], e1 = p.as_ptr[Ia + 1];
+        int cnt = 0;
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            bool ok = false;
+            long long src = -1;
+            unsigned info = 0;
+            if (e < e1) {
+                const uint64_t ent = p.as_ent[e];
+                const uint32_t Ja = static_cast<uint32_t>(ent);
+                const long long off = p.blk_off[p.a_cls[Ja] * p.nclsB + cBp];
+                if (off >= 0) {
+                    ok = true;
+                    src = off + static_cast<long long>(p.a_loc[Ja]) * nBp;
+                    info = static_cast<unsigned>((ent >> 32) & 0xffff) | (static_cast<unsigned>((ent >> 48) & 1) << 31);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+                if (pos < rows) {
+                    ksrc[pos] = src;
+                    kinfo[pos] = info;
+                }
+            }
+            cnt += __popc(mask);
+        }
+        if (lane == 0)
+            s_Kn = cnt < rows ? cnt : rows;
+    }
+    for (int cc = tid; cc < p.nclsB; cc += GEN_THREADS) {
+        const long long off = p.sblk_off[cA * p.nclsB + cc];
+        rowbase[cc] = off >= 0 ? off + static_cast<long long>(ia - p.srow0[cA]) * p.nB_cls[cc] : -1;
+    }
+    __syncthreads();
+    const int Kn = s_Kn;
+    if (Kn == 0)
+        return;
+    const int ldv = p.norb * p.norb;
+    const int c = tid & (tw - 1), m_first = tid / tw, m_step = GEN_THREADS / tw;
+    const uint32_t* tgt0 = p.tgt + p.b_off[cBp];
+    for (int s0 = 0; s0 < nBp; s0 += tw) {
+        for (int idx = tid; idx < Kn * tw; idx += GEN_THREADS) {
+            const int r = idx / tw, cc = idx - r * tw;
+            double v = 0.0;
+            if (s0 + cc < nBp)
+                v = flip_sign(__ldg(p.C + ksrc[r] + s0 + cc), kinfo[r]);
+            Cs[idx] = v;
+        }
+        __syncthreads();
+        if (s0 + c < nBp) {
+            for (int m = m_first; m < p.M; m += m_step) {
+                const uint32_t x = __ldg(tgt0 + static_cast<size_t>(m) * p.nbs + s0 + c);
+                if (x == kNoTarget)
+                    continue;
+                const long long base = rowbase[(x >> 20) & 0x7ff];
+                if (base < 0)
+                    continue;
+                const double* v = p.Vx + static_cast<size_t>(m) * ldv;
+                double acc = 0.0;
+                for (int r = 0; r < Kn; ++r)
+                    acc += __ldg(v + (kinfo[r] & 0xffff)) * Cs[r * tw + c];
+                atomicAdd(p.sigma + base + (x & 0xfffffu), (x >> 31) ? -acc : acc);
+            }
+        }
         __syncthreads();
     }
 }

@@ -198,6 +198,310 @@ __global__ void __launch_bounds__(RG_THREADS) rdm_gemm_kernel(const RdmGemmParam
 }
 
 // ---------------------------------------------------------------------------------------------
+// One-spin blocks (1-RDMs, same-spin 2-RDMs, same-spin 3-RDMs with short parent lists) without the D matrix: for an
+// (N - level)-electron string K of the acting spin with parents I_a = K + A (a = 0 .. m-1),
+//   Gamma[A, A'] += s_A s_A' sum over the determinants of the other spin  L[I_A, .] R[I_A', .]
+// is the m x m Gram matrix of the parent rows -- the transpose of the same-spin sigma contraction (ssg_kernel: rows in,
+// rows out; here rows in, a small matrix out).  One CTA per K runs over the whole row length: the parent rows stream
+// through shared memory in chunks of 64 columns (cp.async, two stages), warp (i, cs) multiplies row tile i against all
+// m parents for the k-steps cs, cs + CS, ... of the chunk (DMMA m16n8k4), and the CTA adds its m x m result into Gamma
+// once.  Operands are the CI vectors themselves for alpha (a row = one alpha string) and their transposed row slabs
+// for beta (the same slabs and plans as the beta same-spin sigma term: SSPlan, BetaPass of sigma.cu).
+struct RdmGramParams {
+    const double* XL;
+    const double* XR;
+    double* out; // [Pops][Pops]
+    const uint32_t* hptr;
+    const uint64_t* hent;
+    const uint32_t *s_cls, *s_loc;
+    const int64_t* xoff; // [classes of the acting spin][column groups] offset in the operand, -1 if absent
+    const uint32_t* g_ncols;
+    const uint32_t* g_ldx;
+    int ngroups, Pops;
+};
+
+constexpr int GRAM_THREADS = 384, GRAM_CHUNK = 64, GRAM_TS = 68;
+constexpr size_t rdm_gram_smem_bytes(int mt, bool same) {
+    return size_t(2) * (same ? 1 : 2) * (16 * mt) * GRAM_TS * 8 + size_t(16 * mt) * (8 + 4 + 4) + 64;
+}
+
+template <int MT, bool AL16, bool SAME>
+__global__ void __launch_bounds__(GRAM_THREADS, 1) rdm_gram_kernel(const RdmGramParams p) {
+    constexpr int ROWS = 16 * MT, CS = (GRAM_THREADS / 32) / MT, NOP = SAME ? 1 : 2;
+    constexpr int TILE = ROWS * GRAM_TS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);                   // [2][NOP][ROWS][TS]
+    long long* src = reinterpret_cast<long long*>(tiles + 2 * NOP * TILE); // [ROWS] offset of the parent row in the group
+    uint32_t* pstr = reinterpret_cast<uint32_t*>(src + ROWS);              // [ROWS] parent string
+    uint32_t* pinfo = pstr + ROWS;                                         // [ROWS] operator index | sign << 31
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t K = blockIdx.x;
+    const uint32_t e0 = p.hptr[K], e1 = p.hptr[K + 1];
+    const int m = static_cast<int>(e1 - e0) < ROWS ? static_cast<int>(e1 - e0) : ROWS;
+    if (m == 0)
+        return;
+    for (int r = tid; r < ROWS; r += GRAM_THREADS) {
+        uint32_t I = 0, info = 0;
+        if (r < m) {
+            const uint64_t ent = p.hent[e0 + r];
+            I = static_cast<uint32_t>(ent);
+            info = static_cast<uint32_t>((ent >> 32) & 0xffff) | (static_cast<uint32_t>((ent >> 48) & 1) << 31);
+        }
+        pstr[r] = I;
+        pinfo[r] = info;
+    }
+    const int wi = warp / CS, cs = warp - wi * CS; // row tile, k-step phase
+    double acc[2 * MT][4];
+#pragma unroll
+    for (int j = 0; j < 2 * MT; ++j)
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+
+    for (int grp = 0; grp < p.ngroups; ++grp) {
+        const int ncols = static_cast<int>(p.g_ncols[grp]);
+        const long long ldx = p.g_ldx[grp];
+        __syncthreads(); // the previous group's tiles and offsets are no longer read; pstr is visible
+        int any = 0;
+        for (int r = tid; r < ROWS; r += GRAM_THREADS) {
+            long long o = -1;
+            if (r < m) {
+                const uint32_t I = pstr[r];
+                const long long xo = p.xoff[static_cast<size_t>(p.s_cls[I]) * p.ngroups + grp];
+                if (xo >= 0) {
+                    o = xo + static_cast<long long>(p.s_loc[I]) * ldx;
+                    any = 1;
+                }
+            }
+            src[r] = o;
+        }
+        if (!__syncthreads_or(any) || ncols == 0)
+            continue;
+        const int nchunks = (ncols + GRAM_CHUNK - 1) / GRAM_CHUNK;
+        auto stage = [&](int chunk, int buf) {
+            if (chunk < nchunks) {
+                const int c0 = chunk * GRAM_CHUNK;
+                constexpr int PIECE = AL16 ? 2 : 1, PPR = GRAM_CHUNK / PIECE; // doubles per piece, pieces per row
+                for (int idx = tid; idx < NOP * ROWS * PPR; idx += GRAM_THREADS) {
+                    const int op = idx / (ROWS * PPR), rem = idx - op * ROWS * PPR;
+                    const int r = rem / PPR, pc = rem - r * PPR;
+                    const int col = c0 + pc * PIECE;
+                    const long long o = src[r];
+                    int bytes = 0;
+                    if (o >= 0 && col < ncols)
+                        bytes = (AL16 && col + 1 < ncols) ? 16 : 8;
+                    const double* gsrc = (op == 0 ? p.XL : p.XR) + (bytes ? o + col : 0);
+                    double* dst = tiles + (buf * NOP + op) * TILE + r * GRAM_TS + pc * PIECE;
+                    if (AL16)
+                        cp_async16(dst, gsrc, bytes);
+                    else
+                        cp_async8(dst, gsrc, bytes);
+                }
+            }
+            cp_async_commit();
+        };
+        stage(0, 0);
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            cp_async_wait<0>();
+            __syncthreads(); // chunk landed for everyone; the other buffer is no longer read
+            stage(chunk + 1, (chunk + 1) & 1);
+            const double* TL = tiles + ((chunk & 1) * NOP) * TILE;
+            const double* TR = SAME ? TL : TL + TILE;
+            const double* ap = TL + (16 * wi + g) * GRAM_TS + t;
+            const double* bp = TR + g * GRAM_TS + t;
+#pragma unroll 2
+            for (int ks = cs; ks < GRAM_CHUNK / 4; ks += CS) {
+                const double a0 = ap[4 * ks], a1 = ap[8 * GRAM_TS + 4 * ks];
+#pragma unroll
+                for (int j = 0; j < 2 * MT; ++j)
+                    dmma_16x8x4(acc[j], a0, a1, bp[8 * j * GRAM_TS + 4 * ks]);
+            }
+        }
+        cp_async_wait<0>();
+    }
+    // accumulator (tile j, element 2h + c): parent a = 16 wi + g + 8 h (of L), parent b = 8 j + 2 t + c (of R)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int a = 16 * wi + g + 8 * h;
+        if (a >= m)
+            continue;
+        const uint32_t ia = pinfo[a];
+        double* orow = p.out + static_cast<size_t>(ia & 0xffff) * p.Pops;
+#pragma unroll
+        for (int j = 0; j < 2 * MT; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int b = 8 * j + 2 * t + c;
+                if (b < m) {
+                    const uint32_t ib = pinfo[b];
+                    const double v = acc[j][2 * h + c];
+                    if (v != 0.0)
+                        atomicAdd(orow + (ib & 0xffff), ((ia ^ ib) >> 31) ? -v : v);
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Opposite-spin 2-RDM for spaces with one determinant block, in the gather form of the opposite-spin sigma term
+// (t3g_kernel read backwards): one CTA per alpha string Ja of the right vector,
+//   D[(v y), Ib]            = <Ib| E^b_vy |Jb> R[Ja, Jb]          gathered from the row R[Ja, :] in shared memory
+//   G[(v y), r]             = sum_Ib D[(v y), Ib] L[Ia_r, Ib]     Ia_r = s_r E^a_{u_r x_r} Ja, the single replacements of Ja
+//   Gamma[u_r, v, x_r, y]  += s_r G[(v y), r]
+// The contraction index is the beta string Ib: 2 n^2 K_a nbs flops per CTA on the FP64 tensor pipe instead of the
+// 2 n^4 nbs of the D-matrix form, and nothing of size n^2 x ndet is ever written.  Warp w owns MW 16-row tiles of (v y);
+// the rows L[Ia_r, chunk] are staged with cp.async (two stages), the table entries (source column and phase of every
+// ((v y), Ib)) are read 16 bytes per lane.  Within a group of 16 beta strings lane t supplies the strings 4 t + s to
+// k-step s (the sum over Ib does not care), which is what makes the 16-byte table reads line up with the fragments.
+struct RdmAbParams {
+    const double* L;
+    const double* R;
+    double* out; // [n][n][n][n]
+    const uint32_t* as_ptr;
+    const uint64_t* as_ent;
+    const uint32_t* gtab; // [mrows][gld]: source column | phase << 31; nbs = no source (the zero slot)
+    int64_t nbs, gld;
+    int norb, n2;
+};
+
+constexpr int AB_THREADS = 256, AB_CHUNK = 32, AB_TS = 33;
+constexpr size_t rdm_ab_smem_bytes(int64_t nbs, int ntp) {
+    return size_t(nbs + 2) * 8 + size_t(2) * (8 * ntp) * AB_TS * 8 + 64;
+}
+
+// gtab from the beta single-replacement list (ELL by source string): <Ib| E_ij |Jb> = sign  ->  gtab[i n + j][Ib] = Jb | neg << 31
+__global__ void rdm_abtab_kernel(const uint64_t* __restrict__ bs_ent, int64_t nbs, int width, int64_t gld, uint32_t* gtab) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= nbs * width)
+        return;
+    const uint64_t ent = bs_ent[idx];
+    if (ent == ~0ull)
+        return;
+    const int64_t Jb = idx % nbs;
+    const uint32_t Ib = static_cast<uint32_t>(ent & 0xfffffff);
+    const uint32_t ij = static_cast<uint32_t>((ent >> 40) & 0xffff);
+    gtab[static_cast<int64_t>(ij) * gld + Ib] = static_cast<uint32_t>(Jb) | (static_cast<uint32_t>((ent >> 56) & 1) << 31);
+}
+
+template <int MW, int NTP>
+__global__ void __launch_bounds__(AB_THREADS, 1) rdm_ab_kernel(const RdmAbParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t nbs = p.nbs;
+    double* row = reinterpret_cast<double*>(smem_raw); // [nbs + 2], the last two are zero
+    double* Ls = row + nbs + 2;                        // [2][8 NTP][AB_TS]
+    __shared__ long long s_lrow[128];                  // offset of row Ia_r in L, -1 past the list
+    __shared__ int s_ux[128];                          // (u n + x) | phase << 30, -1 past the list
+    const uint32_t Ja = blockIdx.x;
+    const double* rsrc = p.R + static_cast<int64_t>(Ja) * nbs;
+    for (int64_t i = tid; i < nbs + 2; i += AB_THREADS)
+        row[i] = i < nbs ? __ldg(rsrc + i) : 0.0;
+    const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
+    const int Kn = e1 - e0 < 128 ? e1 - e0 : 128;
+    for (int r = tid; r < 128; r += AB_THREADS) {
+        if (r < Kn) {
+            // <Ja| E_kl |Ia_r> = s  <=>  Ia_r = s E_lk Ja: creator u = l, annihilator x = k
+            const uint64_t ent = p.as_ent[e0 + r];
+            const int kl = static_cast<int>((ent >> 32) & 0xffff);
+            const int k = kl / p.norb, l = kl - k * p.norb;
+            s_ux[r] = (l * p.norb + k) | (static_cast<int>((ent >> 48) & 1) << 30);
+            s_lrow[r] = static_cast<long long>(static_cast<uint32_t>(ent)) * nbs;
+        } else {
+            s_ux[r] = -1;
+            s_lrow[r] = -1;
+        }
+    }
+    __syncthreads();
+    const int nchunks = static_cast<int>((nbs + AB_CHUNK - 1) / AB_CHUNK);
+    const int mbase = warp * MW * 16;
+    for (int r0 = 0; r0 < Kn; r0 += 8 * NTP) { // pass over the output rows
+        double acc[MW][NTP][4];
+#pragma unroll
+        for (int i = 0; i < MW; ++i)
+#pragma unroll
+            for (int j = 0; j < NTP; ++j)
+                acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0;
+        auto stage = [&](int chunk, int buf) {
+            if (chunk < nchunks) {
+                const int64_t c0 = static_cast<int64_t>(chunk) * AB_CHUNK;
+                for (int idx = tid; idx < 8 * NTP * AB_CHUNK; idx += AB_THREADS) {
+                    const int r = idx / AB_CHUNK, c = idx - r * AB_CHUNK;
+                    const long long o = r0 + r < 128 ? s_lrow[r0 + r] : -1;
+                    const bool in = o >= 0 && c0 + c < nbs;
+                    cp_async8(Ls + (buf * 8 * NTP + r) * AB_TS + c, p.L + (in ? o + c0 + c : 0), in ? 8 : 0);
+                }
+            }
+            cp_async_commit();
+        };
+        __syncthreads(); // the previous pass no longer reads the stages
+        stage(0, 0);
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            cp_async_wait<0>();
+            __syncthreads();
+            stage(chunk + 1, (chunk + 1) & 1);
+            const double* Lb = Ls + ((chunk & 1) * 8 * NTP) * AB_TS;
+#pragma unroll
+            for (int half = 0; half < AB_CHUNK / 16; ++half) {
+                const int64_t ib0 = static_cast<int64_t>(chunk) * AB_CHUNK + 16 * half;
+                // table entries of this lane's four beta strings ib0 + 4 t + {0..3}, rows g and g + 8 of each tile
+                uint4 q[MW][2];
+#pragma unroll
+                for (int i = 0; i < MW; ++i)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        q[i][h] = __ldg(reinterpret_cast<const uint4*>(p.gtab + static_cast<int64_t>(mbase + 16 * i + g + 8 * h) * p.gld +
+                                                                       ib0 + 4 * t));
+                auto gather = [&](uint32_t e) {
+                    const double v = row[e & 0x7fffffffu];
+                    return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
+                };
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    double b[NTP];
+#pragma unroll
+                    for (int j = 0; j < NTP; ++j)
+                        b[j] = Lb[(8 * j + g) * AB_TS + 16 * half + 4 * t + s4];
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) {
+                        const uint32_t ea = s4 == 0 ? q[i][0].x : s4 == 1 ? q[i][0].y : s4 == 2 ? q[i][0].z : q[i][0].w;
+                        const uint32_t eb = s4 == 0 ? q[i][1].x : s4 == 1 ? q[i][1].y : s4 == 2 ? q[i][1].z : q[i][1].w;
+                        const double a0 = gather(ea), a1 = gather(eb);
+#pragma unroll
+                        for (int j = 0; j < NTP; ++j)
+                            dmma_16x8x4(acc[i][j], a0, a1, b[j]);
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        // accumulator (tile i, j, element 2h + c): (v y) = mbase + 16 i + g + 8 h, output row r = r0 + 8 j + 2 t + c
+        const int n = p.norb;
+#pragma unroll
+        for (int i = 0; i < MW; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int mrow = mbase + 16 * i + g + 8 * h;
+                if (mrow >= p.n2)
+                    continue;
+                const int v = mrow / n, y = mrow - v * n;
+#pragma unroll
+                for (int j = 0; j < NTP; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int r = r0 + 8 * j + 2 * t + c;
+                        const int ux = r < 128 ? s_ux[r] : -1;
+                        if (ux < 0)
+                            continue;
+                        const int u = (ux & 0xffff) / n, x = (ux & 0xffff) - u * n;
+                        const double val = acc[i][j][2 * h + c];
+                        if (val != 0.0)
+                            atomicAdd(p.out + ((static_cast<int64_t>(u) * n + v) * n + x) * n + y, (ux & (1 << 30)) ? -val : val);
+                    }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Transition 1-RDM between two CI spaces (different symmetry / GAS restrictions, same orbitals and electron numbers):
 // out[pq] += sign * sum_i L[offL + i strideL] R[offR + i strideR] over a host-built list of matching segments
 // (CISigmaBuilder::compute_s_1trdm, forte2/ci/ci_sigma_builder_1trdm.cc:11-110: its VO string map x the map of the

@@ -241,6 +241,11 @@ struct f2_sigma {
     bool compressed = true;
     // opposite-spin kernel shape
     int t3_ks = 0, t3_warps = 0, t3_msplit = 1;
+    // shape-generic kernels (t3_generic_kernel / ss_generic_kernel) for lists longer than the tensor-core kernels hold
+    bool t3_generic = false;
+    int t3_gen_rows = 0, t3_gen_tw = 0;
+    bool ss_generic[2] = {false, false};
+    int ss_gen_rows[2] = {0, 0}, ss_gen_tw[2] = {0, 0};
     size_t t3_smem = 0;
     // row/column ownership plans: the single-GPU one and the last multi-GPU one
     std::unique_ptr<Part> single, shard;
@@ -274,6 +279,9 @@ struct f2_sigma {
         bool up = false;
     } rdm_lists[2][4];
     DevBuf<double> rdmD[2];
+    DevBuf<uint32_t> rdm_gtab; // opposite-spin 2-RDM: source column and phase of every ((v y), Ib) (rdm_ab_kernel)
+    int64_t rdm_gld = 0;
+    int rdm_gtab_rows = 0;
     // host staging for f2_sigma_apply_host
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
@@ -617,15 +625,40 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
     b.ja.upload(ja);
 }
 
+// widest strip of columns (a power of two, at most GEN_THREADS) whose staged rows fit in shared memory; 0 = none does
+int generic_strip(int rows, int extra8) {
+    for (int tw = GEN_THREADS; tw >= 4; tw >>= 1)
+        if (gen_smem_bytes(rows, tw, extra8) <= size_t(200) * 1024)
+            return tw;
+    return 0;
+}
+
 void plan_t3_shape(f2_sigma& b) {
     const CIStringsHost& h = *b.S->host;
     const DeviceLists& L = h.device_lists();
     b.t3_ks = 0;
     if (h.na < 1 || h.nb < 1 || L.as_max == 0 || h.ndet == 0)
         return;
-    if (L.as_max > 128)
-        throw std::runtime_error("CISigmaBuilder: more than 128 single replacements per alpha string "
-                                 "is not supported by the opposite-spin kernel");
+    b.t3_generic = false;
+    auto go_generic = [&]() {
+        b.t3_generic = true;
+        b.t3_gen_rows = L.as_max;
+        b.t3_gen_tw = generic_strip(L.as_max, static_cast<int>(h.nclsB()));
+        if (b.t3_gen_tw == 0)
+            throw std::runtime_error("CISigmaBuilder: " + std::to_string(L.as_max) + " single replacements per alpha "
+                                     "string do not fit the opposite-spin kernels");
+        b.t3_ks = 4; // non-zero: there is an opposite-spin term
+        b.t3_msplit = 1;
+        b.t3_warps = GEN_THREADS / 32;
+        b.t3_tail = false;
+        b.fold_ok = false;
+        b.t3g = false;
+        b.t3gm = false;
+    };
+    if (L.as_max > 128 || std::getenv("F2_GENERIC_KERNELS") != nullptr) {
+        go_generic();
+        return;
+    }
     b.t3_ks = round_ks(L.as_max);
     const int MT = (b.M + 15) / 16;
     const int maxw = b.t3_ks <= 24 ? 12 : 10;
@@ -645,12 +678,15 @@ void plan_t3_shape(f2_sigma& b) {
     // stays in the string space (no GAS restriction), so that E_ij E_kl needs no outside intermediate
     b.fold_ok = L.as_ent.size() == static_cast<size_t>(h.nas) * (h.na * (h.norb - h.na) + h.na) &&
                 std::getenv("F2_NO_FOLD") == nullptr;
-    if (b.t3_smem > 227 * 1024)
-        throw std::runtime_error("CISigmaBuilder: opposite-spin tile does not fit in shared memory");
+    if (b.t3_smem > 227 * 1024) {
+        go_generic();
+        return;
+    }
     // gather form: one determinant block, rows of C (and the A' block) fit in shared memory
     b.t3g = false;
     if (b.gsrc.p && b.D->al16 && h.nbs % 2 == 0 && b.M >= 33 && std::getenv("F2_NO_T3G") == nullptr) {
-        const int kn = L.as_max;
+        // rows of A': the single replacements of a string, its na diagonal ones (E_kk) merged into one row
+        const int kn = L.as_max - (h.na > 0 ? static_cast<int>(h.na) - 1 : 0);
         const int nm16 = kn / 16, rem = kn % 16;
         b.t3g_nm16 = nm16 + (rem > 8 ? 1 : 0);
         b.t3g_has8 = (rem > 0 && rem <= 8) ? 1 : 0;
@@ -1175,15 +1211,34 @@ void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t
 
 template <int NM16, bool HAS8>
 void launch_t3g_inst(const f2_sigma& b, const T3GParams& p, int nrows, cudaStream_t st) {
-    constexpr int THREADS = NM16 >= 6 ? 256 : 384;
+    // 6 row tiles (CAS(18,18): 90 output rows): 8 target columns per warp item instead of 16, which halves the
+    // accumulators and keeps 12 warps per SM; F2_T3G_WIDE = the 16-column items on 8 warps (the round-1 shape)
+    constexpr int THREADS = 384;
+    const bool wide = std::getenv("F2_T3G_WIDE") != nullptr;
+    if constexpr (NM16 >= 6) {
+        if (wide) {
+            if (b.t3g_long) {
+                F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, true, 256, 2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b.t3g_smem)));
+                t3g_kernel<NM16, HAS8, true, 256, 2><<<nrows, 256, b.t3g_smem, st>>>(p);
+            } else {
+                F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, false, 256, 2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b.t3g_smem)));
+                t3g_kernel<NM16, HAS8, false, 256, 2><<<nrows, 256, b.t3g_smem, st>>>(p);
+            }
+            b.launches += 1;
+            return;
+        }
+    }
+    constexpr int NT = NM16 >= 6 ? 1 : 2;
     if (b.t3g_long) {
-        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, true, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, true, THREADS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(b.t3g_smem)));
-        t3g_kernel<NM16, HAS8, true, THREADS><<<nrows, THREADS, b.t3g_smem, st>>>(p);
+        t3g_kernel<NM16, HAS8, true, THREADS, NT><<<nrows, THREADS, b.t3g_smem, st>>>(p);
     } else {
-        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, false, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, false, THREADS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(b.t3g_smem)));
-        t3g_kernel<NM16, HAS8, false, THREADS><<<nrows, THREADS, b.t3g_smem, st>>>(p);
+        t3g_kernel<NM16, HAS8, false, THREADS, NT><<<nrows, THREADS, b.t3g_smem, st>>>(p);
     }
     b.launches += 1;
 }
@@ -1303,6 +1358,14 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     p.norb = h.norb;
     p.Vx = b.Vx.p;
     p.M = b.M;
+    if (b.t3_generic) {
+        const size_t smem = gen_smem_bytes(b.t3_gen_rows, b.t3_gen_tw, p.nclsB);
+        F2_CUDA(cudaFuncSetAttribute(t3_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        t3_generic_kernel<<<P.nitems, GEN_THREADS, smem, st>>>(p, b.t3_gen_rows, b.t3_gen_tw);
+        b.launches += 1;
+        F2_CUDA(cudaGetLastError());
+        return;
+    }
     switch (b.t3_ks) {
     case 4: launch_t3_ks<4>(b, p, P.nitems, st); break;
     case 8: launch_t3_ks<8>(b, p, P.nitems, st); break;
@@ -1376,6 +1439,32 @@ void launch_same_spin(const f2_sigma& b, int spin, const SSPlan& plan, const dou
         return; // no string has a parent in any block of this plan
     // grid: x = K (fastest: all K of a column panel run together, the panel stays in L2), y = panel
     const size_t nk_grid = gk.ptr ? plan.gk_max : nk;
+    if (b.ss_generic[spin]) {
+        const int rows = b.ss_gen_rows[spin], tw = b.ss_gen_tw[spin];
+        const size_t smem = gen_smem_bytes(rows, tw);
+        F2_CUDA(cudaFuncSetAttribute(ss_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        F2_CUDA(cudaFuncSetAttribute(ss_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        for (size_t k0 = 0; k0 < nk_grid; k0 += size_t(1) << 30) {
+            const uint32_t nkk = static_cast<uint32_t>(std::min<size_t>(size_t(1) << 30, nk_grid - k0));
+            p.klist = D.h2_clist[spin].p + k0;
+            p.nk = static_cast<int>(nkk);
+            SSGroupLists gk0 = gk;
+            if (gk0.ptr && k0 > 0)
+                throw std::runtime_error("CISigmaBuilder: more than 2^30 two-hole strings per column group");
+            for (int t0 = 0; t0 < plan.ntiles; t0 += 65535) {
+                const int nt = std::min(65535, plan.ntiles - t0);
+                p.tiles = plan.tiles.p + 2 * static_cast<size_t>(t0);
+                const dim3 grid(nkk, nt);
+                b.launches += 1;
+                if (gk0.ptr)
+                    ss_generic_kernel<true><<<grid, GEN_THREADS, smem, st>>>(p, gk0, rows, tw);
+                else
+                    ss_generic_kernel<false><<<grid, GEN_THREADS, smem, st>>>(p, gk0, rows, tw);
+            }
+        }
+        F2_CUDA(cudaGetLastError());
+        return;
+    }
     for (size_t k0 = 0; k0 < nk_grid; k0 += size_t(1) << 30) {
         const uint32_t nkk = static_cast<uint32_t>(std::min<size_t>(size_t(1) << 30, nk_grid - k0));
         p.klist = D.h2_clist[spin].p + k0;
@@ -1562,7 +1651,9 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
         }
         F2_CUDA(cudaEventRecord(b.ev[1], st));
     }
-    if (phases & 2) {
+    // 2 = 4 | 8: H0 and both same-spin terms; 4 = H0 and the alpha same-spin term (needs xcols); 8 = the beta same-spin
+    // term (needs only the local rows), after 4
+    if (phases & (2 | 4)) {
         if (P.local_size > 0) {
             scale_copy_kernel<false><<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
             b.launches += 1;
@@ -1572,6 +1663,8 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
         if (h.na >= 1)
             launch_same_spin(b, 0, P.alpha_cols_plan, xcols, ycols, b.W[0].p, st);
         F2_CUDA(cudaEventRecord(b.ev[3], st));
+    }
+    if (phases & (2 | 8)) {
         for (const auto& bp : P.beta_passes) {
             if (bp->ntr_tiles == 0)
                 continue;
@@ -1635,10 +1728,19 @@ f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const 
         build_integrals(*b, E, H, V);
         const DeviceLists& L = strings->host->device_lists();
         for (int s = 0; s < 2; ++s) {
-            if (L.h2_max[s] > 128)
-                throw std::runtime_error("CISigmaBuilder: more than 128 parents per two-hole string "
-                                         "is not supported by the same-spin kernel");
-            b->ss_ks[s] = round_ks(std::max(L.h2_max[s], 1));
+            // the tensor-core kernel keeps two m x m integral blocks in shared memory: up to 112 parents
+            const int mmax = std::max(L.h2_max[s], 1);
+            const int rows16 = (mmax / 16 + (mmax % 16 > 8 ? 1 : 0)) * 16 + ((mmax % 16 > 0 && mmax % 16 <= 8) ? 8 : 0);
+            b->ss_generic[s] = rows16 > 128 || ssg_smem_bytes(rows16) > size_t(227) * 1024 - 1024 ||
+                               std::getenv("F2_GENERIC_KERNELS") != nullptr;
+            if (b->ss_generic[s]) {
+                b->ss_gen_rows[s] = mmax;
+                b->ss_gen_tw[s] = generic_strip(mmax, 0);
+                if (b->ss_gen_tw[s] == 0)
+                    throw std::runtime_error("CISigmaBuilder: " + std::to_string(mmax) + " parents per two-hole string "
+                                             "do not fit the same-spin kernels");
+            }
+            b->ss_ks[s] = round_ks(std::min(mmax, 128));
         }
         plan_t3_shape(*b);
         b->single = make_part(*b, 0, 1);
@@ -2035,6 +2137,151 @@ f2_sigma::RdmLists& rdm_device_lists(f2_sigma& b, int spin, int level) {
     return d;
 }
 
+extern "C++" {
+template <int MT>
+void launch_rdm_gram(const RdmGramParams& q, unsigned nK, bool al16, bool same, cudaStream_t st) {
+    auto go = [&](auto kernel) {
+        const size_t smem = rdm_gram_smem_bytes(MT, same);
+        F2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<nK, GRAM_THREADS, smem, st>>>(q);
+    };
+    if (al16)
+        same ? go(rdm_gram_kernel<MT, true, true>) : go(rdm_gram_kernel<MT, true, false>);
+    else
+        same ? go(rdm_gram_kernel<MT, false, true>) : go(rdm_gram_kernel<MT, false, false>);
+}
+} // extern "C++"
+
+// one-spin block (1-RDM, same-spin 2-RDM, same-spin 3-RDM with at most 64 parents per hole string) as Gram matrices of
+// the parent rows (rdm_gram_kernel): alpha on the vectors themselves, beta on their transposed row slabs (the slabs and
+// plans of the beta same-spin sigma term, inside the set_memory budget)
+void rdm_gram(f2_sigma& b, int spin, int level, const double* L, const double* R, double* out, int64_t Pops,
+              cudaStream_t st) {
+    const CIStringsHost& hs = *b.S->host;
+    const DevStrings& D = *b.D;
+    const HoleLists& HL = hs.hole_lists(spin, level);
+    const unsigned nK = static_cast<unsigned>(HL.nK());
+    if (nK == 0)
+        return;
+    auto& dl = rdm_device_lists(b, spin, level);
+    Part& P = *b.single;
+    const bool same = L == R;
+    RdmGramParams q;
+    q.out = out;
+    q.hptr = dl.ptr.p;
+    q.hent = dl.ent.p;
+    q.s_cls = spin == 0 ? D.a_cls.p : D.b_cls.p;
+    q.s_loc = spin == 0 ? D.a_loc.p : D.b_loc.p;
+    q.Pops = static_cast<int>(Pops);
+    const int mt = std::max(1, (HL.max_parents + 15) / 16);
+    auto launch = [&](const SSPlan& plan, const double* xl, const double* xr) {
+        if (plan.ngroups == 0)
+            return;
+        q.XL = xl;
+        q.XR = xr;
+        q.xoff = plan.xoff.p;
+        q.g_ncols = plan.g_ncols.p;
+        q.g_ldx = plan.g_ldx.p;
+        q.ngroups = plan.ngroups;
+        const bool al16 = plan.al16 && ((reinterpret_cast<uintptr_t>(xl) | reinterpret_cast<uintptr_t>(xr)) & 15) == 0;
+        switch (mt) {
+        case 1: launch_rdm_gram<1>(q, nK, al16, same, st); break;
+        case 2: launch_rdm_gram<2>(q, nK, al16, same, st); break;
+        case 3: launch_rdm_gram<3>(q, nK, al16, same, st); break;
+        case 4: launch_rdm_gram<4>(q, nK, al16, same, st); break;
+        default: throw std::logic_error("rdm_gram: more than 64 parents");
+        }
+        b.launches += 1;
+    };
+    if (spin == 0) {
+        launch(P.alpha_plan, L, R);
+    } else {
+        if (!P.beta_planned)
+            plan_beta(b, P);
+        for (const auto& bp : P.beta_passes) {
+            if (bp->ntr_tiles == 0)
+                continue;
+            transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(L, b.XT.p, bp->tr.p, bp->ntr, false);
+            b.launches += 1;
+            if (!same) {
+                transpose_kernel<false><<<bp->ntr_tiles, 256, 0, st>>>(R, b.YT.p, bp->tr.p, bp->ntr, false);
+                b.launches += 1;
+            }
+            launch(bp->plan, b.XT.p, same ? b.XT.p : b.YT.p);
+        }
+    }
+    F2_CUDA(cudaGetLastError());
+}
+
+extern "C++" {
+template <int MW, int NTP>
+void launch_rdm_ab(const RdmAbParams& q, unsigned nas, size_t smem, cudaStream_t st) {
+    F2_CUDA(cudaFuncSetAttribute(rdm_ab_kernel<MW, NTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    rdm_ab_kernel<MW, NTP><<<nas, AB_THREADS, smem, st>>>(q);
+}
+} // extern "C++"
+
+// opposite-spin 2-RDM in the gather form (rdm_ab_kernel); false when the space does not fit it (several determinant
+// blocks, a row of the vector longer than shared memory, more than 19 orbitals or 128 single replacements)
+bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStream_t st) {
+    const CIStringsHost& hs = *b.S->host;
+    const DevStrings& D = *b.D;
+    const DeviceLists& DL = hs.device_lists();
+    if (hs.nclsA() != 1 || hs.nclsB() != 1 || hs.blocks.size() != 1 || DL.as_max > 128 || DL.as_max < 1)
+        return false;
+    const int n = hs.norb, n2 = n * n;
+    const int mtiles = (n2 + 15) / 16, mw = (mtiles + 7) / 8;
+    if (mw > 3 || hs.nbs >= (int64_t(1) << 31) - 1)
+        return false;
+    const int nt = (DL.as_max + 7) / 8;
+    int ntp;
+    if (mw == 1)
+        ntp = nt <= 4 ? 4 : (nt <= 8 ? 8 : 16);
+    else if (mw == 2)
+        ntp = nt <= 5 ? 5 : 9;
+    else
+        ntp = 6;
+    const size_t smem = rdm_ab_smem_bytes(hs.nbs, ntp);
+    if (smem > size_t(227) * 1024 - 2048)
+        return false;
+    const int rows = 8 * mw * 16;
+    if (!b.rdm_gtab.p || b.rdm_gtab_rows != rows) {
+        b.rdm_gld = (hs.nbs + 31) / 32 * 32;
+        std::vector<uint32_t> fill(static_cast<size_t>(rows) * b.rdm_gld, static_cast<uint32_t>(hs.nbs));
+        b.rdm_gtab.upload(fill);
+        b.rdm_gtab_rows = rows;
+        const int64_t total = hs.nbs * DL.bs_width;
+        if (total > 0)
+            rdm_abtab_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(D.bs_ent.p, hs.nbs, DL.bs_width, b.rdm_gld,
+                                                                                        b.rdm_gtab.p);
+        b.launches += 1;
+    }
+    RdmAbParams q;
+    q.L = L;
+    q.R = R;
+    q.out = out;
+    q.as_ptr = D.as_ptr.p;
+    q.as_ent = D.as_ent.p;
+    q.gtab = b.rdm_gtab.p;
+    q.nbs = hs.nbs;
+    q.gld = b.rdm_gld;
+    q.norb = n;
+    q.n2 = n2;
+    const unsigned nas = static_cast<unsigned>(hs.nas);
+    switch (mw * 100 + ntp) {
+    case 104: launch_rdm_ab<1, 4>(q, nas, smem, st); break;
+    case 108: launch_rdm_ab<1, 8>(q, nas, smem, st); break;
+    case 116: launch_rdm_ab<1, 16>(q, nas, smem, st); break;
+    case 205: launch_rdm_ab<2, 5>(q, nas, smem, st); break;
+    case 209: launch_rdm_ab<2, 9>(q, nas, smem, st); break;
+    case 306: launch_rdm_ab<3, 6>(q, nas, smem, st); break;
+    default: return false;
+    }
+    b.launches += 1;
+    F2_CUDA(cudaGetLastError());
+    return true;
+}
+
 // one spin block <L| (la alpha creators)(lb beta creators)(lb beta annihilators)(la alpha annihilators) |R> as the
 // M x M matrix over rows opA * Pb + opB, M = C(norb, la) C(norb, lb)
 void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, double* out, cudaStream_t st) {
@@ -2057,6 +2304,13 @@ void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, do
     const HoleLists& HB = hs.hole_lists(1, lb);
     const int64_t nKa = static_cast<int64_t>(HA.nK()), nKb = static_cast<int64_t>(HB.nK());
     if (nKa == 0 || nKb == 0)
+        return;
+    // one spin only: Gram matrices of the parent rows, no D matrix (F2_RDM_GENERIC: the gather + GEMM path always)
+    if ((la == 0 || lb == 0) && (la == 0 ? HB : HA).max_parents <= 64 && std::getenv("F2_RDM_GENERIC") == nullptr) {
+        rdm_gram(b, la == 0 ? 1 : 0, la + lb, L, R, out, M, st);
+        return;
+    }
+    if (la == 1 && lb == 1 && std::getenv("F2_RDM_GENERIC") == nullptr && rdm_ab(b, L, R, out, st))
         return;
     auto& LA = rdm_device_lists(b, 0, la);
     auto& LB = rdm_device_lists(b, 1, lb);

@@ -204,8 +204,9 @@ class ShardedSigma:
         self._xplan = plan
         return plan
 
-    def _exchange_add(self, sigma_loc: torch.Tensor):
-        """send the alpha same-spin partials [rows of q][my columns] to q, add what arrives (step 3)"""
+    def _exchange_add_start(self):
+        """send the alpha same-spin partials [rows of q][my columns] to q (step 3); the transfers run beside whatever is
+        launched next, _exchange_add_finish waits for them and adds what arrived"""
         plan = self._exchange_plan()
         ops, sends = [], []
         for q, (send_slices, send_buf, recv_buf, adds) in enumerate(plan):
@@ -226,14 +227,21 @@ class ShardedSigma:
                 ops.append(dist.P2POp(dist.isend, send, q, group=self.group))
             if recv_buf.numel():
                 ops.append(dist.P2POp(dist.irecv, recv_buf, q, group=self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for q, (send_slices, send_buf, recv_buf, adds) in enumerate(plan):
+        works = dist.batch_isend_irecv(ops) if ops else []
+        return works, sends
+
+    def _exchange_add_finish(self, pending, sigma_loc: torch.Tensor):
+        works, sends = pending
+        for w in works:
+            w.wait()
+        for q, (send_slices, send_buf, recv_buf, adds) in enumerate(self._exchange_plan()):
             src = sends[q] if q == self.rank else recv_buf
             for loc, n, nB, cl_q, nc_q, pos in adds:
                 blk = sigma_loc[loc:loc + n * nB].view(n, nB)
                 blk[:, cl_q:cl_q + nc_q] += src[pos:pos + n * nc_q].view(n, nc_q)
+
+    def _exchange_add(self, sigma_loc: torch.Tensor):
+        self._exchange_add_finish(self._exchange_add_start(), sigma_loc)
 
     def _cols_plan(self):
         """rows form, step 1, per peer q: the pieces C[my rows, columns of q] of every block that go to q
@@ -265,9 +273,10 @@ class ShardedSigma:
         self._cplan = plan
         return plan
 
-    def _exchange_cols(self, c_loc: torch.Tensor):
+    def _exchange_cols_start(self, c_loc: torch.Tensor):
         """rows form, step 1: column slabs [all rows][my columns] of C (per block, laid out like the
-        exchange buffer) from the row slabs"""
+        exchange buffer) from the row slabs; the transfers are left in flight (the opposite-spin kernel, which reads the
+        local rows only, runs beside them), _exchange_cols_finish waits and unpacks"""
         ops = []
         plan = self._cols_plan()
         for q, (sends, recvs, send_buf, recv_buf) in enumerate(plan):
@@ -285,16 +294,21 @@ class ShardedSigma:
                 ops.append(dist.P2POp(dist.irecv, self._xcols[recvs[0][0]:recvs[0][0] + recvs[0][1]], q, group=self.group))
             elif recvs:
                 ops.append(dist.P2POp(dist.irecv, recv_buf, q, group=self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for q, (sends, recvs, send_buf, recv_buf) in enumerate(plan):
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def _exchange_cols_finish(self, works):
+        for w in works:
+            w.wait()
+        for q, (sends, recvs, send_buf, recv_buf) in enumerate(self._cols_plan()):
             if recv_buf is None:
                 continue
             pos = 0
             for start, m in recvs:
                 self._xcols[start:start + m].copy_(recv_buf[pos:pos + m])
                 pos += m
+
+    def _exchange_cols(self, c_loc: torch.Tensor):
+        self._exchange_cols_finish(self._exchange_cols_start(c_loc))
 
     def _reduce_scatter_start(self):
         """rows form, step 4: sum over ranks of slot `rank` of the opposite-spin buffers; asynchronous on
@@ -332,18 +346,27 @@ class ShardedSigma:
     def Hamiltonian(self, c_loc: torch.Tensor, sigma_loc: torch.Tensor) -> None:
         assert c_loc.numel() == self.local_size and sigma_loc.numel() == self.local_size
         if self.form == "rows":
-            self._exchange_cols(c_loc)
-            self._mark("all-to-all of C (column slab)")
+            # the two all-to-alls and the reduce-scatter all run beside kernels that do not need their result:
+            #   C column slab  ||  opposite-spin kernel (local rows only)
+            #   reduce-scatter ||  H0 + alpha same-spin + beta same-spin
+            #   alpha same-spin result back to the row owners  ||  beta same-spin kernel
+            cols = self._exchange_cols_start(c_loc)
+            self._mark("pack + start of the all-to-all of C (column slab)")
             args = (c_loc, self._xcols, sigma_loc, self._yexch, self._scatter, self.rank, self.world)
             self.engine.apply_rows(*args, phases=1)
-            self._mark("opposite-spin kernel")
+            self._mark("opposite-spin kernel (all-to-all of C in flight)")
             work = self._reduce_scatter_start()
-            self.engine.apply_rows(*args, phases=2)
-            self._mark("same-spin kernels (reduce-scatter in flight)")
+            self._exchange_cols_finish(cols)
+            self._mark("all-to-all of C: tail + unpack")
+            self.engine.apply_rows(*args, phases=4)
+            self._mark("H0 + alpha same-spin kernel (reduce-scatter in flight)")
+            back = self._exchange_add_start()
+            self.engine.apply_rows(*args, phases=8)
+            self._mark("beta same-spin kernel (all-to-all back in flight)")
             self._reduce_scatter_finish(work, sigma_loc)
             self._mark("reduce-scatter tail + add")
-            self._exchange_add(sigma_loc)
-            self._mark("all-to-all of the alpha same-spin term + add")
+            self._exchange_add_finish(back, sigma_loc)
+            self._mark("all-to-all of the alpha same-spin term: tail + add")
             return
         full = self.all_gather_full(c_loc)
         self._mark("all-gather of C")

@@ -176,8 +176,10 @@ int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4);
  * ycols = alpha same-spin term of [nIa][owned columns] (caller: all-to-all back to the row owners, add);
  * scatter = opposite-spin contributions of the owned INPUT rows to every sigma row in the slot layout
  * above (caller: reduce-scatter over NCCL, add).  phases: 1 = only the opposite-spin term (launched
- * first so that the reduce-scatter can overlap the rest), 2 = only H0 and the same-spin terms, 3 = both;
- * a build is phase 1 followed by phase 2.  Device pointers; stream = cudaStream_t. */
+ * first so that the reduce-scatter can overlap the rest; reads C_local only, so the all-to-all that assembles xcols can
+ * still be in flight), 2 = only H0 and the same-spin terms, 3 = both; 2 splits into 4 = H0 and the alpha same-spin term
+ * (reads xcols, writes ycols: the all-to-all back can start when it is done) and 8 = the beta same-spin term (reads C_local).
+ * A build is phase 1, then 2 (or 4, then 8).  Device pointers; stream = cudaStream_t. */
 int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xcols_dev,
                         double* sigma_local_dev, double* ycols_dev, double* scatter_dev, int rank, int world,
                         int phases, void* stream);

@@ -42,7 +42,10 @@ def main():
     ms = e0.elapsed_time(e1) / steps
     last = b.last_build_ms()
     b.Hamiltonian(y, hy)
-    herm = abs(float(y @ hx) - float(x @ hy)) / (float(hx.norm()) * float(y.norm()))
+    def dot(a, b, step=1 << 30):  # torch.dot stops at 2^31 - 1 elements
+        return sum(float(a[i:i + step] @ b[i:i + step]) for i in range(0, a.numel(), step))
+
+    herm = abs(dot(y, hx) - dot(x, hy)) / (dot(hx, hx) ** 0.5 * dot(y, y) ** 0.5)
     shape = b.t3_shape()
     print(json.dumps({"space": name, "ndet": strings.ndet, "nblocks": strings.nblocks, "setup_s": round(setup, 2),
                       "sigma_ms": ms, "term_ms": {"H0": last[0], "same_spin_alpha": last[1], "same_spin_beta": last[2],

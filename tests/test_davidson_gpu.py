@@ -335,3 +335,34 @@ def test_spin_controlled_determinant_roots_match_the_csf_path(torch_cuda, n, mul
     # without spin control the same solve finds the lowest roots of ANY spin
     free = CISolver(strings, E, H, V, nroot=nroot, log_level=0).run()
     assert np.all(np.asarray(free.E) <= np.asarray(csf.E) + 1e-9)
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas343_54"])
+def test_root_rdms_and_state_average(torch_cuda, name):
+    """make_1rdm / make_2rdm of the solved roots (forte2/ci/ci.py:476-515) and their state average
+    (forte2/base_classes/ci_base.py:104-133): the energy functional E0 + h.G1 + 1/2 V.G2 of root j is its eigenvalue
+    (ci.py:384-392), of the weighted average the weighted energy; <i| a+_p a_q |j> of different roots is traceless"""
+    import forte2_b200 as f2
+    from forte2_b200.ci_solver import CISolver, make_average_rdms
+    space = SPACES[name]
+    n = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(n, "D")
+    strings = f2.CIStrings(*space)
+    s = CISolver(strings, E, H, V, nroot=3, log_level=0).run()
+    assert s.converged
+
+    def functional(g1, g2):
+        return E + np.einsum("pq,pq", H, g1) + 0.5 * np.einsum("pqrs,pqrs", V, g2)
+
+    for j in range(3):
+        assert abs(functional(s.make_1rdm(j), s.make_2rdm(j)) - s.E[j]) <= 1e-9
+        assert abs(np.trace(s.make_1rdm(j)) - (space[0] + space[1])) <= 1e-10
+    assert abs(np.trace(s.make_1rdm(0, 1))) <= 1e-9
+    a, b = s.make_sd_1rdm(2)
+    assert abs(np.trace(a) - space[0]) <= 1e-10 and abs(np.trace(b) - space[1]) <= 1e-10
+    w = [[0.5, 0.3, 0.2]]
+    g1, g2 = make_average_rdms([s], w)
+    assert abs(functional(g1, g2) - float(np.dot(w[0], s.E))) <= 1e-9
+    l2 = s.make_2cumulant(0)
+    g1_0 = s.make_1rdm(0)
+    assert np.allclose(l2, s.make_2rdm(0) - np.einsum("pr,qs->pqrs", g1_0, g1_0) + 0.5 * np.einsum("ps,qr->pqrs", g1_0, g1_0))

@@ -51,9 +51,9 @@ class PortEngine:
         return True, max(L.local_size for L in self.layouts)
 
     def apply_rows(self, c_loc, xcols, sigma_loc, ycols, scatter, rank, world, phases=3):
+        """phases as in f2_sigma_apply_rows: 1 opposite-spin term (local rows only), 2 = 4 | 8, 4 H0 + alpha same-spin
+        term (from xcols), 8 beta same-spin term (local rows)"""
         from oracle import checker
-        if phases == 2:  # the stand-in does everything in phase 1 (or 3)
-            return
         E, H, V = self.ints
         lay = self.layouts[rank]
         rows_only = np.zeros(lay.ndet)
@@ -64,22 +64,29 @@ class PortEngine:
                 continue
             rows_only[off + lo * nB: off + (lo + n) * nB] = c_loc.numpy()[loc:loc + n * nB]
             cols_only[off:off + nA * nB].reshape(nA, nB)[:, cl:cl + nc] = x[yoff:yoff + nA * nc].reshape(nA, nc)
-        local = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_SCALAR | checker.PART_BETA)
-        alpha = checker.port_sigma(self.dets, E, H, V, cols_only, checker.PART_ALPHA)
-        t3 = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_ALPHA_BETA)
-        y = ycols.numpy()
-        for (off, nA, nB), (lo, n, loc), (cl, nc, yoff) in zip(lay.blocks, lay.rows, lay.cols):
-            if nA * nB == 0:
-                continue
-            sigma_loc.numpy()[loc:loc + n * nB] = local[off + lo * nB: off + (lo + n) * nB]
-            y[yoff:yoff + nA * nc] = alpha[off:off + nA * nB].reshape(nA, nB)[:, cl:cl + nc].reshape(-1)
-        _, slot = self.rows_form(rank, world)
-        out = scatter.numpy()
-        out[:] = 0.0
-        for q, L in enumerate(self.layouts):
-            for (off, nA, nB), (lo_q, n_q, loc_q) in zip(L.blocks, L.rows):
+        if phases & (2 | 4):
+            local = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_SCALAR)
+            alpha = checker.port_sigma(self.dets, E, H, V, cols_only, checker.PART_ALPHA)
+            y = ycols.numpy()
+            for (off, nA, nB), (lo, n, loc), (cl, nc, yoff) in zip(lay.blocks, lay.rows, lay.cols):
+                if nA * nB == 0:
+                    continue
+                sigma_loc.numpy()[loc:loc + n * nB] = local[off + lo * nB: off + (lo + n) * nB]
+                y[yoff:yoff + nA * nc] = alpha[off:off + nA * nB].reshape(nA, nB)[:, cl:cl + nc].reshape(-1)
+        if phases & (2 | 8):
+            beta = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_BETA)
+            for (off, nA, nB), (lo, n, loc), (cl, nc, yoff) in zip(lay.blocks, lay.rows, lay.cols):
                 if nA * nB > 0:
-                    out[q * slot + loc_q: q * slot + loc_q + n_q * nB] = t3[off + lo_q * nB: off + (lo_q + n_q) * nB]
+                    sigma_loc.numpy()[loc:loc + n * nB] += beta[off + lo * nB: off + (lo + n) * nB]
+        if phases & 1:
+            t3 = checker.port_sigma(self.dets, E, H, V, rows_only, checker.PART_ALPHA_BETA)
+            _, slot = self.rows_form(rank, world)
+            out = scatter.numpy()
+            out[:] = 0.0
+            for q, L in enumerate(self.layouts):
+                for (off, nA, nB), (lo_q, n_q, loc_q) in zip(L.blocks, L.rows):
+                    if nA * nB > 0:
+                        out[q * slot + loc_q: q * slot + loc_q + n_q * nB] = t3[off + lo_q * nB: off + (lo_q + n_q) * nB]
 
 
 def _worker(rank, world, port, name, form, result_dir):

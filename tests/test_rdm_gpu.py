@@ -126,7 +126,8 @@ print("TRDM-OK")
 """
 
 
-@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas75_odd", "beta_only"])
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h", "gas2_sym4", "cas75_odd", "beta_only", "cas88", "cas21_4",
+                                  "one_each", "gas343_54"])
 def test_rdms_match_the_definitions(name):
     import torch
     if not torch.cuda.is_available():
@@ -143,6 +144,18 @@ def test_rdms_in_several_column_chunks(name):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     env = dict(os.environ, F2_RDM_CHUNK_COLS="37")
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, name], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "RDM-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+@pytest.mark.parametrize("name", ["cas66", "gas3_53", "cas66_d2h"])
+def test_rdms_through_the_d_matrix_path(name):
+    """F2_RDM_GENERIC: every block through the gather + GEMM formulation (what the mixed-spin 3-RDM blocks and the spaces
+    outside the envelope of rdm_gram_kernel / rdm_ab_kernel always use)"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    env = dict(os.environ, F2_RDM_GENERIC="1")
     r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, name], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "RDM-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
 
@@ -171,7 +184,7 @@ def test_rdm_memory_limit_error():
     b = f2.CISigmaBuilder(strings, E, H, V, 0)
     c = np.ones(strings.ndet) / np.sqrt(strings.ndet)
     b.set_memory(1)
-    assert b.ab_2rdm(c, c).shape == (6, 6, 6, 6)
+    assert b.aab_3rdm(c, c).shape == (15, 6, 15, 6)
     b.set_memory(0)
     with pytest.raises(RuntimeError, match="too small for one K-block column"):
-        b.ab_2rdm(c, c)
+        b.aab_3rdm(c, c)

@@ -26,6 +26,7 @@ SPACES = {
     "gas20twin": (10, 10, 0, [[0] * 6, [0] * 8, [0] * 6], [10, 0, 0], [12, 16, 2]),
     "cas16_d2h": (8, 8, 0, [[i % 8 for i in range(16)]], [], []),
     "cas17_89": (8, 9, 0, [[0] * 17], [], []),                                        # na != nb, long rows, 384 threads
+    "cas18_96": (9, 6, 0, [[0] * 18], [], []),                                        # 90 output rows, short rows of C
 }
 
 
@@ -53,7 +54,7 @@ def _build(torch, name, memory_mb=65536):
 
 
 @pytest.mark.parametrize("name,nsamp", [("cas14", 2000), ("cas16", 2000), ("cas16_d2h", 2000), ("gas20twin", 2000),
-                                        ("cas17_89", 1000), ("cas18", 1500), ("gas20", 1500)])
+                                        ("cas17_89", 1000), ("cas18_96", 1000), ("cas18", 1500), ("gas20", 1500)])
 def test_sigma_at_sampled_determinants(torch_cuda, name, nsamp):
     torch = torch_cuda
     from oracle import sampled
@@ -66,6 +67,24 @@ def test_sigma_at_sampled_determinants(torch_cuda, name, nsamp):
     print(f"{name}: ndet={strings.ndet} blocks={strings.nblocks} form={builder.t3_shape()['form']} "
           f"sampled={n} rel L2 error={err:.2e}")
     assert n >= nsamp // 2 and err <= TOL
+    del sigma, c, builder
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("env", [{"F2_T3G_WIDE": "1"}, {"F2_T3G_NSM": "1000"}, {"F2_T3G_NSM": "1000", "F2_T3G_WIDE": "1"}])
+def test_six_row_tile_instances_of_the_gather_kernel(torch_cuda, monkeypatch, env):
+    """90 output rows (9 alpha electrons in 18 orbitals) select t3g_kernel<6, ...>: 8-column items on 12 warps by default,
+    16-column items on 8 warps with F2_T3G_WIDE, each with the whole row of C staged or (F2_T3G_NSM) partly gathered from L2"""
+    torch = torch_cuda
+    from oracle import sampled
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    space, ints, strings, builder, c = _build(torch, "cas18_96")
+    sigma = torch.full_like(c, float("nan"))
+    builder.Hamiltonian(c, sigma)
+    torch.cuda.synchronize()
+    err, n = sampled.sampled_rel_error(space, *ints, c, sigma, nsamp=600)
+    assert builder.t3_shape()["form"] == "gather" and err <= TOL
     del sigma, c, builder
     torch.cuda.empty_cache()
 
