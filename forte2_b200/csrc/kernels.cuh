@@ -477,9 +477,16 @@ constexpr size_t t3g_smem_bytes(int64_t nsm, int rows, int astride) {
 // LONG = false: the whole row is staged (nsm == nbs).  NT = n8 tiles (8 target columns each) per warp work item:
 // 2 up to 88 output rows; 1 above (CAS(18,18): 90 rows = 6 row tiles), which halves the accumulators so that the
 // kernel keeps 12 warps per SM -- the gathers of a long row mostly go to L2 and need the extra warps to hide it.
-template <int NM16, bool HAS8, bool LONG, int THREADS, int NT>
+// NX = output rows beyond the row tiles that are multiplied on the FP64 FMA pipe instead (one DFMA per lane, row and
+// n8 tile and k-step, summed over the four lanes of a column at the end): the DMMA and DFMA instructions share one
+// FP64 datapath on B200 (scripts/micro/fp64_pipes.cu, profiles/r2e_fp64_pipes.log).  On paper a row then costs 1/8 of
+// what it costs inside an 8-row tile; measured, a DFMA issued between DMMAs costs 6-15 pipe cycles instead of 2, so the
+// gain is small: CAS(16,16) 64 rows in tiles + the merged diagonal row (was 72 rows in tiles) 0.9 %, CAS(18,18) 80 + 2
+// (was 88) 2.7 % (profiles/r2j_quick.log, r2j_cas18.log).
+template <int NM16, bool HAS8, bool LONG, int THREADS, int NT, int NX = 0>
 __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
-    constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
+    constexpr int ROWS_MMA = NM16 * 16 + (HAS8 ? 8 : 0);
+    constexpr int ROWS = ROWS_MMA + NX;
     constexpr int CW = 8 * NT; // target columns per work item
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -601,6 +608,12 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
             acc8[nt][0] = acc8[nt][1] = 0.0;
+        double accx[NX > 0 ? NX : 1][NT];
+#pragma unroll
+        for (int x = 0; x < (NX > 0 ? NX : 1); ++x)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                accx[x][nt] = 0.0;
         // lane (g, t) feeds B[k = t][n = g] of every n8 tile; n index gg of tile nt is the actual column
         // n0 + 8 nt + (gg >> 1) + 4 (gg & 1), so that the four lanes of an accumulator row hold four
         // consecutive columns (one full 32-byte sector per reduction instruction and row)
@@ -668,6 +681,32 @@ __global__ void __launch_bounds__(THREADS, 1) t3g_kernel(const T3GParams p) {
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
                     dmma_8x8x4(acc8[nt], a0, b[nt]);
+            }
+            if constexpr (NX > 0) {
+                const double* ax = Asm + ROWS_MMA * S + 4 * ks + t; // b[nt] is D[4 ks + t][column of lane group g]
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    const double av = ax[x * S];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        accx[x][nt] = fma(av, b[nt], accx[x][nt]);
+                }
+            }
+        }
+        if constexpr (NX > 0) {
+            // the four lanes t of a group hold the four quarters of the k sum of column n0 + 8 nt + (g >> 1) + 4 (g & 1)
+            const int cx = n0 + (g >> 1) + 4 * (g & 1);
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                const long long ro = rowoff[ROWS_MMA + x];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    double v = accx[x][nt];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (t == nt && ro >= 0 && cx + 8 * nt < p.nbs)
+                        atomicAdd(p.sigma + ro + cx + 8 * nt, v);
+                }
             }
         }
         // accumulator (row, tile nt, n index 2t + c) is column n0 + 8 nt + 4 c + t
@@ -1040,7 +1079,7 @@ struct SSGroupLists {
 
 // (the F2_SSG_* macros are tuning hooks for scripts/tune_ssg.sh; the defaults are the measured best)
 #ifndef F2_SSG_TW
-#define F2_SSG_TW 256
+#define F2_SSG_TW 512
 #endif
 #ifndef F2_SSG_KG
 #define F2_SSG_KG 8

@@ -221,7 +221,7 @@ struct f2_sigma {
     bool t3g = false;
     bool t3g_long = false; // the row of C does not fit in shared memory: part staged, the rest gathered from L2
     int t3g_nsm = 0;       // staged columns
-    int t3g_nm16 = 0, t3g_has8 = 0, t3g_astride = 0, t3g_mpad = 0;
+    int t3g_nm16 = 0, t3g_has8 = 0, t3g_nx = 0, t3g_astride = 0, t3g_mpad = 0;
     int64_t t3g_gld = 0;
     size_t t3g_smem = 0;
     DevBuf<uint32_t> gsrc;
@@ -690,7 +690,16 @@ void plan_t3_shape(f2_sigma& b) {
         const int nm16 = kn / 16, rem = kn % 16;
         b.t3g_nm16 = nm16 + (rem > 8 ? 1 : 0);
         b.t3g_has8 = (rem > 0 && rem <= 8) ? 1 : 0;
-        const int rows = b.t3g_nm16 * 16 + b.t3g_has8 * 8;
+        b.t3g_nx = 0;
+        // one or two rows beyond the 16-row tiles go to the FMA pipe instead of an 8-row tile (t3g_kernel, NX):
+        // instantiated for 4 and 5 row tiles (CAS(16,16), CAS(18,18) and their neighbours)
+        // (measured, profiles/r2j_quick.log: a DFMA between DMMAs costs far more than its 2 issue cycles -- the gain is
+        // 2.7 % at CAS(18,18), 0.9 % at CAS(16,16) and a loss with 3 row tiles, so 4 and 5 row tiles only)
+        if (rem >= 1 && rem <= 2 && nm16 >= 4 && nm16 <= 5 && std::getenv("F2_T3G_NO_FMA_ROWS") == nullptr) {
+            b.t3g_has8 = 0;
+            b.t3g_nx = rem;
+        }
+        const int rows = b.t3g_nm16 * 16 + b.t3g_has8 * 8 + b.t3g_nx;
         int S = b.t3g_mpad;
         while (S % 16 != 4)
             ++S;
@@ -1209,10 +1218,10 @@ void launch_t3_ks(const f2_sigma& b, const T3Params& p, int nitems, cudaStream_t
 }
 
 
-template <int NM16, bool HAS8>
+template <int NM16, bool HAS8, int NX = 0>
 void launch_t3g_inst(const f2_sigma& b, const T3GParams& p, int nrows, cudaStream_t st) {
-    // 6 row tiles (CAS(18,18): 90 output rows): 8 target columns per warp item instead of 16, which halves the
-    // accumulators and keeps 12 warps per SM; F2_T3G_WIDE = the 16-column items on 8 warps (the round-1 shape)
+    // 6 row tiles: 8 target columns per warp item instead of 16, which halves the accumulators and keeps 12 warps
+    // per SM; F2_T3G_WIDE = the 16-column items on 8 warps (the round-1 shape)
     constexpr int THREADS = 384;
     const bool wide = std::getenv("F2_T3G_WIDE") != nullptr;
     if constexpr (NM16 >= 6) {
@@ -1232,13 +1241,13 @@ void launch_t3g_inst(const f2_sigma& b, const T3GParams& p, int nrows, cudaStrea
     }
     constexpr int NT = NM16 >= 6 ? 1 : 2;
     if (b.t3g_long) {
-        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, true, THREADS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, true, THREADS, NT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(b.t3g_smem)));
-        t3g_kernel<NM16, HAS8, true, THREADS, NT><<<nrows, THREADS, b.t3g_smem, st>>>(p);
+        t3g_kernel<NM16, HAS8, true, THREADS, NT, NX><<<nrows, THREADS, b.t3g_smem, st>>>(p);
     } else {
-        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, false, THREADS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        F2_CUDA(cudaFuncSetAttribute(t3g_kernel<NM16, HAS8, false, THREADS, NT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(b.t3g_smem)));
-        t3g_kernel<NM16, HAS8, false, THREADS, NT><<<nrows, THREADS, b.t3g_smem, st>>>(p);
+        t3g_kernel<NM16, HAS8, false, THREADS, NT, NX><<<nrows, THREADS, b.t3g_smem, st>>>(p);
     }
     b.launches += 1;
 }
@@ -1270,8 +1279,12 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
         nrows = static_cast<int>(h.nas);
     if (nrows == 0)
         return;
-    const int key = b.t3g_nm16 * 2 + b.t3g_has8;
+    const int key = b.t3g_nm16 * 2 + b.t3g_has8 + 100 * b.t3g_nx;
     switch (key) {
+    case 108: launch_t3g_inst<4, false, 1>(b, p, nrows, st); break;
+    case 208: launch_t3g_inst<4, false, 2>(b, p, nrows, st); break;
+    case 110: launch_t3g_inst<5, false, 1>(b, p, nrows, st); break;
+    case 210: launch_t3g_inst<5, false, 2>(b, p, nrows, st); break;
     case 2: launch_t3g_inst<1, false>(b, p, nrows, st); break;
     case 3: launch_t3g_inst<1, true>(b, p, nrows, st); break;
     case 4: launch_t3g_inst<2, false>(b, p, nrows, st); break;
@@ -2084,7 +2097,7 @@ int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
     out5[5] = (h->t3g || h->t3gm) ? 1 : 0;
     out5[0] = h->M;
     if (h->t3g) { // rows of A' actually multiplied, expressed per column of the GEMM K dimension of the list
-        const int rows = h->t3g_nm16 * 16 + h->t3g_has8 * 8;
+        const int rows = h->t3g_nm16 * 16 + h->t3g_has8 * 8 + h->t3g_nx;
         const int kmax = std::max(h->S->host->device_lists().as_max, 1);
         out5[0] = h->M;
         out5[1] = (static_cast<int64_t>(h->t3g_mpad) * rows + kmax - 1) / kmax;
