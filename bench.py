@@ -20,6 +20,7 @@ The JSON line carries, beside the driver contract's keys:
   default_memory  (N = 1) the same step under set_memory(1024), forte2's default ci_builder_memory
                (forte2/base_classes/params.py:149-178); the headline figure uses a budget that holds the
                transposed beta scratch in one slab
+  rdm          (N = 1) device time of the 1- and 2-RDM spin blocks of one vector, tensor roofline of the opposite-spin block
   davidson     (N = 1) one Davidson-Liu iteration of a 3-root solve on the same workload: 3 sigma builds + the
                device solver's streaming passes, with the HBM roofline of those passes (davidson.roofline)
   legs         (N = 8, or --legs) BASELINE.json configs[3] and [4] -- CAS(18e,18o), 2 363 904 400 determinants, and
@@ -394,6 +395,49 @@ def davidson_leg(torch, strings, builder, E, H, V, sigma_ms, nroot=3, iters=6):
     return out
 
 
+def rdm_leg(torch, strings, builder, peak_tflops, memory_mb=1024):
+    """1- and 2-RDMs of one vector of the bench workload (what an MCSCF macro-iteration asks for after the solve:
+    forte2/base_classes/ci_base.py:104-133): device time of every spin block through f2_sigma_rdm (CUDA events, result
+    left on the device), and the tensor roofline of the dominant one (ab_2rdm, rdm_ab_kernel: 2 n^2 K_a nbs^2 nas ... flops
+    executed = 2 x n^2 x (single replacements per alpha string) per determinant)."""
+    from forte2_b200 import _lib, synthetic
+    L = _lib.lib()
+    n, na = strings.norb, strings.na
+    stream = torch.cuda.current_stream().cuda_stream
+    builder.set_memory(memory_mb)
+    c = torch.from_numpy(synthetic.trial_vector(strings.ndet)).cuda()
+    kinds = {"a_1rdm": (0, n), "b_1rdm": (1, n), "aa_2rdm": (3, n * (n - 1) // 2), "bb_2rdm": (4, n * (n - 1) // 2),
+             "ab_2rdm": (5, n * n)}
+    ms, traces = {}, {}
+    for name, (kind, M) in kinds.items():
+        out = torch.empty(M * M, dtype=torch.float64, device="cuda")
+        _lib.check(L.f2_sigma_rdm(builder._h, kind, c.data_ptr(), c.data_ptr(), out.data_ptr(), stream))  # warm-up, tables
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.f2_sigma_rdm(builder._h, kind, c.data_ptr(), c.data_ptr(), out.data_ptr(), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        ms[name] = e0.elapsed_time(e1)
+        traces[name] = float(out.view(M, M).diagonal().sum())
+    nb = strings.nb
+    want = {"a_1rdm": na, "b_1rdm": nb, "aa_2rdm": na * (na - 1) / 2, "bb_2rdm": nb * (nb - 1) / 2, "ab_2rdm": na * nb}
+    norm2 = float(c @ c)
+    trace_err = max(abs(traces[k] / norm2 - want[k]) / max(want[k], 1) for k in kinds)
+    shape = builder.t3_shape()
+    ab_flops = 2.0 * n * n * shape["k_cols"]  # n^2 (v y) rows x every (single replacement of Ja, beta string) pair
+    ab_tf = ab_flops / (ms["ab_2rdm"] * 1e-3) / 1e12
+    total = sum(ms.values())
+    del c
+    torch.cuda.empty_cache()
+    return {"ms": {k: round(v, 3) for k, v in ms.items()}, "sf_1rdm_plus_sf_2rdm_ms": round(total, 3),
+            "set_memory_mb": memory_mb, "trace_rel_err": trace_err,
+            "roofline": {"bound": "tensor", "kernel": "rdm_ab_kernel (opposite-spin 2-RDM, gather form, DMMA)",
+                         "flops_per_launch": ab_flops, "ms": ms["ab_2rdm"], "achieved": ab_tf, "peak": peak_tflops,
+                         "unit": "TFLOP/s", "frac": ab_tf / peak_tflops if peak_tflops else None},
+            "note": "traces: tr(1-RDM) = N_spin, tr(aa) = N(N-1)/2, sum_uv ab[u,v,u,v] = Na Nb, relative to <c|c>"}
+
+
 class Ctx:
     pass
 
@@ -467,6 +511,30 @@ def measure_space(ctx, name, steps, warmup, memory_mb, form="auto", nsamp=2000, 
     if world > 1:  # every rank takes part: one extra build with a CUDA event at each phase boundary
         phases = [(nm, round(ms, 3)) for nm, ms in sharded.profile_phases(c, sigma)]
     ms_per_step = ms_total / steps
+    lib_ms = lib_err = None
+    if world > 1 and sharded.form == "rows":
+        # the same build with the collectives issued by the C library (f2_dist_init / f2_dist_apply, csrc/dist_nccl.inc)
+        try:
+            from forte2_b200.dist import LibraryShardedSigma
+            libsh = LibraryShardedSigma(builder, rank, world)
+            sigma2 = torch.empty_like(sigma)
+            for _ in range(max(warmup, 1)):
+                libsh.Hamiltonian(c, sigma2)
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                libsh.Hamiltonian(c, sigma2)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lib_ms = float(t.item()) / steps
+            sharded.Hamiltonian(c, sigma)
+            lib_err = float((sigma2 - sigma).norm() / sigma.norm())
+            libsh.close()
+            del sigma2
+        except Exception as e:  # noqa: BLE001
+            lib_err = f"library NCCL path failed: {e}"[:200]
     res = {"name": name, "ndet": ndet, "nblocks": strings.nblocks, "setup_s": round(setup_s, 2),
            "strings_and_lists_s": round(t_strings, 2), "ms_per_step": ms_per_step, "value": 1e3 / ms_per_step,
            "steps": steps, "warmup": warmup, "set_memory_mb": memory_mb,
@@ -479,6 +547,7 @@ def measure_space(ctx, name, steps, warmup, memory_mb, form="auto", nsamp=2000, 
     if world > 1:
         res["sharded"] = {"form": sharded.form, "local_compute_ms_rank0": last[4],
                           "exchange_ms_rank0": ms_per_step - last[4], "phases_ms_rank0_one_extra_build": phases,
+                          "library_nccl_ms_per_step": lib_ms, "library_nccl_rel_diff": lib_err,
                           "note": "exchange = step time minus rank 0's kernel time: the NCCL collectives of "
                                   "forte2_b200/dist.py and their pack/unpack copies"}
     if parity:
@@ -668,6 +737,14 @@ def run_ours(args):
         except torch.cuda.OutOfMemoryError as e:  # the 3-root subspace needs 27 vectors
             davidson = {"error": f"out of memory: {e}"[:200]}
 
+    # ---- 1- and 2-RDMs of one vector (N = 1): the other caller after the solve ----
+    rdm = None
+    if world == 1 and not args.no_davidson:
+        try:
+            rdm = rdm_leg(torch, strings, builder, peak)
+        except Exception as e:  # noqa: BLE001 -- the leg is informative, the headline stands without it
+            rdm = {"error": str(e)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -722,7 +799,7 @@ def run_ours(args):
                            "the host (oracle/sampled.py); the bar is 1e-12",
             "term_ms_last_step": res["term_ms_last_step"],
             "roofline": roofline, "roofline_same_spin": same_spin, "default_memory": default_memory,
-            "cpu_baseline": cpu, "e2e": e2e, "davidson": davidson,
+            "cpu_baseline": cpu, "e2e": e2e, "davidson": davidson, "rdm": rdm,
             "sharded": res.get("sharded"), "legs": legs,
             "setup_s": res["setup_s"], "peak_mem_gb": res["peak_mem_gb"],
             "gpu_launches": int(res["launches_per_step"] * args.steps), "clocks": res.get("clocks"),

@@ -51,6 +51,12 @@ SIGNATURES = {
     "f2_sigma_rdm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_sigma_rdm_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_sigma_trdm1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f2_dist_unique_id": (C.c_int, [C.c_char_p]),
+    "f2_dist_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "f2_dist_local_size": (C.c_int, [C.c_void_p, i64p]),
+    "f2_dist_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f2_dist_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "f2_dist_finalize": (C.c_int, [C.c_void_p]),
     "f2_sigma_launch_count": (C.c_int64, [C.c_void_p]),
     "f2_sigma_t3_shape": (C.c_int, [C.c_void_p, i64p]),
     "f2_sigma_part_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p, i64p]),

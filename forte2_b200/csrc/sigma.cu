@@ -203,6 +203,9 @@ struct Part {
 
 using namespace f2;
 
+struct f2_dist; // NCCL state of the sharded build (dist_nccl.inc)
+void destroy_dist(f2_dist* d);
+
 struct f2_sigma {
     f2_strings* S = nullptr;
     DevStrings* D = nullptr;
@@ -249,6 +252,7 @@ struct f2_sigma {
     size_t t3_smem = 0;
     // row/column ownership plans: the single-GPU one and the last multi-GPU one
     std::unique_ptr<Part> single, shard;
+    std::unique_ptr<f2_dist, void (*)(f2_dist*)> dist{nullptr, destroy_dist};
     // host path: the single-GPU partition with the beta same-spin term cut into about eight row slabs,
     // so that finished sigma rows leave for the host while the next slab is computed
     std::unique_ptr<Part> host_part;
@@ -2082,8 +2086,8 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
         // t3g_kernel brings its rows of C in with TMA bulk copies; t3gp_kernel gathers and has no such need
         if (h->t3g && (reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
             throw std::invalid_argument("CISigmaBuilder: the local trial vector must be 16-byte aligned");
-        if (phases < 1 || phases > 3)
-            throw std::invalid_argument("CISigmaBuilder: phases must be 1, 2 or 3");
+        if (phases < 1 || phases > 15)
+            throw std::invalid_argument("CISigmaBuilder: phases must be a combination of 1, 2 (= 4 | 8), 4 and 8");
         Part& P = shard_of(*h, rank, world);
         apply_rows(*h, P, C_local_dev, xcols_dev, sigma_local_dev, ycols_dev, scatter_dev, phases,
                    static_cast<cudaStream_t>(stream));
@@ -2589,3 +2593,5 @@ static int hdiag_part_impl(f2_sigma* h, double* out_local_dev, int rank, int wor
 }
 
 } // extern "C"
+
+#include "dist_nccl.inc"

@@ -375,3 +375,40 @@ class ShardedSigma:
         if self.world > 1:
             self._exchange_add(sigma_loc)
             self._mark("all-to-all of the alpha same-spin term + add")
+
+
+class LibraryShardedSigma:
+    """The rows form with the collectives issued by the C library itself (f2_dist_init / f2_dist_apply: NCCL resolved by
+    the library, two communicators, library-owned streams): what a host without torch.distributed calls.  Here the
+    process group is only the channel that carries the 128-byte NCCL unique id from rank 0 to the others."""
+
+    def __init__(self, builder, rank=None, world=None, group=None):
+        import ctypes
+        self.builder = builder
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        L = _lib.lib()
+        uid = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(L.f2_dist_unique_id(uid))
+        box = [uid.raw if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        _lib.check(L.f2_dist_init(builder._h, box[0], self.rank, self.world))
+        n = np.zeros(1, dtype=np.int64)
+        _lib.check(L.f2_dist_local_size(builder._h, n.ctypes.data_as(_lib.i64p)))
+        self.local_size = int(n[0])
+        self.layout = Layout(builder.ci_strings.blocks(), self.rank, self.world)
+        assert self.layout.local_size == self.local_size
+
+    def Hamiltonian(self, c_loc: torch.Tensor, sigma_loc: torch.Tensor) -> None:
+        assert c_loc.numel() == self.local_size and sigma_loc.numel() == self.local_size
+        stream = torch.cuda.current_stream(self.builder.device).cuda_stream
+        _lib.check(_lib.lib().f2_dist_apply(self.builder._h, c_loc.data_ptr(), sigma_loc.data_ptr(), stream))
+
+    def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
+        stream = torch.cuda.current_stream(self.builder.device).cuda_stream
+        _lib.check(_lib.lib().f2_dist_allreduce(self.builder._h, t.data_ptr(), t.numel(), stream))
+        return t
+
+    def close(self):
+        _lib.check(_lib.lib().f2_dist_finalize(self.builder._h))

@@ -184,6 +184,24 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
                         double* sigma_local_dev, double* ycols_dev, double* scatter_dev, int rank, int world,
                         int phases, void* stream);
 
+/* ---- NCCL inside the library (f2_dist_init): the rows form of the sharded build with its collectives issued
+ * by the library, for hosts that do not bring torch.distributed.  libnccl.so.2 is resolved at run time (dlopen).
+ *   rank 0: f2_dist_unique_id(id) and hands the 128 bytes to every rank (any channel: MPI, a file, torch broadcast);
+ *   every rank: f2_dist_init(builder, id, rank, world)   ncclCommInitRank on the builder's device, exchange plans, buffers;
+ *   f2_dist_apply(builder, C_local, sigma_local, stream)  one sigma build: sigma_local = (H C)_local, both the rank's row slab
+ *                                                         (f2_sigma_part_layout; f2_dist_local_size doubles).  Collective.
+ *   f2_dist_allreduce                                     in-place sum over the ranks (subspace reductions of a Davidson loop)
+ *   f2_dist_finalize                                      destroys the communicators (also done by f2_sigma_destroy).
+ * The all-to-all of C runs beside the opposite-spin kernel, the reduce-scatter beside the same-spin kernels, the all-to-all of
+ * the alpha same-spin result beside the beta same-spin kernel (two communicators, two library-owned streams).
+ * Fails with F2_ERUNTIME where f2_sigma_rows_form reports the rows form unavailable. */
+int f2_dist_unique_id(char* out128);
+int f2_dist_init(f2_sigma* h, const char* id128, int rank, int world);
+int f2_dist_local_size(f2_sigma* h, int64_t* out);
+int f2_dist_apply(f2_sigma* h, const double* C_local_dev, double* sigma_local_dev, void* stream);
+int f2_dist_allreduce(f2_sigma* h, double* buf_dev, int64_t count, void* stream);
+int f2_dist_finalize(f2_sigma* h);
+
 /* <I|H|J> for the n determinants at the given CI-vector addresses, n x n row-major, on the HOST
  * (SlaterRules::slater_rules, forte2/determinant/slater_rules.cc:123-245): the guess Hamiltonian of
  * forte2/ci/ci.py:411-452.  H, V as in f2_sigma_create.  Needs no GPU. */

@@ -53,6 +53,20 @@ def _worker(rank, world, port, spaces, result_dir):
                 sh.Hamiltonian(c_loc, sigma_loc)  # twice: no dependence on leftovers
                 got = sh.all_gather_full(sigma_loc).clone()
                 errs.append(float((got - want).norm() / want.norm()))
+            if "rows" in forms:
+                # the same build with the collectives issued by the C library (f2_dist_init / f2_dist_apply)
+                from forte2_b200.dist import LibraryShardedSigma
+                lib = LibraryShardedSigma(builder, rank, world)
+                c_loc = sh.scatter_full(c_full)
+                sigma_loc = torch.full_like(c_loc, float("nan"))
+                lib.Hamiltonian(c_loc, sigma_loc)
+                lib.Hamiltonian(c_loc, sigma_loc)
+                torch.cuda.synchronize()
+                got = sh.all_gather_full(sigma_loc).clone()
+                errs.append(float((got - want).norm() / want.norm()))
+                one = torch.ones(3, dtype=torch.float64, device="cuda")
+                assert float(lib.allreduce_(one).sum()) == 3.0 * world
+                lib.close()
             if n >= 8 and len(space[3]) == 1 and strings.nbs % 2 == 0 and strings.nas % 2 == 0:
                 assert "rows" in forms, forms
             if strings.nblocks > 1:  # symmetry / GAS blocks: the block-aware gather kernel serves the rows form
