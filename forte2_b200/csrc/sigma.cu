@@ -5,6 +5,8 @@
 // set_memory, set_Hamiltonian validation, Hamiltonian = H0 + one-electron + same-spin + opposite
 // spin, avg_build_time), forte2/determinant/slater_rules.cc:86-121 (determinant energies).
 #include <algorithm>
+#include <condition_variable>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +18,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "handles.hpp"
 #include "kernels.cuh"
@@ -318,23 +323,110 @@ struct f2_sigma {
 namespace {
 
 // host-to-host copy split over a few threads (one memcpy stream does not saturate the memory system)
-void parallel_copy(double* dst, const double* src, size_t count) {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nthr = std::min<size_t>(std::min<unsigned>(hw, 12), std::max<size_t>(1, count >> 18));
-    if (nthr <= 1) {
+// Host copies between the caller's (pageable) vectors and the pinned staging buffers: a persistent pool of threads (no
+// thread creation per 64 MB piece) that writes with non-temporal stores (no read-for-ownership of the destination, no
+// cache pollution).  The way home of sigma is bound by this copy (profiles/r2r_host_path.log): 39 GB/s with 12 threads
+// and plain memcpy.
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool pool;
+        return pool;
+    }
+    void copy(double* dst, const double* src, size_t count) {
+        if (count < (size_t(1) << 18) || workers_.empty()) {
+            stream_copy(dst, src, count);
+            return;
+        }
+        std::unique_lock<std::mutex> lock(m_);
+        dst_ = dst;
+        src_ = src;
+        count_ = count;
+        pending_ = static_cast<int>(workers_.size());
+        ++generation_;
+        cv_.notify_all();
+        done_.wait(lock, [&] { return pending_ == 0; });
+    }
+
+  private:
+    CopyPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n = std::min(hw, 16u);
+        if (n > 1)
+            for (unsigned t = 0; t < n; ++t)
+                workers_.emplace_back([this, t, n] { run(t, n); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+            ++generation_;
+        }
+        cv_.notify_all();
+        for (auto& w : workers_)
+            w.join();
+    }
+    static void stream_copy(double* dst, const double* src, size_t count) {
+#if defined(__SSE2__)
+        size_t i = 0;
+        while (i < count && (reinterpret_cast<uintptr_t>(dst + i) & 15) != 0) {
+            dst[i] = src[i];
+            ++i;
+        }
+        for (; i + 8 <= count; i += 8) {
+            const __m128d a = _mm_loadu_pd(src + i), b = _mm_loadu_pd(src + i + 2);
+            const __m128d c = _mm_loadu_pd(src + i + 4), d = _mm_loadu_pd(src + i + 6);
+            _mm_stream_pd(dst + i, a);
+            _mm_stream_pd(dst + i + 2, b);
+            _mm_stream_pd(dst + i + 4, c);
+            _mm_stream_pd(dst + i + 6, d);
+        }
+        for (; i < count; ++i)
+            dst[i] = src[i];
+        _mm_sfence();
+#else
         std::memcpy(dst, src, count * sizeof(double));
-        return;
+#endif
     }
-    std::vector<std::thread> pool;
-    const size_t per = (count + nthr - 1) / nthr;
-    for (size_t t = 0; t < nthr; ++t) {
-        const size_t lo = t * per, hi = std::min(count, lo + per);
-        if (lo < hi)
-            pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, (hi - lo) * sizeof(double)); });
+    void run(unsigned t, unsigned n) {
+        unsigned long seen = 0;
+        for (;;) {
+            double* dst;
+            const double* src;
+            size_t count;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_)
+                    return;
+                dst = dst_;
+                src = src_;
+                count = count_;
+            }
+            const size_t per = ((count + n - 1) / n + 7) & ~size_t(7);
+            const size_t lo = std::min(count, t * per), hi = std::min(count, lo + per);
+            if (lo < hi)
+                stream_copy(dst + lo, src + lo, hi - lo);
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                if (--pending_ == 0)
+                    done_.notify_one();
+            }
+        }
     }
-    for (auto& th : pool)
-        th.join();
-}
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    double* dst_ = nullptr;
+    const double* src_ = nullptr;
+    size_t count_ = 0;
+    int pending_ = 0;
+    unsigned long generation_ = 0;
+    bool stop_ = false;
+};
+
+void parallel_copy(double* dst, const double* src, size_t count) { CopyPool::get().copy(dst, src, count); }
 
 int round_ks(int count) { // k-steps (of 4) rounded up to the instantiated multiples of 4
     const int ks = (count + 3) / 4;
@@ -1151,6 +1243,7 @@ void plan_beta(f2_sigma& b, Part& P, int64_t cap_elems = 0) {
         b.XT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
         b.YT.alloc(static_cast<size_t>(std::max<int64_t>(max_elems, 1)));
     }
+    F2_CUDA(cudaDeviceSynchronize()); // the plan uploads (pageable memory) have landed before any stream reads them
     P.beta_planned = true;
 }
 
@@ -1716,6 +1809,7 @@ Part& shard_of(f2_sigma& b, int rank, int world) {
         F2_CUDA(cudaSetDevice(b.device));
         F2_CUDA(cudaDeviceSynchronize());
         b.shard = make_part(b, rank, world);
+        F2_CUDA(cudaDeviceSynchronize()); // the uploads (pageable memory) have landed before any stream reads them
     }
     return *b.shard;
 }
@@ -1762,6 +1856,7 @@ f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const 
         plan_t3_shape(*b);
         b->single = make_part(*b, 0, 1);
         plan_hdiag(*b);
+        F2_CUDA(cudaDeviceSynchronize()); // every table upload (pageable memory) has landed before any stream reads it
         return b.release();
     } catch (const std::exception& e) {
         status_of(e);
@@ -1884,6 +1979,13 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
         F2_CUDA(cudaSetDevice(h->device));
         if (!h->own_stream)
             F2_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        const bool trace = std::getenv("F2_TIME_HOST") != nullptr;
+        const auto T0 = std::chrono::steady_clock::now();
+        auto stamp = [&](const char* what) {
+            if (trace)
+                std::fprintf(stderr, "host path: %-34s %8.2f ms\n", what,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
+        };
         const size_t bytes = static_cast<size_t>(std::max<int64_t>(n, 1)) * sizeof(double);
         if (!h->hC) {
             F2_CUDA(cudaMallocHost(&h->hC, bytes));
@@ -1909,8 +2011,11 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
             F2_CUDA(cudaMemsetAsync(h->dS.p, 0, bytes, h->own_stream));
         int64_t rows_done = 0;
         int64_t streamed_launches = 0;
-        const size_t group = 4 * piece; // launch granularity: >= 17 waves of CTAs at CAS(16,16)
-        size_t next_launch = group;
+        // launch granularity: the first opposite-spin launch follows the first piece (the GPU starts after 64 MB, not
+        // 256), later ones grow to four pieces (>= 17 waves of CTAs at CAS(16,16))
+        const size_t group = 4 * piece;
+        size_t group_cur = piece;
+        size_t next_launch = group_cur;
         for (size_t off = 0; off < total; off += piece) {
             const size_t cnt = std::min(piece, total - off);
             parallel_copy(h->hC + off, C_host + off, cnt);
@@ -1927,11 +2032,17 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
                     streamed_launches += 1;
                     rows_done = rows_in;
                 }
-                next_launch = arrived + group;
+                group_cur = std::min(group, 2 * group_cur);
+                next_launch = arrived + group_cur;
             }
         }
         F2_CUDA(cudaEventRecord(h->copy_ev, h->copy_stream));
         F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->copy_ev, 0));
+        stamp("staged + H2D enqueued");
+        if (trace) {
+            F2_CUDA(cudaStreamSynchronize(h->copy_stream));
+            stamp("H2D done");
+        }
         // the way back: sigma rows travel in pieces, each followed by an event the unstaging copy waits for
         struct Piece {
             size_t off, cnt;
@@ -1955,12 +2066,16 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
             }
         };
         if (streamed && s.nb >= 1) {
-            // beta same-spin term last, in about eight row slabs: the rows of a finished slab are final and
+            // beta same-spin term last, in about sixteen row slabs: the rows of a finished slab are final and
             // cross PCIe on the copy stream while the next slab is computed
             if (!h->host_part)
                 h->host_part = make_part(*h, 0, 1);
+            // (the last slab's way home -- D2H and the copy out of the pinned buffer -- is the exposed tail: 16 slabs)
+            int slabs = 16;
+            if (const char* e = std::getenv("F2_HOST_SLABS")) // tuning hook
+                slabs = std::max(1, std::atoi(e));
             if (!h->host_part->beta_planned)
-                plan_beta(*h, *h->host_part, (s.ndet + 7) / 8);
+                plan_beta(*h, *h->host_part, (s.ndet + slabs - 1) / slabs);
             if (!h->pass_ev)
                 F2_CUDA(cudaEventCreateWithFlags(&h->pass_ev, cudaEventDisableTiming));
             const std::function<void(const BetaPass&)> after = [&](const BetaPass& bp) {
@@ -1976,9 +2091,16 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
             send_back(0, total, h->own_stream);
         }
         h->launches += streamed_launches;
+        stamp("kernels + D2H enqueued");
+        if (trace) {
+            F2_CUDA(cudaStreamSynchronize(h->own_stream));
+            stamp("kernels done");
+        }
         size_t returned = 0;
         for (size_t i = 0; i < out.size(); ++i) {
             F2_CUDA(cudaEventSynchronize(h->piece_ev[i]));
+            if (trace && (i == 0 || i + 1 == out.size()))
+                stamp(i == 0 ? "first sigma piece on the host" : "last sigma piece on the host");
             parallel_copy(sigma_host + out[i].off, h->hS + out[i].off, out[i].cnt);
             returned += out[i].cnt;
         }
@@ -1986,6 +2108,7 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
             throw std::logic_error("f2_sigma_apply_host: sigma pieces do not cover the vector");
         F2_CUDA(cudaStreamSynchronize(h->copy_stream));
         F2_CUDA(cudaStreamSynchronize(h->own_stream));
+        stamp("done");
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);
@@ -2149,6 +2272,9 @@ f2_sigma::RdmLists& rdm_device_lists(f2_sigma& b, int spin, int level) {
         const HoleLists& hl = b.S->host->hole_lists(spin, level);
         d.ptr.upload(hl.ptr);
         d.ent.upload(hl.ent);
+        // cudaMemcpy from pageable memory returns once the data is staged: the DMA tail must have landed before a
+        // kernel on the caller's (possibly non-blocking) stream reads the lists
+        F2_CUDA(cudaDeviceSynchronize());
         d.up = true;
     }
     return d;
@@ -2266,6 +2392,7 @@ bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStre
         b.rdm_gld = (hs.nbs + 31) / 32 * 32;
         std::vector<uint32_t> fill(static_cast<size_t>(rows) * b.rdm_gld, static_cast<uint32_t>(hs.nbs));
         b.rdm_gtab.upload(fill);
+        F2_CUDA(cudaDeviceSynchronize()); // the fill has landed before the table kernel on the caller's stream writes
         b.rdm_gtab_rows = rows;
         const int64_t total = hs.nbs * DL.bs_width;
         if (total > 0)
