@@ -512,7 +512,7 @@ def measure_space(ctx, name, steps, warmup, memory_mb, form="auto", nsamp=2000, 
         phases = [(nm, round(ms, 3)) for nm, ms in sharded.profile_phases(c, sigma)]
     ms_per_step = ms_total / steps
     lib_ms = lib_err = None
-    if world > 1 and sharded.form == "rows":
+    if world > 1 and sharded.form == "rows" and sharded._lib is None:
         # the same build with the collectives issued by the C library (f2_dist_init / f2_dist_apply, csrc/dist_nccl.inc)
         try:
             from forte2_b200.dist import LibraryShardedSigma
@@ -545,7 +545,9 @@ def measure_space(ctx, name, steps, warmup, memory_mb, form="auto", nsamp=2000, 
     if sampler:
         res["clocks"] = sampler.summary()
     if world > 1:
-        res["sharded"] = {"form": sharded.form, "local_compute_ms_rank0": last[4],
+        res["sharded"] = {"form": sharded.form,
+                          "collectives": "library (f2_dist_apply)" if sharded._lib is not None else "python (forte2_b200/dist.py)",
+                          "local_compute_ms_rank0": last[4],
                           "exchange_ms_rank0": ms_per_step - last[4], "phases_ms_rank0_one_extra_build": phases,
                           "library_nccl_ms_per_step": lib_ms, "library_nccl_rel_diff": lib_err,
                           "note": "exchange = step time minus rank 0's kernel time: the NCCL collectives of "

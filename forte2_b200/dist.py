@@ -109,7 +109,7 @@ class ShardedSigma:
     the GPU box; the gloo tests pass a CPU stand-in with the same apply_part signature."""
 
     def __init__(self, builder=None, rank=None, world=None, group=None, engine=None, blocks=None, device=None,
-                 form="auto"):
+                 form="auto", collectives="auto"):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -142,6 +142,20 @@ class ShardedSigma:
                 self._rs_out = torch.empty(self._slot, **kw)
         if form == "rows" and self.form != "rows" and self.world > 1:
             raise RuntimeError("the rows form of the sharded build is not available for this string space")
+        # who issues the collectives of the rows form: this module (torch.distributed) or the C library (f2_dist_apply:
+        # one pack / unpack kernel per exchange instead of one copy per block and peer).  "auto": the library for spaces
+        # with many determinant blocks (3 GAS / 20 orbitals, 225 blocks, 8 GPUs: 737 against 784 ms per build), this
+        # module otherwise (one block is received in place: CAS(18,18) 397 against 399 ms)
+        if collectives not in ("auto", "python", "library"):
+            raise ValueError("collectives must be 'auto', 'python' or 'library'")
+        self._lib = None
+        nonempty = sum(1 for _, nA, nB in self.layout.blocks if nA * nB > 0)
+        want_lib = collectives == "library" or (collectives == "auto" and nonempty > 8)
+        if (want_lib and self.form == "rows" and isinstance(self.engine, CudaEngine) and dist.is_initialized()
+                and dist.get_backend(group) == "nccl"):
+            self._lib = LibraryShardedSigma(builder, self.rank, self.world, group)
+        elif collectives == "library":
+            raise RuntimeError("the library-owned collectives need the rows form on CUDA with an NCCL process group")
         if isinstance(self.engine, CudaEngine):
             sizes, rows = self.engine.layout_from_library(len(self.layout.blocks), self.rank, self.world)
             assert int(sizes[0]) == self.layout.local_size and int(sizes[1]) == self.layout.exchange_size
@@ -345,6 +359,10 @@ class ShardedSigma:
 
     def Hamiltonian(self, c_loc: torch.Tensor, sigma_loc: torch.Tensor) -> None:
         assert c_loc.numel() == self.local_size and sigma_loc.numel() == self.local_size
+        if self._lib is not None:
+            self._lib.Hamiltonian(c_loc, sigma_loc)
+            self._mark("f2_dist_apply (collectives issued by the library)")
+            return
         if self.form == "rows":
             # the two all-to-alls and the reduce-scatter all run beside kernels that do not need their result:
             #   C column slab  ||  opposite-spin kernel (local rows only)
