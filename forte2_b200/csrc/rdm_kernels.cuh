@@ -35,6 +35,12 @@ struct RdmGatherParams {
     uint32_t ka0, kb0; // first Ka / Kb of the chunk
     uint32_t nka, nkb; // chunk extent; column = (Ka - ka0) * nkb + (Kb - kb0)
     int64_t ldd;       // nka * nkb rounded up to a multiple of 2 (16-byte rows for cp.async)
+    // point-group symmetry: Gamma[(A B), (A' B')] vanishes unless the two operator tuples have the same irrep h, and a
+    // column (Ka, Kb) has entries in the rows of irrep h only when irrep(Ka) x irrep(Kb) = h x symmetry of the state.
+    // The block of one h is then built from the hole strings of matching irreps only: ka0 / kb0 index these lists
+    // (NULL: all hole strings), rowmap sends an operator row to its row inside the block of h (-1: another irrep).
+    const uint32_t *kaList, *kbList;
+    const int32_t* rowmap;
 };
 
 constexpr int RDM_GATHER_THREADS = 256;
@@ -42,14 +48,15 @@ constexpr int RDM_MAXPA = 512; // parents of one Ka staged per pass
 
 __global__ void __launch_bounds__(RDM_GATHER_THREADS) rdm_gather_kernel(const RdmGatherParams p) {
     __shared__ uint32_t s_cls[RDM_MAXPA], s_loc[RDM_MAXPA], s_row[RDM_MAXPA]; // row = opA * Pb | sign << 31
-    const uint32_t Ka = p.ka0 + blockIdx.x;
+    const uint32_t Ka = p.kaList ? p.kaList[p.ka0 + blockIdx.x] : p.ka0 + blockIdx.x;
     const uint32_t kb = blockIdx.y * RDM_GATHER_THREADS + threadIdx.x; // within the chunk
     const uint32_t a0 = p.ptrA[Ka], a1 = p.ptrA[Ka + 1];
     const int64_t col = static_cast<int64_t>(blockIdx.x) * p.nkb + kb;
     uint32_t b0 = 0, b1 = 0;
     if (kb < p.nkb) {
-        b0 = p.ptrB[p.kb0 + kb];
-        b1 = p.ptrB[p.kb0 + kb + 1];
+        const uint32_t Kb = p.kbList ? p.kbList[p.kb0 + kb] : p.kb0 + kb;
+        b0 = p.ptrB[Kb];
+        b1 = p.ptrB[Kb + 1];
     }
     for (uint32_t base = a0; base < a1; base += RDM_MAXPA) {
         const uint32_t cnt = a1 - base < RDM_MAXPA ? a1 - base : RDM_MAXPA;
@@ -76,8 +83,13 @@ __global__ void __launch_bounds__(RDM_GATHER_THREADS) rdm_gather_kernel(const Rd
                 if (off < 0)
                     continue;
                 const double v = p.X[off + static_cast<int64_t>(s_loc[i]) * nB + lJ];
-                const uint32_t row = (s_row[i] & 0x7fffffffu) + opB;
-                p.D[static_cast<int64_t>(row) * p.ldd + col] = ((s_row[i] >> 31) ^ negB) ? -v : v;
+                int64_t row = (s_row[i] & 0x7fffffffu) + opB;
+                if (p.rowmap) {
+                    row = p.rowmap[row];
+                    if (row < 0)
+                        continue;
+                }
+                p.D[row * p.ldd + col] = ((s_row[i] >> 31) ^ negB) ? -v : v;
             }
         }
     }
@@ -85,9 +97,11 @@ __global__ void __launch_bounds__(RDM_GATHER_THREADS) rdm_gather_kernel(const Rd
 
 // ---------------------------------------------------------------------------------------------
 // C[M x M] += A[M x K] B[M x K]^T, both row-major with the K index contiguous (leading dimension ld, even).
-constexpr int RG_BM = 128, RG_BN = 128, RG_BK = 16, RG_STAGES = 3, RG_THREADS = 256;
+// BM = tile edge: 128 for the full operator sets, 64 / 32 for the small row sets of one irrep (256 / 8 = 32 rows of the
+// opposite-spin 2-RDM at 16 orbitals in D2h: a 128-row tile would multiply 16 x more than there is).
+constexpr int RG_BM = 128, RG_BK = 16, RG_STAGES = 3, RG_THREADS = 256;
 constexpr int RG_LDS = RG_BK + 4; // 20 doubles: rows g = 0..7 of a fragment load fall on disjoint banks
-constexpr size_t rdm_gemm_smem_bytes() { return size_t(RG_STAGES) * (RG_BM + RG_BN) * RG_LDS * 8; }
+constexpr size_t rdm_gemm_smem_bytes(int bm = RG_BM) { return size_t(RG_STAGES) * (2 * bm) * RG_LDS * 8; }
 
 struct RdmGemmParams {
     const double* A;
@@ -96,51 +110,55 @@ struct RdmGemmParams {
     int M;          // rows of A and of B, C is M x M (leading dimension M)
     int64_t K, ld;  // columns of this chunk, leading dimension of A and B
     int ksplit;     // CTAs along K per tile
+    const int32_t* unmap; // NULL, or row of the block -> row of the full result (leading dimension ldc)
+    int ldc;
 };
 
+template <int BM>
 __global__ void __launch_bounds__(RG_THREADS) rdm_gemm_kernel(const RdmGemmParams p) {
+    constexpr int BN = BM, NI = BM / 32, NJ = BM / 32; // per warp: NI 16-row tiles x NJ 8-column tiles
     extern __shared__ __align__(16) unsigned char rg_smem[];
     double* As = reinterpret_cast<double*>(rg_smem);                 // [STAGES][BM][LDS]
-    double* Bs = As + RG_STAGES * RG_BM * RG_LDS;                    // [STAGES][BN][LDS]
+    double* Bs = As + RG_STAGES * BM * RG_LDS;                       // [STAGES][BN][LDS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int tiles_n = (p.M + RG_BN - 1) / RG_BN;
+    const int tiles_n = (p.M + BN - 1) / BN;
     const int tile = blockIdx.x / p.ksplit, ks = blockIdx.x - tile * p.ksplit;
-    const int m0 = (tile / tiles_n) * RG_BM, n0 = (tile % tiles_n) * RG_BN;
+    const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
     // this CTA's share of the K range, in steps of BK
     const int64_t nsteps_all = (p.K + RG_BK - 1) / RG_BK;
     const int64_t s0 = nsteps_all * ks / p.ksplit, s1 = nsteps_all * (ks + 1) / p.ksplit;
     const int nsteps = static_cast<int>(s1 - s0);
     if (nsteps <= 0)
         return;
-    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32; // warp tile 64 x 32
+    const int wm = (warp >> 2) * (BM / 2), wn = (warp & 3) * (BN / 4); // warp tile (BM / 2) x (BN / 4)
 
     auto load_stage = [&](int step, int stage) {
-        // 256 rows (128 of A, 128 of B) x 16 doubles = 8 pieces of 16 bytes per row, 2048 pieces, 8 per thread
+        // 2 BM rows (BM of A, BN of B) x 16 doubles = 8 pieces of 16 bytes per row
         const int64_t k0 = (s0 + step) * RG_BK;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < (2 * BM * 8) / RG_THREADS; ++it) {
             const int idx = tid + it * RG_THREADS;
             const int row = idx >> 3, piece = idx & 7;
-            const bool isB = row >= RG_BM;
-            const int r = isB ? row - RG_BM : row;
+            const bool isB = row >= BM;
+            const int r = isB ? row - BM : row;
             const int grow = (isB ? n0 : m0) + r;
             const int64_t k = k0 + 2 * piece;
             int bytes = 0;
             if (grow < p.M && k < p.K)
                 bytes = (p.K - k >= 2) ? 16 : 8;
             const double* src = (isB ? p.B : p.A) + (bytes ? static_cast<int64_t>(grow) * p.ld + k : 0);
-            double* dst = (isB ? Bs : As) + (stage * (isB ? RG_BN : RG_BM) + r) * RG_LDS + 2 * piece;
+            double* dst = (isB ? Bs : As) + (stage * BM + r) * RG_LDS + 2 * piece;
             cp_async16(dst, src, bytes);
         }
         cp_async_commit();
     };
 
-    double acc[4][4][4];
+    double acc[NI][NJ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
             acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0;
 
 #pragma unroll
@@ -157,42 +175,43 @@ __global__ void __launch_bounds__(RG_THREADS) rdm_gemm_kernel(const RdmGemmParam
             load_stage(step + RG_STAGES - 1, (step + RG_STAGES - 1) % RG_STAGES);
         else
             cp_async_commit();
-        const double* Ast = As + (step % RG_STAGES) * RG_BM * RG_LDS;
-        const double* Bst = Bs + (step % RG_STAGES) * RG_BN * RG_LDS;
+        const double* Ast = As + (step % RG_STAGES) * BM * RG_LDS;
+        const double* Bst = Bs + (step % RG_STAGES) * BN * RG_LDS;
 #pragma unroll
         for (int kk = 0; kk < RG_BK; kk += 4) {
-            double a0[4], a1[4], b[4];
+            double a0[NI], a1[NI], b[NJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NI; ++i) {
                 a0[i] = Ast[(wm + 16 * i + g) * RG_LDS + kk + t];
                 a1[i] = Ast[(wm + 16 * i + g + 8) * RG_LDS + kk + t];
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
                 b[j] = Bst[(wn + 8 * j + g) * RG_LDS + kk + t];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < NI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < NJ; ++j)
                     dmma_16x8x4(acc[i][j], a0[i], a1[i], b[j]);
         }
     }
     cp_async_wait<0>();
     // accumulator (tile i, j): rows wm + 16 i + g (+8), columns wn + 8 j + 2 t (+1)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int row = m0 + wm + 16 * i + g + 8 * h;
             if (row >= p.M)
                 continue;
+            const int64_t crow = static_cast<int64_t>(p.unmap ? p.unmap[row] : row) * p.ldc;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int colc = n0 + wn + 8 * j + 2 * t + c;
                     if (colc < p.M)
-                        atomicAdd(p.C + static_cast<int64_t>(row) * p.M + colc, acc[i][j][2 * h + c]);
+                        atomicAdd(p.C + crow + (p.unmap ? p.unmap[colc] : colc), acc[i][j][2 * h + c]);
                 }
         }
 }

@@ -2459,33 +2459,10 @@ void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, do
     auto& LA = rdm_device_lists(b, 0, la);
     auto& LB = rdm_device_lists(b, 1, lb);
     const bool same = L == R;
-    // the K-block budget of the reference (acquire_local_Kblock_buffers, ci_sigma_builder.cc:70-78,
-    // knowles_handy.cc:15-32): two buffers of M rows inside set_memory; at least one column each
-    const int64_t cap = static_cast<int64_t>(b.memory_size / ((same ? 1 : 2) * sizeof(double)));
-    int64_t kc_max = cap / M;
-    kc_max -= kc_max % 2;
-    if (kc_max < 2)
-        throw std::runtime_error("The CI builder memory limit (" + std::to_string(b.memory_size) +
-                                 " bytes) is too small for one K-block column of " + std::to_string(M) +
-                                 " elements per buffer.");
-    kc_max = std::min<int64_t>(kc_max, int64_t(1) << 30);
-    if (const char* e = std::getenv("F2_RDM_CHUNK_COLS")) // test hook: columns per chunk (several chunks on small spaces)
-        kc_max = std::max<int64_t>(2, std::min<int64_t>(kc_max, std::atoll(e) & ~int64_t(1)));
-    int64_t cka, ckb; // chunk extents
-    if (nKb <= kc_max) {
-        ckb = nKb;
-        cka = std::min<int64_t>(nKa, kc_max / nKb);
-    } else {
-        cka = 1;
-        ckb = kc_max;
-    }
-    ckb = std::min<int64_t>(ckb, int64_t(65535) * RDM_GATHER_THREADS);
-    const int64_t ld_max = (cka * ckb + 1) / 2 * 2;
-    for (int v = 0; v < (same ? 1 : 2); ++v)
-        if (b.rdmD[v].n < static_cast<size_t>(M * ld_max))
-            b.rdmD[v].alloc(static_cast<size_t>(M * ld_max));
-    F2_CUDA(cudaFuncSetAttribute(rdm_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(rdm_gemm_smem_bytes())));
+    F2_CUDA(cudaFuncSetAttribute(rdm_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(rdm_gemm_smem_bytes(128))));
+    F2_CUDA(cudaFuncSetAttribute(rdm_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(rdm_gemm_smem_bytes(64))));
     RdmGatherParams g;
     g.ptrA = LA.ptr.p;
     g.entA = LA.ent.p;
@@ -2499,36 +2476,159 @@ void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, do
     g.blk_off = D.blk_off.p;
     g.nclsB = static_cast<int>(hs.nclsB());
     g.Pb = static_cast<int>(Pb);
-    const int tiles = static_cast<int>((M + RG_BM - 1) / RG_BM);
-    for (int64_t ka0 = 0; ka0 < nKa; ka0 += cka)
-        for (int64_t kb0 = 0; kb0 < nKb; kb0 += ckb) {
-            g.ka0 = static_cast<uint32_t>(ka0);
-            g.kb0 = static_cast<uint32_t>(kb0);
-            g.nka = static_cast<uint32_t>(std::min(cka, nKa - ka0));
-            g.nkb = static_cast<uint32_t>(std::min(ckb, nKb - kb0));
-            const int64_t K = static_cast<int64_t>(g.nka) * g.nkb;
-            g.ldd = (K + 1) / 2 * 2;
-            const dim3 grid(g.nka, (g.nkb + RDM_GATHER_THREADS - 1) / RDM_GATHER_THREADS);
-            for (int v = 0; v < (same ? 1 : 2); ++v) {
-                g.X = v == 0 ? L : R;
-                g.D = b.rdmD[v].p;
-                F2_CUDA(cudaMemsetAsync(g.D, 0, static_cast<size_t>(M * g.ldd) * sizeof(double), st));
-                rdm_gather_kernel<<<grid, RDM_GATHER_THREADS, 0, st>>>(g);
+    g.kaList = g.kbList = nullptr;
+    g.rowmap = nullptr;
+    // one pass of the chunk loop: Mrows operator rows (all of them, or those of one irrep), hole strings
+    // [0, nka_all) x [0, nkb_all) of the lists in g (all hole strings, or those of two matching irreps)
+    auto run = [&](int64_t Mrows, int64_t nka_all, int64_t nkb_all, const int32_t* unmap) {
+        if (Mrows == 0 || nka_all == 0 || nkb_all == 0)
+            return;
+        // the K-block budget of the reference (acquire_local_Kblock_buffers, ci_sigma_builder.cc:70-78,
+        // knowles_handy.cc:15-32): two buffers of M rows inside set_memory; at least one column each
+        const int64_t cap = static_cast<int64_t>(b.memory_size / ((same ? 1 : 2) * sizeof(double)));
+        int64_t kc_max = cap / M; // (sized by the full row count, so that the error does not depend on the symmetry)
+        kc_max -= kc_max % 2;
+        if (kc_max < 2)
+            throw std::runtime_error("The CI builder memory limit (" + std::to_string(b.memory_size) +
+                                     " bytes) is too small for one K-block column of " + std::to_string(M) +
+                                     " elements per buffer.");
+        kc_max = std::min<int64_t>(cap / Mrows - (cap / Mrows) % 2, int64_t(1) << 30);
+        if (const char* e = std::getenv("F2_RDM_CHUNK_COLS")) // test hook: columns per chunk (several chunks on small spaces)
+            kc_max = std::max<int64_t>(2, std::min<int64_t>(kc_max, std::atoll(e) & ~int64_t(1)));
+        int64_t cka, ckb; // chunk extents
+        if (nkb_all <= kc_max) {
+            ckb = nkb_all;
+            cka = std::min<int64_t>(nka_all, kc_max / nkb_all);
+        } else {
+            cka = 1;
+            ckb = kc_max;
+        }
+        ckb = std::min<int64_t>(ckb, int64_t(65535) * RDM_GATHER_THREADS);
+        cka = std::min<int64_t>(cka, 65535 * int64_t(32768));
+        const int64_t ld_max = (cka * ckb + 1) / 2 * 2;
+        for (int v = 0; v < (same ? 1 : 2); ++v)
+            if (b.rdmD[v].n < static_cast<size_t>(Mrows * ld_max))
+                b.rdmD[v].alloc(static_cast<size_t>(Mrows * ld_max));
+        const int bm = Mrows <= 32 ? 32 : (Mrows <= 64 ? 64 : 128);
+        const int tiles = static_cast<int>((Mrows + bm - 1) / bm);
+        for (int64_t ka0 = 0; ka0 < nka_all; ka0 += cka)
+            for (int64_t kb0 = 0; kb0 < nkb_all; kb0 += ckb) {
+                RdmGatherParams gg = g;
+                gg.nka = static_cast<uint32_t>(std::min(cka, nka_all - ka0));
+                gg.nkb = static_cast<uint32_t>(std::min(ckb, nkb_all - kb0));
+                gg.ka0 += static_cast<uint32_t>(ka0);
+                gg.kb0 += static_cast<uint32_t>(kb0);
+                const int64_t K = static_cast<int64_t>(gg.nka) * gg.nkb;
+                gg.ldd = (K + 1) / 2 * 2;
+                const dim3 grid(gg.nka, (gg.nkb + RDM_GATHER_THREADS - 1) / RDM_GATHER_THREADS);
+                for (int v = 0; v < (same ? 1 : 2); ++v) {
+                    gg.X = v == 0 ? L : R;
+                    gg.D = b.rdmD[v].p;
+                    F2_CUDA(cudaMemsetAsync(gg.D, 0, static_cast<size_t>(Mrows * gg.ldd) * sizeof(double), st));
+                    rdm_gather_kernel<<<grid, RDM_GATHER_THREADS, 0, st>>>(gg);
+                    b.launches += 1;
+                }
+                RdmGemmParams q;
+                q.A = b.rdmD[0].p;
+                q.B = same ? b.rdmD[0].p : b.rdmD[1].p;
+                q.C = out;
+                q.M = static_cast<int>(Mrows);
+                q.K = K;
+                q.ld = gg.ldd;
+                q.unmap = unmap;
+                q.ldc = static_cast<int>(M);
+                const int64_t nsteps = (K + RG_BK - 1) / RG_BK;
+                q.ksplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsteps, (2 * 148 + tiles * tiles - 1) / (tiles * tiles))));
+                const unsigned ctas = static_cast<unsigned>(tiles * tiles * q.ksplit);
+                if (bm == 32)
+                    rdm_gemm_kernel<32><<<ctas, RG_THREADS, rdm_gemm_smem_bytes(32), st>>>(q);
+                else if (bm == 64)
+                    rdm_gemm_kernel<64><<<ctas, RG_THREADS, rdm_gemm_smem_bytes(64), st>>>(q);
+                else
+                    rdm_gemm_kernel<128><<<ctas, RG_THREADS, rdm_gemm_smem_bytes(128), st>>>(q);
                 b.launches += 1;
             }
-            RdmGemmParams q;
-            q.A = b.rdmD[0].p;
-            q.B = same ? b.rdmD[0].p : b.rdmD[1].p;
-            q.C = out;
-            q.M = static_cast<int>(M);
-            q.K = K;
-            q.ld = g.ldd;
-            const int64_t nsteps = (K + RG_BK - 1) / RG_BK;
-            q.ksplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nsteps, (2 * 148 + tiles * tiles - 1) / (tiles * tiles))));
-            rdm_gemm_kernel<<<tiles * tiles * q.ksplit, RG_THREADS, rdm_gemm_smem_bytes(), st>>>(q);
-            b.launches += 1;
+    };
+    int nirrep = 1; // irrep labels combine by XOR: group by the power of two that covers them
+    while (nirrep < hs.nirrep)
+        nirrep <<= 1;
+    if (nirrep <= 1 || std::getenv("F2_RDM_NO_IRREP_BLOCKS") != nullptr) {
+        g.ka0 = g.kb0 = 0;
+        run(M, nKa, nKb, nullptr);
+        F2_CUDA(cudaGetLastError());
+        return;
+    }
+    // ---- point-group symmetry: one pass per (irrep h of the operator tuples, irrep of Ka); see RdmGatherParams
+    auto tuple_irreps = [&](int level) { // irrep of every decreasing orbital tuple, in tuple-index order
+        std::vector<int> out;
+        const int n = hs.norb;
+        if (level == 0)
+            out.push_back(0);
+        else if (level == 1)
+            for (int p = 0; p < n; ++p)
+                out.push_back(hs.symmetry_of(1ull << p));
+        else if (level == 2)
+            for (int p = 0; p < n; ++p)
+                for (int q = 0; q < p; ++q)
+                    out.push_back(hs.symmetry_of((1ull << p) | (1ull << q)));
+        else
+            for (int p = 0; p < n; ++p)
+                for (int q = 0; q < p; ++q)
+                    for (int r = 0; r < q; ++r)
+                        out.push_back(hs.symmetry_of((1ull << p) | (1ull << q) | (1ull << r)));
+        return out;
+    };
+    const std::vector<int> irA = tuple_irreps(la), irB = tuple_irreps(lb);
+    if (static_cast<int64_t>(irA.size()) != Pa || static_cast<int64_t>(irB.size()) != Pb)
+        throw std::logic_error("rdm_block: operator tuple count");
+    std::vector<int32_t> rowmap(static_cast<size_t>(nirrep) * M, -1), unmap(static_cast<size_t>(nirrep) * M, 0);
+    std::vector<int64_t> Mh(nirrep, 0);
+    for (int64_t a = 0; a < Pa; ++a)
+        for (int64_t bb = 0; bb < Pb; ++bb) {
+            const int h = irA[a] ^ irB[bb];
+            const int64_t row = a * Pb + bb;
+            rowmap[h * M + row] = static_cast<int32_t>(Mh[h]);
+            unmap[h * M + Mh[h]] = static_cast<int32_t>(row);
+            Mh[h] += 1;
         }
+    auto by_irrep = [&](const HoleLists& HL, std::vector<uint32_t>& flat, std::vector<int64_t>& first) {
+        std::vector<std::vector<uint32_t>> lists(nirrep);
+        for (size_t K = 0; K < HL.nK(); ++K)
+            lists[hs.symmetry_of(HL.kword[K])].push_back(static_cast<uint32_t>(K));
+        first.assign(nirrep + 1, 0);
+        for (int h = 0; h < nirrep; ++h) {
+            first[h + 1] = first[h] + static_cast<int64_t>(lists[h].size());
+            flat.insert(flat.end(), lists[h].begin(), lists[h].end());
+        }
+    };
+    std::vector<uint32_t> kaFlat, kbFlat;
+    std::vector<int64_t> kaFirst, kbFirst;
+    by_irrep(HA, kaFlat, kaFirst);
+    by_irrep(HB, kbFlat, kbFirst);
+    DevBuf<uint32_t> dKa, dKb;
+    DevBuf<int32_t> dRowmap, dUnmap;
+    dKa.upload(kaFlat);
+    dKb.upload(kbFlat);
+    dRowmap.upload(rowmap);
+    dUnmap.upload(unmap);
+    F2_CUDA(cudaDeviceSynchronize()); // the uploads (pageable memory) have landed before the caller's stream reads them
+    g.kaList = dKa.p;
+    g.kbList = dKb.p;
+    for (int h = 0; h < nirrep; ++h) {
+        if (Mh[h] == 0)
+            continue;
+        g.rowmap = dRowmap.p + static_cast<size_t>(h) * M;
+        for (int a = 0; a < nirrep; ++a) {
+            const int bsym = hs.symmetry ^ h ^ a; // irrep(Ka) x irrep(Kb) = h x symmetry of the state
+            if (bsym < 0 || bsym >= nirrep)
+                continue;
+            g.ka0 = static_cast<uint32_t>(kaFirst[a]);
+            g.kb0 = static_cast<uint32_t>(kbFirst[bsym]);
+            run(Mh[h], kaFirst[a + 1] - kaFirst[a], kbFirst[bsym + 1] - kbFirst[bsym], dUnmap.p + static_cast<size_t>(h) * M);
+        }
+    }
     F2_CUDA(cudaGetLastError());
+    F2_CUDA(cudaStreamSynchronize(st)); // the index tables are freed on return
 }
 
 // segments of consecutive strings of right class c that are consecutive strings of one left class

@@ -564,12 +564,15 @@ const HoleLists& CIStringsHost::hole_lists(int spin, int level) const {
     const int ne = spin == 0 ? na : nb;
     h.ptr.assign(1, 0);
     h.ent.clear();
+    h.kword.clear();
     h.max_parents = 0;
     if (level == 0) {
         for (size_t g = 0; g < S.nstr(); ++g) {
             h.ent.push_back(static_cast<uint64_t>(g));
             h.ptr.push_back(static_cast<uint32_t>(h.ent.size()));
         }
+        for (const auto& c : S.cls)
+            h.kword.insert(h.kword.end(), c.begin(), c.end());
         h.max_parents = S.nstr() ? 1 : 0;
         h.built = true;
         return h;
@@ -623,6 +626,8 @@ const HoleLists& CIStringsHost::hole_lists(int spin, int level) const {
         for (size_t i = 0; i < items.size(); ++i) {
             if (i > 0 && items[i].k != items[i - 1].k)
                 h.ptr.push_back(static_cast<uint32_t>(h.ent.size()));
+            if (i == 0 || items[i].k != items[i - 1].k)
+                h.kword.push_back(items[i].k);
             h.ent.push_back(items[i].ent);
         }
         if (!items.empty())

@@ -102,6 +102,7 @@ struct DeviceLists {
 struct HoleLists {
     std::vector<uint32_t> ptr;
     std::vector<uint64_t> ent;
+    std::vector<uint64_t> kword; // occupation word of every K
     int max_parents = 0;
     bool built = false;
     size_t nK() const { return ptr.empty() ? 0 : ptr.size() - 1; }
