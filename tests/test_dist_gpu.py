@@ -152,3 +152,38 @@ def test_sharded_davidson_roots_two_gpus(tmp_path):
         roots = np.load(tmp_path / f"roots_{r}.npy")
         for row in roots:
             assert np.max(np.abs(row[:3] - row[3:])) <= 1e-10, (r, row)
+
+
+def test_one_strings_object_two_devices():
+    """one CIStrings shared by builders on cuda:0 and cuda:1 in the same process (each device keeps its own copy of the
+    lists for as long as the strings object lives): alternating builds give the same sigma on both"""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import forte2_b200 as f2
+    from forte2_b200 import synthetic
+    space = (4, 4, 0, [[0] * 8], [], [])
+    E, H, V = synthetic.integrals(8, "S")
+    strings = f2.CIStrings(*space)
+    b0 = f2.CISigmaBuilder(strings, E, H, V, 0, device=0)
+    b1 = f2.CISigmaBuilder(strings, E, H, V, 0, device=1)
+    c = synthetic.trial_vector(strings.ndet)
+    out = []
+    for rep in range(2):
+        for dev, b in ((0, b0), (1, b1)):
+            with torch.cuda.device(dev):
+                cd = torch.from_numpy(c).to(f"cuda:{dev}")
+                sd = torch.empty_like(cd)
+                b.Hamiltonian(cd, sd)
+                torch.cuda.synchronize(dev)
+                out.append(sd.cpu().numpy())
+                g1 = b.a_1rdm(cd, cd)
+                assert abs(np.trace(g1) - 4.0 * float(c @ c)) <= 1e-10
+    del b0  # the first builder goes away; the second one's lists stay valid
+    with torch.cuda.device(1):
+        cd = torch.from_numpy(c).to("cuda:1")
+        sd = torch.empty_like(cd)
+        b1.Hamiltonian(cd, sd)
+        out.append(sd.cpu().numpy())
+    for o in out[1:]:
+        assert np.linalg.norm(o - out[0]) <= 1e-13 * np.linalg.norm(out[0])
