@@ -1537,6 +1537,71 @@ __global__ void __launch_bounds__(GEN_THREADS) t3_generic_kernel(const T3Params 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The beta replacement tables of the opposite-spin kernels, made on the device from the beta single-replacement list
+// (ELL by source string; 3.4e7 entries at 3 GAS / 20 orbitals, 0.7 s of host loops before).
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint32_t v, int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        p[i] = v;
+}
+
+// tgt[m][Jb] = sign << 31 | class(Ib) << 20 | address(Ib) for <Ib| E_m |Jb> = sign (scatter form); pre-filled with all ones
+__global__ void tgt_table_kernel(const uint64_t* __restrict__ bs_ent, int64_t nbs, int width,
+                                 const uint16_t* __restrict__ rowmap, uint32_t* __restrict__ tgt) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= nbs * width)
+        return;
+    const uint64_t ent = bs_ent[idx];
+    if (ent == ~0ull)
+        return;
+    const int64_t gJ = idx % nbs;
+    const uint32_t m = rowmap[(ent >> 40) & 0xffff];
+    tgt[static_cast<int64_t>(m) * nbs + gJ] = static_cast<uint32_t>(ent & 0xfffff) |
+                                              (static_cast<uint32_t>((ent >> 28) & 0x7ff) << 20) |
+                                              (static_cast<uint32_t>((ent >> 56) & 1) << 31);
+}
+
+// its inverse for one beta class (gather form): gsrc[m][Ib] = Jb | sign; pre-filled with nbs (the zero slot)
+__global__ void gsrc_table_kernel(const uint32_t* __restrict__ tgt, int M, int64_t nbs, int64_t gld, uint32_t* __restrict__ gsrc) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(M) * nbs)
+        return;
+    const uint32_t x = tgt[idx];
+    if (x == kNoTarget)
+        return;
+    const int64_t m = idx / nbs, gJ = idx - m * nbs;
+    gsrc[m * gld + (x & 0xfffffu)] = static_cast<uint32_t>(gJ) | (x & 0x80000000u);
+}
+
+// the inverse for several beta classes (t3gp_kernel): table columns are the targets class by class (gpos), an entry
+// names its source as class << 20 | address; pre-filled with 0x7fffffff.  srccls[target class][m][2]: the (at most two)
+// source classes of integral row m, -2 in slot 0 = more than two (pre-filled with -1).
+__global__ void gm_table_kernel(const uint32_t* __restrict__ tgt, int M, int Mpad, int64_t nbs, int64_t gld,
+                                const uint32_t* __restrict__ gpos, const uint32_t* __restrict__ b_cls,
+                                const uint32_t* __restrict__ b_loc, uint32_t* __restrict__ gsrc, int* __restrict__ srccls) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<int64_t>(M) * nbs)
+        return;
+    const uint32_t x = tgt[idx];
+    if (x == kNoTarget)
+        return;
+    const int64_t m = idx / nbs, gJ = idx - m * nbs;
+    const uint32_t ct = (x >> 20) & 0x7ff;
+    const int cj = static_cast<int>(b_cls[gJ]);
+    gsrc[m * gld + gpos[ct] + (x & 0xfffffu)] = (static_cast<uint32_t>(cj) << 20) | b_loc[gJ] | (x & 0x80000000u);
+    int* sc = srccls + (static_cast<int64_t>(ct) * Mpad + m) * 2;
+    if (sc[0] == cj || sc[0] == -2 || sc[1] == cj) // (plain reads: a stale value only costs the atomics below)
+        return;
+    const int o0 = atomicCAS(&sc[0], -1, cj);
+    if (o0 == -1 || o0 == cj || o0 == -2)
+        return;
+    const int o1 = atomicCAS(&sc[1], -1, cj);
+    if (o1 == -1 || o1 == cj)
+        return;
+    atomicExch(&sc[0], -2);
+}
+
 // sigma = E * C  (ACC: sigma += E * C, when the opposite-spin term has already been streamed in)
 template <bool ACC>
 __global__ void scale_copy_kernel(const double* __restrict__ x, double* __restrict__ y, double s,

@@ -496,36 +496,29 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
         for (size_t c = 0; c < B.nclasses(); ++c)
             if (B.strpcls(c) > (size_t(1) << 20))
                 throw std::overflow_error("CISigmaBuilder: more than 2^20 beta strings in one class");
-        std::vector<uint32_t> T(std::max<size_t>(size_t(b.M) * nbs, 1), kNoTarget);
-        for (int t = 0; t < L.bs_width; ++t)
-            for (size_t gJ = 0; gJ < nbs; ++gJ) {
-                const uint64_t ent = L.bs_ent[size_t(t) * nbs + gJ];
-                if (ent == kNullEntry)
-                    continue;
-                const uint32_t m = rowmap[(ent >> 40) & 0xffff];
-                T[size_t(m) * nbs + gJ] = static_cast<uint32_t>(ent & 0xfffff) |
-                                          (static_cast<uint32_t>((ent >> 28) & 0x7ff) << 20) |
-                                          (static_cast<uint32_t>((ent >> 56) & 1) << 31);
-            }
-        b.tgt.upload(T);
+        const DevStrings& D = *b.D;
+        const int64_t nT = static_cast<int64_t>(b.M) * static_cast<int64_t>(nbs);
+        auto grid_for = [](int64_t n) { return static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, int64_t(1) << 30)); };
+        // (legacy stream throughout: every upload above is a blocking cudaMemcpy on it)
+        b.tgt.alloc(static_cast<size_t>(std::max<int64_t>(nT, 1)));
+        F2_CUDA(cudaMemset(b.tgt.p, 0xff, static_cast<size_t>(std::max<int64_t>(nT, 1)) * sizeof(uint32_t)));
+        const int64_t nent = static_cast<int64_t>(nbs) * L.bs_width;
+        if (nent > 0 && nT > 0)
+            tgt_table_kernel<<<grid_for(nent), 256>>>(D.bs_ent.p, static_cast<int64_t>(nbs), L.bs_width, b.rowmap.p, b.tgt.p);
         // inverse table for the gather form: (row m, target Ib) -> source Jb with <Ib|E_m|Jb> = sign;
         // "no source" points at the zero slot behind the staged row (index nbs).  Single beta class only.
         b.gsrc.release();
         if (B.nclasses() == 1 && h.nclsA() == 1 && nbs < (size_t(1) << 20)) {
             const int Mpad = (b.M + 3) / 4 * 4;
             const size_t gld = (nbs + 15) / 16 * 16;
-            std::vector<uint32_t> Gt(std::max<size_t>(size_t(Mpad) * gld, 1), static_cast<uint32_t>(nbs));
-            for (int m = 0; m < b.M; ++m)
-                for (size_t gJ = 0; gJ < nbs; ++gJ) {
-                    const uint32_t x = T[size_t(m) * nbs + gJ];
-                    if (x == kNoTarget)
-                        continue;
-                    const size_t Ib = x & 0xfffffu;
-                    // E_m Jb = sign Ib.  With pair-compressed rows E_ij and E_ji share row m; otherwise the
-                    // gather row of <Ib|E_ij|Jb> is the row of (i, j) itself
-                    Gt[size_t(m) * gld + Ib] = static_cast<uint32_t>(gJ) | (x & 0x80000000u);
-                }
-            b.gsrc.upload(Gt);
+            const int64_t nG = static_cast<int64_t>(std::max<size_t>(size_t(Mpad) * gld, 1));
+            b.gsrc.alloc(static_cast<size_t>(nG));
+            fill_u32_kernel<<<148 * 8, 256>>>(b.gsrc.p, static_cast<uint32_t>(nbs), nG);
+            // E_m Jb = sign Ib.  With pair-compressed rows E_ij and E_ji share row m; otherwise the
+            // gather row of <Ib|E_ij|Jb> is the row of (i, j) itself
+            if (nT > 0)
+                gsrc_table_kernel<<<grid_for(nT), 256>>>(b.tgt.p, b.M, static_cast<int64_t>(nbs), static_cast<int64_t>(gld),
+                                                         b.gsrc.p);
             b.t3g_mpad = Mpad;
             b.t3g_gld = static_cast<int64_t>(gld);
         }
@@ -544,29 +537,21 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
                 gld += (B.strpcls(c) + 15) / 16 * 16;
             }
             if (static_cast<size_t>(Mpad + 1) * gld * sizeof(uint32_t) <= (size_t(2) << 30) && Mpad < 65535) {
-                std::vector<uint32_t> Gt(std::max<size_t>(size_t(Mpad + 1) * gld, 1), 0x7fffffffu);
+                const int64_t nG = static_cast<int64_t>(std::max<size_t>(size_t(Mpad + 1) * gld, 1));
+                b.gm_gsrc.alloc(static_cast<size_t>(nG));
+                fill_u32_kernel<<<148 * 8, 256>>>(b.gm_gsrc.p, 0x7fffffffu, nG);
+                b.gm_gpos.upload(gpos);
                 // [target class][m] -> source classes (a pair-compressed row serves E_ij and E_ji, which can come
                 // from two different classes); -2 in slot 0 = more than two, keep the row unconditionally
+                DevBuf<int> dsc;
+                dsc.alloc(NCb * Mpad * 2);
+                F2_CUDA(cudaMemset(dsc.p, 0xff, NCb * Mpad * 2 * sizeof(int))); // -1
+                if (nT > 0)
+                    gm_table_kernel<<<grid_for(nT), 256>>>(b.tgt.p, b.M, Mpad, static_cast<int64_t>(nbs), static_cast<int64_t>(gld),
+                                                           b.gm_gpos.p, D.b_cls.p, D.b_loc.p, b.gm_gsrc.p, dsc.p);
+                F2_CUDA(cudaGetLastError());
                 std::vector<int> srccls(NCb * Mpad * 2, -1);
-                for (int m = 0; m < b.M; ++m)
-                    for (size_t gJ = 0; gJ < nbs; ++gJ) {
-                        const uint32_t x = T[size_t(m) * nbs + gJ];
-                        if (x == kNoTarget)
-                            continue;
-                        const uint32_t ct = (x >> 20) & 0x7ff;
-                        const size_t pos = gpos[ct] + (x & 0xfffffu);
-                        Gt[size_t(m) * gld + pos] = (L.b_cls[gJ] << 20) | L.b_loc[gJ] | (x & 0x80000000u);
-                        int* sc = &srccls[(ct * Mpad + m) * 2];
-                        const int cj = static_cast<int>(L.b_cls[gJ]);
-                        if (sc[0] == -2 || sc[0] == cj || sc[1] == cj)
-                            ;
-                        else if (sc[0] == -1)
-                            sc[0] = cj;
-                        else if (sc[1] == -1)
-                            sc[1] = cj;
-                        else
-                            sc[0] = -2;
-                    }
+                F2_CUDA(cudaMemcpy(srccls.data(), dsc.p, srccls.size() * sizeof(int), cudaMemcpyDeviceToHost));
                 std::vector<uint16_t> ml(NCa * NCb * Mpad, static_cast<uint16_t>(Mpad));
                 std::vector<int32_t> mc(NCa * NCb, 0);
                 for (size_t ca = 0; ca < NCa; ++ca)
@@ -585,14 +570,14 @@ void build_integrals(f2_sigma& b, double E, const double* H, const double* V) {
                         }
                         mc[ca * NCb + ct] = n;
                     }
-                b.gm_gsrc.upload(Gt);
-                b.gm_gpos.upload(gpos);
                 b.gm_ml_ent.upload(ml);
                 b.gm_ml_cnt.upload(mc);
                 b.gm_mpad = Mpad;
                 b.gm_gld = static_cast<int64_t>(gld);
             }
         }
+        F2_CUDA(cudaGetLastError());
+        F2_CUDA(cudaDeviceSynchronize());
         bool pair = nbs % 2 == 0;
         for (size_t c = 0; c < B.nclasses(); ++c)
             pair = pair && (B.cls_off[c] % 2 == 0) && (B.strpcls(c) % 2 == 0);
@@ -1832,11 +1817,23 @@ f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const 
         b->device = device;
         b->log_level = log_level;
         b->norb = strings->host->norb;
+        const bool trace = std::getenv("F2_TIME_LISTS") != nullptr;
+        auto T0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (trace) {
+                cudaDeviceSynchronize();
+                const auto t = std::chrono::steady_clock::now();
+                std::fprintf(stderr, "builder: %-28s %.3f s\n", what, std::chrono::duration<double>(t - T0).count());
+                T0 = t;
+            }
+        };
         b->D = device_strings(strings, device);
+        lap("lists on the device");
         for (auto& set : b->evs)
             for (auto& e : set)
                 F2_CUDA(cudaEventCreate(&e));
         build_integrals(*b, E, H, V);
+        lap("integrals + beta tables");
         const DeviceLists& L = strings->host->device_lists();
         for (int s = 0; s < 2; ++s) {
             // the tensor-core kernel keeps two m x m integral blocks in shared memory: up to 112 parents
@@ -1854,8 +1851,11 @@ f2_sigma* f2_sigma_create(f2_strings* strings, double E, const double* H, const 
             b->ss_ks[s] = round_ks(std::min(mmax, 128));
         }
         plan_t3_shape(*b);
+        lap("opposite-spin shape + row tables");
         b->single = make_part(*b, 0, 1);
+        lap("partition, items, K lists");
         plan_hdiag(*b);
+        lap("diagonal plan");
         F2_CUDA(cudaDeviceSynchronize()); // every table upload (pageable memory) has landed before any stream reads it
         return b.release();
     } catch (const std::exception& e) {
