@@ -294,7 +294,8 @@ struct f2_sigma {
     // host staging for f2_sigma_apply_host
     double *hC = nullptr, *hS = nullptr;
     DevBuf<double> dC, dS;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, own_stream2 = nullptr, copy_stream = nullptr;
+    cudaEvent_t t3_ev = nullptr;
     cudaEvent_t copy_ev = nullptr, pass_ev = nullptr;
     std::vector<cudaEvent_t> piece_ev;
 
@@ -311,6 +312,10 @@ struct f2_sigma {
             cudaFreeHost(hS);
         if (own_stream)
             cudaStreamDestroy(own_stream);
+        if (own_stream2)
+            cudaStreamDestroy(own_stream2);
+        if (t3_ev)
+            cudaEventDestroy(t3_ev);
         if (copy_stream)
             cudaStreamDestroy(copy_stream);
         if (copy_ev)
@@ -2007,8 +2012,17 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
             F2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         if (!h->copy_ev)
             F2_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
-        if (streamed)
+        // the streamed opposite-spin launches alternate between two streams: the last, partly filled wave of CTAs of one
+        // launch then runs beside the first waves of the next instead of in front of them
+        if (!h->own_stream2)
+            F2_CUDA(cudaStreamCreateWithFlags(&h->own_stream2, cudaStreamNonBlocking));
+        if (!h->t3_ev)
+            F2_CUDA(cudaEventCreateWithFlags(&h->t3_ev, cudaEventDisableTiming));
+        if (streamed) {
             F2_CUDA(cudaMemsetAsync(h->dS.p, 0, bytes, h->own_stream));
+            F2_CUDA(cudaEventRecord(h->t3_ev, h->own_stream));
+            F2_CUDA(cudaStreamWaitEvent(h->own_stream2, h->t3_ev, 0));
+        }
         int64_t rows_done = 0;
         int64_t streamed_launches = 0;
         // launch granularity: the first opposite-spin launch follows the first piece (the GPU starts after 64 MB, not
@@ -2026,8 +2040,9 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
                 const int64_t rows_in = arrived == total ? s.nas : static_cast<int64_t>(arrived / s.nbs);
                 if (rows_in > rows_done) {
                     F2_CUDA(cudaEventRecord(h->copy_ev, h->copy_stream));
-                    F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->copy_ev, 0));
-                    launch_t3g(*h, h->dC.p, h->dS.p, h->own_stream, static_cast<int>(rows_done),
+                    cudaStream_t ts = (streamed_launches & 1) ? h->own_stream2 : h->own_stream;
+                    F2_CUDA(cudaStreamWaitEvent(ts, h->copy_ev, 0));
+                    launch_t3g(*h, h->dC.p, h->dS.p, ts, static_cast<int>(rows_done),
                                static_cast<int>(rows_in - rows_done));
                     streamed_launches += 1;
                     rows_done = rows_in;
@@ -2038,6 +2053,10 @@ int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, i
         }
         F2_CUDA(cudaEventRecord(h->copy_ev, h->copy_stream));
         F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->copy_ev, 0));
+        if (streamed) { // everything that follows on own_stream comes after the launches on the second stream
+            F2_CUDA(cudaEventRecord(h->t3_ev, h->own_stream2));
+            F2_CUDA(cudaStreamWaitEvent(h->own_stream, h->t3_ev, 0));
+        }
         stamp("staged + H2D enqueued");
         if (trace) {
             F2_CUDA(cudaStreamSynchronize(h->copy_stream));
