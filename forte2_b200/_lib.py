@@ -49,6 +49,7 @@ SIGNATURES = {
     "f2_sigma_last_ms": (C.c_int, [C.c_void_p, f64p]),
     "f2_sigma_hdiag": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_sigma_rdm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f2_sigma_rdm_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "f2_sigma_rdm_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_sigma_trdm1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f2_dist_unique_id": (C.c_int, [C.c_char_p]),

@@ -213,7 +213,9 @@ class CISigmaBuilder:
 
     # ---- reduced density matrices (forte2/api/ci_helpers_api.cc:110-130): device kernels for the spin blocks
     # (f2_sigma_rdm, csrc/rdm_kernels.cuh), the spin-free combinations assembled on the host like the reference
-    def _rdm(self, kind, C_left, C_right, shape):
+    def _rdm(self, kind, C_left, C_right, shape, part=None, device_out=False):
+        """part = (i, n): only the contributions of slice i of n of the hole strings (f2_sigma_rdm_part; the parts add up
+        to the block); device_out: the result stays on the device as a torch tensor (for an all-reduce)"""
         import torch
         dev = torch.device("cuda", self.device)
         ndet = self.ci_strings.ndet
@@ -229,20 +231,24 @@ class CISigmaBuilder:
         left, right = vec(C_left, "C_left"), vec(C_right, "C_right")
         count = int(np.prod(shape))
         if count == 0 or ndet == 0:
-            return np.zeros(shape)
+            return torch.zeros(shape, dtype=torch.float64, device=dev) if device_out else np.zeros(shape)
         out = torch.empty(count, dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(_lib.lib().f2_sigma_rdm(self._h, kind, left.data_ptr(), right.data_ptr(), out.data_ptr(), stream))
-        return out.cpu().numpy().reshape(shape)
+        if part is None:
+            _lib.check(_lib.lib().f2_sigma_rdm(self._h, kind, left.data_ptr(), right.data_ptr(), out.data_ptr(), stream))
+        else:
+            _lib.check(_lib.lib().f2_sigma_rdm_part(self._h, kind, left.data_ptr(), right.data_ptr(), out.data_ptr(),
+                                                    int(part[0]), int(part[1]), stream))
+        return out.view(shape) if device_out else out.cpu().numpy().reshape(shape)
 
-    def a_1rdm(self, C_left, C_right) -> np.ndarray:
+    def a_1rdm(self, C_left, C_right, **kw) -> np.ndarray:
         """<L|a+_p a_q|R> for alpha, (norb, norb) (CISigmaBuilder::compute_a_1rdm, ci_sigma_builder_1rdm.cc:9-65)"""
         n = self.ci_strings.norb
-        return self._rdm(0, C_left, C_right, (n, n))
+        return self._rdm(0, C_left, C_right, (n, n), **kw)
 
-    def b_1rdm(self, C_left, C_right) -> np.ndarray:
+    def b_1rdm(self, C_left, C_right, **kw) -> np.ndarray:
         n = self.ci_strings.norb
-        return self._rdm(1, C_left, C_right, (n, n))
+        return self._rdm(1, C_left, C_right, (n, n), **kw)
 
     def sf_1rdm(self, C_left, C_right) -> np.ndarray:
         """spin-free 1-RDM = alpha + beta (ci_sigma_builder_1rdm.cc:71-81)"""
@@ -252,21 +258,21 @@ class CISigmaBuilder:
         n = self.ci_strings.norb
         return n * (n - 1) // 2
 
-    def aa_2rdm(self, C_left, C_right) -> np.ndarray:
+    def aa_2rdm(self, C_left, C_right, **kw) -> np.ndarray:
         """<L|a+_p a+_q a_s a_r|R>, p > q, r > s, packed (npairs, npairs) (compute_aa_2rdm,
         ci_sigma_builder_2rdm.cc:45-125); (0, 0) with fewer than two orbitals like the reference"""
         m = self._npairs() if self.ci_strings.norb >= 2 else 0
-        return self._rdm(3, C_left, C_right, (m, m))
+        return self._rdm(3, C_left, C_right, (m, m), **kw)
 
-    def bb_2rdm(self, C_left, C_right) -> np.ndarray:
+    def bb_2rdm(self, C_left, C_right, **kw) -> np.ndarray:
         m = self._npairs() if self.ci_strings.norb >= 2 else 0
-        return self._rdm(4, C_left, C_right, (m, m))
+        return self._rdm(4, C_left, C_right, (m, m), **kw)
 
-    def ab_2rdm(self, C_left, C_right) -> np.ndarray:
+    def ab_2rdm(self, C_left, C_right, **kw) -> np.ndarray:
         """<L|a+_u(alpha) a+_v(beta) a_y(beta) a_x(alpha)|R>, (norb,) * 4 (compute_ab_2rdm,
         ci_sigma_builder_2rdm.cc:135-201)"""
         n = self.ci_strings.norb
-        return self._rdm(5, C_left, C_right, (n, n, n, n))
+        return self._rdm(5, C_left, C_right, (n, n, n, n), **kw)
 
     def sf_2rdm(self, C_left, C_right) -> np.ndarray:
         """spin-free 2-RDM (compute_sf_2rdm, ci_sigma_builder_2rdm.cc:203-254)"""
@@ -297,13 +303,13 @@ class CISigmaBuilder:
         m = self._ntriplets() if self.ci_strings.norb >= 3 else 0
         return self._rdm(11, C_left, C_right, (m, m))
 
-    def aab_3rdm(self, C_left, C_right) -> np.ndarray:
+    def aab_3rdm(self, C_left, C_right, **kw) -> np.ndarray:
         """<L|a+_p a+_q b+_r b_u a_t a_s|R>, [(p > q), r, (s > t), u] (compute_aab_3rdm,
         ci_sigma_builder_3rdm.cc:172-262)"""
         n = self.ci_strings.norb
         if n < 2:
             return np.zeros((0, 0, 0, 0))
-        return self._rdm(9, C_left, C_right, (self._npairs(), n, self._npairs(), n))
+        return self._rdm(9, C_left, C_right, (self._npairs(), n, self._npairs(), n), **kw)
 
     def abb_3rdm(self, C_left, C_right) -> np.ndarray:
         """<L|a+_p b+_q b+_r b_u b_t a_s|R>, [p, (q > r), s, (t > u)] (compute_abb_3rdm,

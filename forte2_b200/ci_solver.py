@@ -454,6 +454,35 @@ class ShardedCISolver:
         return self
 
 
+def _sharded_root_rdms(self, left_root: int, right_root=None):
+    """spin-free 1- and 2-RDM of a root (pair) of a sharded solve: full copies of the vectors on every rank, the work of
+    every spin block split over the ranks, one all-reduce per block (forte2_b200/dist.py sharded_rdms)"""
+    from .ci_sigma_builder import assemble_sf_2rdm
+    from .dist import sharded_rdms
+    if not self.executed:
+        raise RuntimeError("CI solver has not been executed yet; call run() first")
+    left = self.evecs[int(left_root)].contiguous()
+    right = None if right_root is None else self.evecs[int(right_root)].contiguous()
+    blocks = sharded_rdms(self.sharded, self.ci_sigma_builder, left, right)
+    n = self.ci_strings.norb
+    g1 = blocks["a_1rdm"] + blocks["b_1rdm"]
+    g2 = assemble_sf_2rdm(n, blocks["ab_2rdm"], blocks["aa_2rdm"] if n >= 2 else None, blocks["bb_2rdm"] if n >= 2 else None)
+    return g1, g2
+
+
+def _sharded_make_sf_1rdm(self, left_root: int, right_root=None):
+    return _sharded_root_rdms(self, left_root, right_root)[0]
+
+
+def _sharded_make_sf_2rdm(self, left_root: int, right_root=None):
+    return _sharded_root_rdms(self, left_root, right_root)[1]
+
+
+ShardedCISolver.make_sf_rdms = _sharded_root_rdms
+ShardedCISolver.make_sf_1rdm = ShardedCISolver.make_1rdm = _sharded_make_sf_1rdm
+ShardedCISolver.make_sf_2rdm = ShardedCISolver.make_2rdm = _sharded_make_sf_2rdm
+
+
 def make_average_rdms(sub_solvers, weights, max_body: int = 2):
     """State-averaged spin-free RDMs over the roots of one or several solved CISolver objects
     (forte2/base_classes/ci_base.py:104-149: make_average_1rdm / make_average_2rdm / make_average_3rdm):

@@ -237,6 +237,7 @@ struct RdmGramParams {
     const uint32_t* g_ncols;
     const uint32_t* g_ldx;
     int ngroups, Pops;
+    uint32_t kfirst; // first hole string of this launch (a slice of them: f2_sigma_rdm_part)
 };
 
 constexpr int GRAM_THREADS = 384, GRAM_CHUNK = 64, GRAM_TS = 68;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) rdm_gram_kernel(const RdmGram
     uint32_t* pinfo = pstr + ROWS;                                         // [ROWS] operator index | sign << 31
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t K = blockIdx.x;
+    const uint32_t K = p.kfirst + blockIdx.x;
     const uint32_t e0 = p.hptr[K], e1 = p.hptr[K + 1];
     const int m = static_cast<int>(e1 - e0) < ROWS ? static_cast<int>(e1 - e0) : ROWS;
     if (m == 0)
@@ -380,6 +381,7 @@ struct RdmAbParams {
     const uint32_t* gtab; // [mrows][gld]: source column | phase << 31; nbs = no source (the zero slot)
     int64_t nbs, gld;
     int norb, n2;
+    uint32_t first; // first alpha string of this launch
 };
 
 constexpr int AB_THREADS = 256, AB_CHUNK = 32, AB_TS = 33;
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) rdm_ab_kernel(const RdmAbParams
     double* Ls = row + nbs + 2;                        // [2][8 NTP][AB_TS]
     __shared__ long long s_lrow[128];                  // offset of row Ia_r in L, -1 past the list
     __shared__ int s_ux[128];                          // (u n + x) | phase << 30, -1 past the list
-    const uint32_t Ja = blockIdx.x;
+    const uint32_t Ja = p.first + blockIdx.x;
     const double* rsrc = p.R + static_cast<int64_t>(Ja) * nbs;
     for (int64_t i = tid; i < nbs + 2; i += AB_THREADS)
         row[i] = i < nbs ? __ldg(rsrc + i) : 0.0;

@@ -2318,11 +2318,13 @@ void launch_rdm_gram(const RdmGramParams& q, unsigned nK, bool al16, bool same, 
 // the parent rows (rdm_gram_kernel): alpha on the vectors themselves, beta on their transposed row slabs (the slabs and
 // plans of the beta same-spin sigma term, inside the set_memory budget)
 void rdm_gram(f2_sigma& b, int spin, int level, const double* L, const double* R, double* out, int64_t Pops,
-              cudaStream_t st) {
+              cudaStream_t st, int part, int nparts) {
     const CIStringsHost& hs = *b.S->host;
     const DevStrings& D = *b.D;
     const HoleLists& HL = hs.hole_lists(spin, level);
-    const unsigned nK = static_cast<unsigned>(HL.nK());
+    const unsigned nK_all = static_cast<unsigned>(HL.nK());
+    const unsigned kfirst = static_cast<unsigned>(static_cast<uint64_t>(nK_all) * part / nparts);
+    const unsigned nK = static_cast<unsigned>(static_cast<uint64_t>(nK_all) * (part + 1) / nparts) - kfirst;
     if (nK == 0)
         return;
     auto& dl = rdm_device_lists(b, spin, level);
@@ -2335,6 +2337,7 @@ void rdm_gram(f2_sigma& b, int spin, int level, const double* L, const double* R
     q.s_cls = spin == 0 ? D.a_cls.p : D.b_cls.p;
     q.s_loc = spin == 0 ? D.a_loc.p : D.b_loc.p;
     q.Pops = static_cast<int>(Pops);
+    q.kfirst = kfirst;
     const int mt = std::max(1, (HL.max_parents + 15) / 16);
     auto launch = [&](const SSPlan& plan, const double* xl, const double* xr) {
         if (plan.ngroups == 0)
@@ -2385,7 +2388,7 @@ void launch_rdm_ab(const RdmAbParams& q, unsigned nas, size_t smem, cudaStream_t
 
 // opposite-spin 2-RDM in the gather form (rdm_ab_kernel); false when the space does not fit it (several determinant
 // blocks, a row of the vector longer than shared memory, more than 19 orbitals or 128 single replacements)
-bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStream_t st) {
+bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStream_t st, int part, int nparts) {
     const CIStringsHost& hs = *b.S->host;
     const DevStrings& D = *b.D;
     const DeviceLists& DL = hs.device_lists();
@@ -2430,7 +2433,10 @@ bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStre
     q.gld = b.rdm_gld;
     q.norb = n;
     q.n2 = n2;
-    const unsigned nas = static_cast<unsigned>(hs.nas);
+    q.first = static_cast<uint32_t>(hs.nas * part / nparts);
+    const unsigned nas = static_cast<unsigned>(hs.nas * (part + 1) / nparts) - q.first;
+    if (nas == 0)
+        return true;
     switch (mw * 100 + ntp) {
     case 104: launch_rdm_ab<1, 4>(q, nas, smem, st); break;
     case 108: launch_rdm_ab<1, 8>(q, nas, smem, st); break;
@@ -2447,7 +2453,12 @@ bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStre
 
 // one spin block <L| (la alpha creators)(lb beta creators)(lb beta annihilators)(la alpha annihilators) |R> as the
 // M x M matrix over rows opA * Pb + opB, M = C(norb, la) C(norb, lb)
-void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, double* out, cudaStream_t st) {
+// part / nparts: only the contributions of that slice of the hole strings (of the input alpha strings in the gather form):
+// the sum over the parts is the block (f2_sigma_rdm_part: one part per GPU, then one all-reduce)
+void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, double* out, cudaStream_t st,
+               int part = 0, int nparts = 1) {
+    if (nparts < 1 || part < 0 || part >= nparts)
+        throw std::invalid_argument("f2_sigma_rdm_part: need 0 <= part < nparts");
     const CIStringsHost& hs = *b.S->host;
     const DevStrings& D = *b.D;
     if (la < 0 || lb < 0 || la + lb < 1 || la + lb > 3)
@@ -2470,10 +2481,10 @@ void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, do
         return;
     // one spin only: Gram matrices of the parent rows, no D matrix (F2_RDM_GENERIC: the gather + GEMM path always)
     if ((la == 0 || lb == 0) && (la == 0 ? HB : HA).max_parents <= 64 && std::getenv("F2_RDM_GENERIC") == nullptr) {
-        rdm_gram(b, la == 0 ? 1 : 0, la + lb, L, R, out, M, st);
+        rdm_gram(b, la == 0 ? 1 : 0, la + lb, L, R, out, M, st, part, nparts);
         return;
     }
-    if (la == 1 && lb == 1 && std::getenv("F2_RDM_GENERIC") == nullptr && rdm_ab(b, L, R, out, st))
+    if (la == 1 && lb == 1 && std::getenv("F2_RDM_GENERIC") == nullptr && rdm_ab(b, L, R, out, st, part, nparts))
         return;
     auto& LA = rdm_device_lists(b, 0, la);
     auto& LB = rdm_device_lists(b, 1, lb);
@@ -2530,10 +2541,11 @@ void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, do
                 b.rdmD[v].alloc(static_cast<size_t>(Mrows * ld_max));
         const int bm = Mrows <= 32 ? 32 : (Mrows <= 64 ? 64 : 128);
         const int tiles = static_cast<int>((Mrows + bm - 1) / bm);
-        for (int64_t ka0 = 0; ka0 < nka_all; ka0 += cka)
+        const int64_t ka_lo = nka_all * part / nparts, ka_hi = nka_all * (part + 1) / nparts; // this part's hole strings
+        for (int64_t ka0 = ka_lo; ka0 < ka_hi; ka0 += cka)
             for (int64_t kb0 = 0; kb0 < nkb_all; kb0 += ckb) {
                 RdmGatherParams gg = g;
-                gg.nka = static_cast<uint32_t>(std::min(cka, nka_all - ka0));
+                gg.nka = static_cast<uint32_t>(std::min(cka, ka_hi - ka0));
                 gg.nkb = static_cast<uint32_t>(std::min(ckb, nkb_all - kb0));
                 gg.ka0 += static_cast<uint32_t>(ka0);
                 gg.kb0 += static_cast<uint32_t>(kb0);
@@ -2682,6 +2694,23 @@ int f2_sigma_rdm_block(f2_sigma* h, int la, int lb, const double* L_dev, const d
             throw std::invalid_argument("null argument");
         F2_CUDA(cudaSetDevice(h->device));
         rdm_block(*h, la, lb, L_dev, R_dev, out_dev, static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_rdm_part(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, int part, int nparts,
+                      void* stream) {
+    static const int levels[][2] = {{1, 0}, {0, 1}, {-1, -1}, {2, 0}, {0, 2}, {1, 1}, {-1, -1}, {-1, -1},
+                                    {3, 0}, {2, 1}, {1, 2}, {0, 3}};
+    try {
+        if (!h || !L_dev || !R_dev || !out_dev)
+            throw std::invalid_argument("null argument");
+        if (kind < 0 || kind > 11 || levels[kind][0] < 0)
+            throw std::invalid_argument("f2_sigma_rdm_part: kind must be 0, 1, 3, 4, 5 or 8 .. 11 (f2_sigma_rdm)");
+        F2_CUDA(cudaSetDevice(h->device));
+        rdm_block(*h, levels[kind][0], levels[kind][1], L_dev, R_dev, out_dev, static_cast<cudaStream_t>(stream), part, nparts);
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);

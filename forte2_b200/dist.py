@@ -430,3 +430,24 @@ class LibraryShardedSigma:
 
     def close(self):
         _lib.check(_lib.lib().f2_dist_finalize(self.builder._h))
+
+
+def sharded_rdms(sharded: ShardedSigma, builder, left_loc: torch.Tensor, right_loc: torch.Tensor | None = None,
+                 kinds=("a_1rdm", "b_1rdm", "aa_2rdm", "bb_2rdm", "ab_2rdm")):
+    """RDM spin blocks of sharded vectors: every rank all-gathers the vector(s) into full copies (18.9 GB each at
+    CAS(18,18)), computes its slice of the hole strings of every block (f2_sigma_rdm_part: the work, not the vectors, is
+    what is split) and the blocks are summed with one all-reduce each.  Returns {kind: numpy array}, the same on every
+    rank, shaped as CISigmaBuilder.<kind> returns them."""
+    full_l = sharded.all_gather_full(left_loc)
+    if right_loc is None or right_loc is left_loc:
+        full_r = full_l
+    else:
+        full_l = full_l.clone()  # all_gather_full reuses its buffer
+        full_r = sharded.all_gather_full(right_loc)
+    out = {}
+    for kind in kinds:
+        t = getattr(builder, kind)(full_l, full_r, part=(sharded.rank, sharded.world), device_out=True).contiguous()
+        if sharded.world > 1 and t.numel() > 0:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=sharded.group)
+        out[kind] = t.cpu().numpy()
+    return out

@@ -151,6 +151,12 @@ int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev
  * K blocks are (ci_sigma_builder_3rdm.cc:235-258); the same "too small for one K-block column" error. */
 int f2_sigma_rdm_block(f2_sigma* h, int la, int lb, const double* L_dev, const double* R_dev, double* out_dev,
                        void* stream);
+/* One part of nparts of an RDM block (kinds of f2_sigma_rdm): the contributions of a slice of the hole strings (of the input
+ * alpha strings for the gather-form opposite-spin block).  The blocks of all parts add up to the block: several GPUs that
+ * each hold full copies of the two vectors compute one part each and all-reduce (forte2_b200/dist.py sharded_rdm; the
+ * state-averaged RDMs of a sharded solve, forte2/base_classes/ci_base.py:104-149). */
+int f2_sigma_rdm_part(f2_sigma* h, int kind, const double* L_dev, const double* R_dev, double* out_dev, int part, int nparts,
+                      void* stream);
 /* transition 1-RDM <L| a+_p a_q |R> of spin 0 (alpha) / 1 (beta) between the CI spaces of two builders with the same orbitals
  * and electron numbers (different symmetry or GAS restrictions): norb x norb doubles (CISigmaBuilder::compute_a_1trdm /
  * compute_b_1trdm, forte2/ci/ci_sigma_builder_1trdm.cc:11-118; same error messages).  Synchronises the stream. */

@@ -136,6 +136,11 @@ def _solver_worker(rank, world, port, result_dir):
             sharded = ShardedCISolver(strings, E, H, V, nroot=3, davidson_liu_params=params, log_level=0,
                                       device=rank, form=form).run()
             out.append(np.concatenate([np.asarray(single.E), np.asarray(sharded.E)]))
+            # RDMs of a root of the sharded solve (full copies, work split over the ranks, all-reduce) against the single-GPU
+            # ones; the roots can differ by a sign, the RDMs of a state with itself cannot
+            for kind in ("make_sf_1rdm", "make_sf_2rdm"):
+                a, b2 = getattr(single, kind)(1), getattr(sharded, kind)(1)
+                assert np.max(np.abs(a - b2)) <= 1e-7, (kind, float(np.max(np.abs(a - b2))))
         np.save(os.path.join(result_dir, f"roots_{rank}.npy"), np.array(out))
         dist.destroy_process_group()
     except BaseException:

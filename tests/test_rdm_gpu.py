@@ -188,3 +188,29 @@ def test_rdm_memory_limit_error():
     b.set_memory(0)
     with pytest.raises(RuntimeError, match="too small for one K-block column"):
         b.aab_3rdm(c, c)
+
+
+@pytest.mark.parametrize("name", ["cas88", "cas66_d2h", "gas343_54"])
+def test_rdm_parts_add_up(name):
+    """f2_sigma_rdm_part: the blocks of the parts (slices of the hole strings / input strings, one per GPU in a sharded
+    run) add up to the block, for the Gram, the gather-form and the D-matrix kernels"""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import forte2_b200 as f2
+    from forte2_b200 import synthetic
+    from cases import SMALL_SPACES
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(n, "S")
+    strings = f2.CIStrings(*space)
+    b = f2.CISigmaBuilder(strings, E, H, V, 0)
+    rng = np.random.default_rng(23)
+    left, right = rng.normal(size=strings.ndet), rng.normal(size=strings.ndet)
+    for kind in ("a_1rdm", "b_1rdm", "aa_2rdm", "bb_2rdm", "ab_2rdm", "aab_3rdm"):
+        want = getattr(b, kind)(left, right)
+        for nparts in (2, 3, 8):
+            got = sum(getattr(b, kind)(left, right, part=(i, nparts)) for i in range(nparts))
+            assert np.max(np.abs(got - want), initial=0.0) <= 1e-12 * max(1.0, np.max(np.abs(want), initial=0.0)), (kind, nparts)
