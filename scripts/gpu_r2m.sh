@@ -16,4 +16,4 @@ print('rdm', d.get('rdm'))
 print('davidson', {k: d['davidson'].get(k) for k in ('iter_ms_steady', 'solver_ms_per_iter')} if d.get('davidson') else None)
 print('cpu', d.get('cpu_baseline'))
 "
-F2_LIB_PATH=$PWD/tune_variants/libf2_tw1024.so timeout 300 python scripts/quick_perf.py 16 > gpurun_out/${TAG}_tw1024.log 2>&1; tail -1 gpurun_out/${TAG}_tw1024.log
+
