@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "handles.hpp"
+#include "nvtx_ranges.hpp"
 
 namespace f2 {
 
@@ -406,6 +407,7 @@ int64_t f2_dl_workspace_doubles(void) { return DL_WS; }
 int f2_dl_dots(const double* A, int64_t lda, int p, const double* X, int64_t ldx, int q, int64_t n,
                double* out_dev, double* work_dev, void* stream) {
     try {
+        f2::NvtxRange nvtx("davidson: subspace dots");
         if (p < 1 || p > DL_MAXV || q < 1 || q > DL_MAXV || n < 0)
             throw std::invalid_argument("f2_dl_dots: need 1 <= p, q <= 16 and n >= 0");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -442,6 +444,7 @@ int f2_dl_dots(const double* A, int64_t lda, int p, const double* X, int64_t ldx
 int f2_dl_combine(const double* A, int64_t lda, int p, const double* coef_host, double* Y, int64_t ldy,
                   int k, double beta, int64_t n, double* sumsq_dev, double* work_dev, void* stream) {
     try {
+        f2::NvtxRange nvtx("davidson: combine");
         if (p < 0 || p > DL_MAXV || k < 1 || k > DL_MAXV || n < 0)
             throw std::invalid_argument("f2_dl_combine: need 0 <= p <= 16, 1 <= k <= 16 and n >= 0");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -501,6 +504,7 @@ int f2_dl_residual(const double* B, const double* S, int64_t ld, int m, const do
                    const double* lam_host, const double* hdiag, double* R, int64_t ldr, int k,
                    double denom_threshold, int64_t n, double* rnorm2_dev, double* work_dev, void* stream) {
     try {
+        f2::NvtxRange nvtx("davidson: residual");
         if (m < 1 || m > DL_MAXV || k < 1 || k > DL_MAXV || n < 0)
             throw std::invalid_argument("f2_dl_residual: need 1 <= m, k <= 16 and n >= 0");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -603,6 +607,7 @@ int f2_dl_residual_fused(const double* B, const double* S, int64_t ld, int m, co
                          const double* lam_host, const double* hdiag, double* R, int64_t ldr, int k,
                          double denom_threshold, int64_t n, double* out_dev, double* work_dev, void* stream) {
     try {
+        f2::NvtxRange nvtx("davidson: residual + preconditioner + projection");
         if (m < 1 || m > DL_MAXV || k < 1 || k > DLF_MAXK || n < 0)
             throw std::invalid_argument("f2_dl_residual_fused: need 1 <= m <= 16, 1 <= k <= 4 and n >= 0");
         DlfCoef a;
@@ -625,6 +630,7 @@ int f2_dl_project(const double* B, int64_t ld, int m, const double* Yin, int64_t
                   const double* T_host, double* Zout, int64_t ldout, int kout, int64_t n, double* out_dev,
                   double* work_dev, void* stream) {
     try {
+        f2::NvtxRange nvtx("davidson: block Gram-Schmidt pass");
         if (m < 0 || m > DL_MAXV || kin < 1 || kin > DLF_MAXK || kout < 1 || kout > DLF_MAXK || n < 0)
             throw std::invalid_argument("f2_dl_project: need 0 <= m <= 16, 1 <= kin, kout <= 4 and n >= 0");
         DlfCoef c;

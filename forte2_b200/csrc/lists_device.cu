@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include "lists_device.hpp"
+#include "nvtx_ranges.hpp"
 
 namespace f2 {
 
@@ -221,6 +222,7 @@ uint32_t grid_for(size_t n) { return static_cast<uint32_t>((n + 127) / 128); }
 } // namespace
 
 void build_lists_on_device(const CIStringsHost& h) {
+    NvtxRange nvtx("replacement lists on the device");
     DeviceLists& d = h.lists_storage();
     h.lists_prologue();
     const auto& A = h.space(0, K_STR_N);

@@ -382,6 +382,7 @@ struct RdmAbParams {
     int64_t nbs, gld;
     int norb, n2;
     uint32_t first; // first alpha string of this launch
+    int nsm;        // columns of the row of R staged in shared memory (LONG: the rest is gathered from L2)
 };
 
 constexpr int AB_THREADS = 256, AB_CHUNK = 32, AB_TS = 33;
@@ -403,20 +404,23 @@ __global__ void rdm_abtab_kernel(const uint64_t* __restrict__ bs_ent, int64_t nb
     gtab[static_cast<int64_t>(ij) * gld + Ib] = static_cast<uint32_t>(Jb) | (static_cast<uint32_t>((ent >> 56) & 1) << 31);
 }
 
-template <int MW, int NTP>
+// LONG: the row of R is longer than shared memory (CAS(18,18): 389 KB): nsm columns are staged, the others are gathered
+// from global memory, where the row stays L2-resident while its CTA runs (as t3g_kernel does)
+template <int MW, int NTP, bool LONG>
 __global__ void __launch_bounds__(AB_THREADS, 1) rdm_ab_kernel(const RdmAbParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int64_t nbs = p.nbs;
-    double* row = reinterpret_cast<double*>(smem_raw); // [nbs + 2], the last two are zero
-    double* Ls = row + nbs + 2;                        // [2][8 NTP][AB_TS]
+    const int nsm = LONG ? p.nsm : static_cast<int>(nbs);
+    double* row = reinterpret_cast<double*>(smem_raw); // [nsm + 2], the last two are zero
+    double* Ls = row + nsm + 2;                        // [2][8 NTP][AB_TS]
     __shared__ long long s_lrow[128];                  // offset of row Ia_r in L, -1 past the list
     __shared__ int s_ux[128];                          // (u n + x) | phase << 30, -1 past the list
     const uint32_t Ja = p.first + blockIdx.x;
     const double* rsrc = p.R + static_cast<int64_t>(Ja) * nbs;
-    for (int64_t i = tid; i < nbs + 2; i += AB_THREADS)
-        row[i] = i < nbs ? __ldg(rsrc + i) : 0.0;
+    for (int i = tid; i < nsm + 2; i += AB_THREADS)
+        row[i] = i < nsm ? __ldg(rsrc + i) : 0.0;
     const int e0 = p.as_ptr[Ja], e1 = p.as_ptr[Ja + 1];
     const int Kn = e1 - e0 < 128 ? e1 - e0 : 128;
     for (int r = tid; r < 128; r += AB_THREADS) {
@@ -473,7 +477,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) rdm_ab_kernel(const RdmAbParams
                         q[i][h] = __ldg(reinterpret_cast<const uint4*>(p.gtab + static_cast<int64_t>(mbase + 16 * i + g + 8 * h) * p.gld +
                                                                        ib0 + 4 * t));
                 auto gather = [&](uint32_t e) {
-                    const double v = row[e & 0x7fffffffu];
+                    const uint32_t idx = e & 0x7fffffffu; // nbs = no source
+                    double v;
+                    if constexpr (LONG) {
+                        v = row[idx < static_cast<uint32_t>(nsm) ? idx : static_cast<uint32_t>(nsm)];
+                        if (idx >= static_cast<uint32_t>(nsm) && idx < static_cast<uint32_t>(nbs))
+                            v = __ldg(rsrc + idx);
+                    } else {
+                        v = row[idx];
+                    }
                     return __hiloint2double(__double2hiint(v) ^ static_cast<int>(e & 0x80000000u), __double2loint(v));
                 };
 #pragma unroll

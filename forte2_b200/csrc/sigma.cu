@@ -25,6 +25,7 @@
 #include "handles.hpp"
 #include "kernels.cuh"
 #include "lists_device.hpp"
+#include "nvtx_ranges.hpp"
 #include "rdm_kernels.cuh"
 
 namespace f2 {
@@ -1658,6 +1659,9 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
     if (h.ndet == 0)
         return;
     b.launches = 0;
+    NvtxRange nvtx_build("f2_sigma build");
+    NvtxPhases nvtx;
+    nvtx.next("H0 (scalar energy)");
     F2_CUDA(cudaEventRecord(b.ev[0], st));
     if (P.world == 1) {
         if (t3_streamed)
@@ -1670,6 +1674,7 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         b.launches += 1;
     }
     F2_CUDA(cudaEventRecord(b.ev[1], st));
+    nvtx.next("same-spin alpha");
     const bool gather = b.t3g && P.world == 1 && P.nitems > 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
     const bool gather_m = !gather && b.t3gm && P.world == 1 && P.nitems > 0;
     const bool fold = !gather && !gather_m && b.fold_ok && P.world == 1 && P.nitems > 0;
@@ -1681,6 +1686,7 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
         launch_same_spin(b, 0, P.alpha_plan, C, P.world == 1 ? sigma : yexch, b.W[0].p, st);
     }
     F2_CUDA(cudaEventRecord(b.ev[2], st));
+    nvtx.next("same-spin beta (transposed row slabs)");
     for (const auto& bp : P.beta_passes) {
         if (bp->ntr_tiles == 0)
             continue;
@@ -1693,6 +1699,7 @@ void apply(f2_sigma& b, Part& P, const double* C, double* sigma, double* yexch, 
             (*after_beta_pass)(*bp);
     }
     F2_CUDA(cudaEventRecord(b.ev[3], st));
+    nvtx.next("opposite spin");
     if (t3_streamed)
         ; // done by the caller, piece by piece
     else if (gather)
@@ -1737,7 +1744,9 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
     if (h.ndet == 0)
         return;
     // event order of this form: start, [opposite spin], e1, [H0], e2, [alpha], e3, [beta], e4
+    NvtxPhases nvtx;
     if (phases & 1) {
+        nvtx.next("rows form: opposite spin into the scatter slots");
         F2_CUDA(cudaEventRecord(b.ev[0], st));
         F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_elems * sizeof(double), st));
         if (h.na >= 1 && h.nb >= 1 && P.local_size > 0) {
@@ -1754,6 +1763,7 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
     // 2 = 4 | 8: H0 and both same-spin terms; 4 = H0 and the alpha same-spin term (needs xcols); 8 = the beta same-spin
     // term (needs only the local rows), after 4
     if (phases & (2 | 4)) {
+        nvtx.next("rows form: H0 + same-spin alpha on the column slab");
         if (P.local_size > 0) {
             scale_copy_kernel<false><<<148 * 8, 256, 0, st>>>(Cloc, sigma, b.E, P.local_size);
             b.launches += 1;
@@ -1765,6 +1775,7 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
         F2_CUDA(cudaEventRecord(b.ev[3], st));
     }
     if (phases & (2 | 8)) {
+        nvtx.next("rows form: same-spin beta on the owned rows");
         for (const auto& bp : P.beta_passes) {
             if (bp->ntr_tiles == 0)
                 continue;
@@ -1976,6 +1987,7 @@ int f2_sigma_apply_batch(f2_sigma* h, const double* C_dev, double* sigma_dev, in
 
 int f2_sigma_apply_host(f2_sigma* h, const double* C_host, double* sigma_host, int64_t n) {
     try {
+        NvtxRange nvtx("f2_sigma_apply_host (numpy to numpy)");
         const CIStringsHost& s = *h->S->host;
         if (n != s.ndet)
             throw std::invalid_argument("CISigmaBuilder.Hamiltonian: vectors must have ndet = " +
@@ -2261,6 +2273,7 @@ int f2_sigma_t3_shape(const f2_sigma* h, int64_t* out5) {
 
 int f2_sigma_hdiag(f2_sigma* h, double* out_dev, void* stream) {
     try {
+        NvtxRange nvtx("determinant energies");
         F2_CUDA(cudaSetDevice(h->device));
         if (h->hd_rows == 0)
             return F2_OK;
@@ -2322,6 +2335,7 @@ void rdm_gram(f2_sigma& b, int spin, int level, const double* L, const double* R
     const CIStringsHost& hs = *b.S->host;
     const DevStrings& D = *b.D;
     const HoleLists& HL = hs.hole_lists(spin, level);
+    NvtxRange nvtx("rdm: Gram form (1-RDM / same-spin blocks)");
     const unsigned nK_all = static_cast<unsigned>(HL.nK());
     const unsigned kfirst = static_cast<unsigned>(static_cast<uint64_t>(nK_all) * part / nparts);
     const unsigned nK = static_cast<unsigned>(static_cast<uint64_t>(nK_all) * (part + 1) / nparts) - kfirst;
@@ -2380,15 +2394,23 @@ void rdm_gram(f2_sigma& b, int spin, int level, const double* L, const double* R
 
 extern "C++" {
 template <int MW, int NTP>
-void launch_rdm_ab(const RdmAbParams& q, unsigned nas, size_t smem, cudaStream_t st) {
-    F2_CUDA(cudaFuncSetAttribute(rdm_ab_kernel<MW, NTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    rdm_ab_kernel<MW, NTP><<<nas, AB_THREADS, smem, st>>>(q);
+void launch_rdm_ab(const RdmAbParams& q, unsigned nas, size_t smem, bool long_rows, cudaStream_t st) {
+    if (long_rows) {
+        F2_CUDA(cudaFuncSetAttribute(rdm_ab_kernel<MW, NTP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+        rdm_ab_kernel<MW, NTP, true><<<nas, AB_THREADS, smem, st>>>(q);
+    } else {
+        F2_CUDA(cudaFuncSetAttribute(rdm_ab_kernel<MW, NTP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+        rdm_ab_kernel<MW, NTP, false><<<nas, AB_THREADS, smem, st>>>(q);
+    }
 }
 } // extern "C++"
 
 // opposite-spin 2-RDM in the gather form (rdm_ab_kernel); false when the space does not fit it (several determinant
 // blocks, a row of the vector longer than shared memory, more than 19 orbitals or 128 single replacements)
 bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStream_t st, int part, int nparts) {
+    NvtxRange nvtx("rdm: opposite-spin 2-RDM, gather form");
     const CIStringsHost& hs = *b.S->host;
     const DevStrings& D = *b.D;
     const DeviceLists& DL = hs.device_lists();
@@ -2406,9 +2428,18 @@ bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStre
         ntp = nt <= 5 ? 5 : 9;
     else
         ntp = 6;
-    const size_t smem = rdm_ab_smem_bytes(hs.nbs, ntp);
-    if (smem > size_t(227) * 1024 - 2048)
+    // rows longer than shared memory (CAS(18,18)): stage what fits beside the L stages, gather the rest from L2
+    size_t smem = rdm_ab_smem_bytes(hs.nbs, ntp);
+    const size_t smem_cap = size_t(227) * 1024 - 2048;
+    int64_t nsm = hs.nbs;
+    if (const char* e = std::getenv("F2_RDM_AB_NSM")) // test hook: exercise the long-row variant on a small space
+        nsm = std::min<int64_t>(nsm, std::max<int64_t>(0, std::atoll(e)));
+    if (smem > smem_cap)
+        nsm = std::min<int64_t>(nsm, (static_cast<int64_t>(smem_cap) - static_cast<int64_t>(rdm_ab_smem_bytes(0, ntp))) / 8);
+    if (nsm < 0)
         return false;
+    const bool long_rows = nsm < hs.nbs;
+    smem = rdm_ab_smem_bytes(nsm, ntp);
     const int rows = 8 * mw * 16;
     if (!b.rdm_gtab.p || b.rdm_gtab_rows != rows) {
         b.rdm_gld = (hs.nbs + 31) / 32 * 32;
@@ -2433,17 +2464,18 @@ bool rdm_ab(f2_sigma& b, const double* L, const double* R, double* out, cudaStre
     q.gld = b.rdm_gld;
     q.norb = n;
     q.n2 = n2;
+    q.nsm = static_cast<int>(nsm);
     q.first = static_cast<uint32_t>(hs.nas * part / nparts);
     const unsigned nas = static_cast<unsigned>(hs.nas * (part + 1) / nparts) - q.first;
     if (nas == 0)
         return true;
     switch (mw * 100 + ntp) {
-    case 104: launch_rdm_ab<1, 4>(q, nas, smem, st); break;
-    case 108: launch_rdm_ab<1, 8>(q, nas, smem, st); break;
-    case 116: launch_rdm_ab<1, 16>(q, nas, smem, st); break;
-    case 205: launch_rdm_ab<2, 5>(q, nas, smem, st); break;
-    case 209: launch_rdm_ab<2, 9>(q, nas, smem, st); break;
-    case 306: launch_rdm_ab<3, 6>(q, nas, smem, st); break;
+    case 104: launch_rdm_ab<1, 4>(q, nas, smem, long_rows, st); break;
+    case 108: launch_rdm_ab<1, 8>(q, nas, smem, long_rows, st); break;
+    case 116: launch_rdm_ab<1, 16>(q, nas, smem, long_rows, st); break;
+    case 205: launch_rdm_ab<2, 5>(q, nas, smem, long_rows, st); break;
+    case 209: launch_rdm_ab<2, 9>(q, nas, smem, long_rows, st); break;
+    case 306: launch_rdm_ab<3, 6>(q, nas, smem, long_rows, st); break;
     default: return false;
     }
     b.launches += 1;
@@ -2459,6 +2491,7 @@ void rdm_block(f2_sigma& b, int la, int lb, const double* L, const double* R, do
                int part = 0, int nparts = 1) {
     if (nparts < 1 || part < 0 || part >= nparts)
         throw std::invalid_argument("f2_sigma_rdm_part: need 0 <= part < nparts");
+    NvtxRange nvtx("rdm: spin block");
     const CIStringsHost& hs = *b.S->host;
     const DevStrings& D = *b.D;
     if (la < 0 || lb < 0 || la + lb < 1 || la + lb > 3)
@@ -2731,6 +2764,7 @@ int f2_sigma_rdm(f2_sigma* h, int kind, const double* L_dev, const double* R_dev
 int f2_sigma_trdm1(f2_sigma* hl, f2_sigma* hr, int spin, const double* L_dev, const double* R_dev, double* out_dev,
                    void* stream) {
     try {
+        NvtxRange nvtx("transition 1-RDM");
         if (!hl || !hr || !L_dev || !R_dev || !out_dev || spin < 0 || spin > 1)
             throw std::invalid_argument("f2_sigma_trdm1: null argument or spin outside {0, 1}");
         const CIStringsHost& SL = *hl->S->host;

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "handles.hpp"
+#include "nvtx_ranges.hpp"
 
 namespace f2 {
 namespace {
@@ -394,6 +395,7 @@ int f2_adapter_conf_ranges(const f2_adapter* h, int64_t* out) {
 
 int f2_adapter_csf_to_det(f2_adapter* h, const double* csf_dev, double* det_dev, int device, void* stream) {
     try {
+        f2::NvtxRange nvtx("CSF -> determinant transform");
         to_device(*h, device);
         F2A_CUDA(cudaSetDevice(device));
         launch_rows(h->d_det_ptr.p, h->d_det_csf.p, h->d_det_coef.p, csf_dev, det_dev, h->ndet, false,
@@ -406,6 +408,7 @@ int f2_adapter_csf_to_det(f2_adapter* h, const double* csf_dev, double* det_dev,
 
 int f2_adapter_det_to_csf(f2_adapter* h, const double* det_dev, double* csf_dev, int device, void* stream) {
     try {
+        f2::NvtxRange nvtx("determinant -> CSF transform");
         to_device(*h, device);
         F2A_CUDA(cudaSetDevice(device));
         launch_rows(h->d_csf_ptr.p, h->d_csf_det.p, h->d_csf_coef.p, det_dev, csf_dev, h->ncsf, false,
@@ -461,6 +464,7 @@ int f2_adapter_det_to_csf_host(f2_adapter* h, const double* det_host, int64_t nd
 int f2_adapter_hdiag_csf(f2_adapter* h, const double* det_energies_dev, double* out_csf_dev, int device,
                          void* stream) {
     try {
+        f2::NvtxRange nvtx("CSF preconditioner");
         to_device(*h, device);
         F2A_CUDA(cudaSetDevice(device));
         launch_rows(h->d_csf_ptr.p, h->d_csf_det.p, h->d_csf_coef.p, det_energies_dev, out_csf_dev, h->ncsf, true,

@@ -160,6 +160,18 @@ def test_rdms_through_the_d_matrix_path(name):
     assert r.returncode == 0 and "RDM-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
 
 
+@pytest.mark.parametrize("name,nsm", [("cas66", 7), ("cas88", 0), ("cas88", 33), ("cas75_odd", 16)])
+def test_ab_2rdm_long_row_variant(name, nsm):
+    """F2_RDM_AB_NSM: rdm_ab_kernel<..., LONG> (rows of R longer than shared memory, CAS(18,18)): only nsm columns of the
+    row are staged, the others are gathered from global memory"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    env = dict(os.environ, F2_RDM_AB_NSM=str(nsm))
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, name], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "RDM-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
 def test_transition_1rdms_between_two_spaces():
     import torch
     if not torch.cuda.is_available():
