@@ -1087,6 +1087,9 @@ struct SSGroupLists {
 #ifndef F2_SSG_PFB
 #define F2_SSG_PFB 2
 #endif
+#ifndef F2_SSG_MINB
+#define F2_SSG_MINB 2
+#endif
 constexpr int SSG_TW = F2_SSG_TW; // columns per CTA: a panel of all rows x SSG_TW columns of X and Y stays in L2
 constexpr int SSG_KG = F2_SSG_KG; // (N-2)-electron strings per CTA, software-pipelined
 __host__ __device__ constexpr int ssg_astride(int rows) { // smallest stride >= rows, == 4 (mod 16)
@@ -1115,7 +1118,7 @@ __device__ __forceinline__ double flip_sign(double v, unsigned signbit31) {
 // Reference counterpart: CISigmaBuilder::H2_hz_same_spin and H1_hz
 // (ci_sigma_builder_harrison_zarrabian.cc:14-195).
 template <int NM16, bool HAS8, bool AL16, bool GK>
-__global__ void __launch_bounds__(256, 2) ssg_kernel(const SSParams p, const SSGroupLists gk) {
+__global__ void __launch_bounds__(256, F2_SSG_MINB) ssg_kernel(const SSParams p, const SSGroupLists gk) {
     constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
     constexpr int S = ssg_astride(ROWS);
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -27,6 +27,7 @@
 #include "lists_device.hpp"
 #include "nvtx_ranges.hpp"
 #include "rdm_kernels.cuh"
+#include "same_spin_staged.cuh"
 
 namespace f2 {
 
@@ -1481,8 +1482,24 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     F2_CUDA(cudaGetLastError());
 }
 
+// ssb_kernel (parent rows staged in shared memory, same_spin_staged.cuh) where two CTAs of it fit one SM, else ssg_kernel
+inline bool use_staged_same_spin() {
+    static const bool on = std::getenv("F2_NO_SSB") == nullptr;
+    return on;
+}
+
 template <int NM16, bool HAS8, bool AL16, bool GK>
 void launch_ssg_variant(const SSParams& p, const SSGroupLists& gk, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem_b = ssb_smem_bytes(NM16 * 16 + (HAS8 ? 8 : 0));
+    if constexpr (2 * (smem_b + 1024 + 64) <= size_t(227) * 1024) {
+        if (use_staged_same_spin()) {
+            if (smem_b > 48 * 1024)
+                F2_CUDA(cudaFuncSetAttribute(ssb_kernel<NM16, HAS8, AL16, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem_b)));
+            ssb_kernel<NM16, HAS8, AL16, GK><<<grid, 256, smem_b, st>>>(p, gk);
+            return;
+        }
+    }
     constexpr size_t smem = ssg_smem_bytes(NM16 * 16 + (HAS8 ? 8 : 0));
     if (smem > 48 * 1024)
         F2_CUDA(cudaFuncSetAttribute(ssg_kernel<NM16, HAS8, AL16, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Device time of every RDM spin block of CAS(n,n) through f2_sigma_rdm (CUDA events around the C-ABI call, result left
-on the device): usage rdm_time.py n [memory_mb] [max body].  Prints one JSON line per block: ms, executed DMMA flops
+on the device): usage rdm_time.py n [memory_mb] [max body]; RDM_KINDS=ab_2rdm,... restricts the blocks.  Prints one JSON line per block: ms, executed DMMA flops
 (2 M_pad^2 K with the 128-row tile padding), useful flops (2 M^2 K), TFLOP/s of both."""
 import json
 import os
@@ -29,7 +29,7 @@ def main():
     kinds = {"a_1rdm": (0, 1, 0), "b_1rdm": (1, 0, 1), "aa_2rdm": (3, 2, 0), "bb_2rdm": (4, 0, 2), "ab_2rdm": (5, 1, 1),
              "aaa_3rdm": (8, 3, 0), "aab_3rdm": (9, 2, 1), "abb_3rdm": (10, 1, 2), "bbb_3rdm": (11, 0, 3)}
     for name, (kind, la, lb) in kinds.items():
-        if la + lb > body:
+        if la + lb > body or (os.environ.get("RDM_KINDS") and name not in os.environ["RDM_KINDS"].split(",")):
             continue
         M = comb(n, la) * comb(n, lb)
         K = comb(n, na - la) * comb(n, nb - lb)
@@ -44,7 +44,8 @@ def main():
         ms = e0.elapsed_time(e1)
         Mp = (M + 127) // 128 * 128
         tr = float(out.view(M, M).diagonal().sum())
-        want_tr = comb(na, la) * comb(nb, lb) * float(c @ c)
+        cc = sum(float(c[i:i + (1 << 30)] @ c[i:i + (1 << 30)]) for i in range(0, c.numel(), 1 << 30))  # dot stops at 2^31 - 1
+        want_tr = comb(na, la) * comb(nb, lb) * cc
         print(json.dumps({"n": n, "block": name, "M": M, "K": K, "ms": round(ms, 3), "launches": b.launch_count(),
                           "useful_tflops": round(2 * M * M * K / ms / 1e9, 2),
                           "executed_tflops": round(2 * Mp * Mp * K / ms / 1e9, 2),
