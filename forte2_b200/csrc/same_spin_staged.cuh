@@ -28,9 +28,16 @@ __host__ __device__ constexpr int ssb_astride(int rows) { // smallest stride >= 
         ++s;
     return s;
 }
-constexpr size_t ssb_smem_bytes(int rows) {
+__host__ __device__ constexpr size_t ssb_smem_bytes(int rows, int nwarps) {
     return 2 * size_t(rows) * ssb_astride(rows) * 8 + size_t(SSG_KG) * rows * (8 + 8 + 4) +
-           size_t(8) * SSB_NSTG * SSB_STAGE * 8 + 16;
+           size_t(nwarps) * SSB_NSTG * SSB_STAGE * 8 + 16;
+}
+// two CTAs of 8 warps per SM, which fit up to 56 parent rows per string.  One CTA of 16 warps for 57..80 rows (the
+// shape of the 3-GAS / 20-orbital spaces) was measured and is slower than ssg_kernel there (13.5 against 10.6 ms per
+// spin on the 22 M determinant twin, profiles/r3a_quick_ssb_16_warps.log): those shapes stay with ssg_kernel.
+__host__ __device__ constexpr int ssb_warps(int) { return 8; }
+__host__ __device__ constexpr bool ssb_fits(int rows) {
+    return 2 * (ssb_smem_bytes(rows, ssb_warps(rows)) + 1024 + 64) <= size_t(227) * 1024;
 }
 
 template <int N> __device__ __forceinline__ void cp_async_wait_n() {
@@ -47,13 +54,15 @@ __device__ __forceinline__ int ssb_pos(int c) {
 }
 
 template <int NM16, bool HAS8, bool AL16, bool GK>
-__global__ void __launch_bounds__(256, 2) ssb_kernel(const SSParams p, const SSGroupLists gk) {
+__global__ void __launch_bounds__(32 * ssb_warps(NM16 * 16 + (HAS8 ? 8 : 0)), ssb_warps(NM16 * 16 + (HAS8 ? 8 : 0)) == 8 ? 2 : 1)
+    ssb_kernel(const SSParams p, const SSGroupLists gk) {
     constexpr int ROWS = NM16 * 16 + (HAS8 ? 8 : 0);
     constexpr int S = ssb_astride(ROWS);
+    constexpr int NW = ssb_warps(ROWS);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Abuf = reinterpret_cast<double*>(smem_raw);                        // [2][ROWS][S]
-    double* Bring = Abuf + 2 * ROWS * S;                                       // [8 warps][SSB_NSTG][8][SSB_BSTR]
-    long long* msrcK = reinterpret_cast<long long*>(Bring + 8 * SSB_NSTG * SSB_STAGE); // [SSG_KG][ROWS]
+    double* Bring = Abuf + 2 * ROWS * S;                                       // [NW warps][SSB_NSTG][8][SSB_BSTR]
+    long long* msrcK = reinterpret_cast<long long*>(Bring + NW * SSB_NSTG * SSB_STAGE); // [SSG_KG][ROWS]
     long long* mdstK = msrcK + SSG_KG * ROWS;
     unsigned* minfoK = reinterpret_cast<unsigned*>(mdstK + SSG_KG * ROWS);
     __shared__ int s_m[SSG_KG];
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(256, 2) ssb_kernel(const SSParams p, const SSG
                          : (p.nk - k_first < SSG_KG ? p.nk - k_first : SSG_KG);
 
     // parent lists of all strings of this CTA, one string per warp
-    for (int j = warp; j < SSG_KG; j += 8) {
+    for (int j = warp; j < SSG_KG; j += NW) {
         long long* msrc = msrcK + j * ROWS;
         long long* mdst = mdstK + j * ROWS;
         unsigned* minfo = minfoK + j * ROWS;
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(256, 2) ssb_kernel(const SSParams p, const SSG
         const int m = s_m[j];
         double* A = Abuf + (j & 1) * ROWS * S;
         const int rows_used = ((m + 15) >> 4) << 4; // only the 16-row tiles that hold parents are multiplied
-        for (int idx = tid; idx < (rows_used < ROWS ? rows_used : ROWS) * S; idx += 256) {
+        for (int idx = tid; idx < (rows_used < ROWS ? rows_used : ROWS) * S; idx += 32 * NW) {
             const int a = idx / S, b = idx - a * S;
             const bool in = a < m && b < m;
             const double* src = in ? p.W + static_cast<size_t>(minfo[a] & 0xffff) * p.P + (minfo[b] & 0xffff) : p.W;
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(256, 2) ssb_kernel(const SSParams p, const SSG
             // advance: next stage of the chunk, else the next chunk of the string, else the next string
             if (++ps >= (m + 7) >> 3) {
                 ps = 0;
-                pc += 8;
+                pc += NW;
                 if (pc >= nchunks) {
                     pc = warp;
                     ++pj;
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) ssb_kernel(const SSParams p, const SSG
                 esg |= (minfo[8 * i + g] >> 31) << i;
         }
         const double* ap = Abuf + (j & 1) * ROWS * S + g * S + t;
-        for (int chunk = warp; chunk < nchunks && m > 0; chunk += 8) {
+        for (int chunk = warp; chunk < nchunks && m > 0; chunk += NW) {
             const int n0 = j0 + (chunk << 4);
             double acc[NM16 > 0 ? NM16 : 1][2][4];
             double acc8[2][2];
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(256, 2) ssb_kernel(const SSParams p, const SSG
         }
         // the block of string j + 1 is older than the SSB_NSTG - 1 stages in flight, so the ring is not drained -
         // unless this warp committed fewer groups than that since the block copy (no parents, no chunk, short lists)
-        if (m > 0 && warp < nchunks && nst * ((nchunks - warp + 7) >> 3) >= SSB_NSTG - 1)
+        if (m > 0 && warp < nchunks && nst * ((nchunks - warp + NW - 1) / NW) >= SSB_NSTG - 1)
             cp_async_wait_n<SSB_NSTG - 1>();
         else
             cp_async_wait<0>();

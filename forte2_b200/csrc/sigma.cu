@@ -1482,21 +1482,27 @@ void launch_t3(const f2_sigma& b, const Part& P, const double* C, double* sigma,
     F2_CUDA(cudaGetLastError());
 }
 
-// ssb_kernel (parent rows staged in shared memory, same_spin_staged.cuh) where two CTAs of it fit one SM, else ssg_kernel
-inline bool use_staged_same_spin() {
-    static const bool on = std::getenv("F2_NO_SSB") == nullptr;
-    return on;
+// ssb_kernel (parent rows staged in shared memory, same_spin_staged.cuh) or ssg_kernel (parent rows through registers).
+// Measured (profiles/r2x_quick.log): ssb_kernel is 24 % faster on symmetry-blocked spaces (CAS(16,16) D2h: 3.63 against
+// 4.78 ms per spin), where strings without parents in a column group and short lists break ssg_kernel's register
+// pipeline; on one determinant block both sit at the same L2 reduction rate and ssg_kernel is 4 % faster (19.4 / 20.2 ms
+// at CAS(16,16)).  Default: ssb_kernel for spaces with per-group string lists and up to 56 parent rows per string (two CTAs of
+// it per SM); CAS(16,16) C2v: 5.48 against 6.25 ms per spin (profiles/r3a_quick_ssb_16_warps.log).
+// F2_NO_SSB: never; F2_SSB_ALWAYS: wherever it fits.
+inline int staged_same_spin_mode() {
+    return std::getenv("F2_NO_SSB") ? 0 : (std::getenv("F2_SSB_ALWAYS") ? 2 : 1); // read per launch: a test hook
 }
 
 template <int NM16, bool HAS8, bool AL16, bool GK>
 void launch_ssg_variant(const SSParams& p, const SSGroupLists& gk, dim3 grid, cudaStream_t st) {
-    constexpr size_t smem_b = ssb_smem_bytes(NM16 * 16 + (HAS8 ? 8 : 0));
-    if constexpr (2 * (smem_b + 1024 + 64) <= size_t(227) * 1024) {
-        if (use_staged_same_spin()) {
+    constexpr int rows_b = NM16 * 16 + (HAS8 ? 8 : 0);
+    if constexpr (ssb_fits(rows_b)) {
+        if (staged_same_spin_mode() == 2 || (staged_same_spin_mode() == 1 && GK)) {
+            constexpr size_t smem_b = ssb_smem_bytes(rows_b, ssb_warps(rows_b));
             if (smem_b > 48 * 1024)
                 F2_CUDA(cudaFuncSetAttribute(ssb_kernel<NM16, HAS8, AL16, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem_b)));
-            ssb_kernel<NM16, HAS8, AL16, GK><<<grid, 256, smem_b, st>>>(p, gk);
+            ssb_kernel<NM16, HAS8, AL16, GK><<<grid, 32 * ssb_warps(rows_b), smem_b, st>>>(p, gk);
             return;
         }
     }

@@ -71,3 +71,40 @@ def test_spaces_with_long_lists(torch_cuda, name):
     err, ns = sampled.sampled_rel_error(space, E, H, V, c, sigma, nsamp=800)
     print(name, strings.ndet, ns, err)
     assert ns > 100 and err <= TOL
+
+
+# ---- ssb_kernel (same-spin term with the parent rows staged in shared memory, csrc/same_spin_staged.cuh): the default
+# for spaces with several determinant blocks; forced everywhere with F2_SSB_ALWAYS, switched off with F2_NO_SSB
+STAGED_SHAPES = {
+    # 66 / 78 parents per (N-2)-electron string: beyond the staged kernel's 56 rows (ssg_kernel in every mode), one block
+    "a3b2_13": (3, 2, 0, [[0] * 13], [], []),
+    # the same with symmetry: per-group string lists, strings without parents in a group
+    "a3b3_13_sym": (3, 3, 1, [[0, 1, 2, 3] * 3 + [0]], [], []),
+    # 55 parents (CAS(18,18)'s shape, 56 rows, two CTAs of 8 warps), odd row lengths: the 8-byte copy path
+    "a4b3_13": (4, 3, 0, [[0] * 13], [], []),
+    # two GAS spaces, up to 91 / 105 parents: beyond the staged kernel's envelope (ssg_kernel in every mode)
+    "gas_15": (3, 2, 0, [[0] * 7, [0] * 8], [0, 0], [5, 5]),
+}
+
+
+@pytest.mark.parametrize("mode", ["F2_SSB_ALWAYS", "F2_NO_SSB"])
+@pytest.mark.parametrize("name", sorted(SMALL_SPACES) + sorted(STAGED_SHAPES))
+def test_staged_same_spin_kernel(torch_cuda, monkeypatch, name, mode):
+    import forte2_b200 as f2
+    from oracle import checker, sampled
+    torch = torch_cuda
+    monkeypatch.setenv(mode, "1")
+    space = SMALL_SPACES.get(name) or STAGED_SHAPES[name]
+    n = sum(len(s) for s in space[3])
+    E, H, V = synthetic.integrals(n, "S")
+    strings = f2.CIStrings(*space)
+    b = f2.CISigmaBuilder(strings, E, H, V, 0)
+    c = synthetic.trial_vector(max(strings.ndet, 1))[: strings.ndet].copy()
+    got = np.full_like(c, np.nan)
+    b.Hamiltonian(c, got)
+    if strings.ndet <= 20000:
+        want, _ = checker.sigma(space, E, H, V, c, dets=strings.make_determinants())
+        assert _rel(got, want) <= TOL
+    else:
+        err, nsamp = sampled.sampled_rel_error(space, E, H, V, torch.from_numpy(c).cuda(), torch.from_numpy(got).cuda(), nsamp=1500)
+        assert err <= TOL, (name, err)
