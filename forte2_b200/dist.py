@@ -395,6 +395,26 @@ class ShardedSigma:
             self._mark("all-to-all of the alpha same-spin term + add")
 
 
+    def Hamiltonian_host(self, c_loc_host, sigma_loc_host) -> None:
+        """The local shard from and to host memory (numpy arrays or CPU tensors of local_size doubles; pinned memory makes
+        both copies asynchronous DMA): H2D of the shard, the sharded build, D2H of the result, all on the current
+        stream, which is synchronised before returning - what a host-resident solver (forte2's numpy Davidson-Liu on
+        each rank's slice, forte2/helpers/davidsonliu.py) calls."""
+        ch = torch.from_numpy(c_loc_host) if isinstance(c_loc_host, np.ndarray) else c_loc_host
+        sh = torch.from_numpy(sigma_loc_host) if isinstance(sigma_loc_host, np.ndarray) else sigma_loc_host
+        if ch.numel() != self.local_size or sh.numel() != self.local_size:
+            raise ValueError(f"Hamiltonian_host: the local vectors must have {self.local_size} elements")
+        if ch.dtype != torch.float64 or sh.dtype != torch.float64 or ch.is_cuda or sh.is_cuda:
+            raise ValueError("Hamiltonian_host: float64 host vectors expected")
+        if getattr(self, "_host_c", None) is None:
+            self._host_c = torch.empty(max(self.local_size, 1), **self._kw)[: self.local_size]
+            self._host_s = torch.empty(max(self.local_size, 1), **self._kw)[: self.local_size]
+        self._host_c.copy_(ch.reshape(-1), non_blocking=True)
+        self.Hamiltonian(self._host_c, self._host_s)
+        sh.reshape(-1).copy_(self._host_s, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
+
 class LibraryShardedSigma:
     """The rows form with the collectives issued by the C library itself (f2_dist_init / f2_dist_apply: NCCL resolved by
     the library, two communicators, library-owned streams): what a host without torch.distributed calls.  Here the

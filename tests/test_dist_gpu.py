@@ -53,6 +53,15 @@ def _worker(rank, world, port, spaces, result_dir):
                 sh.Hamiltonian(c_loc, sigma_loc)  # twice: no dependence on leftovers
                 got = sh.all_gather_full(sigma_loc).clone()
                 errs.append(float((got - want).norm() / want.norm()))
+                # the shard from and to host memory (pageable numpy, then pinned tensors)
+                c_np = c_loc.cpu().numpy()
+                s_np = np.full_like(c_np, np.nan)
+                sh.Hamiltonian_host(c_np, s_np)
+                c_pin = torch.empty(c_loc.numel(), dtype=torch.float64, pin_memory=True).copy_(c_loc)
+                s_pin = torch.full((c_loc.numel(),), float("nan"), dtype=torch.float64).pin_memory()
+                sh.Hamiltonian_host(c_pin, s_pin)
+                assert np.linalg.norm(s_np - s_pin.numpy()) <= 1e-12 * np.linalg.norm(s_np)  # reductions commute, not bitwise
+                errs.append(float((sh.all_gather_full(s_pin.cuda()) - want).norm() / want.norm()))
             if "rows" in forms:
                 # the same build with the collectives issued by the C library (f2_dist_init / f2_dist_apply)
                 from forte2_b200.dist import LibraryShardedSigma
