@@ -792,8 +792,19 @@ constexpr uint32_t kNoRow = 0xffffffffu;
 //     multiplies (8 + 8 independent loads per lane instead of 2 + 2);
 //   * accumulators are T3GP_TG tiles only (wider row sets re-gather the operand per tile group), which leaves
 //     registers for 16 warps per SM.
-constexpr int T3GP_KB = 4;
-constexpr int T3GP_TG = 2;
+// (the F2_T3GP_* macros are tuning hooks like F2_SSG_*; the defaults are the measured best)
+#ifndef F2_T3GP_KB
+#define F2_T3GP_KB 4
+#endif
+#ifndef F2_T3GP_TG
+#define F2_T3GP_TG 2
+#endif
+#ifndef F2_T3GP_THREADS
+#define F2_T3GP_THREADS 512
+#endif
+constexpr int T3GP_KB = F2_T3GP_KB;
+constexpr int T3GP_TG = F2_T3GP_TG;
+constexpr int T3GP_THREADS = F2_T3GP_THREADS;
 constexpr int T3GP_MAXROWS = 128;
 
 constexpr size_t t3gp_smem_bytes(int rows, int astride, int nclsB, int mpad) {
@@ -801,9 +812,13 @@ constexpr size_t t3gp_smem_bytes(int rows, int astride, int nclsB, int mpad) {
            size_t(nclsB) * rows + size_t(nclsB) * mpad * 2 + 64;
 }
 
-template <int THREADS>
+// KB (k-steps per batch) and TG (row tiles per work item) are template parameters: the best pair depends on the lengths
+// of the per-class k lists and row sets of the space (profiles/r3d_quick_t3gp_shapes.log: (3, 2) is 5 % faster than
+// (4, 2) on the 3-GAS / 20-orbital twin and 9 % slower on CAS(16,16) D2h, (4, 1) is 5 % faster on D2h and 18 % slower
+// on C2v); the host tries six instances on the first builds of a builder and keeps the fastest (launch_t3gm).
+template <int THREADS, int KB = T3GP_KB, int TG = T3GP_TG>
 __global__ void __launch_bounds__(THREADS, 1) t3gp_kernel(const T3GMParams p) {
-    constexpr int KB = T3GP_KB, TG = T3GP_TG, NW = THREADS / 32;
+    constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;

@@ -282,6 +282,17 @@ struct f2_sigma {
     double last_ms[5] = {0, 0, 0, 0, 0};
     long builds = 0;
     mutable int64_t launches = 0; // kernels launched by the last build
+    // t3gp_kernel: shape (k-steps per batch, row tiles per item) chosen by timing the candidates on the first builds
+    struct T3gpTune {
+        static constexpr int kCand = 6;
+        int choice = -1;   // index of the chosen candidate, -1 while trying
+        int calls = 0;     // launches so far (the first one is not timed: first-use costs)
+        int trial = 0;     // candidate of the launch whose events are pending
+        bool pending = false;
+        float ms[kCand] = {};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+    };
+    mutable T3gpTune t3gp_tune;
     // reduced density matrices: hole lists of (spin, level) on the device (uploaded on first use) and the two
     // D buffers of the gather + GEMM formulation (csrc/rdm_kernels.cuh)
     struct RdmLists {
@@ -318,6 +329,9 @@ struct f2_sigma {
             cudaStreamDestroy(own_stream2);
         if (t3_ev)
             cudaEventDestroy(t3_ev);
+        for (cudaEvent_t e : t3gp_tune.ev)
+            if (e)
+                cudaEventDestroy(e);
         if (copy_stream)
             cudaStreamDestroy(copy_stream);
         if (copy_ev)
@@ -1393,6 +1407,23 @@ void launch_t3g(const f2_sigma& b, const double* C, double* sigma, cudaStream_t 
 // gather-form opposite-spin term for spaces with several determinant blocks.  One GPU: every alpha string,
 // C and sigma in the CI-vector layout.  Sharded (P given): the owned input strings, C = the local vector,
 // sigma = the reduce-scatter buffer in the slot layout.
+template <int KB, int TG>
+void launch_t3gp_inst(const T3GMParams& p, int nrows, size_t smem, cudaStream_t st) {
+    constexpr int THREADS = T3GP_THREADS;
+    F2_CUDA(cudaFuncSetAttribute(t3gp_kernel<THREADS, KB, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    t3gp_kernel<THREADS, KB, TG><<<nrows, THREADS, smem, st>>>(p);
+}
+void launch_t3gp_shape(int shape, const T3GMParams& p, int nrows, size_t smem, cudaStream_t st) {
+    switch (shape) {
+    case 1: launch_t3gp_inst<3, 2>(p, nrows, smem, st); break;
+    case 2: launch_t3gp_inst<4, 1>(p, nrows, smem, st); break;
+    case 3: launch_t3gp_inst<3, 1>(p, nrows, smem, st); break;
+    case 4: launch_t3gp_inst<5, 1>(p, nrows, smem, st); break;
+    case 5: launch_t3gp_inst<3, 3>(p, nrows, smem, st); break;
+    default: launch_t3gp_inst<T3GP_KB, T3GP_TG>(p, nrows, smem, st); break;
+    }
+}
+
 void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t st, const Part* P = nullptr) {
     const CIStringsHost& h = *b.S->host;
     const DevStrings& D = *b.D;
@@ -1422,10 +1453,43 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     const int nrows = P ? P->njlist : static_cast<int>(h.nas);
     if (nrows == 0)
         return;
-    constexpr int THREADS = 512;
-    F2_CUDA(cudaFuncSetAttribute(t3gp_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(b.gm_smem)));
-    t3gp_kernel<THREADS><<<nrows, THREADS, b.gm_smem, st>>>(p);
+    // candidates (KB, TG): (4, 2), (3, 2), (4, 1), (3, 1), (5, 1), (3, 3) - the instances without register spills at 512
+    // threads.  Every candidate computes the same sigma, so the first builds of a builder simply take turns (launch 0
+    // untimed, then one timed launch each) and the fastest one is kept; F2_T3GP_SHAPE=<0..5> pins one (tests, tuning).
+    f2_sigma::T3gpTune& T = b.t3gp_tune;
+    if (T.choice < 0) {
+        if (const char* e = std::getenv("F2_T3GP_SHAPE")) {
+            T.choice = std::min(std::max(std::atoi(e), 0), f2_sigma::T3gpTune::kCand - 1);
+        } else {
+            if (T.pending) {
+                F2_CUDA(cudaEventSynchronize(T.ev[1]));
+                F2_CUDA(cudaEventElapsedTime(&T.ms[T.trial], T.ev[0], T.ev[1]));
+                T.pending = false;
+            }
+            if (T.calls > f2_sigma::T3gpTune::kCand) {
+                T.choice = static_cast<int>(std::min_element(T.ms, T.ms + f2_sigma::T3gpTune::kCand) - T.ms);
+                if (std::getenv("F2_T3GP_TRACE"))
+                    std::fprintf(stderr, "t3gp_kernel shapes (KB, TG) = (4, 2) %.3f, (3, 2) %.3f, (4, 1) %.3f, (3, 1) %.3f, (5, 1) %.3f, "
+                                         "(3, 3) %.3f ms: shape %d kept\n",
+                                 T.ms[0], T.ms[1], T.ms[2], T.ms[3], T.ms[4], T.ms[5], T.choice);
+            }
+        }
+    }
+    const bool timing = T.choice < 0 && T.calls >= 1;
+    const int shape = T.choice >= 0 ? T.choice : (T.calls == 0 ? 0 : T.calls - 1);
+    if (timing) {
+        for (cudaEvent_t& e : T.ev)
+            if (!e)
+                F2_CUDA(cudaEventCreate(&e));
+        F2_CUDA(cudaEventRecord(T.ev[0], st));
+    }
+    launch_t3gp_shape(shape, p, nrows, b.gm_smem, st);
+    if (timing) {
+        F2_CUDA(cudaEventRecord(T.ev[1], st));
+        T.trial = shape;
+        T.pending = true;
+    }
+    T.calls += 1;
     b.launches += 1;
     F2_CUDA(cudaGetLastError());
 }

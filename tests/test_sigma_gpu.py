@@ -284,3 +284,24 @@ def test_gather_form_over_several_beta_classes(ref, torch_cuda, monkeypatch, nam
     gb.Hamiltonian(c, got)
     rb.Hamiltonian(c, want)
     assert _rel(got, want) <= TOL
+
+
+@pytest.mark.parametrize("shape", ["0", "1", "2", "3", "4", "5", "auto"])
+@pytest.mark.parametrize("name", ["gas343_54", "cas66_d2h", "gas2_sym4"])
+def test_block_aware_gather_kernel_shapes(ref, torch_cuda, monkeypatch, name, shape):
+    """t3gp_kernel<512, KB, TG>: the six (k-steps per batch, row tiles per item) instances pinned with F2_T3GP_SHAPE, and
+    the default: the first builds of a builder take turns through them (launch_t3gm times each once) and the fastest is
+    kept - nine builds in a row, every one against the reference."""
+    if shape != "auto":
+        monkeypatch.setenv("F2_T3GP_SHAPE", shape)
+    space = SMALL_SPACES[name]
+    n = sum(len(s) for s in space[3])
+    rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
+    assert gb.t3_shape()["form"] == "gather"
+    want = np.zeros(rs.ndet)
+    for i in range(9 if shape == "auto" else 2):
+        c = synthetic.trial_vector(rs.ndet) * (1.0 + 0.25 * i)
+        rb.Hamiltonian(c, want)
+        got = np.full_like(c, np.nan)
+        gb.Hamiltonian(c, got)
+        assert _rel(got, want) <= TOL, (name, shape, i)
