@@ -804,9 +804,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         for name in names:
             torch.cuda.reset_peak_memory_stats(dev)
-            # spaces with several determinant blocks: the first seven builds of a builder take turns through the shapes of
+            # spaces with several determinant blocks: the first four builds of a builder take turns through the shapes of
             # t3gp_kernel (launch_t3gm) - they are warm-up, not measurement
-            r, lv = measure_space(ctx, name, 3, 7 if name.startswith("gas") else 1, 64 * 1024, form=args.form, nsamp=1024,
+            r, lv = measure_space(ctx, name, 3, 4 if name.startswith("gas") else 1, 64 * 1024, form=args.form, nsamp=1024,
                                   parity=not args.no_parity)
             lastn = [r["term_ms_last_step"][k] for k in ("H0", "same_spin_alpha", "same_spin_beta", "opposite_spin", "total")]
             if rank == 0:

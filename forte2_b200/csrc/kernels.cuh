@@ -815,7 +815,7 @@ constexpr size_t t3gp_smem_bytes(int rows, int astride, int nclsB, int mpad) {
 // KB (k-steps per batch) and TG (row tiles per work item) are template parameters: the best pair depends on the lengths
 // of the per-class k lists and row sets of the space (profiles/r3d_quick_t3gp_shapes.log: (3, 2) is 5 % faster than
 // (4, 2) on the 3-GAS / 20-orbital twin and 9 % slower on CAS(16,16) D2h, (4, 1) is 5 % faster on D2h and 18 % slower
-// on C2v); the host tries six instances on the first builds of a builder and keeps the fastest (launch_t3gm).
+// on C2v); the host tries three instances on the first builds of a builder and keeps the fastest (launch_t3gm).
 template <int THREADS, int KB = T3GP_KB, int TG = T3GP_TG>
 __global__ void __launch_bounds__(THREADS, 1) t3gp_kernel(const T3GMParams p) {
     constexpr int NW = THREADS / 32;

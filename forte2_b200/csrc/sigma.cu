@@ -284,7 +284,8 @@ struct f2_sigma {
     mutable int64_t launches = 0; // kernels launched by the last build
     // t3gp_kernel: shape (k-steps per batch, row tiles per item) chosen by timing the candidates on the first builds
     struct T3gpTune {
-        static constexpr int kCand = 6;
+        static constexpr int kCand = 3;   // instances that take part in the timing
+        static constexpr int kShapes = 6; // instances that exist (F2_T3GP_SHAPE pins any of them)
         int choice = -1;   // index of the chosen candidate, -1 while trying
         int calls = 0;     // launches so far (the first one is not timed: first-use costs)
         int trial = 0;     // candidate of the launch whose events are pending
@@ -1453,13 +1454,14 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
     const int nrows = P ? P->njlist : static_cast<int>(h.nas);
     if (nrows == 0)
         return;
-    // candidates (KB, TG): (4, 2), (3, 2), (4, 1), (3, 1), (5, 1), (3, 3) - the instances without register spills at 512
-    // threads.  Every candidate computes the same sigma, so the first builds of a builder simply take turns (launch 0
-    // untimed, then one timed launch each) and the fastest one is kept; F2_T3GP_SHAPE=<0..5> pins one (tests, tuning).
+    // shapes (KB, TG): (4, 2), (3, 2), (4, 1) take part in the timing; (3, 1), (5, 1), (3, 3) exist (no register spills at
+    // 512 threads) but won on none of the measured spaces (profiles/r3f_spaces_t3gp_six_shapes.log) and are only reachable
+    // through F2_T3GP_SHAPE=<0..5>, which pins a shape (tests, tuning).  Every shape computes the same sigma, so the first
+    // builds of a builder simply take turns (launch 0 untimed, then one timed launch each) and the fastest one is kept.
     f2_sigma::T3gpTune& T = b.t3gp_tune;
     if (T.choice < 0) {
         if (const char* e = std::getenv("F2_T3GP_SHAPE")) {
-            T.choice = std::min(std::max(std::atoi(e), 0), f2_sigma::T3gpTune::kCand - 1);
+            T.choice = std::min(std::max(std::atoi(e), 0), f2_sigma::T3gpTune::kShapes - 1);
         } else {
             if (T.pending) {
                 F2_CUDA(cudaEventSynchronize(T.ev[1]));
@@ -1469,9 +1471,8 @@ void launch_t3gm(const f2_sigma& b, const double* C, double* sigma, cudaStream_t
             if (T.calls > f2_sigma::T3gpTune::kCand) {
                 T.choice = static_cast<int>(std::min_element(T.ms, T.ms + f2_sigma::T3gpTune::kCand) - T.ms);
                 if (std::getenv("F2_T3GP_TRACE"))
-                    std::fprintf(stderr, "t3gp_kernel shapes (KB, TG) = (4, 2) %.3f, (3, 2) %.3f, (4, 1) %.3f, (3, 1) %.3f, (5, 1) %.3f, "
-                                         "(3, 3) %.3f ms: shape %d kept\n",
-                                 T.ms[0], T.ms[1], T.ms[2], T.ms[3], T.ms[4], T.ms[5], T.choice);
+                    std::fprintf(stderr, "t3gp_kernel shapes (KB, TG) = (4, 2) %.3f, (3, 2) %.3f, (4, 1) %.3f ms: shape %d kept\n", T.ms[0],
+                                 T.ms[1], T.ms[2], T.choice);
             }
         }
     }

@@ -291,7 +291,7 @@ def test_gather_form_over_several_beta_classes(ref, torch_cuda, monkeypatch, nam
 def test_block_aware_gather_kernel_shapes(ref, torch_cuda, monkeypatch, name, shape):
     """t3gp_kernel<512, KB, TG>: the six (k-steps per batch, row tiles per item) instances pinned with F2_T3GP_SHAPE, and
     the default: the first builds of a builder take turns through them (launch_t3gm times each once) and the fastest is
-    kept - nine builds in a row, every one against the reference."""
+    kept - six builds in a row, every one against the reference."""
     if shape != "auto":
         monkeypatch.setenv("F2_T3GP_SHAPE", shape)
     space = SMALL_SPACES[name]
@@ -299,7 +299,7 @@ def test_block_aware_gather_kernel_shapes(ref, torch_cuda, monkeypatch, name, sh
     rs, rb, gs, gb = _pair(ref, space, synthetic.integrals(n, "S"))
     assert gb.t3_shape()["form"] == "gather"
     want = np.zeros(rs.ndet)
-    for i in range(9 if shape == "auto" else 2):
+    for i in range(6 if shape == "auto" else 2):
         c = synthetic.trial_vector(rs.ndet) * (1.0 + 0.25 * i)
         rb.Hamiltonian(c, want)
         got = np.full_like(c, np.nan)
