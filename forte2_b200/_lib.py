@@ -70,6 +70,8 @@ SIGNATURES = {
     "f2_sigma_rows_form": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p]),
     "f2_sigma_apply_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "f2_sigma_apply_rows_t3_piece": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                               C.c_int, C.c_void_p]),
     "f2_slater_matrix": (C.c_int, [C.c_void_p, C.c_double, f64p, f64p, i64p, C.c_int, f64p]),
     "f2_adapter_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "f2_adapter_destroy": (None, [C.c_void_p]),

@@ -1879,6 +1879,35 @@ void apply_rows(f2_sigma& b, Part& P, const double* Cloc, const double* xcols, d
     F2_CUDA(cudaGetLastError());
 }
 
+// Phase 1 of apply_rows in pieces (one determinant block, t3g_kernel): the opposite-spin term of the local input rows
+// [row0, row0 + nrows) only, so that a host-resident shard can be multiplied while its later rows are still crossing
+// PCIe.  flags: 1 = first piece of a build (event set, scatter zeroed), 2 = last piece (closes the term's time).
+void apply_rows_t3_piece(f2_sigma& b, Part& P, const double* Cloc, double* scatter, int64_t row0, int64_t nrows, int flags,
+                         cudaStream_t st) {
+    const CIStringsHost& h = *b.S->host;
+    F2_CUDA(cudaSetDevice(b.device));
+    if (!b.t3g)
+        throw std::runtime_error("CISigmaBuilder: the opposite-spin term in pieces needs the one-block gather kernel");
+    const int64_t rows = P.hi[0] - P.lo[0];
+    if (row0 < 0 || nrows < 0 || row0 + nrows > rows)
+        throw std::invalid_argument("CISigmaBuilder: piece outside the local rows");
+    NvtxRange nvtx("rows form: opposite spin, one piece of the local rows");
+    if (flags & 1) {
+        begin_build(b);
+        b.t3_first[b.ev_idx] = true;
+        b.launches = 0;
+        if (!P.beta_planned)
+            plan_beta(b, P);
+        F2_CUDA(cudaEventRecord(b.ev[0], st));
+        F2_CUDA(cudaMemsetAsync(scatter, 0, static_cast<size_t>(P.world) * P.slot_elems * sizeof(double), st));
+    }
+    if (h.na >= 1 && h.nb >= 1 && nrows > 0)
+        launch_t3g(b, Cloc - P.lo[0] * h.nbs, scatter, st, static_cast<int>(P.lo[0] + row0), static_cast<int>(nrows), P.rowpad.p);
+    if (flags & 2)
+        F2_CUDA(cudaEventRecord(b.ev[1], st));
+    F2_CUDA(cudaGetLastError());
+}
+
 // the rows form needs the gather-form kernel and 16-byte aligned row slabs (even nbs)
 bool rows_form_ok(const f2_sigma& b) {
     const CIStringsHost& h = *b.S->host;
@@ -2333,6 +2362,24 @@ int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xc
         Part& P = shard_of(*h, rank, world);
         apply_rows(*h, P, C_local_dev, xcols_dev, sigma_local_dev, ycols_dev, scatter_dev, phases,
                    static_cast<cudaStream_t>(stream));
+        return F2_OK;
+    } catch (const std::exception& e) {
+        return status_of(e);
+    }
+}
+
+int f2_sigma_apply_rows_t3_piece(f2_sigma* h, const double* C_local_dev, double* scatter_dev, int rank, int world,
+                                 int64_t row_first, int64_t row_count, int flags, void* stream) {
+    try {
+        if (!h || !C_local_dev || !scatter_dev)
+            throw std::invalid_argument("null argument");
+        if (world <= 1 || !rows_form_ok(*h) || !h->t3g)
+            throw std::runtime_error("CISigmaBuilder: the opposite-spin term in pieces needs the rows form of a space with one "
+                                     "determinant block (f2_sigma_rows_form, f2_sigma_t3_shape)");
+        if ((reinterpret_cast<uintptr_t>(C_local_dev) & 15) != 0)
+            throw std::invalid_argument("CISigmaBuilder: the local trial vector must be 16-byte aligned");
+        Part& P = shard_of(*h, rank, world);
+        apply_rows_t3_piece(*h, P, C_local_dev, scatter_dev, row_first, row_count, flags, static_cast<cudaStream_t>(stream));
         return F2_OK;
     } catch (const std::exception& e) {
         return status_of(e);

@@ -96,6 +96,11 @@ class CudaEngine:
                                                   sigma_loc.data_ptr(), ycols.data_ptr(), scatter.data_ptr(),
                                                   rank, world, phases, stream))
 
+    def apply_rows_t3_piece(self, c_loc, scatter, rank, world, row_first, row_count, flags):
+        stream = torch.cuda.current_stream(self.builder.device).cuda_stream
+        _lib.check(_lib.lib().f2_sigma_apply_rows_t3_piece(self.builder._h, c_loc.data_ptr(), scatter.data_ptr(), rank, world,
+                                                           int(row_first), int(row_count), int(flags), stream))
+
     def layout_from_library(self, nblocks, rank, world):
         sizes = np.zeros(2, dtype=np.int64)
         rows = np.zeros((nblocks, 6), dtype=np.int64)
@@ -409,10 +414,71 @@ class ShardedSigma:
         if getattr(self, "_host_c", None) is None:
             self._host_c = torch.empty(max(self.local_size, 1), **self._kw)[: self.local_size]
             self._host_s = torch.empty(max(self.local_size, 1), **self._kw)[: self.local_size]
-        self._host_c.copy_(ch.reshape(-1), non_blocking=True)
-        self.Hamiltonian(self._host_c, self._host_s)
-        sh.reshape(-1).copy_(self._host_s, non_blocking=True)
+            self._host_copy_stream = torch.cuda.Stream(self.device)
+        ch, sh = ch.reshape(-1), sh.reshape(-1)
+        if self._streamed_host_ok(ch):
+            self._hamiltonian_rows_streamed(ch, self._host_s)
+        else:
+            self._host_c.copy_(ch, non_blocking=True)
+            self.Hamiltonian(self._host_c, self._host_s)
+        sh.copy_(self._host_s, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+
+    def _streamed_host_ok(self, ch) -> bool:
+        """one determinant block in the rows form, pinned source, collectives issued here: the opposite-spin term of the
+        rows that have arrived runs while the rest of the shard is still crossing PCIe (F2_NO_STREAMED_SHARD: off)"""
+        import os
+        nonempty = [b for b in self.layout.blocks if b[1] * b[2] > 0]
+        if not (self.form == "rows" and self._lib is None and isinstance(self.engine, CudaEngine) and len(nonempty) == 1
+                and len(self.layout.blocks) == 1 and ch.is_pinned() and self.local_size > 0
+                and os.environ.get("F2_NO_STREAMED_SHARD") is None):
+            return False
+        if getattr(self, "_pieces_ok", None) is None:
+            try:  # an empty piece: validates that the one-block gather kernel serves this space
+                self.engine.apply_rows_t3_piece(self._host_c, self._scatter, self.rank, self.world, 0, 0, 0)
+                self._pieces_ok = True
+            except (RuntimeError, ValueError):
+                self._pieces_ok = False
+        return self._pieces_ok
+
+    def _hamiltonian_rows_streamed(self, c_host: torch.Tensor, sigma_loc: torch.Tensor, pieces: int = 4) -> None:
+        """Hamiltonian() of the rows form with the H2D copy of the shard inside: the shard is copied in `pieces` row
+        pieces on a copy stream; the opposite-spin kernel of piece 0 starts when it has arrived, the all-to-all of the
+        column slab when all of them have, beside the opposite-spin kernels of the other pieces."""
+        (_, nA, nB), (lo, nr, loc) = self.layout.blocks[0], self.layout.rows[0]
+        c_loc = self._host_c
+        main = torch.cuda.current_stream(self.device)
+        copy = self._host_copy_stream
+        copy.wait_stream(main)  # the previous build no longer reads c_loc
+        bounds = [nr * i // pieces for i in range(pieces + 1)]
+        events = []
+        with torch.cuda.stream(copy):
+            for i in range(pieces):
+                a, b = bounds[i] * nB, bounds[i + 1] * nB
+                if b > a:
+                    c_loc[a:b].copy_(c_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                events.append(ev)
+        args = (c_loc, self._xcols, sigma_loc, self._yexch, self._scatter, self.rank, self.world)
+
+        def piece(i):
+            flags = (1 if i == 0 else 0) | (2 if i == pieces - 1 else 0)
+            self.engine.apply_rows_t3_piece(c_loc, self._scatter, self.rank, self.world, bounds[i], bounds[i + 1] - bounds[i], flags)
+
+        main.wait_event(events[0])
+        piece(0)
+        main.wait_event(events[-1])
+        cols = self._exchange_cols_start(c_loc)
+        for i in range(1, pieces):
+            piece(i)
+        work = self._reduce_scatter_start()
+        self._exchange_cols_finish(cols)
+        self.engine.apply_rows(*args, phases=4)
+        back = self._exchange_add_start()
+        self.engine.apply_rows(*args, phases=8)
+        self._reduce_scatter_finish(work, sigma_loc)
+        self._exchange_add_finish(back, sigma_loc)
 
 
 class LibraryShardedSigma:

@@ -189,6 +189,13 @@ int f2_sigma_rows_form(f2_sigma* h, int rank, int world, int64_t* out4);
 int f2_sigma_apply_rows(f2_sigma* h, const double* C_local_dev, const double* xcols_dev,
                         double* sigma_local_dev, double* ycols_dev, double* scatter_dev, int rank, int world,
                         int phases, void* stream);
+/* Phase 1 of f2_sigma_apply_rows in pieces, for spaces with one determinant block: the opposite-spin term of the local
+ * input rows [row_first, row_first + row_count) (rows counted inside the rank's slab), so that a shard that lives in host
+ * memory is multiplied while its later rows are still being copied.  flags: 1 = first piece of a build (scatter is
+ * zeroed), 2 = last piece; a build is the pieces in any order covering every local row once, then phase 2 (or 4, 8) of
+ * f2_sigma_apply_rows.  No reference counterpart (the reference holds its vectors in host memory and has no device). */
+int f2_sigma_apply_rows_t3_piece(f2_sigma* h, const double* C_local_dev, double* scatter_dev, int rank, int world,
+                                 int64_t row_first, int64_t row_count, int flags, void* stream);
 
 /* ---- NCCL inside the library (f2_dist_init): the rows form of the sharded build with its collectives issued
  * by the library, for hosts that do not bring torch.distributed.  libnccl.so.2 is resolved at run time (dlopen).
