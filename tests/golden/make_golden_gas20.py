@@ -24,7 +24,7 @@ def main():
         rs = ref.RefCIStrings(*SPACE)
         E, H, V = synthetic.integrals(20, "S")
         rb = ref.RefCISigmaBuilder(rs, E, H, V)
-        rb.set_algorithm(os.environ.get("F2_GOLDEN_ALGORITHM", "kh"))  # "hz" is several times faster here
+        rb.set_algorithm(os.environ.get("F2_GOLDEN_ALGORITHM", "kh"))  # "hz" did not finish in 90 minutes on 8 cores either
         rb.set_memory(16384)
         c = synthetic.trial_vector(rs.ndet)
         sg = np.zeros_like(c)
